@@ -1,0 +1,87 @@
+/*
+ * b200_graph.h — C-ABI of the graph executor in libb200ops.so (row a10 of SURVEY.md §8).
+ *
+ * A neutral, plain-C mirror of the slice of ggml's graph IR that llm_build_llama / llm_build_qwen2
+ * emit (/root/reference/llama.cpp/src/llama-model.cpp:5968-6122, llama-graph.cpp): a node = op + dst
+ * + sources with ggml's ne[] (elements) / nb[] (byte strides) conventions (ggml/include/ggml.h:613-645).
+ * The ggml backend plug-in (include/ggml_b200.h) translates a ggml_cgraph into this form 1:1; tests
+ * and bench.py build the same node lists directly.  Replaces the node loop, fusion and CUDA-graph
+ * capture of ggml-cuda (ggml/src/ggml-cuda/ggml-cuda.cu:2845-3010, 2784-2843, 2593-2782).
+ *
+ * What the executor does with a node list:
+ *   - skips view ops, launches one hand-written sm_100a kernel per remaining node, or fewer:
+ *       RMS_NORM+MUL(+activation quantisation), MUL_MAT+ADD(bias)+ADD(residual),
+ *       MUL_MAT(up)+MUL_MAT(gate)+GLU, several MUL_MATs of one activation in one launch (QKV),
+ *   - quantises each activation tensor once per consumer group (the reference re-quantises per matmul),
+ *   - captures the whole list into a CUDA graph keyed by its topology and replays it while the
+ *     topology is unchanged (decode), so ~600 nodes cost one launch.
+ */
+#ifndef B200_GRAPH_H
+#define B200_GRAPH_H
+
+#include "b200_ops.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* tensor element types beyond b200_type, numerically equal to enum ggml_type */
+enum { B200_TYPE_I32 = 26, B200_TYPE_I64 = 27 };
+
+enum b200_op {
+    B200_OP_NONE = 0,        /* RESHAPE / VIEW / PERMUTE / TRANSPOSE / NONE: metadata only (ggml-cuda.cu:2404-2409) */
+    B200_OP_MUL_MAT,         /* src0 weights [K,M], src1 f32 [K,N]  -> dst f32 [M,N]                 */
+    B200_OP_RMS_NORM,        /* op_params[0] = eps (f32 bits)                                         */
+    B200_OP_MUL,             /* broadcasting f32                                                      */
+    B200_OP_ADD,
+    B200_OP_ROPE,            /* src0 x [hd,n_head,n_tok], src1 pos i32, src2 freq_factors (optional); op_params as ggml (rope.cu:347-368) */
+    B200_OP_SET_ROWS,        /* src0 f32 rows, src1 i64 ids, dst = cache (F32/F16/Q8_0)               */
+    B200_OP_FLASH_ATTN_EXT,  /* src0 q, src1 k, src2 v, src3 mask f16 (optional); op_params {scale,max_bias,softcap,prec} */
+    B200_OP_GLU_SWIGLU,      /* src0 gate, src1 up (split form, ggml.c:2796)                          */
+    B200_OP_GET_ROWS,        /* src0 f32 [ncols, nrows], src1 i32 ids                                  */
+    B200_OP_CPY,             /* src0 f32 -> dst f16 / f32, contiguous                                  */
+    B200_OP_COUNT
+};
+
+#define B200_MAX_SRC 6
+
+typedef struct b200_tensor {
+    uint64_t id;             /* identity for dependency analysis (plug-in: the ggml_tensor address); 0 = absent */
+    void    *data;           /* device pointer                                                          */
+    int32_t  type;           /* ggml_type value                                                         */
+    int32_t  flags;          /* reserved                                                                */
+    int64_t  ne[4];
+    int64_t  nb[4];
+} b200_tensor;
+
+typedef struct b200_node {
+    int32_t     op;          /* enum b200_op */
+    int32_t     n_src;
+    b200_tensor dst;
+    b200_tensor src[B200_MAX_SRC];
+    int32_t     op_params[16];
+} b200_node;
+
+enum {
+    B200_EXEC_CUDA_GRAPHS = 1,   /* capture / replay (off: GGML_B200_DISABLE_GRAPHS, like GGML_CUDA_DISABLE_GRAPHS ggml-cuda.cu:2937) */
+    B200_EXEC_FUSION      = 2,   /* cross-node fusion (off: GGML_B200_DISABLE_FUSION, like ggml-cuda.cu:2862)                          */
+};
+
+typedef struct b200_executor b200_executor;
+
+B200_API b200_executor *b200_executor_create(int device);
+B200_API void           b200_executor_free(b200_executor *ex);
+/* 1 if the executor can run this node exactly (the plug-in's supports_op answers with this) */
+B200_API int            b200_executor_supports(const b200_node *node);
+/* run the list in order on `stream`; asynchronous.  Returns b200_status. */
+B200_API int            b200_executor_compute(b200_executor *ex, const b200_node *nodes, int n_nodes, void *stream, int flags);
+/* counters for tests / bench: kernels launched by the last compute (inside a replayed graph too),
+ * number of CUDA-graph captures and replays so far */
+B200_API int64_t        b200_executor_last_kernels(const b200_executor *ex);
+B200_API int64_t        b200_executor_graph_captures(const b200_executor *ex);
+B200_API int64_t        b200_executor_graph_replays(const b200_executor *ex);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,192 @@
+/*
+ * b200_ops.h — C-ABI of libb200ops.so: the hand-written sm_100a kernels for the GGUF-quantized
+ * decode / prefill hot path.  Plain pointers and sizes only (device pointers unless stated);
+ * no ggml, no torch, no C++ types.  Every entry point names the reference function it replaces
+ * (paths relative to /root/reference/llama.cpp/).
+ *
+ * The ggml backend plug-in (include/ggml_b200.h, libggml-b200.so) is a thin adapter that maps
+ * ggml_cgraph nodes onto these calls; tests/ and bench.py bind this header with ctypes.
+ *
+ * Conventions
+ *   - tensor data use ggml's in-memory formats (ggml/src/ggml-common.h:170-344) unless a
+ *     function says "repacked" (see b200_repack_rows).
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return value: B200_OK or a negative b200_status; nothing aborts the process
+ *     (the reference's CUDA_CHECK aborts: ggml-cuda/common.cuh:142-150).
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns B200_ERR_CUDA.
+ */
+#ifndef B200_OPS_H
+#define B200_OPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#  define B200_API __declspec(dllexport)
+#else
+#  define B200_API __attribute__((visibility("default")))
+#endif
+
+enum b200_status {
+    B200_OK              =  0,
+    B200_ERR_UNSUPPORTED = -1,   /* type / shape not handled by the hot path               */
+    B200_ERR_INVALID     = -2,   /* bad argument (alignment, size not a block multiple ...) */
+    B200_ERR_CUDA        = -3,   /* CUDA runtime error (see b200_last_error)                */
+};
+
+/* numerically equal to enum ggml_type (ggml/include/ggml.h:377-418) */
+enum b200_type {
+    B200_TYPE_F32  = 0,
+    B200_TYPE_F16  = 1,
+    B200_TYPE_Q4_0 = 2,
+    B200_TYPE_Q8_0 = 8,
+    B200_TYPE_Q4_K = 12,
+    B200_TYPE_Q5_K = 13,
+    B200_TYPE_Q6_K = 14,
+};
+
+/* ---- library / device ------------------------------------------------------------------ */
+B200_API int         b200_abi_version(void);               /* bumps on any signature change   */
+B200_API int         b200_device_count(void);              /* 0 when no CUDA device            */
+B200_API int         b200_device_sm_count(int device);
+B200_API const char *b200_last_error(void);                /* thread-local, never NULL         */
+B200_API int64_t     b200_kernel_launches(void);           /* kernels launched by this library */
+
+/* block geometry of a weight / cache type: elements and bytes per block, bytes per row of k */
+B200_API int64_t b200_block_elems(int type);
+B200_API int64_t b200_block_bytes(int type);
+B200_API int64_t b200_row_bytes(int type, int64_t k);
+
+/* ---- weight repack (load time) --------------------------------------------------------- *
+ * Q4_0 / Q8_0 / Q6_K blocks are 18 / 34 / 210 bytes, which defeats 16-byte loads
+ * (ggml-cuda reads them with 2-/4-byte loads: vecdotq.cuh:18-29).  We permute the bytes
+ * INSIDE each row, in place, into a structure-of-arrays row:
+ *     Q4_0: [qs 16B x nb][d f16 x nb]          Q8_0: [qs 32B x nb][d f16 x nb]
+ *     Q6_K: [ql 128B x nb][qh 64B x nb][scales 16B x nb][d f16 x nb]
+ * Row size and row offsets are unchanged, so ggml views / strides stay valid.  Q4_K / Q5_K
+ * (144 / 176-byte blocks) are left as they are.  b200_unpack_rows is the exact inverse.
+ * Replaces nothing in ggml-cuda; plays the role ggml-cpu/repack.cpp plays for the CPU backend. */
+B200_API int b200_repack_rows(int type, void *rows, int64_t nrows, int64_t k, void *stream);
+B200_API int b200_unpack_rows(int type, void *rows, int64_t nrows, int64_t k, void *stream);
+B200_API int b200_type_is_repacked(int type);              /* 1 for Q4_0/Q8_0/Q6_K            */
+
+/* ---- activation quantisation (replaces quantize_row_q8_1_cuda, ggml-cuda/quantize.cu:148-160)
+ * We quantise the way the CPU ORACLE does, so integer partial sums are bit-identical:
+ *   K-quant weights  -> q8_K: 256-wide, iscale=-127/max, f32 d, bsums/16 (ggml-quants.c:2555-2592)
+ *   Q4_0/Q8_0 weights-> q8_0: 32-wide, d=max/127 as f16, RNE (ggml-cpu/arch/x86/quants.c:290-360)
+ * Output is an SoA "act buffer" per column (all sections 16-byte aligned):
+ *   kind 0 (q8_K): int8 qs[k] | float d[k/256] | int16 bsums[k/16]
+ *   kind 1 (q8_0): int8 qs[k] | float d[k/32] (value of the f16-rounded scale) | int16 bsum[k/32]
+ * b200_act_col_bytes gives the per-column stride. */
+B200_API int     b200_act_kind_for(int weight_type);       /* 0 = q8_K, 1 = q8_0, <0 unsupported */
+B200_API int64_t b200_act_col_bytes(int kind, int64_t k);
+B200_API int64_t b200_act_d_offset(int kind, int64_t k);
+B200_API int64_t b200_act_bsum_offset(int kind, int64_t k);
+B200_API int b200_quantize_act(int kind, const float *x, int64_t x_col_stride /* floats */,
+                               void *act, int64_t k, int64_t ncols, void *stream);
+
+/* fused RMS_NORM * weight -> act buffer (and optionally the f32 normalised row too);
+ * replaces rms_norm_f32<…,do_multiply> + quantize_q8_1 (norm.cu:107-164, quantize.cu:4-48) */
+B200_API int b200_rms_norm_quantize(const float *x, const float *w, float *y_or_null, void *act0, int kind0,
+                                    void *act1_or_null, int kind1, int64_t k, int64_t ncols, float eps, void *stream);
+
+/* ---- MUL_MAT, decode matvec (replaces ggml_cuda_mul_mat_vec_q, mmvq.cu:500-570,139-226) -
+ * dst[c][r] = sum_k W[r][k] * x[c][k] (+ bias[r]) (+ residual[c][r]),  ncols <= 8
+ *   W        : m rows of `type` (repacked for Q4_0/Q8_0/Q6_K), row stride b200_row_bytes(type,k),
+ *              16-byte aligned, readable up to the next 16-byte boundary past the end
+ *   act      : act buffer of kind b200_act_kind_for(type), ncols columns
+ *   dst      : f32, column stride dst_col_stride floats
+ *   bias     : f32 [m] or NULL (Qwen2 QKV bias, binbcast.cu)   residual: f32 like dst or NULL */
+B200_API int b200_mul_mat_vec_q(int type, const void *W, const void *act, float *dst, int64_t dst_col_stride,
+                                const float *bias, const float *residual,
+                                int64_t m, int64_t k, int64_t ncols, void *stream);
+
+/* several weight matrices against the same act buffer in ONE launch (fused QKV / gate+up):
+ * descriptors live in device or pinned host memory; n_mats <= 4 */
+typedef struct b200_mmv_desc {
+    const void  *W;        /* weights of `type`                         */
+    float       *dst;      /* f32 output [ncols][m] (col stride = m)    */
+    const float *bias;     /* optional                                  */
+    int64_t      m;
+    int32_t      type;
+    int32_t      _pad;
+} b200_mmv_desc;
+B200_API int b200_mul_mat_vec_q_multi(const b200_mmv_desc *descs, int n_mats, const void *act_q8K, const void *act_q80,
+                                      int64_t k, int64_t ncols, void *stream);
+
+/* gate & up matvec + SwiGLU in one launch: dst[c][r] = silu(Wg[r].x[c]) * (Wu[r].x[c])
+ * (replaces 2x mul_mat_vec_q + unary_gated_op_kernel, unary.cu:209-230) */
+B200_API int b200_mul_mat_vec_q_swiglu(int type_gate, const void *Wg, int type_up, const void *Wu,
+                                       const void *act_q8K, const void *act_q80, float *dst,
+                                       int64_t m, int64_t k, int64_t ncols, void *stream);
+
+/* ---- MUL_MAT, batched / prefill (replaces ggml_cuda_mul_mat_q, mmq.cu:71-143) -----------
+ * dst[c][r] for any ncols; X is f32 [ncols][k].  Internally: activation quantisation as above,
+ * then tiles on the tensor cores (tcgen05, TMEM accumulators) when ncols >= B200_MMQ_MIN_COLS,
+ * else column groups of 8 through the matvec kernel.  `workspace` must hold
+ * b200_mul_mat_q_workspace(type,m,k,ncols) bytes. */
+B200_API int64_t b200_mul_mat_q_workspace(int type, int64_t m, int64_t k, int64_t ncols);
+B200_API int b200_mul_mat_q(int type, const void *W, const float *X, int64_t x_col_stride,
+                            float *dst, int64_t dst_col_stride, int64_t m, int64_t k, int64_t ncols,
+                            void *workspace, void *stream);
+
+/* ---- RMS_NORM (+MUL) (replaces ggml_cuda_op_rms_norm[_fused], norm.cu:420-495) ---------- */
+B200_API int b200_rms_norm(const float *x, const float *w_or_null, float *y, int64_t ncols, int64_t nrows,
+                           int64_t x_row_stride, int64_t y_row_stride, float eps, void *stream);
+
+/* ---- ROPE (replaces ggml_cuda_op_rope, rope.cu:324-446) ---------------------------------
+ * x,y: [n_tok][n_head][head_dim] f32 with strides in floats; pos i32 [n_tok];
+ * mode 0 = NORM, 2 = NEOX.  theta is built iteratively like the CPU oracle (ops.cpp:6077-6086). */
+typedef struct b200_rope_params {
+    int32_t n_dims, mode, n_ctx_orig, _pad;
+    float freq_base, freq_scale, ext_factor, attn_factor, beta_fast, beta_slow;
+} b200_rope_params;
+B200_API int b200_rope(const float *x, float *y, const int32_t *pos, const float *freq_factors_or_null,
+                       int64_t head_dim, int64_t n_head, int64_t n_tok,
+                       int64_t x_head_stride, int64_t x_tok_stride, int64_t y_head_stride, int64_t y_tok_stride,
+                       const b200_rope_params *p, void *stream);
+
+/* ---- SET_ROWS (KV store; replaces ggml_cuda_op_set_rows, set-rows.cu:166-275) ------------
+ * dst row ids[i] <- convert(src row i);  dst_type F32 / F16 / Q8_0 (ggml-native layout) */
+B200_API int b200_set_rows(const float *src, int64_t src_row_stride /* floats */, const int64_t *ids,
+                           void *dst, int dst_type, int64_t dst_row_stride /* bytes */,
+                           int64_t ncols, int64_t nrows, void *stream);
+
+/* fused decode-step tail of the QKV projection: rope(q) in place, rope(k) -> K cache row,
+ * v -> V cache row (replaces 2x rope + 2x set_rows launches) */
+B200_API int b200_rope_kv_store(float *q, const float *k, const float *v, const int32_t *pos, const float *freq_factors_or_null,
+                                const int64_t *kv_ids, void *k_cache, void *v_cache, int kv_type, int64_t kv_row_stride,
+                                int64_t head_dim, int64_t n_head, int64_t n_head_kv, int64_t n_tok,
+                                const b200_rope_params *p, void *stream);
+
+/* ---- FLASH_ATTN_EXT (replaces ggml_cuda_flash_attn_ext, fattn.cu:271-338) ----------------
+ *   q    f32, element (d, tok, head) at q + tok*q_tok_stride + head*q_head_stride (floats)
+ *   k,v  cache rows of kv_type (F16 or Q8_0): (pos, kv_head) at base + pos*row_stride + kv_head*head_stride (bytes)
+ *   mask f16 [n_tok_padded][n_kv] (row stride mask_row_stride halves) or NULL; -inf = masked
+ *   dst  f32 [n_tok][n_head][dv] contiguous
+ *   workspace: b200_flash_attn_workspace(...) bytes for split-KV partials */
+B200_API int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv);
+B200_API int b200_flash_attn_ext(const float *q, int64_t q_tok_stride, int64_t q_head_stride,
+                                 const void *k, int64_t k_row_stride, int64_t k_head_stride,
+                                 const void *v, int64_t v_row_stride, int64_t v_head_stride,
+                                 const void *mask, int64_t mask_row_stride, float *dst,
+                                 int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv,
+                                 int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap,
+                                 void *workspace, void *stream);
+
+/* ---- glue (replaces binbcast.cu, unary.cu:291, getrows.cu, cpy.cu) ----------------------- */
+B200_API int b200_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows, void *stream);
+B200_API int b200_mul(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows, void *stream);
+B200_API int b200_swiglu(const float *gate, const float *up, float *y, int64_t n, void *stream);
+B200_API int b200_get_rows_f32(const float *src, int64_t src_row_stride, const int32_t *ids, float *dst, int64_t ncols, int64_t n_ids, void *stream);
+B200_API int b200_cpy_f32_f16(const float *src, void *dst_f16, int64_t n, void *stream);
+B200_API int b200_argmax_f32(const float *x, int32_t *idx_out, int64_t n, int64_t nrows, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_OPS_H */

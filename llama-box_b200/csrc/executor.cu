@@ -1,0 +1,500 @@
+// executor.cu — graph executor: node list -> fused kernel launches -> CUDA-graph capture / replay.
+// C-ABI in include/b200_graph.h.  Replaces ggml-cuda's evaluate_and_capture_cuda_graph / compute_forward
+// (ggml/src/ggml-cuda/ggml-cuda.cu:2845-3010, 2207-2493), its RMS_NORM+MUL fusion (:2784-2843) and the
+// graph-property check that decides on re-capture (:2726-2782).  Host code only; kernels live in the
+// other translation units and are reached through the same C-ABI the tests use (b200_ops.h).
+#include "common.cuh"
+#include "../../include/b200_graph.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+inline bool is_weight_type(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q4_K || t == B200_TYPE_Q5_K || t == B200_TYPE_Q6_K; }
+inline int64_t nrows_of(const b200_tensor & t) { return t.ne[1] * t.ne[2] * t.ne[3]; }
+inline int64_t nelem(const b200_tensor & t) { return t.ne[0] * t.ne[1] * t.ne[2] * t.ne[3]; }
+inline int64_t elem_size(int type) {
+    switch (type) { case B200_TYPE_F32: case B200_TYPE_I32: return 4; case B200_TYPE_F16: return 2; case B200_TYPE_I64: return 8; default: return 0; }
+}
+// fully contiguous f32/f16/int tensor in ggml's sense
+inline bool contiguous(const b200_tensor & t) {
+    const int64_t es = elem_size(t.type);
+    if (es == 0) return false;
+    int64_t s = es;
+    for (int i = 0; i < 4; i++) { if (t.ne[i] != 1 && t.nb[i] != s) return false; s *= t.ne[i]; }
+    return true;
+}
+inline bool same_shape(const b200_tensor & a, const b200_tensor & b) { return a.ne[0] == b.ne[0] && a.ne[1] == b.ne[1] && a.ne[2] == b.ne[2] && a.ne[3] == b.ne[3]; }
+inline bool aligned16(const void * p) { return ((uintptr_t)p & 15) == 0; }
+inline float f32_param(const b200_node & n, int i) { float f; memcpy(&f, &n.op_params[i], 4); return f; }
+
+inline size_t tensor_bytes(const b200_tensor & t) {
+    if (!t.data) return 0;
+    if (is_weight_type(t.type)) return (size_t)(nrows_of(t) > 0 ? (t.ne[1] - 1) * t.nb[1] + (t.ne[2] - 1) * t.nb[2] + (t.ne[3] - 1) * t.nb[3] + type_block_bytes(t.type) * (t.ne[0] / type_block_elems(t.type)) : 0);
+    size_t b = (size_t)elem_size(t.type);
+    for (int i = 0; i < 4; i++) b += (size_t)(t.ne[i] - 1) * (size_t)t.nb[i];
+    return b;
+}
+inline bool overlaps(const b200_tensor & a, const b200_tensor & b) {
+    if (!a.data || !b.data) return false;
+    const uintptr_t a0 = (uintptr_t)a.data, a1 = a0 + tensor_bytes(a), b0 = (uintptr_t)b.data, b1 = b0 + tensor_bytes(b);
+    return a0 < b1 && b0 < a1;
+}
+
+bool mul_mat_ok(const b200_node & n) {
+    const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
+    if (!is_weight_type(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    const int64_t k = w.ne[0], m = w.ne[1];
+    if (k <= 0 || k % 256 != 0 || (w.type == B200_TYPE_Q6_K && k % 2048 != 0)) return false;
+    if (w.ne[2] != 1 || w.ne[3] != 1 || x.ne[2] != 1 || x.ne[3] != 1) return false;            // no broadcast batches on this path
+    if (w.nb[1] != type_block_bytes(w.type) * (k / type_block_elems(w.type))) return false;
+    if (x.ne[0] != k || x.nb[0] != 4 || (x.nb[1] & 15) || d.ne[0] != m || d.ne[1] != x.ne[1] || d.nb[0] != 4 || (d.nb[1] & 3)) return false;
+    return aligned16(w.data) && aligned16(x.data);
+}
+bool rows_f32_ok(const b200_tensor & t) { return t.type == B200_TYPE_F32 && contiguous(t) && t.ne[0] % 4 == 0 && aligned16(t.data); }
+bool bin_ok(const b200_node & n) {
+    const b200_tensor & a = n.src[0], & b = n.src[1], & d = n.dst;
+    if (!rows_f32_ok(a) || !rows_f32_ok(d) || !same_shape(a, d) || b.type != B200_TYPE_F32 || !contiguous(b) || !aligned16(b.data)) return false;
+    if (same_shape(a, b)) return true;
+    return b.ne[0] == a.ne[0] && b.ne[2] == 1 && b.ne[3] == 1 && b.ne[1] > 0 && a.ne[1] % b.ne[1] == 0;
+}
+bool rope_ok(const b200_node & n) {
+    const b200_tensor & x = n.src[0], & p = n.src[1], & d = n.dst;
+    if (x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32 || p.type != B200_TYPE_I32 || x.nb[0] != 4 || d.nb[0] != 4) return false;
+    if (x.ne[3] != 1 || !same_shape(x, d) || (x.ne[0] & 1) || p.ne[0] < x.ne[2]) return false;
+    const int mode = n.op_params[2], n_dims = n.op_params[1];
+    if ((mode & ~2) || n_dims <= 0 || n_dims > x.ne[0] || (n_dims & 1)) return false;
+    if ((x.nb[1] | x.nb[2] | d.nb[1] | d.nb[2]) & 3) return false;
+    if (n.n_src > 2 && n.src[2].data && (n.src[2].type != B200_TYPE_F32 || n.src[2].ne[0] < n_dims / 2)) return false;
+    return true;
+}
+bool set_rows_ok(const b200_node & n) {
+    const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+    if (s.type != B200_TYPE_F32 || ids.type != B200_TYPE_I64 || s.nb[0] != 4 || (s.nb[1] & 15) || !aligned16(s.data)) return false;
+    if (d.type != B200_TYPE_F32 && d.type != B200_TYPE_F16 && d.type != B200_TYPE_Q8_0) return false;
+    if (s.ne[2] != 1 || s.ne[3] != 1 || d.ne[2] != 1 || d.ne[3] != 1 || s.ne[0] != d.ne[0] || s.ne[0] % 32 != 0 || ids.ne[0] != s.ne[1]) return false;
+    if (d.type != B200_TYPE_Q8_0 && (((uintptr_t)d.data | (uintptr_t)d.nb[1]) & 15)) return false;
+    return true;
+}
+bool fattn_ok(const b200_node & n) {
+    const b200_tensor & q = n.src[0], & k = n.src[1], & v = n.src[2], & d = n.dst;
+    if (n.n_src > 4 && n.src[4].data) return false;                                  // attention sinks: not on this path
+    if (q.type != B200_TYPE_F32 || d.type != B200_TYPE_F32 || k.type != v.type) return false;
+    if (k.type != B200_TYPE_F16 && k.type != B200_TYPE_Q8_0) return false;
+    const int64_t dk = q.ne[0], dv = v.ne[0];
+    if (dk != dv || (dk != 64 && dk != 128) || k.ne[0] != dk) return false;
+    if (q.ne[3] != 1 || k.ne[3] != 1 || v.ne[3] != 1 || k.ne[1] != v.ne[1] || k.ne[2] != v.ne[2] || k.ne[2] <= 0 || q.ne[2] % k.ne[2] != 0) return false;
+    if (q.nb[0] != 4 || (q.nb[1] & 15) || (q.nb[2] & 15) || !aligned16(q.data)) return false;
+    if (k.type == B200_TYPE_F16 && ((((uintptr_t)k.data | (uintptr_t)v.data) & 15) || ((k.nb[1] | k.nb[2] | v.nb[1] | v.nb[2]) & 15))) return false;
+    if (!contiguous(d) || d.ne[0] != dv || d.ne[1] != q.ne[2] || d.ne[2] != q.ne[1] || q.ne[1] > 65535) return false;
+    if (n.n_src > 3 && n.src[3].data) {
+        const b200_tensor & m = n.src[3];
+        if (m.type != B200_TYPE_F16 || m.nb[0] != 2 || m.ne[0] != k.ne[1] || m.ne[1] < q.ne[1] || m.ne[2] != 1 || m.ne[3] != 1) return false;
+    }
+    return true;
+}
+
+bool node_ok(const b200_node & n) {
+    switch (n.op) {
+        case B200_OP_NONE:     return true;
+        case B200_OP_MUL_MAT:  return n.n_src >= 2 && mul_mat_ok(n);
+        case B200_OP_RMS_NORM: return n.n_src >= 1 && rows_f32_ok(n.src[0]) && rows_f32_ok(n.dst) && same_shape(n.src[0], n.dst) && n.src[0].ne[0] * 4 <= 200 * 1024;
+        case B200_OP_MUL: case B200_OP_ADD: return n.n_src >= 2 && bin_ok(n);
+        case B200_OP_ROPE:     return n.n_src >= 2 && rope_ok(n);
+        case B200_OP_SET_ROWS: return n.n_src >= 2 && set_rows_ok(n);
+        case B200_OP_FLASH_ATTN_EXT: return n.n_src >= 3 && fattn_ok(n);
+        case B200_OP_GLU_SWIGLU: return n.n_src >= 2 && rows_f32_ok(n.src[0]) && rows_f32_ok(n.src[1]) && rows_f32_ok(n.dst) && same_shape(n.src[0], n.src[1]) && same_shape(n.src[0], n.dst);
+        case B200_OP_GET_ROWS: {
+            const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+            return n.n_src >= 2 && s.type == B200_TYPE_F32 && ids.type == B200_TYPE_I32 && s.nb[0] == 4 && (s.nb[1] & 15) == 0 && s.ne[2] == 1 && s.ne[3] == 1 &&
+                   s.ne[0] % 4 == 0 && aligned16(s.data) && d.type == B200_TYPE_F32 && contiguous(d) && aligned16(d.data) && ids.ne[1] == 1 && ids.ne[2] == 1 && d.ne[1] == ids.ne[0];
+        }
+        case B200_OP_CPY: {
+            const b200_tensor & s = n.src[0], & d = n.dst;
+            return n.n_src >= 1 && s.type == B200_TYPE_F32 && contiguous(s) && contiguous(d) && nelem(s) == nelem(d) && (d.type == B200_TYPE_F16 || d.type == B200_TYPE_F32) && aligned16(s.data) && ((uintptr_t)d.data & 7) == 0;
+        }
+        default: return false;
+    }
+}
+
+struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; uint64_t last_use = 0; };
+
+} // namespace
+
+struct b200_executor {
+    int device = 0;
+    // workspace: [act q8_K][act q8_0][fattn partials]
+    uint8_t * ws = nullptr; size_t ws_bytes = 0;
+    size_t off_act[2] = {0, 0}, act_bytes[2] = {0, 0}, off_fa = 0, fa_bytes = 0;
+    uint64_t act_id[2] = {0, 0}; const void * act_ptr[2] = {nullptr, nullptr}; int64_t act_cols[2] = {0, 0};
+    std::unordered_map<uint64_t, GraphEntry> graphs;
+    std::unordered_map<uint64_t, int> seen;      // topology -> times seen before capture (first sighting runs eagerly)
+    uint64_t tick = 0;
+    int64_t last_kernels = 0, captures = 0, replays = 0;
+    bool env_no_graphs = false, env_no_fusion = false;
+};
+
+namespace {
+
+struct Runner {
+    b200_executor * ex; const b200_node * nodes; int n; cudaStream_t st; bool fuse;
+    std::vector<uint8_t> done;
+    std::unordered_map<uint64_t, int> uses;
+
+    int use_count(const b200_tensor & t) const { auto it = uses.find(t.id); return it == uses.end() ? 0 : it->second; }
+    int next_compute(int i) const { for (int j = i + 1; j < n; j++) if (!done[j] && nodes[j].op != B200_OP_NONE) return j; return -1; }
+
+    void invalidate_act(const b200_tensor & written) {
+        for (int kd = 0; kd < 2; kd++) if (ex->act_id[kd] && ex->act_ptr[kd] == written.data) ex->act_id[kd] = 0;
+    }
+    uint8_t * act_buf(int kind) const { return ex->ws + ex->off_act[kind]; }
+
+    // make sure the act buffer of `kind` holds the quantised form of x (n cols of k)
+    int ensure_act(const b200_tensor & x, int kind) {
+        if (ex->act_id[kind] == x.id && x.id != 0 && ex->act_ptr[kind] == x.data && ex->act_cols[kind] == x.ne[1]) return B200_OK;
+        int s = b200_quantize_act(kind, (const float *)x.data, x.nb[1] / 4, act_buf(kind), x.ne[0], x.ne[1], st);
+        if (s != B200_OK) return s;
+        ex->act_id[kind] = x.id; ex->act_ptr[kind] = x.data; ex->act_cols[kind] = x.ne[1];
+        return B200_OK;
+    }
+
+    int run_rms_norm(int i) {
+        const b200_node & n = nodes[i];
+        const float eps = f32_param(n, 0);
+        const b200_tensor & x = n.src[0];
+        const int64_t ncols = x.ne[0], nrows = nrows_of(x);
+        // RMS_NORM -> MUL(weight row): llama-graph.cpp:605-619 (build_norm)
+        const int j = fuse ? next_compute(i) : -1;
+        if (j >= 0 && nodes[j].op == B200_OP_MUL && use_count(n.dst) == 1) {
+            const b200_node & mu = nodes[j];
+            const b200_tensor * w = nullptr;
+            if (mu.src[0].id == n.dst.id && mu.src[0].data == n.dst.data) w = &mu.src[1];
+            else if (mu.src[1].id == n.dst.id && mu.src[1].data == n.dst.data) w = &mu.src[0];
+            if (w && w->ne[0] == ncols && nrows_of(*w) == 1 && same_shape(mu.dst, x)) {
+                done[j] = 1;
+                // if the next consumer is a decode-shaped quantised MUL_MAT, emit its activation format too
+                const int c = next_compute(j);
+                if (c >= 0 && nodes[c].op == B200_OP_MUL_MAT && nodes[c].src[1].id == mu.dst.id && nodes[c].src[1].data == mu.dst.data &&
+                    nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4) {
+                    const int kind = b200_act_kind_for(nodes[c].src[0].type);
+                    int s = b200_rms_norm_quantize((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, act_buf(kind), kind, nullptr, 0, ncols, nrows, eps, st);
+                    if (s != B200_OK) return s;
+                    invalidate_act(mu.dst);
+                    ex->act_id[kind] = mu.dst.id; ex->act_ptr[kind] = mu.dst.data; ex->act_cols[kind] = nrows;
+                    return B200_OK;
+                }
+                invalidate_act(mu.dst);
+                return b200_rms_norm((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, ncols, nrows, ncols, ncols, eps, st);
+            }
+        }
+        invalidate_act(n.dst);
+        return b200_rms_norm((const float *)x.data, nullptr, (float *)n.dst.data, ncols, nrows, ncols, ncols, eps, st);
+    }
+
+    // may node j (a later MUL_MAT of the same activation) be executed now, at position i?
+    bool can_hoist(int i, int j) const {
+        const b200_tensor & d = nodes[j].dst;
+        for (int q = i; q < j; q++) {
+            if (done[q]) continue;
+            const b200_node & m = nodes[q];
+            if (m.op == B200_OP_NONE) continue;
+            if (overlaps(d, m.dst)) return false;
+            for (int s = 0; s < m.n_src && s < B200_MAX_SRC; s++) if (overlaps(d, m.src[s])) return false;
+        }
+        return true;
+    }
+
+    int run_mul_mat(int i) {
+        const b200_node & n = nodes[i];
+        const b200_tensor & w = n.src[0], & x = n.src[1];
+        const int64_t k = w.ne[0], m = w.ne[1], ncols = x.ne[1];
+        if (ncols > 8) {
+            invalidate_act(n.dst);
+            ex->act_id[0] = ex->act_id[1] = 0;           // the batched path owns the act buffers
+            const int kind = b200_act_kind_for(w.type);
+            return b200_mul_mat_q(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, ncols, act_buf(kind), st);
+        }
+        const int kind = b200_act_kind_for(w.type);
+        int s = ensure_act(x, kind);
+        if (s != B200_OK) return s;
+
+        if (fuse) {
+            // (1) up, gate, GLU (llama-graph.cpp:647-693): MUL_MAT(up,x) MUL_MAT(gate,x) GLU(gate,up)
+            const int j = next_compute(i);
+            if (j >= 0 && nodes[j].op == B200_OP_MUL_MAT && nodes[j].src[1].id == x.id && nodes[j].src[1].data == x.data && nodes[j].src[0].ne[1] == m && nodes[j].src[1].ne[1] == ncols) {
+                const int g = next_compute(j);
+                if (g >= 0 && nodes[g].op == B200_OP_GLU_SWIGLU && use_count(n.dst) == 1 && use_count(nodes[j].dst) == 1 &&
+                    n.dst.nb[1] == m * 4 && nodes[j].dst.nb[1] == m * 4) {
+                    const b200_node & G = nodes[g];
+                    const b200_node * gate = nullptr, * up = nullptr;
+                    if (G.src[0].data == nodes[j].dst.data && G.src[1].data == n.dst.data) { gate = &nodes[j]; up = &n; }
+                    else if (G.src[0].data == n.dst.data && G.src[1].data == nodes[j].dst.data) { gate = &n; up = &nodes[j]; }
+                    if (gate) {
+                        const int kg = b200_act_kind_for(gate->src[0].type), ku = b200_act_kind_for(up->src[0].type);
+                        if ((s = ensure_act(x, kg)) != B200_OK || (s = ensure_act(x, ku)) != B200_OK) return s;
+                        done[j] = done[g] = 1;
+                        invalidate_act(G.dst);
+                        return b200_mul_mat_vec_q_swiglu(gate->src[0].type, gate->src[0].data, up->src[0].type, up->src[0].data,
+                                                         act_buf(0), act_buf(1), (float *)G.dst.data, m, k, ncols, st);
+                    }
+                }
+            }
+            // (2) several projections of one activation (QKV, llama-model.cpp:6004-6022) in one launch;
+            //     later MUL_MATs are hoisted only if their outputs alias nothing that is still live
+            int group[MAX_GROUP] = { i }; int ng = 1;
+            for (int j2 = i + 1; j2 < n_limit(i) && ng < MAX_GROUP; j2++) {
+                if (done[j2] || nodes[j2].op != B200_OP_MUL_MAT) continue;
+                const b200_node & o = nodes[j2];
+                if (o.src[1].id != x.id || o.src[1].data != x.data || o.src[1].ne[1] != ncols || o.src[0].ne[0] != k) continue;
+                if (o.dst.nb[1] != o.src[0].ne[1] * 4 || !can_hoist(i, j2)) continue;
+                group[ng++] = j2;
+            }
+            if (ng > 1 && n.dst.nb[1] == m * 4) {
+                b200_mmv_desc descs[MAX_GROUP];
+                for (int q = 0; q < ng; q++) {
+                    const b200_node & o = nodes[group[q]];
+                    const int ko = b200_act_kind_for(o.src[0].type);
+                    if ((s = ensure_act(x, ko)) != B200_OK) return s;
+                    descs[q] = { o.src[0].data, (float *)o.dst.data, nullptr, o.src[0].ne[1], o.src[0].type, 0 };
+                    if (q) done[group[q]] = 1;
+                    // bias ADD right after the projection (Qwen2 QKV bias, llama-model.cpp:6006-6020)
+                    const int a = next_compute(group[q]);
+                    if (a >= 0 && nodes[a].op == B200_OP_ADD && use_count(o.dst) == 1 && nodes[a].src[0].data == o.dst.data && nrows_of(nodes[a].src[1]) == 1 &&
+                        nodes[a].src[1].ne[0] == o.src[0].ne[1] && nodes[a].dst.nb[1] == o.src[0].ne[1] * 4 && (q == 0 || can_hoist(i, a))) {
+                        descs[q].bias = (const float *)nodes[a].src[1].data; descs[q].dst = (float *)nodes[a].dst.data; done[a] = 1;
+                        invalidate_act(nodes[a].dst);
+                    }
+                    invalidate_act(o.dst);
+                }
+                return b200_mul_mat_vec_q_multi(descs, ng, act_buf(0), act_buf(1), k, ncols, st);
+            }
+            // (3) epilogue: + bias row, + residual (wo / ffn_down followed by ADD, llama-model.cpp:6052,6095)
+            const float * bias = nullptr, * resid = nullptr; const b200_tensor * out = &n.dst;
+            int cur = i;
+            for (int step = 0; step < 2; step++) {
+                const int a = next_compute(cur);
+                if (a < 0 || nodes[a].op != B200_OP_ADD || use_count(*out) != 1) break;
+                const b200_node & A = nodes[a];
+                const b200_tensor * other = A.src[0].data == out->data ? &A.src[1] : (A.src[1].data == out->data ? &A.src[0] : nullptr);
+                if (!other || A.dst.nb[1] != out->nb[1] || !same_shape(A.dst, *out)) break;
+                if (!bias && !resid && nrows_of(*other) == 1 && other->ne[0] == m) bias = (const float *)other->data;
+                else if (!resid && same_shape(*other, *out) && other->nb[1] == out->nb[1]) resid = (const float *)other->data;
+                else break;
+                done[a] = 1; out = &A.dst; cur = a;
+            }
+            invalidate_act(*out);
+            return b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)out->data, out->nb[1] / 4, bias, resid, m, k, ncols, st);
+        }
+        invalidate_act(n.dst);
+        return b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)n.dst.data, n.dst.nb[1] / 4, nullptr, nullptr, m, k, ncols, st);
+    }
+    static constexpr int MAX_GROUP = 4;
+    int n_limit(int i) const { return i + 24 < n ? i + 24 : n; }
+
+    int run_node(int i) {
+        const b200_node & n = nodes[i];
+        switch (n.op) {
+            case B200_OP_NONE: return B200_OK;
+            case B200_OP_RMS_NORM: return run_rms_norm(i);
+            case B200_OP_MUL_MAT:  return run_mul_mat(i);
+            case B200_OP_MUL: case B200_OP_ADD: {
+                invalidate_act(n.dst);
+                const b200_tensor & a = n.src[0], & b = n.src[1];
+                const int64_t rows = nrows_of(a), brows = same_shape(a, b) ? rows : b.ne[1];
+                return n.op == B200_OP_ADD ? b200_add((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st)
+                                           : b200_mul((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st);
+            }
+            case B200_OP_ROPE: {
+                invalidate_act(n.dst);
+                const b200_tensor & x = n.src[0];
+                b200_rope_params p; memset(&p, 0, sizeof(p));
+                p.n_dims = n.op_params[1]; p.mode = n.op_params[2]; p.n_ctx_orig = n.op_params[4];
+                p.freq_base = f32_param(n, 5); p.freq_scale = f32_param(n, 6); p.ext_factor = f32_param(n, 7);
+                p.attn_factor = f32_param(n, 8); p.beta_fast = f32_param(n, 9); p.beta_slow = f32_param(n, 10);
+                const float * ff = n.n_src > 2 ? (const float *)n.src[2].data : nullptr;
+                return b200_rope((const float *)x.data, (float *)n.dst.data, (const int32_t *)n.src[1].data, ff, x.ne[0], x.ne[1], x.ne[2],
+                                 x.nb[1] / 4, x.nb[2] / 4, n.dst.nb[1] / 4, n.dst.nb[2] / 4, &p, st);
+            }
+            case B200_OP_SET_ROWS: {
+                const b200_tensor & s = n.src[0];
+                return b200_set_rows((const float *)s.data, s.nb[1] / 4, (const int64_t *)n.src[1].data, n.dst.data, n.dst.type, n.dst.nb[1], s.ne[0], s.ne[1], st);
+            }
+            case B200_OP_FLASH_ATTN_EXT: {
+                invalidate_act(n.dst);
+                const b200_tensor & q = n.src[0], & k = n.src[1], & v = n.src[2];
+                const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
+                const int64_t mrs = mask ? n.src[3].nb[1] / 2 : 0;
+                return b200_flash_attn_ext((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
+                                           (float *)n.dst.data, k.type, q.ne[0], v.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1],
+                                           f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st);
+            }
+            case B200_OP_GLU_SWIGLU:
+                invalidate_act(n.dst);
+                return b200_swiglu((const float *)n.src[0].data, (const float *)n.src[1].data, (float *)n.dst.data, nelem(n.dst), st);
+            case B200_OP_GET_ROWS:
+                invalidate_act(n.dst);
+                return b200_get_rows_f32((const float *)n.src[0].data, n.src[0].nb[1] / 4, (const int32_t *)n.src[1].data, (float *)n.dst.data, n.src[0].ne[0], n.src[1].ne[0], st);
+            case B200_OP_CPY:
+                invalidate_act(n.dst);
+                if (n.dst.type == B200_TYPE_F16) return b200_cpy_f32_f16((const float *)n.src[0].data, n.dst.data, nelem(n.dst), st);
+                return b200_check(cudaMemcpyAsync(n.dst.data, n.src[0].data, (size_t)nelem(n.dst) * 4, cudaMemcpyDeviceToDevice, st), "cpy f32");
+            default:
+                b200_set_error("executor: op %d not supported", n.op);
+                return B200_ERR_UNSUPPORTED;
+        }
+    }
+
+    int run_all() {
+        done.assign(n, 0);
+        uses.clear();
+        for (int i = 0; i < n; i++) for (int s = 0; s < nodes[i].n_src && s < B200_MAX_SRC; s++) if (nodes[i].src[s].id) uses[nodes[i].src[s].id]++;
+        ex->act_id[0] = ex->act_id[1] = 0;
+        for (int i = 0; i < n; i++) {
+            if (done[i]) continue;
+            const int s = run_node(i);
+            if (s != B200_OK) return s;
+        }
+        return B200_OK;
+    }
+};
+
+uint64_t mix(uint64_t h, uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); return h * 0xff51afd7ed558ccdull; }
+
+uint64_t topology_key(const b200_node * nodes, int n, int flags) {
+    uint64_t h = 0x12345678abcdefull ^ (uint64_t)n ^ ((uint64_t)flags << 48);
+    for (int i = 0; i < n; i++) {
+        const b200_node & nd = nodes[i];
+        h = mix(h, (uint64_t)nd.op | ((uint64_t)nd.n_src << 32));
+        h = mix(h, (uint64_t)(uintptr_t)nd.dst.data); h = mix(h, (uint64_t)nd.dst.ne[0] ^ ((uint64_t)nd.dst.ne[1] << 24) ^ ((uint64_t)nd.dst.ne[2] << 48)); h = mix(h, (uint64_t)nd.dst.nb[1]);
+        for (int s = 0; s < nd.n_src && s < B200_MAX_SRC; s++) {
+            const b200_tensor & t = nd.src[s];
+            h = mix(h, (uint64_t)(uintptr_t)t.data); h = mix(h, (uint64_t)t.ne[0] ^ ((uint64_t)t.ne[1] << 24) ^ ((uint64_t)t.ne[2] << 48)); h = mix(h, (uint64_t)t.nb[1] ^ ((uint64_t)t.nb[2] << 20) ^ ((uint64_t)t.type << 56));
+        }
+        if (nd.op != B200_OP_NONE) for (int p = 0; p < 12; p += 2) h = mix(h, (uint64_t)(uint32_t)nd.op_params[p] | ((uint64_t)(uint32_t)nd.op_params[p + 1] << 32));
+    }
+    return h;
+}
+
+// workspace needs of a node list (no allocation may happen during stream capture)
+int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
+    size_t act[2] = { 0, 0 }, fa = 0;
+    for (int i = 0; i < n; i++) {
+        const b200_node & nd = nodes[i];
+        if (nd.op == B200_OP_MUL_MAT) {
+            const int64_t k = nd.src[0].ne[0], cols = nd.src[1].ne[1];
+            for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(cols * act_col_bytes(kd, k)); if (b > act[kd]) act[kd] = b; }
+        } else if (nd.op == B200_OP_RMS_NORM) {
+            for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(8 * act_col_bytes(kd, (nd.src[0].ne[0] + 255) / 256 * 256)); if (b > act[kd]) act[kd] = b; }
+        } else if (nd.op == B200_OP_FLASH_ATTN_EXT) {
+            const size_t b = (size_t)b200_flash_attn_workspace(nd.src[2].ne[0], nd.src[0].ne[2], nd.src[0].ne[1], nd.src[1].ne[1]);
+            if (b > fa) fa = b;
+        }
+    }
+    if (act[0] <= ex->act_bytes[0] && act[1] <= ex->act_bytes[1] && fa <= ex->fa_bytes && ex->ws) return B200_OK;
+    for (int kd = 0; kd < 2; kd++) if (act[kd] < ex->act_bytes[kd]) act[kd] = ex->act_bytes[kd];
+    if (fa < ex->fa_bytes) fa = ex->fa_bytes;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t total = up(act[0]) + up(act[1]) + up(fa) + 256;
+    // growing invalidates every captured graph (they hold the old pointers)
+    for (auto & g : ex->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    ex->graphs.clear();
+    if (ex->ws) { cudaDeviceSynchronize(); cudaFree(ex->ws); ex->ws = nullptr; }
+    if (cudaMalloc((void **)&ex->ws, total) != cudaSuccess) { cudaGetLastError(); b200_set_error("executor: cannot allocate %zu bytes of workspace", total); return B200_ERR_CUDA; }
+    ex->ws_bytes = total;
+    ex->off_act[0] = 0; ex->off_act[1] = up(act[0]); ex->off_fa = up(act[0]) + up(act[1]);
+    ex->act_bytes[0] = act[0]; ex->act_bytes[1] = act[1]; ex->fa_bytes = fa;
+    return B200_OK;
+}
+
+} // namespace
+
+extern "C" b200_executor * b200_executor_create(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); b200_set_error("executor: no CUDA device %d", device); return nullptr; }
+    b200_executor * ex = new b200_executor();
+    ex->device = device;
+    ex->env_no_graphs = getenv("GGML_B200_DISABLE_GRAPHS") != nullptr;
+    ex->env_no_fusion = getenv("GGML_B200_DISABLE_FUSION") != nullptr;
+    return ex;
+}
+
+extern "C" void b200_executor_free(b200_executor * ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    for (auto & g : ex->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    if (ex->ws) cudaFree(ex->ws);
+    delete ex;
+}
+
+extern "C" int b200_executor_supports(const b200_node * node) { return node && node_ok(*node) ? 1 : 0; }
+
+extern "C" int b200_executor_compute(b200_executor * ex, const b200_node * nodes, int n_nodes, void * stream, int flags) {
+    if (!ex || (!nodes && n_nodes > 0) || n_nodes < 0) { b200_set_error("executor: bad arguments"); return B200_ERR_INVALID; }
+    B200_CUDA(cudaSetDevice(ex->device));
+    for (int i = 0; i < n_nodes; i++) if (!node_ok(nodes[i])) { b200_set_error("executor: node %d (op %d) is not supported", i, nodes[i].op); return B200_ERR_UNSUPPORTED; }
+    int s = plan_workspace(ex, nodes, n_nodes);
+    if (s != B200_OK) return s;
+    cudaStream_t st = (cudaStream_t)stream;
+    Runner r{ ex, nodes, n_nodes, st, (flags & B200_EXEC_FUSION) && !ex->env_no_fusion, {}, {} };
+
+    // CUDA graphs only pay for small-batch (decode / verify) lists; prefill lists are few big kernels
+    bool small = true;
+    for (int i = 0; i < n_nodes && small; i++) if (nodes[i].op == B200_OP_MUL_MAT && nodes[i].src[1].ne[1] > 8) small = false;
+    // the legacy default stream cannot be captured
+    const bool use_graph = (flags & B200_EXEC_CUDA_GRAPHS) && !ex->env_no_graphs && small && n_nodes >= 8 && st != nullptr && st != cudaStreamLegacy;
+    if (!use_graph) {
+        const int64_t l0 = b200_kernel_launches();
+        s = r.run_all();
+        ex->last_kernels = b200_kernel_launches() - l0;
+        return s;
+    }
+    const uint64_t key = topology_key(nodes, n_nodes, flags);
+    ex->tick++;
+    auto it = ex->graphs.find(key);
+    if (it == ex->graphs.end() && ex->seen[key]++ == 0) {
+        // first sighting: run eagerly (also warms per-function attributes outside of capture), like the
+        // reference's warm-up evaluation (ggml-cuda.cu:2964-2976)
+        if (ex->seen.size() > 4096) ex->seen.clear();
+        const int64_t l0 = b200_kernel_launches();
+        s = r.run_all();
+        ex->last_kernels = b200_kernel_launches() - l0;
+        return s;
+    }
+    if (it == ex->graphs.end()) {
+        if (ex->graphs.size() >= 64) {                      // evict the least recently used entry
+            auto lru = ex->graphs.begin();
+            for (auto g = ex->graphs.begin(); g != ex->graphs.end(); ++g) if (g->second.last_use < lru->second.last_use) lru = g;
+            if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+            ex->graphs.erase(lru);
+        }
+        cudaGraph_t graph = nullptr;
+        B200_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        const int64_t l0 = b200_kernel_launches();
+        s = r.run_all();
+        const int64_t kernels = b200_kernel_launches() - l0;
+        b200_count_launch(-(int)kernels);                    // recorded, not run: counted at launch below
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (s != B200_OK) { if (graph) cudaGraphDestroy(graph); return s; }
+        B200_CUDA(e);
+        GraphEntry ge; ge.kernels = kernels;
+        e = cudaGraphInstantiate(&ge.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        B200_CUDA(e);
+        ex->captures++;
+        it = ex->graphs.emplace(key, ge).first;
+    } else {
+        ex->replays++;
+    }
+    it->second.last_use = ex->tick;
+    ex->last_kernels = it->second.kernels;
+    b200_count_launch((int)it->second.kernels);
+    B200_CUDA(cudaGraphLaunch(it->second.exec, st));
+    return B200_OK;
+}
+
+extern "C" int64_t b200_executor_last_kernels(const b200_executor * ex)  { return ex ? ex->last_kernels : 0; }
+extern "C" int64_t b200_executor_graph_captures(const b200_executor * ex) { return ex ? ex->captures : 0; }
+extern "C" int64_t b200_executor_graph_replays(const b200_executor * ex)  { return ex ? ex->replays : 0; }

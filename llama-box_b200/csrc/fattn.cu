@@ -1,0 +1,276 @@
+// fattn.cu — FLASH_ATTN_EXT over the F16 / Q8_0 KV cache, split-KV "vector" kernel (sm_100a).
+//
+// Replaces ggml_cuda_flash_attn_ext -> flash_attn_vec_ext_f32<D,1,K,V> + flash_attn_combine_results
+// (ggml-cuda/fattn.cu:271-338, fattn-vec-f32.cuh:10-361, fattn-common.cuh:645-701).
+// Numerics follow the CPU oracle (ggml-cpu/ops.cpp:8169-8405): the Q row is converted to K's
+// vec_dot type (f16 for F16 K; RNE q8_0 for Q8_0 K, integer block dots), s = dot*scale
+// (+softcap) + slope*mask, online softmax in f32, quantised V expanded to f32.  (With F16 V the
+// oracle accumulates in fp16; we accumulate in f32, which is strictly more accurate.)
+//
+// Mapping: D/8 lanes per KV position (8 elements = one 16-byte load per lane for F16), so a warp
+// streams 2 (D=128) or 4 (D=64) positions per step with fully coalesced rows; up to 4 query heads of
+// one GQA group share every K/V load; KV is split over CTAs (grid.x) to fill 148 SMs, each split
+// writes (m, l, acc) partials that a second kernel merges.  HBM-bound: bytes = K+V rows once per
+// head tile.
+#include "common.cuh"
+#include <math.h>
+
+#define FA_WARPS 4
+
+
+__device__ __forceinline__ void unpack_h8(const uint4 & r, float (&f)[8]) {
+    const __half2 * h = (const __half2 *)&r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// load 8 int8 of a native q8_0 row (34-byte blocks, 2-byte aligned) + the block scale
+__device__ __forceinline__ void load_q80_8(const uint8_t * row, int dl, int (&q)[2], float & d) {
+    const uint8_t * blk = row + (dl >> 2) * 34;
+    const uint16_t * p = (const uint16_t *)(blk + 2 + (dl & 3) * 8);
+    d = h2f(__ldg((const uint16_t *)blk));
+    q[0] = (int)((uint32_t)__ldg(p)     | ((uint32_t)__ldg(p + 1) << 16));
+    q[1] = (int)((uint32_t)__ldg(p + 2) | ((uint32_t)__ldg(p + 3) << 16));
+}
+
+template <int D, int KVT, int G>
+__global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
+        const float * __restrict__ q, int64_t q_ts, int64_t q_hs,
+        const uint8_t * __restrict__ kc, int64_t k_rs, int64_t k_hs,
+        const uint8_t * __restrict__ vc, int64_t v_rs, int64_t v_hs,
+        const uint16_t * __restrict__ mask, int64_t mask_rs,
+        float * __restrict__ dst, float * __restrict__ ws,
+        int n_head, int n_head_kv, int n_kv, int split_len, int n_splits,
+        float scale, float max_bias, float softcap, float m0, float m1, int nh_log2) {
+    constexpr int LP  = D / 8;          // lanes per position
+    constexpr int PPW = 32 / LP;        // positions per warp step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sg = lane / LP, dl = lane % LP;
+    const int split = blockIdx.x, tile = blockIdx.y, tok = blockIdx.z;
+    const int gq = n_head / n_head_kv;                  // query heads per kv head
+    const int h0 = tile * G;                            // first query head of this tile
+    const int hk = h0 / gq;
+    pdl_wait();
+
+    // ---- query slices: q8[g][8] as f32 (f16-rounded) or int8 + scale -------------------------
+    float qf[G][8]; int qi[G][2]; float qd[G]; float slope[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int h = h0 + g;
+        const float * qp = q + (int64_t)tok * q_ts + (int64_t)h * q_hs + dl * 8;
+        const float4 a = *(const float4 *)qp, b = *(const float4 *)(qp + 4);
+        float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+        if (KVT == B200_TYPE_F16) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) qf[g][e] = __half2float(__float2half_rn(v[e]));
+            qi[g][0] = qi[g][1] = 0; qd[g] = 0.0f;
+        } else {
+            float am = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; e++) am = fmaxf(am, fabsf(v[e]));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+            am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+            const float id = am != 0.0f ? __fdiv_rn(127.0f, am) : 0.0f;
+            int t[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) t[e] = __float2int_rn(__fmul_rn(v[e], id)) & 0xff;
+            qi[g][0] = t[0] | (t[1] << 8) | (t[2] << 16) | (t[3] << 24);
+            qi[g][1] = t[4] | (t[5] << 8) | (t[6] << 16) | (t[7] << 24);
+            qd[g] = __half2float(__float2half_rn(__fdiv_rn(am, 127.0f)));
+#pragma unroll
+            for (int e = 0; e < 8; e++) qf[g][e] = 0.0f;
+        }
+        slope[g] = max_bias > 0.0f ? (h < nh_log2 ? powf(m0, (float)(h + 1)) : powf(m1, (float)(2 * (h - nh_log2) + 1))) : 1.0f;
+    }
+
+    float M[G], L[G], acc[G][8];
+#pragma unroll
+    for (int g = 0; g < G; g++) { M[g] = -INFINITY; L[g] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[g][e] = 0.0f; }
+
+    const unsigned gmask = ((1u << LP) - 1u) << (sg * LP);   // lanes sharing one KV position (converged inside the loop)
+    const int p_begin = split * split_len;
+    const int p_end   = min(n_kv, p_begin + split_len);
+    const uint16_t * mrow = mask ? mask + (int64_t)tok * mask_rs : nullptr;
+
+    for (int p = p_begin + warp * PPW + sg; p < p_end; p += FA_WARPS * PPW) {
+        const float mraw = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
+        if (mraw == -INFINITY && max_bias <= 0.0f) continue;     // masked (uniform inside the LP-lane group)
+        const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
+        const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
+        float kf[8], vf[8]; int kq[2]; float kd = 0.0f;
+        if (KVT == B200_TYPE_F16) {
+            unpack_h8(ldg_stream16(krow + dl * 16), kf);
+            unpack_h8(ldg_stream16(vrow + dl * 16), vf);
+        } else {
+            load_q80_8(krow, dl, kq, kd);
+            int vq[2]; float vd;
+            load_q80_8(vrow, dl, vq, vd);
+#pragma unroll
+            for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)((vq[e >> 2] >> (8 * (e & 3))) & 0xff), vd);
+        }
+        float s[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            if (KVT == B200_TYPE_F16) {
+                float a = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 8; e++) a = fmaf(kf[e], qf[g][e], a);
+#pragma unroll
+                for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
+                s[g] = a;
+            } else {
+                int is = dp4a_s(kq[0], qi[g][0], 0);
+                is = dp4a_s(kq[1], qi[g][1], is);
+                is += __shfl_xor_sync(gmask, is, 1, LP);          // whole 32-element block
+                is += __shfl_xor_sync(gmask, is, 2, LP);
+                float a = __fmul_rn((float)is, __fmul_rn(kd, qd[g]));   // ggml-cpu/quants.c:305-333
+                a = (dl & 3) == 0 ? a : 0.0f;
+#pragma unroll
+                for (int o = LP / 2; o >= 4; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
+                s[g] = __shfl_sync(gmask, a, 0, LP);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            float sv = s[g] * scale;
+            if (softcap != 0.0f) sv = softcap * tanhf(sv);
+            sv += slope[g] * mraw;
+            if (sv == -INFINITY) continue;
+            float ms = 1.0f, vs = 1.0f;
+            if (sv > M[g]) { ms = expf(M[g] - sv); M[g] = sv;
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[g][e] *= ms;
+            } else vs = expf(sv - M[g]);
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[g][e] = fmaf(vf[e], vs, acc[g][e]);
+            L[g] = L[g] * ms + vs;
+        }
+    }
+
+    // ---- merge the PPW position groups of the warp, then the warps, then write ------------------
+    __shared__ float sM[FA_WARPS][G], sL[FA_WARPS][G];
+    __shared__ float sA[FA_WARPS][G][D];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#pragma unroll
+        for (int o = LP; o < 32; o <<= 1) {
+            const float Mo = __shfl_xor_sync(0xffffffffu, M[g], o), Lo = __shfl_xor_sync(0xffffffffu, L[g], o);
+            const float Mn = fmaxf(M[g], Mo);
+            const float sa = M[g] == -INFINITY ? 0.0f : expf(M[g] - Mn), sb = Mo == -INFINITY ? 0.0f : expf(Mo - Mn);
+#pragma unroll
+            for (int e = 0; e < 8; e++) { const float ao = __shfl_xor_sync(0xffffffffu, acc[g][e], o); acc[g][e] = acc[g][e] * sa + ao * sb; }
+            L[g] = L[g] * sa + Lo * sb; M[g] = Mn;
+        }
+        if (sg == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) sA[warp][g][dl * 8 + e] = acc[g][e];
+            if (dl == 0) { sM[warp][g] = M[g]; sL[warp][g] = L[g]; }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * D; idx += FA_WARPS * 32) {
+        const int g = idx / D, e = idx % D;
+        float Mn = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < FA_WARPS; w++) Mn = fmaxf(Mn, sM[w][g]);
+        float a = 0.0f, l = 0.0f;
+#pragma unroll
+        for (int w = 0; w < FA_WARPS; w++) {
+            const float sc = sM[w][g] == -INFINITY ? 0.0f : expf(sM[w][g] - Mn);
+            a += sA[w][g][e] * sc; l += sL[w][g] * sc;
+        }
+        const int h = h0 + g;
+        if (n_splits == 1) {
+            dst[((int64_t)tok * n_head + h) * D + e] = a * (1.0f / l);            // ops.cpp:8390-8392
+        } else {
+            float * wp = ws + (((int64_t)split * gridDim.z + tok) * n_head + h) * (D + 2);
+            wp[e] = a;
+            if (e == 0) { wp[D] = Mn; wp[D + 1] = l; }
+        }
+    }
+    pdl_trigger();
+}
+
+template <int D>
+__global__ void __launch_bounds__(D) fattn_combine_kernel(const float * __restrict__ ws, float * __restrict__ dst, int n_splits, int n_rows) {
+    pdl_wait();
+    const int row = blockIdx.x, e = threadIdx.x;           // row = tok*n_head + head
+    float Mn = -INFINITY;
+    for (int s = 0; s < n_splits; s++) Mn = fmaxf(Mn, ws[((int64_t)s * n_rows + row) * (D + 2) + D]);
+    float a = 0.0f, l = 0.0f;
+    for (int s = 0; s < n_splits; s++) {
+        const float * wp = ws + ((int64_t)s * n_rows + row) * (D + 2);
+        const float sc = wp[D] == -INFINITY ? 0.0f : expf(wp[D] - Mn);
+        a += wp[e] * sc; l += wp[D + 1] * sc;
+    }
+    dst[(int64_t)row * D + e] = a * (1.0f / l);
+    pdl_trigger();
+}
+
+static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_len) {
+    const int sms = b200_sm_count();
+    int64_t base = n_tiles * n_tok;
+    int64_t want = (2 * (int64_t)sms + base - 1) / base;
+    int64_t maxs = (n_kv + 63) / 64;
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    int64_t len = (n_kv + want - 1) / want;
+    len = (len + 31) / 32 * 32;
+    *split_len = (int)len;
+    return (int)((n_kv + len - 1) / len);
+}
+
+extern "C" int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
+    const int64_t maxs = (n_kv + 63) / 64;
+    return maxs * n_tok * n_head * (dv + 2) * (int64_t)sizeof(float);
+}
+
+template <int D, int KVT, int G>
+static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
+                     const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst, float * ws,
+                     int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float softcap, cudaStream_t st) {
+    int split_len = 0;
+    const int n_tiles = (int)(n_head / G);
+    const int n_splits = fa_splits(n_tiles, n_tok, n_kv, &split_len);
+    const int nh_log2 = 1 << (int)floor(log2((double)n_head));
+    const float m0 = powf(2.0f, -(max_bias) / (float)nh_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / (float)nh_log2);
+    if (softcap != 0.0f) scale /= softcap;
+    dim3 grid((unsigned)n_splits, (unsigned)n_tiles, (unsigned)n_tok);
+    fattn_vec_kernel<D, KVT, G><<<grid, FA_WARPS * 32, 0, st>>>(q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
+        (const uint16_t *)mask, mask_rs, dst, ws, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2);
+    B200_LAUNCH_CHECK();
+    if (n_splits > 1) {
+        fattn_combine_kernel<D><<<(unsigned)(n_tok * n_head), D, 0, st>>>(ws, dst, n_splits, (int)(n_tok * n_head));
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
+                                   const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst,
+                                   int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
+                                   float scale, float max_bias, float softcap, void * workspace, void * stream) {
+    if (!q || !k || !v || !dst) { b200_set_error("flash_attn: null pointer"); return B200_ERR_INVALID; }
+    if (dk != dv || (dk != 64 && dk != 128)) { b200_set_error("flash_attn: head size %lld/%lld unsupported (64 or 128)", (long long)dk, (long long)dv); return B200_ERR_UNSUPPORTED; }
+    if (kv_type != B200_TYPE_F16 && kv_type != B200_TYPE_Q8_0) { b200_set_error("flash_attn: kv type %d unsupported", kv_type); return B200_ERR_UNSUPPORTED; }
+    if (n_head_kv <= 0 || n_head % n_head_kv != 0 || n_tok <= 0 || n_kv <= 0) { b200_set_error("flash_attn: bad head counts"); return B200_ERR_INVALID; }
+    if (((uintptr_t)q & 15) || (q_ts & 3) || (q_hs & 3)) { b200_set_error("flash_attn: q must be 16-byte aligned"); return B200_ERR_INVALID; }
+    if (kv_type == B200_TYPE_F16 && ((((uintptr_t)k | (uintptr_t)v) & 15) || ((k_rs | k_hs | v_rs | v_hs) & 15))) { b200_set_error("flash_attn: f16 K/V rows must be 16-byte aligned"); return B200_ERR_INVALID; }
+    if (n_tok > 65535) { b200_set_error("flash_attn: n_tok too large for one launch"); return B200_ERR_UNSUPPORTED; }
+    const int64_t gq = n_head / n_head_kv;
+    const int G = gq % 4 == 0 ? 4 : (gq % 2 == 0 ? 2 : 1);
+    if (!workspace && (n_kv + 63) / 64 > 1) { b200_set_error("flash_attn: workspace required"); return B200_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream; float * ws = (float *)workspace;
+#define FA_CASE(DD, KK, GG) return fa_launch<DD, KK, GG>(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, ws, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, st)
+    if (dk == 128) {
+        if (kv_type == B200_TYPE_F16) { if (G == 4) FA_CASE(128, B200_TYPE_F16, 4); if (G == 2) FA_CASE(128, B200_TYPE_F16, 2); FA_CASE(128, B200_TYPE_F16, 1); }
+        else                          { if (G == 4) FA_CASE(128, B200_TYPE_Q8_0, 4); if (G == 2) FA_CASE(128, B200_TYPE_Q8_0, 2); FA_CASE(128, B200_TYPE_Q8_0, 1); }
+    } else {
+        if (kv_type == B200_TYPE_F16) { if (G == 4) FA_CASE(64, B200_TYPE_F16, 4); if (G == 2) FA_CASE(64, B200_TYPE_F16, 2); FA_CASE(64, B200_TYPE_F16, 1); }
+        else                          { if (G == 4) FA_CASE(64, B200_TYPE_Q8_0, 4); if (G == 2) FA_CASE(64, B200_TYPE_Q8_0, 2); FA_CASE(64, B200_TYPE_Q8_0, 1); }
+    }
+#undef FA_CASE
+    return B200_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,29 @@
+// mmq.cu — batched MUL_MAT on quantised weights (prefill), host orchestration.
+// Replaces ggml_cuda_mul_mat_q (ggml-cuda/mmq.cu:71-143).  Round-1 state: activations are quantised
+// like the CPU oracle (quantize.cu) and columns are streamed through the matvec kernel in groups of
+// 8 (weights re-read from L2/HBM per group).  The tcgen05 tile kernel replaces the inner call when
+// ncols >= B200_MMQ_MIN_COLS (see mmq_tc.cu once present).
+#include "common.cuh"
+
+extern "C" int64_t b200_mul_mat_q_workspace(int type, int64_t m, int64_t k, int64_t ncols) {
+    (void)m;
+    const int kind = b200_act_kind_for(type);
+    if (kind < 0 || k <= 0 || k % 256 != 0 || ncols <= 0) return 0;
+    return ncols * act_col_bytes(kind, k);
+}
+
+extern "C" int b200_mul_mat_q(int type, const void * W, const float * X, int64_t x_col_stride, float * dst, int64_t dst_col_stride,
+                              int64_t m, int64_t k, int64_t ncols, void * workspace, void * stream) {
+    const int kind = b200_act_kind_for(type);
+    if (kind < 0) { b200_set_error("mul_mat_q: unsupported weight type %d", type); return B200_ERR_UNSUPPORTED; }
+    if (!workspace || ((uintptr_t)workspace & 15)) { b200_set_error("mul_mat_q: workspace missing or unaligned"); return B200_ERR_INVALID; }
+    int s = b200_quantize_act(kind, X, x_col_stride, workspace, k, ncols, stream);
+    if (s != B200_OK) return s;
+    const int64_t colb = act_col_bytes(kind, k);
+    for (int64_t c0 = 0; c0 < ncols; c0 += 8) {
+        const int64_t nc = ncols - c0 < 8 ? ncols - c0 : 8;
+        s = b200_mul_mat_vec_q(type, W, (const uint8_t *)workspace + c0 * colb, dst + c0 * dst_col_stride, dst_col_stride, nullptr, nullptr, m, k, nc, stream);
+        if (s != B200_OK) return s;
+    }
+    return B200_OK;
+}

@@ -1,0 +1,59 @@
+// repack.cu — load-time, in-place, per-row byte permutation of Q4_0 / Q8_0 / Q6_K weights into a
+// 16-byte-aligned structure-of-arrays row (see b200_ops.h).  Plays the role ggml-cpu/repack.cpp
+// plays for the CPU backend; the CUDA reference instead keeps the 18/34/210-byte blocks and pays
+// with 2-/4-byte loads (ggml-cuda/vecdotq.cuh:18-29).  Row size and offsets do not change.
+//
+// One CTA per row: the row is read into shared memory (coalesced 2-byte units — every field
+// offset in the three formats is even), then written back permuted.
+#include "common.cuh"
+
+// native byte offset -> repacked byte offset, for 2-byte unit `u` of a row with nb blocks
+__device__ __forceinline__ int64_t repacked_off(int type, int64_t nb, int64_t off) {
+    if (type == B200_TYPE_Q4_0) {
+        const int64_t b = off / 18, o = off % 18;
+        return o < 2 ? nb * 16 + b * 2 + o : b * 16 + (o - 2);
+    } else if (type == B200_TYPE_Q8_0) {
+        const int64_t b = off / 34, o = off % 34;
+        return o < 2 ? nb * 32 + b * 2 + o : b * 32 + (o - 2);
+    } else { // Q6_K: ql[128] qh[64] sc[16] d[2]
+        const int64_t b = off / 210, o = off % 210;
+        if (o < 128) return b * 128 + o;
+        if (o < 192) return nb * 128 + b * 64 + (o - 128);
+        if (o < 208) return nb * 192 + b * 16 + (o - 192);
+        return nb * 208 + b * 2 + (o - 208);
+    }
+}
+
+__global__ void __launch_bounds__(256) repack_rows_kernel(uint8_t * rows, int type, int64_t nb, int64_t rb, int inverse) {
+    extern __shared__ __align__(16) uint8_t srow[];
+    uint8_t * row = rows + (int64_t)blockIdx.x * rb;
+    const int64_t units = rb / 2;
+    for (int64_t u = threadIdx.x; u < units; u += blockDim.x) ((uint16_t *)srow)[u] = ((const uint16_t *)row)[u];
+    __syncthreads();
+    for (int64_t u = threadIdx.x; u < units; u += blockDim.x) {
+        const int64_t nat = u * 2, rep = repacked_off(type, nb, nat);
+        if (!inverse) *(uint16_t *)(row + rep) = *(const uint16_t *)(srow + nat);
+        else          *(uint16_t *)(row + nat) = *(const uint16_t *)(srow + rep);
+    }
+}
+
+extern "C" int b200_type_is_repacked(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q6_K; }
+
+static int repack_impl(int type, void * rows, int64_t nrows, int64_t k, int inverse, cudaStream_t st) {
+    if (!b200_type_is_repacked(type)) return B200_OK;           // Q4_K / Q5_K / F16 / F32 stay native
+    const int64_t be = type_block_elems(type);
+    if (!rows || nrows < 0 || k <= 0 || k % be != 0) { b200_set_error("repack: k must be a multiple of the block size"); return B200_ERR_INVALID; }
+    if (nrows == 0) return B200_OK;
+    const int64_t nb = k / be, rb = nb * type_block_bytes(type);
+    if (rb > 200 * 1024) { b200_set_error("repack: row of %lld bytes exceeds shared memory", (long long)rb); return B200_ERR_UNSUPPORTED; }
+    cudaFuncSetAttribute(repack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int64_t r0 = 0; r0 < nrows; r0 += 1 << 30) {
+        const int64_t n = nrows - r0 < (1 << 30) ? nrows - r0 : (1 << 30);
+        repack_rows_kernel<<<(unsigned)n, 256, (size_t)rb, st>>>((uint8_t *)rows + r0 * rb, type, nb, rb, inverse);
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_repack_rows(int type, void * rows, int64_t nrows, int64_t k, void * stream) { return repack_impl(type, rows, nrows, k, 0, (cudaStream_t)stream); }
+extern "C" int b200_unpack_rows(int type, void * rows, int64_t nrows, int64_t k, void * stream) { return repack_impl(type, rows, nrows, k, 1, (cudaStream_t)stream); }

@@ -187,17 +187,19 @@ def rand_f16_scale(rng, n, lo=1e-3, hi=2e-2, signed=False):
     return v.astype(np.float16).view(np.uint16)
 
 
-def rand_blocks(rng, t, nrows, k):
+def rand_blocks(rng, t, nrows, k, scale_mul=1.0):
     """Random but valid quant blocks (every bit pattern of qs/scales is legal; d finite)."""
+    _rs = rand_f16_scale
+    rand_f16_scale_l = lambda rng, n, lo=1e-3, hi=2e-2, signed=False: _rs(rng, n, lo * scale_mul, hi * scale_mul, signed)  # noqa: E731
     nb = nrows * (k // BLOCK_ELEMS[t])
     raw = rng.integers(0, 256, size=(nb, BLOCK_BYTES[t]), dtype=np.uint8)
     if t in (Q4_0, Q8_0):
-        raw[:, 0:2] = rand_f16_scale(rng, nb, signed=True).view(np.uint8).reshape(nb, 2)
+        raw[:, 0:2] = rand_f16_scale_l(rng, nb, signed=True).view(np.uint8).reshape(nb, 2)
     elif t in (Q4_K, Q5_K):
-        raw[:, 0:2] = rand_f16_scale(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
-        raw[:, 2:4] = rand_f16_scale(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
+        raw[:, 0:2] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
+        raw[:, 2:4] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
     elif t == Q6_K:
-        raw[:, 208:210] = rand_f16_scale(rng, nb, 1e-5, 2e-4, signed=True).view(np.uint8).reshape(nb, 2)
+        raw[:, 208:210] = rand_f16_scale_l(rng, nb, 1e-5, 2e-4, signed=True).view(np.uint8).reshape(nb, 2)
     return raw.reshape(nrows, -1)
 
 
