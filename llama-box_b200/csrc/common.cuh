@@ -14,6 +14,7 @@ void b200_set_error(const char * fmt, ...);
 int  b200_check(cudaError_t e, const char * what);       // returns B200_OK / B200_ERR_CUDA
 void b200_count_launch(int n = 1);
 int  b200_sm_count();                                     // SMs of the current device (cached)
+bool b200_pdl_enabled();                                  // programmatic dependent launch (off: GGML_B200_DISABLE_PDL)
 
 #define B200_CUDA(expr) do { int _s = b200_check((expr), #expr); if (_s != B200_OK) return _s; } while (0)
 #define B200_LAUNCH_CHECK() do { b200_count_launch(); int _s = b200_check(cudaGetLastError(), "kernel launch"); if (_s != B200_OK) return _s; } while (0)
@@ -85,6 +86,22 @@ __device__ __forceinline__ uint16_t f2h_rn(float f) { return __half_as_ushort(__
 
 __device__ __forceinline__ int dp4a_s(int a, int b, int c) { return __dp4a(a, b, c); }      // s8 x s8
 __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) { return __dp4a((int)a, b, c); } // weight bytes are < 128: s8 == u8
+
+// silu exactly as the x86 CPU oracle evaluates it: x / (1 + ggml_v_expf(-x)) (ggml-cpu/vec.h:785-820); the same
+// polynomial with an FMA at every step is bit-identical on the GPU, so SwiGLU outputs — which are re-quantised
+// for ffn_down — do not pick up 1-ulp differences that would flip int8 roundings
+__device__ __forceinline__ float silu_x86(float x) {
+    const float nx = __fsub_rn(0.0f, x);
+    const float r = 0x1.8p23f;
+    const float z = __fmaf_rn(nx, 0x1.715476p+0f, r);
+    const float n = __fsub_rn(z, r);
+    const float b = __fmaf_rn(-n, 0x1.7f7d1cp-20f, __fmaf_rn(-n, 0x1.62e4p-1f, nx));
+    const float u = __fmul_rn(b, b);
+    const float j = __fmaf_rn(__fmaf_rn(__fmaf_rn(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, __fmaf_rn(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u, __fmaf_rn(0x1.ffffecp-1f, b, 1.0f));
+    float e = ldexpf(j, (int)n);
+    if (fabsf(n) > 192.0f) e = n <= 0.0f ? 0.0f : INFINITY;
+    return __fdiv_rn(x, __fadd_rn(1.0f, e));
+}
 
 // ---- mbarrier + bulk async copy (TMA engine, 1-D): SASS UBLKCP / SYNCS ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }

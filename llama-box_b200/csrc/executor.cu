@@ -75,8 +75,11 @@ bool set_rows_ok(const b200_node & n) {
     const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
     if (s.type != B200_TYPE_F32 || ids.type != B200_TYPE_I64 || s.nb[0] != 4 || (s.nb[1] & 15) || !aligned16(s.data)) return false;
     if (d.type != B200_TYPE_F32 && d.type != B200_TYPE_F16 && d.type != B200_TYPE_Q8_0) return false;
-    if (s.ne[2] != 1 || s.ne[3] != 1 || d.ne[2] != 1 || d.ne[3] != 1 || s.ne[0] != d.ne[0] || s.ne[0] % 32 != 0 || ids.ne[0] != s.ne[1]) return false;
-    if (d.type != B200_TYPE_Q8_0 && (((uintptr_t)d.data | (uintptr_t)d.nb[1]) & 15)) return false;
+    // batches (ggml.c:3661-3686): dst [ne0, rows, ne2, ne3], src [ne0, n, ne2, ne3], ids [n, ne11, ne12] broadcast over dims 2/3
+    if (s.ne[2] != d.ne[2] || s.ne[3] != d.ne[3] || s.ne[0] != d.ne[0] || s.ne[0] % 32 != 0 || ids.ne[0] != s.ne[1] || ids.ne[3] != 1) return false;
+    if (ids.ne[1] <= 0 || ids.ne[2] <= 0 || s.ne[2] % ids.ne[1] != 0 || s.ne[3] % ids.ne[2] != 0) return false;
+    if ((s.nb[2] | s.nb[3]) & 15) return false;
+    if (d.type != B200_TYPE_Q8_0 && (((uintptr_t)d.data | (uintptr_t)d.nb[1] | (uintptr_t)d.nb[2] | (uintptr_t)d.nb[3]) & 15)) return false;
     return true;
 }
 bool fattn_ok(const b200_node & n) {
@@ -319,8 +322,15 @@ struct Runner {
                                  x.nb[1] / 4, x.nb[2] / 4, n.dst.nb[1] / 4, n.dst.nb[2] / 4, &p, st);
             }
             case B200_OP_SET_ROWS: {
-                const b200_tensor & s = n.src[0];
-                return b200_set_rows((const float *)s.data, s.nb[1] / 4, (const int64_t *)n.src[1].data, n.dst.data, n.dst.type, n.dst.nb[1], s.ne[0], s.ne[1], st);
+                const b200_tensor & s = n.src[0], & ids = n.src[1];
+                for (int64_t i3 = 0; i3 < s.ne[3]; i3++) for (int64_t i2 = 0; i2 < s.ne[2]; i2++) {
+                    const int64_t i11 = i2 % ids.ne[1], i12 = i3 % ids.ne[2];
+                    const int r = b200_set_rows((const float *)((const char *)s.data + i2 * s.nb[2] + i3 * s.nb[3]), s.nb[1] / 4,
+                                                (const int64_t *)((const char *)ids.data + i11 * ids.nb[1] + i12 * ids.nb[2]),
+                                                (char *)n.dst.data + i2 * n.dst.nb[2] + i3 * n.dst.nb[3], n.dst.type, n.dst.nb[1], s.ne[0], s.ne[1], st);
+                    if (r != B200_OK) return r;
+                }
+                return B200_OK;
             }
             case B200_OP_FLASH_ATTN_EXT: {
                 invalidate_act(n.dst);

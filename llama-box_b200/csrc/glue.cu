@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const float * __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 a = ((const float4 *)g)[i], b = ((const float4 *)u)[i];
         float4 o;
-        o.x = (a.x / (1.0f + expf(-a.x))) * b.x; o.y = (a.y / (1.0f + expf(-a.y))) * b.y;
-        o.z = (a.z / (1.0f + expf(-a.z))) * b.z; o.w = (a.w / (1.0f + expf(-a.w))) * b.w;
+        o.x = __fmul_rn(silu_x86(a.x), b.x); o.y = __fmul_rn(silu_x86(a.y), b.y);
+        o.z = __fmul_rn(silu_x86(a.z), b.z); o.w = __fmul_rn(silu_x86(a.w), b.w);
         ((float4 *)y)[i] = o;
     }
     pdl_trigger();

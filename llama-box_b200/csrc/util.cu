@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -27,6 +28,12 @@ int b200_sm_count() {
         cache[dev] = n;
     }
     return cache[dev];
+}
+
+bool b200_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("GGML_B200_DISABLE_PDL") ? 0 : 1;
+    return v == 1;
 }
 
 extern "C" int b200_abi_version(void) { return 1; }

@@ -22,6 +22,19 @@
 #include <string>
 #include <vector>
 
+static FILE * g_dump = nullptr;
+// eval callback (ggml-backend.h:282-289): print a checksum of every f32 node so two backends can be diffed
+static bool dump_cb(struct ggml_tensor * t, bool ask, void *) {
+    if (ask) return true;
+    if (!g_dump || t->type != GGML_TYPE_F32) return true;
+    std::vector<float> buf(ggml_nelements(t));
+    if (!ggml_is_contiguous(t)) return true;
+    ggml_backend_tensor_get(t, buf.data(), 0, ggml_nbytes(t));
+    double s = 0, a = 0; for (float v : buf) { s += v; a += v < 0 ? -v : v; }
+    fprintf(g_dump, "%-28s %-14s [%lld,%lld,%lld,%lld] sum=%.9g abs=%.9g\n", t->name, ggml_op_name(t->op), (long long)t->ne[0], (long long)t->ne[1], (long long)t->ne[2], (long long)t->ne[3], s, a);
+    return true;
+}
+
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main(int argc, char ** argv) {
@@ -48,6 +61,7 @@ int main(int argc, char ** argv) {
         else if (a == "--ctv")        ctv = ty(next());
         else if (a == "--ts")         ts = next();
         else if (a == "--logits-out") logits_out = next();
+        else if (a == "--dump")       { g_dump = fopen(next().c_str(), "w"); }
         else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
     }
     llama_log_set([](ggml_log_level lvl, const char * txt, void *) { if (lvl >= GGML_LOG_LEVEL_WARN) fputs(txt, stderr); }, nullptr);
@@ -79,6 +93,7 @@ int main(int argc, char ** argv) {
     cp.n_ctx = ctx; cp.n_batch = ubatch > 2048 ? ubatch : 2048; cp.n_ubatch = ubatch; cp.n_seq_max = 1;
     cp.n_threads = threads; cp.n_threads_batch = threads;
     cp.flash_attn = fa; cp.type_k = ctk; cp.type_v = ctv; cp.no_perf = true;
+    if (g_dump) { cp.cb_eval = dump_cb; cp.cb_eval_user_data = nullptr; }
     llama_context * lctx = llama_init_from_model(model, cp);
     if (!lctx) { fprintf(stderr, "context init failed\n"); return 4; }
 

@@ -444,8 +444,23 @@ void orc_flash_attn_ext(const void *q, int64_t q_nb1, int64_t q_nb2,
 }
 
 /* ---- glue ---- */
-void orc_swiglu(const float *gate, const float *up, float *y, int64_t n) {   /* vec.h:691, ops.cpp swiglu */
-    for (int64_t i = 0; i < n; i++) y[i] = (gate[i] / (1.0f + expf(-gate[i]))) * up[i];
+/* exp() as the x86 CPU backend evaluates it inside silu: ggml_v_expf (ggml-cpu/vec.h:785-810 AVX512,
+ * :828-860 AVX2 — same constants, FMA at every step), restated with scalar fmaf so that it is bit-identical
+ * for the finite range silu needs (|n| <= 126). */
+static float v_expf(float x) {
+    const float r = 0x1.8p23f;
+    const float z = fmaf(x, 0x1.715476p+0f, r);
+    const float n = z - r;
+    const float b = fmaf(-n, 0x1.7f7d1cp-20f, fmaf(-n, 0x1.62e4p-1f, x));
+    const float u = b * b;
+    const float j = fmaf(fmaf(fmaf(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, fmaf(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u, fmaf(0x1.ffffecp-1f, b, 1.0f));
+    if (fabsf(n) > 192.0f) return n <= 0.0f ? 0.0f : INFINITY;
+    return ldexpf(j, (int)n);
+}
+/* ggml_vec_swiglu_f32 (ggml-cpu/vec.cpp:260-282): silu(x) = x / (1 + v_expf(-x)), then * up; rows on this path are
+ * multiples of 16 so the vector body covers every element */
+void orc_swiglu(const float *gate, const float *up, float *y, int64_t n) {
+    for (int64_t i = 0; i < n; i++) y[i] = (gate[i] / (1.0f + v_expf(0.0f - gate[i]))) * up[i];
 }
 void orc_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows) {
     for (int64_t r = 0; r < nrows; r++)

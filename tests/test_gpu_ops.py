@@ -352,10 +352,27 @@ def test_flash_attn(b200, kvt, dk, nh, nhkv, nt, nkv):
                                             scale, 0.0, 0.0, b200.p(ws), b200.stream()))
     got = dst.cpu().numpy()
     assert np.isfinite(got).all()
-    # F16 V: the oracle accumulates in fp16 (ops.cpp:8278-8340) so it is the less exact side
-    tol = 2e-3 if kvt == F16 else 2e-5
-    assert np.abs(got - want).max() <= tol * np.abs(want).max(), np.abs(got - want).max()
-    assert nmse(got, want) < (5e-6 if kvt == F16 else 1e-9)
+    if kvt == Q8_0:
+        # integer K.Q block sums are identical to the oracle's; V accumulates in f32 on both sides
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), np.abs(got - want).max()
+        assert nmse(got, want) < 1e-9
+    else:
+        # F16 V: the oracle accumulates V in fp16 (ops.cpp:8278-8340) — its rounding noise grows with n_kv and
+        # dwarfs ours, so the tight check is against an f64 evaluation of the same f16-rounded Q/K/V, and the
+        # oracle only has to agree to fp16-accumulator accuracy.
+        q16 = q.astype(np.float16).astype(np.float64)
+        kk = orc_dequant(F16, kc[:nkv], nkv, nhkv * dk).astype(np.float64); vv = orc_dequant(F16, vc[:nkv], nkv, nhkv * dk).astype(np.float64)
+        truth = np.zeros((nt, nh, dk))
+        for t in range(nt):
+            for h in range(nh):
+                hk = h // (nh // nhkv)
+                s = (kk[:, hk * dk:(hk + 1) * dk] @ q16[t, h]) * scale + mask16[t].astype(np.float64)
+                p = np.exp(s - s.max()); truth[t, h] = (p[:, None] * vv[:, hk * dk:(hk + 1) * dk]).sum(0) / p.sum()
+        sc = np.abs(truth).max()
+        err_gpu, err_orc = np.abs(got - truth).max(), np.abs(want - truth).max()
+        assert err_gpu <= 2e-5 * sc, (err_gpu, sc)
+        assert err_gpu <= err_orc, (err_gpu, err_orc)
+        assert np.abs(got - want).max() <= 5e-2 * sc, (np.abs(got - want).max(), sc)
 
 
 def test_flash_attn_f16_closer_to_f64_than_oracle(b200):
