@@ -369,15 +369,103 @@ def run_e2e(args, model, ex, ops, G, stream, flags, n_kv_of, nodes_for, total, V
 
 
 def run_b200_pipeline(args, G, M, ops, rank, world, local):
-    """N > 1: contiguous layer ranges per rank, hidden state handed over with NCCL send/recv, `world` sequences in
-    flight (one per pipeline slot) so that every GPU streams its slice of the weights once per tick."""
+    """N > 1: the reference's LLAMA_SPLIT_MODE_LAYER (llama-model.cpp:1917-1958): rank r owns a contiguous range of
+    layers and their KV; the hidden state [n_embd] f32 is handed to rank r+1 with one NCCL send/recv per boundary
+    (the reference: cudaMemcpyPeerAsync, ggml-cuda.cu:2556-2577), the sampled token goes back to rank 0.
+    `world` independent sequences are kept in flight, one per pipeline slot, so that every GPU streams its slice of
+    the weights once per tick; `value` = tokens emitted by the last stage per second (all sequences)."""
     import torch
     import torch.distributed as dist
     full = M.CONFIGS[args.model]
     L = args.layers or full["n_layer"]
     lo, hi = rank * L // world, (rank + 1) * L // world
-    model = M.SyntheticLlama(args.model, args.ftype, n_ctx=args.ctx, kv_type=G.F16, n_layer=L, layer_range=(lo, hi), first=rank == 0, last=rank == world - 1)
-    raise SystemExit("multi-GPU pipeline bench: implemented in a later commit")
+    first, last = rank == 0, rank == world - 1
+    model = M.SyntheticLlama(args.model, args.ftype, n_ctx=args.ctx, kv_type=G.F16, n_layer=L, layer_range=(lo, hi), first=first, last=last, n_seq=world)
+    c = model.c
+    V, E = c["n_vocab"], c["n_embd"]
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7 + rank)
+    for ly in model.layers:
+        for caches in (ly["k_caches"], ly["v_caches"]):
+            for cache in caches:
+                n = args.n_past * G.row_size(G.F16, c["n_head_kv"] * c["head_dim"]) // 2
+                cache.view(torch.float16)[:n] = (torch.randn(n, device="cuda", generator=gen) * 0.5).half()
+    ex = G.Executor(local)
+    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION)
+    n_kv_of = lambda pos: max(256, (pos + 1 + 255) // 256 * 256)  # noqa: E731
+    total_ticks = args.warmup + args.steps + world            # pipeline fill + timed region
+    steps_per_seq = (total_ticks + world - 1) // world + 1
+    assert n_kv_of(args.n_past + steps_per_seq) <= args.ctx
+    stream = torch.cuda.current_stream()
+    st = C.c_void_p(stream.cuda_stream)
+    graphs = {}
+    neg = torch.full((n_kv_of(args.n_past + steps_per_seq),), float("-inf"), device="cuda")
+
+    def nodes_for(n_kv, seq):
+        key = (n_kv, seq)
+        if key not in graphs:
+            graphs[key] = model.build(1, n_kv, seq=seq)
+        return graphs[key]
+    tok = torch.ones(1, dtype=torch.int32, device="cuda")
+    seq_pos = [args.n_past] * world
+    handoff_ev = []
+
+    def tick(t, timed):
+        seq = (t - rank) % world
+        if t < rank:
+            return                                                  # pipeline fill
+        pos = seq_pos[seq]; seq_pos[seq] += 1
+        n_kv = n_kv_of(pos)
+        nodes, io = nodes_for(n_kv, seq)
+        if first:
+            if t >= world:                                          # the token this sequence sampled `world` ticks ago
+                dist.recv(tok, src=world - 1)
+            io["tokens"].copy_(tok)
+        else:
+            dist.recv(io["hidden_in"], src=rank - 1)
+        io["pos"].fill_(pos); io["kv_idx"].fill_(pos)
+        m = neg[:n_kv].clone(); m[:pos + 1] = 0
+        io["mask"][0].copy_(m)
+        ex.compute(nodes, flags, stream=st)
+        if last:
+            ops.check(ops.lib.b200_argmax_f32(ops.p(io["logits"]), ops.p(tok), V, 1, st))
+            if t + 1 < total_ticks:                                 # rank 0 stops receiving after the last tick
+                dist.send(tok, dst=0)
+        else:
+            dist.send(io["hidden_out"], dst=rank + 1)
+
+    for t in range(args.warmup + world - 1):
+        tick(t, False)
+    torch.cuda.synchronize(); dist.barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.lib.b200_kernel_launches()
+    e0.record(stream)
+    for t in range(args.warmup + world - 1, args.warmup + world - 1 + args.steps):
+        tick(t, True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.barrier()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)                     # device time, max over ranks
+    launches = torch.tensor([ops.lib.b200_kernel_launches() - l0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(launches)
+    clocks = sampler.stop()
+    # drain: the last stage still owes rank 0 nothing (sends are matched tick by tick)
+    if rank == 0:
+        ms_per_step = float(ms.item()) / args.steps
+        hbm_peak, peak_src = peaks()
+        wbytes = None
+        line = {"metric": "decode tok/s Llama-3-8B Q4_K_M bs=1", "value": 1000.0 / ms_per_step, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "q4_K/q6_K x q8_K int8 dot (dp4a), f32 accumulate", "data": "synthetic",
+                "config": {"workload": f"{args.model} {args.ftype} batch-1 decode per sequence, {world} sequences in flight (one per pipeline stage), -c {args.ctx}, n_past {args.n_past}, F16 KV",
+                           "parallelism": f"layer split over {world} GPUs (--tensor-split {','.join(['1'] * world)}), NCCL send/recv hidden-state handoff",
+                           "l2_policy": "inputs larger than L2"},
+                "clocks": clocks, "e2e": None, "gpu_launches": int(launches.item()), "roofline": None, "cpu_baseline": None,
+                "note": "a step = one pipeline tick: every GPU streams its 1/N slice of the weights for one sequence; one token leaves the last stage per tick"}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

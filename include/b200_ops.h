@@ -118,6 +118,26 @@ typedef struct b200_mmv_desc {
 B200_API int b200_mul_mat_vec_q_multi(const b200_mmv_desc *descs, int n_mats, const void *act_q8K, const void *act_q80,
                                       int64_t k, int64_t ncols, void *stream);
 
+/* general form: up to 4 matrices (or gate+up with SwiGLU) against one activation, with the activation
+ * optionally produced INSIDE the kernel prologue from f32 (act_source 1) or from f32 through RMS_NORM * weight
+ * (act_source 2) — fuses rms_norm + mul + quantize_q8 + mul_mat_vec_q (+ bias / residual / SwiGLU) into one launch
+ * (the reference runs 3-5 kernels: norm.cu:444-495, quantize.cu:148-160, mmvq.cu:500-570, binbcast.cu, unary.cu:291) */
+typedef struct b200_mmv_launch {
+    b200_mmv_desc mats[4];
+    const float  *residual[4];      /* optional, same layout as the mat's dst                        */
+    int64_t       dst_col_stride[4];/* floats; 0 = m                                                  */
+    int32_t       n_mats;
+    int32_t       swiglu;           /* 1: mats[0] = gate, mats[1] = up, result in mats[0].dst         */
+    int64_t       k, ncols;
+    int32_t       act_source;       /* 0: act_q8K/act_q80 buffers, 1: quantise x, 2: rms_norm(x)*norm_w then quantise */
+    float         eps;
+    const void   *act_q8K, *act_q80;
+    const float  *x;  int64_t x_col_stride;
+    const float  *norm_w;
+    float        *y_out;            /* optional f32 copy of the (normalised) activation [ncols][k]    */
+} b200_mmv_launch;
+B200_API int b200_mul_mat_vec_q_launch(const b200_mmv_launch *launch, void *stream);
+
 /* gate & up matvec + SwiGLU in one launch: dst[c][r] = silu(Wg[r].x[c]) * (Wu[r].x[c])
  * (replaces 2x mul_mat_vec_q + unary_gated_op_kernel, unary.cu:209-230) */
 B200_API int b200_mul_mat_vec_q_swiglu(int type_gate, const void *Wg, int type_up, const void *Wu,
@@ -163,12 +183,19 @@ B200_API int b200_rope_kv_store(float *q, const float *k, const float *v, const 
                                 int64_t head_dim, int64_t n_head, int64_t n_head_kv, int64_t n_tok,
                                 const b200_rope_params *p, void *stream);
 
+/* same, with q roped out of place and separate K / V row-id tensors and row strides (what the ggml graph provides) */
+B200_API int b200_rope_kv_store2(const float *q_src, float *q_dst, const float *k, const float *v, const int32_t *pos, const float *freq_factors_or_null,
+                                 const int64_t *k_ids, const int64_t *v_ids, void *k_cache, void *v_cache, int kv_type,
+                                 int64_t k_row_stride, int64_t v_row_stride, int64_t head_dim, int64_t n_head, int64_t n_head_kv, int64_t n_tok,
+                                 const b200_rope_params *p, void *stream);
+
 /* ---- FLASH_ATTN_EXT (replaces ggml_cuda_flash_attn_ext, fattn.cu:271-338) ----------------
  *   q    f32, element (d, tok, head) at q + tok*q_tok_stride + head*q_head_stride (floats)
  *   k,v  cache rows of kv_type (F16 or Q8_0): (pos, kv_head) at base + pos*row_stride + kv_head*head_stride (bytes)
  *   mask f16 [n_tok_padded][n_kv] (row stride mask_row_stride halves) or NULL; -inf = masked
  *   dst  f32 [n_tok][n_head][dv] contiguous
- *   workspace: b200_flash_attn_workspace(...) bytes for split-KV partials */
+ *   workspace: b200_flash_attn_workspace(...) bytes for split-KV partials + completion counters; zero it ONCE
+ *   (the counters reset themselves at the end of every launch) */
 B200_API int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv);
 B200_API int b200_flash_attn_ext(const float *q, int64_t q_tok_stride, int64_t q_head_stride,
                                  const void *k, int64_t k_row_stride, int64_t k_head_stride,

@@ -133,6 +133,8 @@ struct b200_executor {
     uint8_t * ws = nullptr; size_t ws_bytes = 0;
     size_t off_act[2] = {0, 0}, act_bytes[2] = {0, 0}, off_fa = 0, fa_bytes = 0;
     uint64_t act_id[2] = {0, 0}; const void * act_ptr[2] = {nullptr, nullptr}; int64_t act_cols[2] = {0, 0};
+    // a RMS_NORM(+MUL) whose only consumers are decode matvecs is not launched: the matvec prologue computes it
+    struct { uint64_t out_id = 0; const void * out_data = nullptr; b200_tensor x, out; const float * w = nullptr; float eps = 0; } norm;
     std::unordered_map<uint64_t, GraphEntry> graphs;
     std::unordered_map<uint64_t, int> seen;      // topology -> times seen before capture (first sighting runs eagerly)
     uint64_t tick = 0;
@@ -152,6 +154,16 @@ struct Runner {
 
     void invalidate_act(const b200_tensor & written) {
         for (int kd = 0; kd < 2; kd++) if (ex->act_id[kd] && ex->act_ptr[kd] == written.data) ex->act_id[kd] = 0;
+        if (ex->norm.out_id && (overlaps(written, ex->norm.x) || overlaps(written, ex->norm.out))) ex->norm.out_id = 0;
+    }
+    // how a decode matvec obtains its activation: from a pending norm (2), or by quantising the f32 tensor itself (1)
+    void fill_act_source(b200_mmv_launch & L, const b200_tensor & x) const {
+        if (ex->norm.out_id && ex->norm.out_id == x.id && ex->norm.out_data == x.data) {
+            L.act_source = 2; L.x = (const float *)ex->norm.x.data; L.x_col_stride = ex->norm.x.nb[1] / 4; L.norm_w = ex->norm.w; L.eps = ex->norm.eps;
+        } else {
+            L.act_source = 1; L.x = (const float *)x.data; L.x_col_stride = x.nb[1] / 4; L.norm_w = nullptr; L.eps = 0.0f;
+        }
+        L.act_q8K = nullptr; L.act_q80 = nullptr; L.y_out = nullptr;
     }
     uint8_t * act_buf(int kind) const { return ex->ws + ex->off_act[kind]; }
 
@@ -178,6 +190,18 @@ struct Runner {
             else if (mu.src[1].id == n.dst.id && mu.src[1].data == n.dst.data) w = &mu.src[0];
             if (w && w->ne[0] == ncols && nrows_of(*w) == 1 && same_shape(mu.dst, x)) {
                 done[j] = 1;
+                // all consumers are decode-shaped quantised MUL_MATs of this tensor: no kernel at all, the matvec
+                // prologue normalises and quantises (b200_mul_mat_vec_q_launch act_source = 2)
+                if (nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4 && x.nb[1] == ncols * 4) {
+                    int consumers = 0, mm = 0;
+                    for (int q = j + 1; q < this->n; q++) for (int sidx = 0; sidx < nodes[q].n_src && sidx < B200_MAX_SRC; sidx++)
+                        if (nodes[q].src[sidx].id == mu.dst.id) { consumers++; if (nodes[q].op == B200_OP_MUL_MAT && sidx == 1 && !done[q] && nodes[q].src[1].ne[1] <= 8) mm++; }
+                    if (consumers > 0 && consumers == mm) {
+                        ex->norm.out_id = mu.dst.id; ex->norm.out_data = mu.dst.data; ex->norm.x = x; ex->norm.out = mu.dst;
+                        ex->norm.w = (const float *)w->data; ex->norm.eps = eps;
+                        return B200_OK;
+                    }
+                }
                 // if the next consumer is a decode-shaped quantised MUL_MAT, emit its activation format too
                 const int c = next_compute(j);
                 if (c >= 0 && nodes[c].op == B200_OP_MUL_MAT && nodes[c].src[1].id == mu.dst.id && nodes[c].src[1].data == mu.dst.data &&
@@ -220,10 +244,9 @@ struct Runner {
             const int kind = b200_act_kind_for(w.type);
             return b200_mul_mat_q(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, ncols, act_buf(kind), st);
         }
-        const int kind = b200_act_kind_for(w.type);
-        int s = ensure_act(x, kind);
-        if (s != B200_OK) return s;
-
+        int s = B200_OK;
+        b200_mmv_launch L; memset(&L, 0, sizeof(L));
+        L.k = k; L.ncols = ncols;
         if (fuse) {
             // (1) up, gate, GLU (llama-graph.cpp:647-693): MUL_MAT(up,x) MUL_MAT(gate,x) GLU(gate,up)
             const int j = next_compute(i);
@@ -235,13 +258,15 @@ struct Runner {
                     const b200_node * gate = nullptr, * up = nullptr;
                     if (G.src[0].data == nodes[j].dst.data && G.src[1].data == n.dst.data) { gate = &nodes[j]; up = &n; }
                     else if (G.src[0].data == n.dst.data && G.src[1].data == nodes[j].dst.data) { gate = &n; up = &nodes[j]; }
-                    if (gate) {
-                        const int kg = b200_act_kind_for(gate->src[0].type), ku = b200_act_kind_for(up->src[0].type);
-                        if ((s = ensure_act(x, kg)) != B200_OK || (s = ensure_act(x, ku)) != B200_OK) return s;
+                    if (gate && G.dst.nb[1] == m * 4) {
+                        fill_act_source(L, x);
+                        L.n_mats = 2; L.swiglu = 1;
+                        L.mats[0] = { gate->src[0].data, (float *)G.dst.data, nullptr, m, gate->src[0].type, 0 };
+                        L.mats[1] = { up->src[0].data, (float *)G.dst.data, nullptr, m, up->src[0].type, 0 };
                         done[j] = done[g] = 1;
+                        s = b200_mul_mat_vec_q_launch(&L, st);
                         invalidate_act(G.dst);
-                        return b200_mul_mat_vec_q_swiglu(gate->src[0].type, gate->src[0].data, up->src[0].type, up->src[0].data,
-                                                         act_buf(0), act_buf(1), (float *)G.dst.data, m, k, ncols, st);
+                        return s;
                     }
                 }
             }
@@ -256,23 +281,25 @@ struct Runner {
                 group[ng++] = j2;
             }
             if (ng > 1 && n.dst.nb[1] == m * 4) {
-                b200_mmv_desc descs[MAX_GROUP];
+                fill_act_source(L, x);
+                L.n_mats = ng;
+                const b200_tensor * written[2 * MAX_GROUP]; int nw = 0;
                 for (int q = 0; q < ng; q++) {
                     const b200_node & o = nodes[group[q]];
-                    const int ko = b200_act_kind_for(o.src[0].type);
-                    if ((s = ensure_act(x, ko)) != B200_OK) return s;
-                    descs[q] = { o.src[0].data, (float *)o.dst.data, nullptr, o.src[0].ne[1], o.src[0].type, 0 };
+                    L.mats[q] = { o.src[0].data, (float *)o.dst.data, nullptr, o.src[0].ne[1], o.src[0].type, 0 };
                     if (q) done[group[q]] = 1;
+                    written[nw++] = &o.dst;
                     // bias ADD right after the projection (Qwen2 QKV bias, llama-model.cpp:6006-6020)
                     const int a = next_compute(group[q]);
                     if (a >= 0 && nodes[a].op == B200_OP_ADD && use_count(o.dst) == 1 && nodes[a].src[0].data == o.dst.data && nrows_of(nodes[a].src[1]) == 1 &&
                         nodes[a].src[1].ne[0] == o.src[0].ne[1] && nodes[a].dst.nb[1] == o.src[0].ne[1] * 4 && (q == 0 || can_hoist(i, a))) {
-                        descs[q].bias = (const float *)nodes[a].src[1].data; descs[q].dst = (float *)nodes[a].dst.data; done[a] = 1;
-                        invalidate_act(nodes[a].dst);
+                        L.mats[q].bias = (const float *)nodes[a].src[1].data; L.mats[q].dst = (float *)nodes[a].dst.data; done[a] = 1;
+                        written[nw++] = &nodes[a].dst;
                     }
-                    invalidate_act(o.dst);
                 }
-                return b200_mul_mat_vec_q_multi(descs, ng, act_buf(0), act_buf(1), k, ncols, st);
+                s = b200_mul_mat_vec_q_launch(&L, st);
+                for (int q = 0; q < nw; q++) invalidate_act(*written[q]);
+                return s;
             }
             // (3) epilogue: + bias row, + residual (wo / ffn_down followed by ADD, llama-model.cpp:6052,6095)
             const float * bias = nullptr, * resid = nullptr; const b200_tensor * out = &n.dst;
@@ -288,13 +315,62 @@ struct Runner {
                 else break;
                 done[a] = 1; out = &A.dst; cur = a;
             }
+            fill_act_source(L, x);
+            L.n_mats = 1;
+            L.mats[0] = { w.data, (float *)out->data, bias, m, w.type, 0 };
+            L.residual[0] = resid; L.dst_col_stride[0] = out->nb[1] / 4;
+            s = b200_mul_mat_vec_q_launch(&L, st);
             invalidate_act(*out);
-            return b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)out->data, out->nb[1] / 4, bias, resid, m, k, ncols, st);
+            return s;
         }
+        const int kind = b200_act_kind_for(w.type);
+        s = ensure_act(x, kind);
+        if (s != B200_OK) return s;
         invalidate_act(n.dst);
         return b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)n.dst.data, n.dst.nb[1] / 4, nullptr, nullptr, m, k, ncols, st);
     }
     static constexpr int MAX_GROUP = 4;
+    int last_status = B200_OK;
+
+    // ROPE(q) ROPE(k) SET_ROWS(k -> K cache) SET_ROWS(v -> V cache) -> one launch (llama-model.cpp:6029-6043 +
+    // llama-kv-cache-unified.cpp:1103-1160).  The roped K is consumed only by the KV store, so it is never written as f32.
+    bool try_rope_kv_store(int i) {
+        const b200_node & rq = nodes[i];
+        const int j = next_compute(i); if (j < 0 || nodes[j].op != B200_OP_ROPE) return false;
+        const b200_node & rk = nodes[j];
+        const int sk = next_compute(j); if (sk < 0 || nodes[sk].op != B200_OP_SET_ROWS) return false;
+        const int sv = next_compute(sk); if (sv < 0 || nodes[sv].op != B200_OP_SET_ROWS) return false;
+        const b200_node & SK = nodes[sk], & SV = nodes[sv];
+        if (memcmp(rq.op_params, rk.op_params, sizeof(rq.op_params)) != 0 || rq.src[1].data != rk.src[1].data) return false;
+        if ((rq.n_src > 2 ? rq.src[2].data : nullptr) != (rk.n_src > 2 ? rk.src[2].data : nullptr)) return false;
+        const b200_tensor & q = rq.src[0], & k = rk.src[0], & v = SV.src[0];
+        const int64_t hd = q.ne[0], nh = q.ne[1], nhk = k.ne[1], nt = q.ne[2];
+        auto dense3 = [&](const b200_tensor & t) { return t.nb[0] == 4 && t.nb[1] == t.ne[0] * 4 && t.nb[2] == t.ne[0] * t.ne[1] * 4; };
+        if (!dense3(q) || !dense3(k) || !dense3(rq.dst) || !dense3(rk.dst) || k.ne[0] != hd || k.ne[2] != nt || (nhk * hd) % 256 != 0) return false;
+        // K store consumes exactly the roped K (through a reshape view), V store a dense [n_embd_v, n_tok] f32 tensor
+        if (SK.src[0].data != rk.dst.data || SK.src[0].ne[0] != nhk * hd || SK.src[0].ne[1] != nt || SK.src[0].nb[1] != nhk * hd * 4) return false;
+        if (v.ne[0] != nhk * hd || v.ne[1] != nt || v.nb[1] != nhk * hd * 4 || v.ne[2] != 1 || SK.src[0].ne[2] != 1 || SK.dst.ne[2] != 1 || SV.dst.ne[2] != 1) return false;
+        if (SK.dst.type != SV.dst.type || (SK.dst.type != B200_TYPE_F16 && SK.dst.type != B200_TYPE_Q8_0)) return false;
+        // the roped K must have no other reader: it feeds SET_ROWS directly or through exactly one view node
+        // (identity by tensor id — buffers are recycled by the graph allocator, pointers are not identities)
+        if (SK.src[0].id != rk.dst.id) {
+            if (use_count(rk.dst) != 1 || use_count(SK.src[0]) != 1) return false;
+            bool via_view = false;
+            for (int q2 = j + 1; q2 < sk; q2++) if (nodes[q2].op == B200_OP_NONE && nodes[q2].dst.id == SK.src[0].id && nodes[q2].src[0].id == rk.dst.id) via_view = true;
+            if (!via_view) return false;
+        } else if (use_count(rk.dst) != 1) return false;
+        b200_rope_params p; memset(&p, 0, sizeof(p));
+        p.n_dims = rq.op_params[1]; p.mode = rq.op_params[2]; p.n_ctx_orig = rq.op_params[4];
+        p.freq_base = f32_param(rq, 5); p.freq_scale = f32_param(rq, 6); p.ext_factor = f32_param(rq, 7);
+        p.attn_factor = f32_param(rq, 8); p.beta_fast = f32_param(rq, 9); p.beta_slow = f32_param(rq, 10);
+        const float * ff = rq.n_src > 2 ? (const float *)rq.src[2].data : nullptr;
+        last_status = b200_rope_kv_store2((const float *)q.data, (float *)rq.dst.data, (const float *)k.data, (const float *)v.data, (const int32_t *)rq.src[1].data, ff,
+                                          (const int64_t *)SK.src[1].data, (const int64_t *)SV.src[1].data, SK.dst.data, SV.dst.data, SK.dst.type,
+                                          SK.dst.nb[1], SV.dst.nb[1], hd, nh, nhk, nt, &p, st);
+        done[j] = done[sk] = done[sv] = 1;
+        invalidate_act(rq.dst);
+        return true;
+    }
     int n_limit(int i) const { return i + 24 < n ? i + 24 : n; }
 
     int run_node(int i) {
@@ -311,6 +387,7 @@ struct Runner {
                                            : b200_mul((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st);
             }
             case B200_OP_ROPE: {
+                if (fuse && try_rope_kv_store(i)) return last_status;
                 invalidate_act(n.dst);
                 const b200_tensor & x = n.src[0];
                 b200_rope_params p; memset(&p, 0, sizeof(p));
@@ -362,6 +439,7 @@ struct Runner {
         uses.clear();
         for (int i = 0; i < n; i++) for (int s = 0; s < nodes[i].n_src && s < B200_MAX_SRC; s++) if (nodes[i].src[s].id) uses[nodes[i].src[s].id]++;
         ex->act_id[0] = ex->act_id[1] = 0;
+        ex->norm.out_id = 0;
         for (int i = 0; i < n; i++) {
             if (done[i]) continue;
             const int s = run_node(i);
@@ -412,7 +490,7 @@ int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
     for (auto & g : ex->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     ex->graphs.clear();
     if (ex->ws) { cudaDeviceSynchronize(); cudaFree(ex->ws); ex->ws = nullptr; }
-    if (cudaMalloc((void **)&ex->ws, total) != cudaSuccess) { cudaGetLastError(); b200_set_error("executor: cannot allocate %zu bytes of workspace", total); return B200_ERR_CUDA; }
+    if (cudaMalloc((void **)&ex->ws, total) != cudaSuccess || cudaMemset(ex->ws, 0, total) != cudaSuccess) {   /* zeroed once: flash-attn split counters */ cudaGetLastError(); b200_set_error("executor: cannot allocate %zu bytes of workspace", total); return B200_ERR_CUDA; }
     ex->ws_bytes = total;
     ex->off_act[0] = 0; ex->off_act[1] = up(act[0]); ex->off_fa = up(act[0]) + up(act[1]);
     ex->act_bytes[0] = act[0]; ex->act_bytes[1] = act[1]; ex->fa_bytes = fa;

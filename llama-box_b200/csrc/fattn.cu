@@ -16,6 +16,7 @@
 #include <math.h>
 
 #define FA_WARPS 4
+#define FA_MAX_SPLITS 64
 
 
 __device__ __forceinline__ void unpack_h8(const uint4 & r, float (&f)[8]) {
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         const uint8_t * __restrict__ kc, int64_t k_rs, int64_t k_hs,
         const uint8_t * __restrict__ vc, int64_t v_rs, int64_t v_hs,
         const uint16_t * __restrict__ mask, int64_t mask_rs,
-        float * __restrict__ dst, float * __restrict__ ws,
+        float * __restrict__ dst, float * __restrict__ ws, unsigned int * __restrict__ counters,
         int n_head, int n_head_kv, int n_kv, int split_len, int n_splits,
         float scale, float max_bias, float softcap, float m0, float m1, int nh_log2) {
     constexpr int LP  = D / 8;          // lanes per position
@@ -190,6 +191,54 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
             if (e == 0) { wp[D] = Mn; wp[D + 1] = l; }
         }
     }
+    if (n_splits > 1) {
+        // the last CTA of this (token, head tile) to finish merges all splits (replaces the separate
+        // flash_attn_combine_results launch, fattn-common.cuh:645-701); the counter cleans itself for the next launch
+        __shared__ unsigned int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(&counters[tok * gridDim.y + tile], 1u);
+            s_last = prev == (unsigned int)(n_splits - 1);
+            if (s_last) counters[tok * gridDim.y + tile] = 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            // phase 1: per-split maxima / sums of this tile's G heads -> scale factors in shared memory
+            __shared__ float s_sc[FA_MAX_SPLITS][G];
+            __shared__ float s_inv[G];
+            const int n_rows = gridDim.z * n_head;
+            for (int idx = threadIdx.x; idx < n_splits * G; idx += FA_WARPS * 32) {
+                const int sp = idx / G, g = idx % G;
+                s_sc[sp][g] = __ldcg(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D);
+            }
+            __syncthreads();
+            if (threadIdx.x < G) {
+                const int g = threadIdx.x;
+                float Mn = -INFINITY;
+                for (int sp = 0; sp < n_splits; sp++) Mn = fmaxf(Mn, s_sc[sp][g]);
+                float l = 0.0f;
+                for (int sp = 0; sp < n_splits; sp++) {
+                    const float m = s_sc[sp][g];
+                    const float sc = m == -INFINITY ? 0.0f : expf(m - Mn);
+                    l += __ldcg(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D + 1) * sc;
+                    s_sc[sp][g] = sc;
+                }
+                s_inv[g] = 1.0f / l;
+            }
+            __syncthreads();
+            // phase 2: independent, coalesced loads of the partial accumulators
+            for (int idx = threadIdx.x; idx < G * D; idx += FA_WARPS * 32) {
+                const int g = idx / D, e = idx % D;
+                const int row = tok * n_head + h0 + g;
+                float a = 0.0f;
+#pragma unroll 8
+                for (int sp = 0; sp < n_splits; sp++) a = fmaf(__ldcg(ws + ((int64_t)sp * n_rows + row) * (D + 2) + e), s_sc[sp][g], a);
+                dst[(int64_t)row * D + e] = a * s_inv[g];
+            }
+        }
+    }
     pdl_trigger();
 }
 
@@ -209,11 +258,13 @@ __global__ void __launch_bounds__(D) fattn_combine_kernel(const float * __restri
     pdl_trigger();
 }
 
+// KV splits: ~2 CTAs of 128 threads per SM, at least 32 positions per split, at most FA_MAX_SPLITS
 static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_len) {
     const int sms = b200_sm_count();
     int64_t base = n_tiles * n_tok;
     int64_t want = (2 * (int64_t)sms + base - 1) / base;
-    int64_t maxs = (n_kv + 63) / 64;
+    int64_t maxs = (n_kv + 31) / 32;
+    if (maxs > FA_MAX_SPLITS) maxs = FA_MAX_SPLITS;
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     int64_t len = (n_kv + want - 1) / want;
@@ -222,9 +273,14 @@ static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_l
     return (int)((n_kv + len - 1) / len);
 }
 
+// workspace = split partials [(n_kv/32) splits][n_tok][n_head][dv + 2] f32, then one u32 counter per (token, head tile).
+// It must be zero-initialised ONCE by the caller (the counters clean themselves after every launch).
+static int64_t fa_partial_bytes(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
+    const int64_t maxs = (n_kv + 31) / 32;
+    return (maxs * n_tok * n_head * (dv + 2) * (int64_t)sizeof(float) + 255) & ~(int64_t)255;
+}
 extern "C" int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
-    const int64_t maxs = (n_kv + 63) / 64;
-    return maxs * n_tok * n_head * (dv + 2) * (int64_t)sizeof(float);
+    return fa_partial_bytes(dv, n_head, n_tok, n_kv) + n_tok * n_head * (int64_t)sizeof(unsigned int) + 256;
 }
 
 template <int D, int KVT, int G>
@@ -238,13 +294,10 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     const float m0 = powf(2.0f, -(max_bias) / (float)nh_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / (float)nh_log2);
     if (softcap != 0.0f) scale /= softcap;
     dim3 grid((unsigned)n_splits, (unsigned)n_tiles, (unsigned)n_tok);
+    unsigned int * counters = ws ? (unsigned int *)((uint8_t *)ws + fa_partial_bytes(D, n_head, n_tok, n_kv)) : nullptr;
     fattn_vec_kernel<D, KVT, G><<<grid, FA_WARPS * 32, 0, st>>>(q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
-        (const uint16_t *)mask, mask_rs, dst, ws, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2);
+        (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2);
     B200_LAUNCH_CHECK();
-    if (n_splits > 1) {
-        fattn_combine_kernel<D><<<(unsigned)(n_tok * n_head), D, 0, st>>>(ws, dst, n_splits, (int)(n_tok * n_head));
-        B200_LAUNCH_CHECK();
-    }
     return B200_OK;
 }
 
@@ -261,7 +314,7 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
     if (n_tok > 65535) { b200_set_error("flash_attn: n_tok too large for one launch"); return B200_ERR_UNSUPPORTED; }
     const int64_t gq = n_head / n_head_kv;
     const int G = gq % 4 == 0 ? 4 : (gq % 2 == 0 ? 2 : 1);
-    if (!workspace && (n_kv + 63) / 64 > 1) { b200_set_error("flash_attn: workspace required"); return B200_ERR_INVALID; }
+    if (!workspace && (n_kv + 31) / 32 > 1) { b200_set_error("flash_attn: workspace required"); return B200_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream; float * ws = (float *)workspace;
 #define FA_CASE(DD, KK, GG) return fa_launch<DD, KK, GG>(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, ws, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, st)
     if (dk == 128) {

@@ -18,6 +18,7 @@
 // Rows of Q4_0/Q8_0/Q6_K are repacked at load time so every part of a segment is 16-byte aligned
 // (repack.cu); Q4_K/Q5_K keep the GGUF layout.
 #include "common.cuh"
+#include "actquant.cuh"
 
 #define MMV_WARPS 16
 #define MMV_MAX_MATS 4
@@ -32,8 +33,11 @@ struct MmvMat {
     const float *   residual;
     int64_t         m;
     int64_t         dst_col_stride;
+    int64_t         rb;         // bytes per row
+    int32_t         nb;         // blocks per row
     int32_t         type;
-    int32_t         pair0;      // first row-pair index of this matrix in the launch
+    int32_t         pair0;      // first unit index of this matrix in the launch
+    int32_t         _pad;
 };
 struct MmvArgs {
     MmvMat  mat[MMV_MAX_MATS];
@@ -42,47 +46,25 @@ struct MmvArgs {
     int32_t n_mats;
     int32_t total_pairs;
     int32_t act_bytes[2];       // bytes to stage per kind (ncols * col_bytes), 0 if unused
-    int32_t segc;               // chunks (32 elements) per segment
+    int32_t segc;               // chunks (32 elements) per compute segment (64 = fast paths)
     int32_t nseg;               // segments per row
     int32_t stages;             // ring depth per warp
-    int32_t slot_bytes;         // bytes of one ring slot (two row segments of the widest type in the launch)
+    int32_t slot_bytes;         // bytes of one ring slot: R whole rows of the widest type in the launch
+    int32_t rows_per_unit;      // R: 1 or 2 (SwiGLU: one gate row + one up row)
+    int32_t segs_per_part;      // G: a unit is split into K-parts of G segments so that >= 2 ring slots fit per warp
+    int32_t parts;              // P = ceil(nseg / G)
+    int32_t row_stride;         // byte distance between the two rows inside a slot
+    // activation source: 0 = quantised act buffers (bulk copy), 1 = f32 x quantised in the prologue,
+    // 2 = f32 x with RMS norm * norm_w, then quantised (fuses rms_norm + mul + quantize into this kernel)
+    int32_t act_source;
+    int32_t ncols;
+    const float * x;            // [ncols][x_col_stride]
+    const float * norm_w;       // [k] or null
+    float *       y_out;        // optional f32 copy of the (normalised) activations, written by CTA 0
+    int64_t       x_col_stride;
+    float         eps;
+    int32_t       _pad2;
 };
-
-// ---- per-type geometry of a row segment [c0, c0+segc) chunks ------------------------------------
-// bytes one row contributes to a ring slot
-__host__ __device__ inline int seg_row_bytes(int type, int segc) {
-    switch (type) {
-        case B200_TYPE_Q4_0: return segc * 18;
-        case B200_TYPE_Q8_0: return segc * 34;
-        case B200_TYPE_Q4_K: return segc / 8 * 144;
-        case B200_TYPE_Q5_K: return segc / 8 * 176;
-        default:             return segc / 8 * 210;     // Q6_K
-    }
-}
-
-// lane 0 only: copy the segment `seg` of one (repacked) row into smem at `dst`, completing on `bar`
-__device__ __forceinline__ void issue_row(int type, uint8_t * dst, const uint8_t * row, int64_t nb, int seg, int segc, uint64_t * bar) {
-    const int64_t c0 = (int64_t)seg * segc;
-    switch (type) {
-        case B200_TYPE_Q4_K: bulk_g2s(dst, row + c0 / 8 * 144, segc / 8 * 144, bar); break;
-        case B200_TYPE_Q5_K: bulk_g2s(dst, row + c0 / 8 * 176, segc / 8 * 176, bar); break;
-        case B200_TYPE_Q4_0:
-            bulk_g2s(dst, row + c0 * 16, segc * 16, bar);
-            bulk_g2s(dst + segc * 16, row + nb * 16 + c0 * 2, segc * 2, bar);
-            break;
-        case B200_TYPE_Q8_0:
-            bulk_g2s(dst, row + c0 * 32, segc * 32, bar);
-            bulk_g2s(dst + segc * 32, row + nb * 32 + c0 * 2, segc * 2, bar);
-            break;
-        default: { // Q6_K: ql | qh | sc | d
-            const int64_t s0 = c0 / 8; const int ns = segc / 8;
-            bulk_g2s(dst,            row + s0 * 128,            ns * 128, bar);
-            bulk_g2s(dst + ns * 128, row + nb * 128 + s0 * 64,  ns * 64,  bar);
-            bulk_g2s(dst + ns * 192, row + nb * 192 + s0 * 16,  ns * 16,  bar);
-            bulk_g2s(dst + ns * 208, row + nb * 208 + s0 * 2,   ns * 2,   bar);
-        }
-    }
-}
 
 // ---- activation view in shared memory --------------------------------------------------------
 struct ActView { const uint8_t * qs; const float * d; const int16_t * bs; };
@@ -99,6 +81,20 @@ __device__ __forceinline__ int dot16s(const uint4 & a, const uint4 & w) {
     s = dp4a_s((int)w.z, (int)a.z, s);
     return dp4a_s((int)w.w, (int)a.w, s);
 }
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t w, uint32_t a, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(a), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dot16m(const uint4 & a, const uint4 & w, uint32_t m) {
+    int s = dp4a_u8s8(w.x & m, a.x, 0);
+    s = dp4a_u8s8(w.y & m, a.y, s);
+    s = dp4a_u8s8(w.z & m, a.z, s);
+    return dp4a_u8s8(w.w & m, a.w, s);
+}
+__device__ __forceinline__ int byte_of(uint32_t w, int sh8) { return (int)__byte_perm(w, 0, 0x4440 | (sh8 >> 3)); }   // one PRMT
+
 
 // 6-bit scale / min of sub-block `is` from the q4_K/q5_K header regs (ggml-quants.c:703-711)
 __device__ __forceinline__ void k4_scale_min(const uint4 & hdr, int is, int & sc, int & mn) {
@@ -118,22 +114,22 @@ template <int T> struct WChunk;
 
 template <> struct WChunk<B200_TYPE_Q4_0> {
     uint4 qs; uint16_t d;
-    __device__ __forceinline__ void load(const uint8_t * s, int segc, int lc) { qs = *(const uint4 *)(s + lc * 16); d = *(const uint16_t *)(s + segc * 16 + lc * 2); }
+    __device__ __forceinline__ void load(const uint8_t * s, int nb, int i) { qs = *(const uint4 *)(s + i * 16); d = *(const uint16_t *)(s + nb * 16 + i * 2); }
     __device__ __forceinline__ float dot(const ActView & a, int i) const {
         const int sw = (i >> 2) & 1;
         const uint4 A = *(const uint4 *)(a.qs + i * 32 + sw * 16);
         const uint4 B = *(const uint4 *)(a.qs + i * 32 + (sw ^ 1) * 16);
-        const int shA = sw * 4, shB = (sw ^ 1) * 4;                   // low nibbles <-> elements 0..15
-        int s = dot16(A, (qs.x >> shA) & 0x0F0F0F0Fu, (qs.y >> shA) & 0x0F0F0F0Fu, (qs.z >> shA) & 0x0F0F0F0Fu, (qs.w >> shA) & 0x0F0F0F0Fu);
-        s    += dot16(B, (qs.x >> shB) & 0x0F0F0F0Fu, (qs.y >> shB) & 0x0F0F0F0Fu, (qs.z >> shB) & 0x0F0F0F0Fu, (qs.w >> shB) & 0x0F0F0F0Fu);
+        // low nibbles <-> elements 0..15; high nibbles stay in place: u8 x s8 dp4a on (q & 0xF0), sum >> 4
+        const uint32_t mA = sw ? 0xF0F0F0F0u : 0x0F0F0F0Fu;
+        int s = (dot16m(A, qs, mA) >> (sw * 4)) + (dot16m(B, qs, ~mA) >> (4 - sw * 4));
         s -= 8 * (int)a.bs[i];
         return __fmul_rn(__fmul_rn((float)s, h2f(d)), a.d[i]);          // ggml-cpu/quants.c:146
     }
 };
 template <> struct WChunk<B200_TYPE_Q8_0> {
     uint4 q0, q1; uint16_t d;
-    __device__ __forceinline__ void load(const uint8_t * s, int segc, int lc) {
-        q0 = *(const uint4 *)(s + lc * 32); q1 = *(const uint4 *)(s + lc * 32 + 16); d = *(const uint16_t *)(s + segc * 32 + lc * 2);
+    __device__ __forceinline__ void load(const uint8_t * s, int nb, int i) {
+        q0 = *(const uint4 *)(s + i * 32); q1 = *(const uint4 *)(s + i * 32 + 16); d = *(const uint16_t *)(s + nb * 32 + i * 2);
     }
     __device__ __forceinline__ float dot(const ActView & a, int i) const {
         const int sw = (i >> 2) & 1;
@@ -145,7 +141,7 @@ template <> struct WChunk<B200_TYPE_Q8_0> {
 };
 template <> struct WChunk<B200_TYPE_Q4_K> {
     uint4 hdr, qs;
-    __device__ __forceinline__ void load(const uint8_t * s, int, int lc) { const uint8_t * b = s + (lc >> 3) * 144; hdr = *(const uint4 *)b; qs = *(const uint4 *)(b + 16 + (lc & 7) * 16); }
+    __device__ __forceinline__ void load(const uint8_t * s, int, int i) { const uint8_t * b = s + (i >> 3) * 144; hdr = *(const uint4 *)b; qs = *(const uint4 *)(b + 16 + (i & 7) * 16); }
     __device__ __forceinline__ float dot(const ActView & a, int i) const {
         const int sb = i >> 3, j = i & 7, c = j >> 1, h = j & 1, sw = c >> 1;
         const int is0 = 2 * c + sw, is1 = 2 * c + (sw ^ 1);           // sub-block (32 elems) of each part
@@ -167,8 +163,8 @@ template <> struct WChunk<B200_TYPE_Q4_K> {
 };
 template <> struct WChunk<B200_TYPE_Q5_K> {
     uint4 hdr, qh, qs;
-    __device__ __forceinline__ void load(const uint8_t * s, int, int lc) {
-        const uint8_t * b = s + (lc >> 3) * 176; hdr = *(const uint4 *)b; qh = *(const uint4 *)(b + 16 + (lc & 1) * 16); qs = *(const uint4 *)(b + 48 + (lc & 7) * 16);
+    __device__ __forceinline__ void load(const uint8_t * s, int, int i) {
+        const uint8_t * b = s + (i >> 3) * 176; hdr = *(const uint4 *)b; qh = *(const uint4 *)(b + 16 + (i & 1) * 16); qs = *(const uint4 *)(b + 48 + (i & 7) * 16);
     }
     __device__ __forceinline__ float dot(const ActView & a, int i) const {
         const int sb = i >> 3, j = i & 7, c = j >> 1, h = j & 1, sw = c >> 1;
@@ -193,13 +189,13 @@ template <> struct WChunk<B200_TYPE_Q5_K> {
 };
 template <> struct WChunk<B200_TYPE_Q6_K> {
     uint4 ql, qh; uint32_t sc; uint16_t d;
-    __device__ __forceinline__ void load(const uint8_t * s, int segc, int lc) {
-        const int ns = segc >> 3, sb = lc >> 3, j = lc & 7, hh = j >> 2, ii = j & 3;
+    __device__ __forceinline__ void load(const uint8_t * s, int nb, int i) {
+        const int sb = i >> 3, j = i & 7, hh = j >> 2, ii = j & 3;
         ql = *(const uint4 *)(s + sb * 128 + hh * 64 + ii * 16);
-        qh = *(const uint4 *)(s + ns * 128 + sb * 64 + hh * 32 + (ii & 1) * 16);
-        const uint8_t * scp = s + ns * 192 + sb * 16 + hh * 8 + ii;     // scales 8hh+ii and 8hh+ii+4
+        qh = *(const uint4 *)(s + nb * 128 + sb * 64 + hh * 32 + (ii & 1) * 16);
+        const uint8_t * scp = s + nb * 192 + sb * 16 + hh * 8 + ii;     // scales 8hh+ii and 8hh+ii+4
         sc = (uint32_t)scp[0] | ((uint32_t)scp[4] << 8);
-        d = *(const uint16_t *)(s + ns * 208 + sb * 2);
+        d = *(const uint16_t *)(s + nb * 208 + sb * 2);
     }
     __device__ __forceinline__ float dot(const ActView & a, int i) const {
         const int sb = i >> 3, j = i & 7, hh = j >> 2, ii = j & 3, sw = hh;
@@ -222,16 +218,130 @@ template <> struct WChunk<B200_TYPE_Q6_K> {
     }
 };
 
-// both rows of a slot, all chunks of the segment, all columns
-template <int T, int NCOLS>
-__device__ __forceinline__ void slot_dot(const uint8_t * s0, const uint8_t * s1, int segc, int seg, const uint8_t * act_s, int64_t k, int kind, int lane, float (&acc)[2][NCOLS]) {
+
+// ---- fast paths for 2048-element segments (segc == 64: 8 super-blocks per row segment) -------------
+// The generic WChunk code above spends ~100 instructions per 32 weights (6-bit scale unpack and nibble
+// shifts per chunk), which makes the matvec ISSUE-bound long before HBM is saturated (ncu: 2 TB/s).
+// Here one lane owns 64 elements of ONE super-block for both rows: scales are decoded once per
+// super-block with 32-bit SIMD masks (the utmp trick of ggml-cpu/quants.c:586-592), high nibbles are
+// used in place through an unsigned-by-signed dp4a on (q & 0xF0F0F0F0) followed by one >>4 of the sum,
+// and every bank-conflict "swap" folds into lane-constant masks / selectors.  ~40 instructions / 32 weights.
+template <int NCOLS, int NR>
+__device__ __forceinline__ void slot_dot_q4K_fast(const uint8_t * s0, const uint8_t * s1, int nb, int lseg, int seg, const uint8_t * act_s, int64_t k, int lane, float (&acc)[2][NCOLS]) {
+    const int q = lane >> 3, s = (lane >> 2) & 1, jj = lane & 3, c = jj >> 1, h = jj & 1;
+    const int sb = q + 4 * s, gsb = seg * 8 + sb, lsb = lseg * 8 + sb;     // gsb: in the row (activations), lsb: in the slot
+    // "first" = the 16-element part this lane reads first (low-nibble part on s=0 lanes, high-nibble part on s=1)
+    const uint32_t mF = s ? 0xF0F0F0F0u : 0x0F0F0F0Fu, mS = ~mF;
+    const int shF = 4 * s, shS = 4 - shF;
+    const int isF = 2 * c + s, isS = 2 * c + 1 - s;                 // sub-block ids of pass A (pass B: +4)
+    const int eF = 8 * isF, eS = 8 * isS;                            // byte selectors in the decoded scale words
+    uint4 hdr[2], qa[2], qb[2];
+    {
+        const uint8_t * b0 = s0 + lsb * 144, * b1 = s1 + lsb * 144;
+        hdr[0] = *(const uint4 *)b0; qa[0] = *(const uint4 *)(b0 + 16 + jj * 16); qb[0] = *(const uint4 *)(b0 + 80 + jj * 16);
+        if (NR > 1) { hdr[1] = *(const uint4 *)b1; qa[1] = *(const uint4 *)(b1 + 16 + jj * 16); qb[1] = *(const uint4 *)(b1 + 80 + jj * 16); }
+    }
+    int scAF[2], scAS[2], scBF[2], scBS[2], mnAF[2], mnAS[2], mnBF[2], mnBS[2]; float dw[2], dm[2];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const uint32_t y = hdr[r].y, z = hdr[r].z, w = hdr[r].w;
+        const uint32_t sc03 = y & 0x3f3f3f3fu, mn03 = z & 0x3f3f3f3fu;
+        const uint32_t sc47 = (w & 0x0f0f0f0fu) | (((y >> 6) & 0x03030303u) << 4);
+        const uint32_t mn47 = ((w >> 4) & 0x0f0f0f0fu) | (((z >> 6) & 0x03030303u) << 4);
+        scAF[r] = byte_of(sc03, eF); scAS[r] = byte_of(sc03, eS); scBF[r] = byte_of(sc47, eF); scBS[r] = byte_of(sc47, eS);
+        mnAF[r] = byte_of(mn03, eF); mnAS[r] = byte_of(mn03, eS); mnBF[r] = byte_of(mn47, eF); mnBS[r] = byte_of(mn47, eS);
+        dw[r] = h2f((uint16_t)(hdr[r].x & 0xffff)); dm[r] = h2f((uint16_t)(hdr[r].x >> 16));
+    }
+    const int64_t colb = act_col_bytes(0, k), doff = act_d_off(0, k), boff = act_bsum_off(0, k);
+#pragma unroll
+    for (int col = 0; col < NCOLS; col++) {
+        const uint8_t * ab = act_s + col * colb;
+        const uint8_t * base = ab + gsb * 256 + c * 64 + h * 16;
+        const uint4 FA = *(const uint4 *)(base + 32 * s), SA = *(const uint4 *)(base + 32 - 32 * s);
+        const uint4 FB = *(const uint4 *)(base + 128 + 32 * s), SB = *(const uint4 *)(base + 160 - 32 * s);
+        const int16_t * bs = (const int16_t *)(ab + boff) + gsb * 16 + h;
+        const int bFA = bs[isF * 2], bSA = bs[isS * 2], bFB = bs[isF * 2 + 8], bSB = bs[isS * 2 + 8];
+        const float da = ((const float *)(ab + doff))[gsb];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const int dFA = dot16m(FA, qa[r], mF) >> shF, dSA = dot16m(SA, qa[r], mS) >> shS;
+            const int dFB = dot16m(FB, qb[r], mF) >> shF, dSB = dot16m(SB, qb[r], mS) >> shS;
+            const int isum = scAF[r] * dFA + scAS[r] * dSA + scBF[r] * dFB + scBS[r] * dSB;
+            const int imin = mnAF[r] * bFA + mnAS[r] * bSA + mnBF[r] * bFB + mnBS[r] * bSB;
+            acc[r][col] += __fmul_rn(dw[r], da) * (float)isum - __fmul_rn(dm[r], da) * (float)imin;
+        }
+    }
+}
+
+template <int NCOLS, int NR>
+__device__ __forceinline__ void slot_dot_q6K_fast(const uint8_t * s0, const uint8_t * s1, int nb, int lseg, int seg, const uint8_t * act_s, int64_t k, int lane, float (&acc)[2][NCOLS]) {
+    const int q = lane >> 3, s = (lane >> 2) & 1, ii = lane & 3;
+    const int sb = q + 4 * s, gsb = seg * 8 + sb, lsb = lseg * 8 + sb;
+    const uint32_t mF = s ? 0xF0F0F0F0u : 0x0F0F0F0Fu, mS = ~mF;
+    const int shF = 4 * s, shS = 4 - shF;
+    const int hsF = (ii >> 1) * 2 + 4 * s, hsS = (ii >> 1) * 2 + 4 - 4 * s;     // 2-bit highs of the first / second part
+    const int eF = 8 * (ii & 3) , eS = eF;                                          // scale byte ii (+4 parts: other word)
+    uint4 ql0[2], ql1[2], qh0[2], qh1[2], scv[2]; float dw[2];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const uint8_t * sr = r ? s1 : s0;
+        ql0[r] = *(const uint4 *)(sr + lsb * 128 + ii * 16);
+        ql1[r] = *(const uint4 *)(sr + lsb * 128 + 64 + ii * 16);
+        qh0[r] = *(const uint4 *)(sr + nb * 128 + lsb * 64 + (ii & 1) * 16);
+        qh1[r] = *(const uint4 *)(sr + nb * 128 + lsb * 64 + 32 + (ii & 1) * 16);
+        scv[r] = *(const uint4 *)(sr + nb * 192 + lsb * 16);
+        dw[r]  = h2f(*(const uint16_t *)(sr + nb * 208 + lsb * 2));
+    }
+    // scales (int8): half hh uses bytes 8hh + ii (low-nibble part) and 8hh + ii + 4 (high-nibble part)
+    int scF0[2], scS0[2], scF1[2], scS1[2];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        const uint32_t lo0 = scv[r].x, hi0 = scv[r].y, lo1 = scv[r].z, hi1 = scv[r].w;   // bytes 0-3, 4-7, 8-11, 12-15
+        const int a0 = (int)(int8_t)byte_of(lo0, eF), b0 = (int)(int8_t)byte_of(hi0, eF);
+        const int a1 = (int)(int8_t)byte_of(lo1, eF), b1 = (int)(int8_t)byte_of(hi1, eF);
+        scF0[r] = s ? b0 : a0; scS0[r] = s ? a0 : b0; scF1[r] = s ? b1 : a1; scS1[r] = s ? a1 : b1;
+    }
+    (void)eS;
+    const int64_t colb = act_col_bytes(0, k), doff = act_d_off(0, k), boff = act_bsum_off(0, k);
+#pragma unroll
+    for (int col = 0; col < NCOLS; col++) {
+        const uint8_t * ab = act_s + col * colb;
+        const uint8_t * base = ab + gsb * 256 + ii * 16;
+        const uint4 F0 = *(const uint4 *)(base + 64 * s), S0 = *(const uint4 *)(base + 64 - 64 * s);          // half 0
+        const uint4 F1 = *(const uint4 *)(base + 128 + 64 * s), S1 = *(const uint4 *)(base + 192 - 64 * s);   // half 1
+        const int16_t * bs = (const int16_t *)(ab + boff) + gsb * 16 + ii;
+        const int bF0 = bs[4 * s], bS0 = bs[4 - 4 * s], bF1 = bs[8 + 4 * s], bS1 = bs[12 - 4 * s];
+        const float da = ((const float *)(ab + doff))[gsb];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+#define H2(qh, sh) dot16m_h(qh, sh)
+            auto h2dot = [](const uint4 & a, const uint4 & qh, int sh) {
+                int t = __dp4a((int)((qh.x >> sh) & 0x03030303u), (int)a.x, 0);
+                t = __dp4a((int)((qh.y >> sh) & 0x03030303u), (int)a.y, t);
+                t = __dp4a((int)((qh.z >> sh) & 0x03030303u), (int)a.z, t);
+                return __dp4a((int)((qh.w >> sh) & 0x03030303u), (int)a.w, t);
+            };
+#undef H2
+            const int vF0 = (dot16m(F0, ql0[r], mF) >> shF) + 16 * h2dot(F0, qh0[r], hsF) - 32 * bF0;
+            const int vS0 = (dot16m(S0, ql0[r], mS) >> shS) + 16 * h2dot(S0, qh0[r], hsS) - 32 * bS0;
+            const int vF1 = (dot16m(F1, ql1[r], mF) >> shF) + 16 * h2dot(F1, qh1[r], hsF) - 32 * bF1;
+            const int vS1 = (dot16m(S1, ql1[r], mS) >> shS) + 16 * h2dot(S1, qh1[r], hsS) - 32 * bS1;
+            const int isum = scF0[r] * vF0 + scS0[r] * vS0 + scF1[r] * vF1 + scS1[r] * vS1;
+            acc[r][col] += __fmul_rn(dw[r], da) * (float)isum;
+        }
+    }
+}
+
+// both rows of a slot, all chunks of one segment, all columns
+template <int T, int NCOLS, int NR>
+__device__ __forceinline__ void slot_dot(const uint8_t * s0, const uint8_t * s1, int nb, int segc, int lseg, int seg, const uint8_t * act_s, int64_t k, int kind, int lane, float (&acc)[2][NCOLS]) {
     const int64_t colb = act_col_bytes(kind, k);
     const int64_t doff = act_d_off(kind, k), boff = act_bsum_off(kind, k);
 #pragma unroll 2
     for (int lc = lane; lc < segc; lc += 32) {
+        const int i = seg * segc + lc, li = lseg * segc + lc;      // chunk in the row (activations) / in the slot (weights)
         WChunk<T> w0, w1;
-        w0.load(s0, segc, lc); w1.load(s1, segc, lc);
-        const int i = seg * segc + lc;
+        w0.load(s0, nb, li); if (NR > 1) w1.load(s1, nb, li);
 #pragma unroll
         for (int c = 0; c < NCOLS; c++) {
             ActView a;
@@ -239,76 +349,116 @@ __device__ __forceinline__ void slot_dot(const uint8_t * s0, const uint8_t * s1,
             a.d  = (const float *)(act_s + c * colb + doff);
             a.bs = (const int16_t *)(act_s + c * colb + boff);
             acc[0][c] += w0.dot(a, i);
-            acc[1][c] += w1.dot(a, i);
+            if (NR > 1) acc[1][c] += w1.dot(a, i);
         }
     }
 }
 
-template <int NCOLS>
-__device__ __forceinline__ void slot_one_type(int t, const uint8_t * s0, const uint8_t * s1, int segc, int seg, const uint8_t * a0, const uint8_t * a1,
+template <int NCOLS, int NR>
+__device__ __forceinline__ void slot_one_type(int t, const uint8_t * s0, const uint8_t * s1, int nb, int segc, int lseg, int seg, const uint8_t * a0, const uint8_t * a1,
                                               int64_t k, int lane, float (&acc)[2][NCOLS]) {
+    if (segc == 64 && t == B200_TYPE_Q4_K) { slot_dot_q4K_fast<NCOLS, NR>(s0, s1, nb, lseg, seg, a0, k, lane, acc); return; }
+    if (segc == 64 && t == B200_TYPE_Q6_K) { slot_dot_q6K_fast<NCOLS, NR>(s0, s1, nb, lseg, seg, a0, k, lane, acc); return; }
     switch (t) {
-        case B200_TYPE_Q4_K: slot_dot<B200_TYPE_Q4_K, NCOLS>(s0, s1, segc, seg, a0, k, 0, lane, acc); break;
-        case B200_TYPE_Q5_K: slot_dot<B200_TYPE_Q5_K, NCOLS>(s0, s1, segc, seg, a0, k, 0, lane, acc); break;
-        case B200_TYPE_Q6_K: slot_dot<B200_TYPE_Q6_K, NCOLS>(s0, s1, segc, seg, a0, k, 0, lane, acc); break;
-        case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS>(s0, s1, segc, seg, a1, k, 1, lane, acc); break;
-        default:             slot_dot<B200_TYPE_Q8_0, NCOLS>(s0, s1, segc, seg, a1, k, 1, lane, acc); break;
+        case B200_TYPE_Q4_K: slot_dot<B200_TYPE_Q4_K, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a0, k, 0, lane, acc); break;
+        case B200_TYPE_Q5_K: slot_dot<B200_TYPE_Q5_K, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a0, k, 0, lane, acc); break;
+        case B200_TYPE_Q6_K: slot_dot<B200_TYPE_Q6_K, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a0, k, 0, lane, acc); break;
+        case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a1, k, 1, lane, acc); break;
+        default:             slot_dot<B200_TYPE_Q8_0, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a1, k, 1, lane, acc); break;
     }
 }
 
-template <int NCOLS, int TT>
-__device__ __forceinline__ void slot_dispatch(int t0, int t1, const uint8_t * s0, const uint8_t * s1, int segc, int seg, const uint8_t * a0, const uint8_t * a1,
-                                              int64_t k, int lane, float (&acc)[2][NCOLS]) {
+// rows s0 (type t0, nb0) and s1 (type t1, nb1); TT >= 0: the launch is uniform in that type
+template <int NCOLS, int TT, int NR>
+__device__ __forceinline__ void slot_dispatch(int t0, int t1, const uint8_t * s0, const uint8_t * s1, int nb0, int nb1, int segc, int lseg, int seg,
+                                              const uint8_t * a0, const uint8_t * a1, int64_t k, int lane, float (&acc)[2][NCOLS]) {
     if (TT >= 0) {
-        switch (TT) {       // uniform-type launch: a single path is compiled
-            case B200_TYPE_Q4_K: slot_dot<B200_TYPE_Q4_K, NCOLS>(s0, s1, segc, seg, a0, k, 0, lane, acc); break;
-            case B200_TYPE_Q5_K: slot_dot<B200_TYPE_Q5_K, NCOLS>(s0, s1, segc, seg, a0, k, 0, lane, acc); break;
-            case B200_TYPE_Q6_K: slot_dot<B200_TYPE_Q6_K, NCOLS>(s0, s1, segc, seg, a0, k, 0, lane, acc); break;
-            case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS>(s0, s1, segc, seg, a1, k, 1, lane, acc); break;
-            default:             slot_dot<B200_TYPE_Q8_0, NCOLS>(s0, s1, segc, seg, a1, k, 1, lane, acc); break;
+        if (segc == 64 && TT == B200_TYPE_Q4_K) { slot_dot_q4K_fast<NCOLS, NR>(s0, s1, nb0, lseg, seg, a0, k, lane, acc); return; }
+        if (segc == 64 && TT == B200_TYPE_Q6_K) { slot_dot_q6K_fast<NCOLS, NR>(s0, s1, nb0, lseg, seg, a0, k, lane, acc); return; }
+        switch (TT) {
+            case B200_TYPE_Q4_K: slot_dot<B200_TYPE_Q4_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc); break;
+            case B200_TYPE_Q5_K: slot_dot<B200_TYPE_Q5_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc); break;
+            case B200_TYPE_Q6_K: slot_dot<B200_TYPE_Q6_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc); break;
+            case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
+            default:             slot_dot<B200_TYPE_Q8_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
         }
     } else if (t0 == t1) {
-        slot_one_type<NCOLS>(t0, s0, s1, segc, seg, a0, a1, k, lane, acc);
+        slot_one_type<NCOLS, NR>(t0, s0, s1, nb0, segc, lseg, seg, a0, a1, k, lane, acc);
     } else {
         // SwiGLU pair with different gate / up types: one row each (second accumulator of each call unused)
         float t[2][NCOLS];
 #pragma unroll
         for (int c = 0; c < NCOLS; c++) { t[0][c] = 0.0f; t[1][c] = 0.0f; }
-        slot_one_type<NCOLS>(t0, s0, s0, segc, seg, a0, a1, k, lane, t);
+        slot_one_type<NCOLS, 1>(t0, s0, s0, nb0, segc, lseg, seg, a0, a1, k, lane, t);
 #pragma unroll
         for (int c = 0; c < NCOLS; c++) { acc[0][c] += t[0][c]; t[0][c] = 0.0f; t[1][c] = 0.0f; }
-        slot_one_type<NCOLS>(t1, s1, s1, segc, seg, a0, a1, k, lane, t);
+        slot_one_type<NCOLS, 1>(t1, s1, s1, nb1, segc, lseg, seg, a0, a1, k, lane, t);
 #pragma unroll
         for (int c = 0; c < NCOLS; c++) acc[1][c] += t[0][c];
     }
 }
 
-struct PairInfo { const uint8_t * row0, * row1; int t0, t1; int64_t nb0, nb1; };
+// One unit of work for a warp = R rows x one K-part (G segments of 2048 elements).  The K-parts of a row group
+// are consecutive units of the same warp (accumulators persist), so every ring slot is a few KB and >= 2 slots fit
+// per warp even for n_ff-long rows.  A part of a row is 1 contiguous byte range (Q4_K/Q5_K) or 2 / 4 ranges
+// (repacked Q4_0/Q8_0: qs | d;  Q6_K: ql | qh | scales | d) -> that many bulk copies.
+struct RowGroup { const uint8_t * row0, * row1; int t0, t1, nb0, nb1; int64_t r0; int rows; };
 
 template <int MODE>
-__device__ __forceinline__ PairInfo pair_info(const MmvArgs & args, int p, MmvMat & M, int64_t & r0, bool & two) {
-    PairInfo pi;
-    const int64_t k = args.k;
+__device__ __forceinline__ RowGroup group_info(const MmvArgs & args, int g, MmvMat & M) {
+    RowGroup rg;
     if (MODE == MMV_MODE_SWIGLU) {
-        const MmvMat & g = args.mat[0]; const MmvMat & u = args.mat[1];
-        pi.t0 = g.type; pi.t1 = u.type;
-        pi.nb0 = k / type_block_elems(g.type); pi.nb1 = k / type_block_elems(u.type);
-        pi.row0 = g.W + (int64_t)p * pi.nb0 * type_block_bytes(g.type);
-        pi.row1 = u.W + (int64_t)p * pi.nb1 * type_block_bytes(u.type);
-        M = g; r0 = p; two = true;
+        const MmvMat & gt = args.mat[0]; const MmvMat & up = args.mat[1];
+        M = gt;
+        rg.t0 = gt.type; rg.t1 = up.type; rg.nb0 = gt.nb; rg.nb1 = up.nb;
+        rg.row0 = gt.W + (int64_t)g * gt.rb; rg.row1 = up.W + (int64_t)g * up.rb;
+        rg.r0 = g; rg.rows = 2;
     } else {
         M = args.mat[0];
+        if (args.n_mats > 1) {
 #pragma unroll
-        for (int q = 1; q < MMV_MAX_MATS; q++) if (q < args.n_mats && p >= args.mat[q].pair0) M = args.mat[q];
-        r0 = (int64_t)(p - M.pair0) * 2;
-        two = r0 + 1 < M.m;
-        pi.t0 = pi.t1 = M.type;
-        pi.nb0 = pi.nb1 = k / type_block_elems(M.type);
-        const int64_t rb = pi.nb0 * type_block_bytes(M.type);
-        pi.row0 = M.W + r0 * rb;
-        pi.row1 = two ? pi.row0 + rb : pi.row0;
+            for (int q = 1; q < MMV_MAX_MATS; q++) if (q < args.n_mats && g >= args.mat[q].pair0) M = args.mat[q];
+        }
+        const int R = args.rows_per_unit;
+        rg.r0 = (int64_t)(g - M.pair0) * R;
+        rg.rows = (int)(M.m - rg.r0 < R ? M.m - rg.r0 : R);
+        rg.t0 = rg.t1 = M.type; rg.nb0 = rg.nb1 = M.nb;
+        rg.row0 = M.W + rg.r0 * M.rb; rg.row1 = rg.rows > 1 ? rg.row0 + M.rb : rg.row0;
     }
-    return pi;
+    return rg;
+}
+
+// bytes of `nsb8` segments (8 super-blocks / 64 small blocks each) of one row of `type`
+__device__ __forceinline__ uint32_t part_bytes(int type, int nchunks) {
+    switch (type) {
+        case B200_TYPE_Q4_0: return nchunks * 18;
+        case B200_TYPE_Q8_0: return nchunks * 34;
+        case B200_TYPE_Q4_K: return nchunks / 8 * 144;
+        case B200_TYPE_Q5_K: return nchunks / 8 * 176;
+        default:             return nchunks / 8 * 210;
+    }
+}
+// lane 0: copy chunks [c0, c0 + n) of a row into the slot, laid out like a short row of n chunks
+__device__ __forceinline__ void issue_part(int type, uint8_t * dst, const uint8_t * row, int64_t nb, int c0, int n, uint64_t * bar) {
+    switch (type) {
+        case B200_TYPE_Q4_K: bulk_g2s(dst, row + (int64_t)(c0 >> 3) * 144, (n >> 3) * 144, bar); break;
+        case B200_TYPE_Q5_K: bulk_g2s(dst, row + (int64_t)(c0 >> 3) * 176, (n >> 3) * 176, bar); break;
+        case B200_TYPE_Q4_0:
+            bulk_g2s(dst, row + (int64_t)c0 * 16, n * 16, bar);
+            bulk_g2s(dst + n * 16, row + nb * 16 + (int64_t)c0 * 2, n * 2, bar);
+            break;
+        case B200_TYPE_Q8_0:
+            bulk_g2s(dst, row + (int64_t)c0 * 32, n * 32, bar);
+            bulk_g2s(dst + n * 32, row + nb * 32 + (int64_t)c0 * 2, n * 2, bar);
+            break;
+        default: {
+            const int64_t s0 = c0 >> 3; const int ns = n >> 3;
+            bulk_g2s(dst,            row + s0 * 128,           ns * 128, bar);
+            bulk_g2s(dst + ns * 128, row + nb * 128 + s0 * 64, ns * 64,  bar);
+            bulk_g2s(dst + ns * 192, row + nb * 192 + s0 * 16, ns * 16,  bar);
+            bulk_g2s(dst + ns * 208, row + nb * 208 + s0 * 2,  ns * 2,   bar);
+        }
+    }
 }
 
 template <int NCOLS, int TT, int MODE>
@@ -317,7 +467,7 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
     __shared__ __align__(8) uint64_t act_bar;
     __shared__ __align__(8) uint64_t full_bar[MMV_WARPS][MMV_MAX_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = args.stages, segc = args.segc, nseg = args.nseg;
+    const int S = args.stages, segc = args.segc, nseg = args.nseg, G = args.segs_per_part, P = args.parts;
 
     uint8_t * act_s0 = smem;
     uint8_t * act_s1 = smem + args.act_bytes[0];
@@ -328,69 +478,133 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
     mbar_fence_init();
     __syncthreads();
 
-    // this warp's work: pairs gw, gw + TW, ...; each pair = nseg units (one ring slot each)
+    // this warp's row groups: gw, gw + TW, ... (consecutive groups -> consecutive SMs); counters only, no div/mod
     const int TW = gridDim.x * MMV_WARPS;
-    const int gw = warp * gridDim.x + blockIdx.x;                 // consecutive pairs -> consecutive SMs
-    const int my_pairs = gw < args.total_pairs ? (args.total_pairs - gw + TW - 1) / TW : 0;
-    const int n_units = my_pairs * nseg;
+    const int gw = warp * gridDim.x + blockIdx.x;
+    const int total = args.total_pairs;
 
-    auto issue = [&](int t) {                                     // lane 0 only
-        const int p = gw + (t / nseg) * TW, seg = t % nseg, slot = t % S;
-        MmvMat M; int64_t r0; bool two;
-        const PairInfo pi = pair_info<MODE>(args, p, M, r0, two);
-        uint8_t * dst = ring + (size_t)slot * args.slot_bytes;
-        const int b0 = seg_row_bytes(pi.t0, segc), b1 = seg_row_bytes(pi.t1, segc);
-        mbar_expect_tx(&full_bar[warp][slot], (uint32_t)(b0 + b1));
-        issue_row(pi.t0, dst, pi.row0, pi.nb0, seg, segc, &full_bar[warp][slot]);
-        issue_row(pi.t1, dst + (args.slot_bytes >> 1), pi.row1, pi.nb1, seg, segc, &full_bar[warp][slot]);
+    int ig = gw, ip = 0, islot = 0;                               // issue cursor: group, part, slot
+    auto issue_next = [&]() {                                     // lane 0 only
+        MmvMat M;
+        const RowGroup rg = group_info<MODE>(args, ig, M);
+        const int c0 = ip * G * segc;
+        const int n = (ip == P - 1 ? nseg - ip * G : G) * segc;
+        uint8_t * dst = ring + (size_t)islot * args.slot_bytes;
+        const uint32_t b0 = part_bytes(rg.t0, n), b1 = (MODE == MMV_MODE_SWIGLU || rg.rows > 1) ? part_bytes(rg.t1, n) : 0;
+        mbar_expect_tx(&full_bar[warp][islot], b0 + b1);
+        issue_part(rg.t0, dst, rg.row0, rg.nb0, c0, n, &full_bar[warp][islot]);
+        if (b1) issue_part(rg.t1, dst + args.row_stride, rg.row1, rg.nb1, c0, n, &full_bar[warp][islot]);
+        if (++ip == P) { ip = 0; ig += TW; }
+        if (++islot == S) islot = 0;
     };
 
     // prime the ring: weights do not depend on the previous kernel (PDL overlap)
-    if (lane == 0) for (int t = 0; t < S && t < n_units; t++) issue(t);
+    if (lane == 0) for (int s = 0; s < S && ig < total; s++) issue_next();
     pdl_trigger();
     pdl_wait();
-    if (tid == 0) {
-        mbar_expect_tx(&act_bar, (uint32_t)(args.act_bytes[0] + args.act_bytes[1]));
-        if (args.act_bytes[0]) bulk_g2s(act_s0, args.act[0], (uint32_t)args.act_bytes[0], &act_bar);
-        if (args.act_bytes[1]) bulk_g2s(act_s1, args.act[1], (uint32_t)args.act_bytes[1], &act_bar);
-    }
-    mbar_wait(&act_bar, 0);
-
-    const int64_t k = args.k;
-    float acc[2][NCOLS];
-    for (int t = 0; t < n_units; t++) {
-        const int pi_idx = t / nseg, seg = t % nseg, slot = t % S;
-        const int p = gw + pi_idx * TW;
-        if (seg == 0) {
-#pragma unroll
-            for (int c = 0; c < NCOLS; c++) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
+    if (args.act_source == 0) {
+        if (tid == 0) {
+            mbar_expect_tx(&act_bar, (uint32_t)(args.act_bytes[0] + args.act_bytes[1]));
+            if (args.act_bytes[0]) bulk_g2s(act_s0, args.act[0], (uint32_t)args.act_bytes[0], &act_bar);
+            if (args.act_bytes[1]) bulk_g2s(act_s1, args.act[1], (uint32_t)args.act_bytes[1], &act_bar);
         }
-        MmvMat M; int64_t r0; bool two;
-        const PairInfo pi = pair_info<MODE>(args, p, M, r0, two);
-        mbar_wait(&full_bar[warp][slot], (uint32_t)((t / S) & 1));
-        const uint8_t * s0 = ring + (size_t)slot * args.slot_bytes;
-        slot_dispatch<NCOLS, TT>(pi.t0, pi.t1, s0, s0 + (args.slot_bytes >> 1), segc, seg, act_s0, act_s1, k, lane, acc);
-        __syncwarp();                                             // every lane is done reading the slot
-        if (lane == 0 && t + S < n_units) issue(t + S);           // refill it
-        if (seg == nseg - 1) {
+        mbar_wait(&act_bar, 0);
+    } else {
+        // every CTA builds the quantised activation vector itself, straight into shared memory:
+        // [rms_norm * w ->] q8_K / q8_0 exactly as the CPU oracle quantises (no separate kernels, no HBM round trip)
+        __shared__ double red[MMV_WARPS];
+        __shared__ float s_scale;
+        const int nblk = (int)(args.k >> 8);
+        for (int col = 0; col < args.ncols; col++) {
+            const float * xc = args.x + (int64_t)col * args.x_col_stride;
+            float scale = 1.0f;
+            if (args.act_source == 2) {
+                double acc2 = 0.0;                                  // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
+                for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
+                    const float4 a = *(const float4 *)(xc + blk * 256 + lane * 8), b = *(const float4 *)(xc + blk * 256 + lane * 8 + 4);
+                    acc2 += (double)__fmul_rn(a.x, a.x); acc2 += (double)__fmul_rn(a.y, a.y); acc2 += (double)__fmul_rn(a.z, a.z); acc2 += (double)__fmul_rn(a.w, a.w);
+                    acc2 += (double)__fmul_rn(b.x, b.x); acc2 += (double)__fmul_rn(b.y, b.y); acc2 += (double)__fmul_rn(b.z, b.z); acc2 += (double)__fmul_rn(b.w, b.w);
+                }
 #pragma unroll
-            for (int c = 0; c < NCOLS; c++) { acc[0][c] = warp_sum(acc[0][c]); acc[1][c] = warp_sum(acc[1][c]); }
-            if (MODE == MMV_MODE_SWIGLU) {
-                if (lane == 0) {
+                for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+                if (lane == 0) red[warp] = acc2;
+                __syncthreads();
+                if (tid == 0) {
+                    double t = 0.0;
+                    for (int i = 0; i < MMV_WARPS; i++) t += red[i];
+                    s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k), args.eps)));
+                }
+                __syncthreads();
+                scale = s_scale;
+            }
+            for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
+                const int64_t i = (int64_t)blk * 256 + lane * 8;
+                const float4 a = *(const float4 *)(xc + i), b = *(const float4 *)(xc + i + 4);
+                float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+                if (args.act_source == 2) {
 #pragma unroll
-                    for (int c = 0; c < NCOLS; c++) {
-                        M.dst[c * M.dst_col_stride + r0] = __fmul_rn(silu_x86(acc[0][c]), acc[1][c]);   // ggml-cpu/vec.cpp:260-282
+                    for (int j = 0; j < 8; j++) v[j] = __fmul_rn(v[j], scale);
+                    if (args.norm_w) {
+                        const float4 wa = *(const float4 *)(args.norm_w + i), wb = *(const float4 *)(args.norm_w + i + 4);
+                        v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
+                        v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
                     }
                 }
-            } else if (lane < 2 && (lane == 0 || two)) {
-                const int64_t r = r0 + lane;
-#pragma unroll
-                for (int c = 0; c < NCOLS; c++) {
-                    float v = lane == 0 ? acc[0][c] : acc[1][c];
-                    if (M.bias)     v += M.bias[r];
-                    if (M.residual) v += M.residual[c * M.dst_col_stride + r];
-                    M.dst[c * M.dst_col_stride + r] = v;
+                if (args.y_out && blockIdx.x == 0) {
+                    float * yo = args.y_out + (int64_t)col * args.k + i;
+                    *(float4 *)yo = make_float4(v[0], v[1], v[2], v[3]); *(float4 *)(yo + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 }
+                if (args.act_bytes[0]) warp_quant_q8K(v, act_sections(act_s0, 0, args.k, col), blk, lane);
+                if (args.act_bytes[1]) warp_quant_q80(v, act_sections(act_s1, 1, args.k, col), blk, lane);
+            }
+            if (args.act_source == 2) __syncthreads();             // red / s_scale are reused by the next column
+        }
+        __syncthreads();
+    }
+
+    const int64_t k = args.k;
+    int slot = 0; uint32_t phase = 0;
+    for (int g = gw; g < total; g += TW) {
+        MmvMat M;
+        const RowGroup rg = group_info<MODE>(args, g, M);
+        float acc[2][NCOLS];
+#pragma unroll
+        for (int c = 0; c < NCOLS; c++) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
+        for (int p = 0; p < P; p++) {
+            const int nsegs = p == P - 1 ? nseg - p * G : G;
+            mbar_wait(&full_bar[warp][slot], phase);
+            const uint8_t * s0 = ring + (size_t)slot * args.slot_bytes;
+            const uint8_t * s1 = s0 + args.row_stride;
+            // inside the slot a part looks like a short row of nsegs*segc chunks
+            const int lnb0 = rg.t0 >= B200_TYPE_Q4_K ? nsegs * (segc >> 3) : nsegs * segc;
+            const int lnb1 = rg.t1 >= B200_TYPE_Q4_K ? nsegs * (segc >> 3) : nsegs * segc;
+            if (MODE == MMV_MODE_SWIGLU || rg.rows > 1) {
+                for (int ls = 0; ls < nsegs; ls++)
+                    slot_dispatch<NCOLS, TT, 2>(rg.t0, rg.t1, s0, s1, lnb0, lnb1, segc, ls, p * G + ls, act_s0, act_s1, k, lane, acc);
+            } else {
+                for (int ls = 0; ls < nsegs; ls++)
+                    slot_dispatch<NCOLS, TT, 1>(rg.t0, rg.t0, s0, s0, lnb0, lnb0, segc, ls, p * G + ls, act_s0, act_s1, k, lane, acc);
+            }
+            __syncwarp();                                         // every lane is done reading the slot
+            if (lane == 0 && ig < total) issue_next();            // refill it
+            if (++slot == S) { slot = 0; phase ^= 1; }
+        }
+#pragma unroll
+        for (int c = 0; c < NCOLS; c++) { acc[0][c] = warp_sum(acc[0][c]); acc[1][c] = warp_sum(acc[1][c]); }
+        if (MODE == MMV_MODE_SWIGLU) {
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < NCOLS; c++)
+                    M.dst[c * M.dst_col_stride + rg.r0] = __fmul_rn(silu_x86(acc[0][c]), acc[1][c]);   // ggml-cpu/vec.cpp:260-282
+            }
+        } else if (lane < rg.rows) {
+            const int64_t r = rg.r0 + lane;
+#pragma unroll
+            for (int c = 0; c < NCOLS; c++) {
+                float v = lane == 0 ? acc[0][c] : acc[1][c];
+                if (M.bias)     v += M.bias[r];
+                if (M.residual) v += M.residual[c * M.dst_col_stride + r];
+                M.dst[c * M.dst_col_stride + r] = v;
             }
         }
     }
@@ -440,42 +654,88 @@ template <int NCOLS> static int mmv_launch_n(const MmvArgs & a, int mode, size_t
 
 static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
     if (ncols < 1 || ncols > 8) { b200_set_error("mmvq: ncols must be 1..8"); return B200_ERR_INVALID; }
+    a.ncols = (int32_t)ncols;
+    if (a.act_source != 0 && (!a.x || ((uintptr_t)a.x & 15) || (a.x_col_stride & 3) || ((uintptr_t)a.norm_w & 15))) { b200_set_error("mmvq: f32 activation source must be 16-byte aligned"); return B200_ERR_INVALID; }
     bool need[2] = { false, false };
-    bool has_q6 = false;
     for (int i = 0; i < a.n_mats; i++) {
         const MmvMat & M = a.mat[i];
         if (!mmv_type_ok(M.type)) { b200_set_error("mmvq: unsupported weight type %d", M.type); return B200_ERR_UNSUPPORTED; }
         if (!mmv_k_ok(M.type, a.k)) { b200_set_error("mmvq: k=%lld not supported for type %d (needs k%%256==0, Q6_K k%%2048==0)", (long long)a.k, M.type); return B200_ERR_UNSUPPORTED; }
         if (((uintptr_t)M.W & 15) || !M.W || !M.dst || M.m <= 0) { b200_set_error("mmvq: weights must be 16-byte aligned / non-null"); return B200_ERR_INVALID; }
         need[b200_act_kind_for(M.type)] = true;
-        has_q6 |= M.type == B200_TYPE_Q6_K;
     }
     size_t act = 0;
     for (int kd = 0; kd < 2; kd++) {
         a.act_bytes[kd] = 0;
         if (need[kd]) {
-            if (!a.act[kd] || ((uintptr_t)a.act[kd] & 15)) { b200_set_error("mmvq: missing/unaligned act buffer of kind %d", kd); return B200_ERR_INVALID; }
+            if (a.act_source == 0 && (!a.act[kd] || ((uintptr_t)a.act[kd] & 15))) { b200_set_error("mmvq: missing/unaligned act buffer of kind %d", kd); return B200_ERR_INVALID; }
             a.act_bytes[kd] = (int32_t)(ncols * act_col_bytes(kd, a.k));
             act += a.act_bytes[kd];
         } else a.act[kd] = nullptr;
     }
-    // segment = the largest divisor of the row's chunk count that is a multiple of 8 and <= 64
-    // (64 chunks = 2048 elements: Q6_K needs exactly that for 16-byte aligned scale/d parts)
+    // compute segment: 64 chunks (2048 elements) selects the fast paths; otherwise the largest divisor <= 64
     const int nchunks = (int)(a.k / 32);
     int segc = 8;
     for (int c = 64; c >= 8; c -= 8) if (nchunks % c == 0) { segc = c; break; }
-    if (has_q6 && segc != 64) { b200_set_error("mmvq: Q6_K rows need k %% 2048 == 0"); return B200_ERR_UNSUPPORTED; }
     a.segc = segc; a.nseg = nchunks / segc;
-    int slot = 0;
-    for (int i = 0; i < a.n_mats; i++) { const int b = 2 * seg_row_bytes(a.mat[i].type, segc); if (b > slot) slot = b; }
-    a.slot_bytes = (slot + 255) & ~255;
+    int64_t rbmax = 0;
+    for (int i = 0; i < a.n_mats; i++) {
+        a.mat[i].nb = (int32_t)(a.k / type_block_elems(a.mat[i].type));
+        a.mat[i].rb = (int64_t)a.mat[i].nb * type_block_bytes(a.mat[i].type);
+        if (a.mat[i].rb > rbmax) rbmax = a.mat[i].rb;
+    }
+    // unit = R rows x G segments: pick the largest G (<= nseg) such that two slots per warp fit; prefer R = 2
+    // (activation registers shared by both rows), fall back to R = 1, then to a single slot, then to column halves
     const size_t budget = 216 * 1024;
     const size_t act_al = (act + 127) & ~(size_t)127;
-    if (act_al + (size_t)MMV_WARPS * 2 * a.slot_bytes > budget) { b200_set_error("mmvq: activations (%zu bytes) leave no room for the weight ring", act); return B200_ERR_UNSUPPORTED; }
-    int stages = (int)((budget - act_al) / ((size_t)MMV_WARPS * a.slot_bytes));
+    int64_t segb = 0;                                  // bytes of one segment of the widest row type
+    for (int i = 0; i < a.n_mats; i++) { const int64_t b = a.mat[i].rb / a.nseg; if (b > segb) segb = b; }
+    const int rows_in_slot = 2;                        // SwiGLU: gate + up;  plain: R (decided below)
+    int R = 2, G = 0, stages = 0;
+    auto try_cfg = [&](int r, int want_stages) {
+        for (int g = a.nseg; g >= 1; g--) {
+            const size_t slot = (size_t)(((r * g * segb) + 255) & ~(int64_t)255);
+            const size_t room = budget > act_al ? (budget - act_al) / ((size_t)MMV_WARPS * slot) : 0;
+            if ((int)room >= want_stages) { R = r; G = g; stages = (int)room; return true; }
+        }
+        return false;
+    };
+    bool ok = try_cfg(2, 2);
+    if (!ok && mode != MMV_MODE_SWIGLU) ok = try_cfg(1, 2);
+    if (!ok) ok = try_cfg(2, 1);
+    if (!ok && mode != MMV_MODE_SWIGLU) ok = try_cfg(1, 1);
+    (void)rows_in_slot;
+    if (!ok) {
+        // the columns of a long row do not leave room for even one slot per warp: run the columns in two halves
+        // (weights are streamed twice; only speculative-verify batches of 5..8 tokens on n_ff-long rows get here)
+        if (ncols < 2) { b200_set_error("mmvq: k=%lld rows (%lld bytes) exceed shared memory", (long long)a.k, (long long)rbmax); return B200_ERR_UNSUPPORTED; }
+        const int64_t h0 = ncols / 2, h1 = ncols - h0;
+        MmvArgs lo = a, hi = a;
+        for (int kd = 0; kd < 2; kd++) if (hi.act[kd]) hi.act[kd] += h0 * act_col_bytes(kd, a.k);
+        if (hi.x) hi.x += h0 * a.x_col_stride;
+        if (hi.y_out) hi.y_out += h0 * a.k;
+        for (int i = 0; i < a.n_mats; i++) {
+            hi.mat[i].dst += h0 * a.mat[i].dst_col_stride;
+            if (hi.mat[i].residual) hi.mat[i].residual += h0 * a.mat[i].dst_col_stride;
+        }
+        const int s0 = mmv_launch(lo, mode, h0, st);
+        return s0 != B200_OK ? s0 : mmv_launch(hi, mode, h1, st);
+    }
+    const size_t row_stride = (size_t)(((G * segb) + 127) & ~(int64_t)127);
+    const size_t slot = (size_t)(((R * G * segb) + 255) & ~(int64_t)255) < 2 * row_stride && R == 2 ? 2 * row_stride : (size_t)(((R * G * segb) + 255) & ~(int64_t)255);
+    a.segs_per_part = G; a.parts = (a.nseg + G - 1) / G; a.row_stride = (int32_t)row_stride;
+    if (budget - act_al < (size_t)MMV_WARPS * stages * slot) stages = (int)((budget - act_al) / ((size_t)MMV_WARPS * slot));
+    if (stages < 1) { b200_set_error("mmvq: internal smem planning error"); return B200_ERR_UNSUPPORTED; }
+    a.rows_per_unit = R; a.slot_bytes = (int32_t)slot;
     if (stages > MMV_MAX_STAGES) stages = MMV_MAX_STAGES;
     a.stages = stages;
-    const size_t smem = act_al + (size_t)MMV_WARPS * stages * a.slot_bytes;
+    // units: per matrix ceil(m / R) (SwiGLU: one per output row)
+    if (mode != MMV_MODE_SWIGLU) {
+        int32_t units = 0;
+        for (int i = 0; i < a.n_mats; i++) { a.mat[i].pair0 = units; units += (int32_t)((a.mat[i].m + R - 1) / R); }
+        a.total_pairs = units;
+    }
+    const size_t smem = act_al + (size_t)MMV_WARPS * stages * slot;
     const int sms = b200_sm_count();
     int grid = (a.total_pairs + MMV_WARPS - 1) / MMV_WARPS;
     if (grid > sms) grid = sms;
@@ -495,7 +755,7 @@ static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
 extern "C" int b200_mul_mat_vec_q(int type, const void * W, const void * act, float * dst, int64_t dst_col_stride,
                                   const float * bias, const float * residual, int64_t m, int64_t k, int64_t ncols, void * stream) {
     MmvArgs a = {};
-    a.mat[0] = { (const uint8_t *)W, dst, bias, residual, m, dst_col_stride, type, 0 };
+    a.mat[0] = { (const uint8_t *)W, dst, bias, residual, m, dst_col_stride, 0, 0, type, 0, 0 };
     a.n_mats = 1; a.k = k;
     a.total_pairs = (int32_t)((m + 1) / 2);
     const int kind = b200_act_kind_for(type);
@@ -510,7 +770,7 @@ extern "C" int b200_mul_mat_vec_q_multi(const b200_mmv_desc * descs, int n_mats,
     MmvArgs a = {};
     int32_t pairs = 0;
     for (int i = 0; i < n_mats; i++) {
-        a.mat[i] = { (const uint8_t *)descs[i].W, descs[i].dst, descs[i].bias, nullptr, descs[i].m, descs[i].m, descs[i].type, pairs };
+        a.mat[i] = { (const uint8_t *)descs[i].W, descs[i].dst, descs[i].bias, nullptr, descs[i].m, descs[i].m, 0, 0, descs[i].type, pairs, 0 };
         pairs += (int32_t)((descs[i].m + 1) / 2);
     }
     a.n_mats = n_mats; a.k = k; a.total_pairs = pairs;
@@ -522,9 +782,24 @@ extern "C" int b200_mul_mat_vec_q_swiglu(int type_gate, const void * Wg, int typ
                                          const void * act_q8K, const void * act_q80, float * dst,
                                          int64_t m, int64_t k, int64_t ncols, void * stream) {
     MmvArgs a = {};
-    a.mat[0] = { (const uint8_t *)Wg, dst, nullptr, nullptr, m, m, type_gate, 0 };
-    a.mat[1] = { (const uint8_t *)Wu, dst, nullptr, nullptr, m, m, type_up, 0 };
+    a.mat[0] = { (const uint8_t *)Wg, dst, nullptr, nullptr, m, m, 0, 0, type_gate, 0, 0 };
+    a.mat[1] = { (const uint8_t *)Wu, dst, nullptr, nullptr, m, m, 0, 0, type_up, 0, 0 };
     a.n_mats = 2; a.k = k; a.total_pairs = (int32_t)m;
     a.act[0] = (const uint8_t *)act_q8K; a.act[1] = (const uint8_t *)act_q80;
     return mmv_launch(a, MMV_MODE_SWIGLU, ncols, (cudaStream_t)stream);
+}
+
+// general launch: several matrices / SwiGLU / fused activation prologue in one descriptor (see b200_ops.h)
+extern "C" int b200_mul_mat_vec_q_launch(const b200_mmv_launch * L, void * stream) {
+    if (!L || L->n_mats < 1 || L->n_mats > MMV_MAX_MATS) { b200_set_error("mmvq_launch: bad descriptor"); return B200_ERR_INVALID; }
+    if (L->swiglu && L->n_mats != 2) { b200_set_error("mmvq_launch: swiglu needs exactly gate and up"); return B200_ERR_INVALID; }
+    if (L->act_source < 0 || L->act_source > 2) { b200_set_error("mmvq_launch: act_source must be 0..2"); return B200_ERR_INVALID; }
+    MmvArgs a = {};
+    for (int i = 0; i < L->n_mats; i++)
+        a.mat[i] = { (const uint8_t *)L->mats[i].W, L->mats[i].dst, L->mats[i].bias, L->residual[i], L->mats[i].m, L->dst_col_stride[i] ? L->dst_col_stride[i] : L->mats[i].m, 0, 0, L->mats[i].type, 0, 0 };
+    a.n_mats = L->n_mats; a.k = L->k;
+    a.total_pairs = L->swiglu ? (int32_t)L->mats[0].m : 0;
+    a.act[0] = (const uint8_t *)L->act_q8K; a.act[1] = (const uint8_t *)L->act_q80;
+    a.act_source = L->act_source; a.x = L->x; a.x_col_stride = L->x_col_stride; a.norm_w = L->norm_w; a.eps = L->eps; a.y_out = L->y_out;
+    return mmv_launch(a, L->swiglu ? MMV_MODE_SWIGLU : MMV_MODE_PLAIN, L->ncols, (cudaStream_t)stream);
 }

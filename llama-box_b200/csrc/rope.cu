@@ -155,9 +155,10 @@ extern "C" int b200_set_rows(const float * src, int64_t src_row_stride, const in
 
 // ---- fused: rope(q) in place, rope(k) -> K cache, v -> V cache --------------------------------
 // q [n_tok][n_head][hd], k/v [n_tok][n_head_kv][hd] contiguous f32.  One CTA (256 threads) per token.
-__global__ void __launch_bounds__(256) rope_kv_store_kernel(float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v,
-                                                            const int32_t * __restrict__ pos, const float * __restrict__ ff, const int64_t * __restrict__ kv_ids,
-                                                            void * __restrict__ kc, void * __restrict__ vc, int kv_type, int64_t kv_row_stride,
+__global__ void __launch_bounds__(256) rope_kv_store_kernel(const float * q, float * qo, const float * __restrict__ k, const float * __restrict__ v,
+                                                            const int32_t * __restrict__ pos, const float * __restrict__ ff,
+                                                            const int64_t * __restrict__ k_ids, const int64_t * __restrict__ v_ids,
+                                                            void * __restrict__ kc, void * __restrict__ vc, int kv_type, int64_t k_row_stride, int64_t v_row_stride,
                                                             int64_t hd, int64_t n_head, int64_t n_head_kv, RopeDev rp) {
     extern __shared__ __align__(16) float sm[];
     float * cs = sm;                          // n_dims floats
@@ -169,10 +170,11 @@ __global__ void __launch_bounds__(256) rope_kv_store_kernel(float * __restrict__
     __syncthreads();
     const int half = rp.n_dims / 2;
     const int64_t hp = hd / 2;
-    float * qt = q + t * n_head * hd;
+    const float * qt = q + t * n_head * hd; float * qd = qo + t * n_head * hd;
     for (int64_t w = tid; w < n_head * hp; w += blockDim.x) {
         const int64_t h = w / hp; const int i = (int)(w % hp);
-        if (i < half) rope_pair(qt + h * hd, qt + h * hd, i, cs, rp);
+        if (i < half) rope_pair(qt + h * hd, qd + h * hd, i, cs, rp);
+        else if (qd != qt) { const int e = rp.n_dims + 2 * (i - half); qd[h * hd + e] = qt[h * hd + e]; qd[h * hd + e + 1] = qt[h * hd + e + 1]; }
     }
     const float * kt = k + t * n_head_kv * hd;
     for (int64_t w = tid; w < n_head_kv * hp; w += blockDim.x) {
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__(256) rope_kv_store_kernel(float * __restrict__
     }
     __syncthreads();
     const int64_t n = n_head_kv * hd;          // multiple of 256 required by the host wrapper
-    uint8_t * krow = (uint8_t *)kc + kv_ids[t] * kv_row_stride;
-    uint8_t * vrow = (uint8_t *)vc + kv_ids[t] * kv_row_stride;
+    uint8_t * krow = (uint8_t *)kc + k_ids[t] * k_row_stride;
+    uint8_t * vrow = (uint8_t *)vc + v_ids[t] * v_row_stride;
     const float * vt = v + t * n;
     for (int64_t e = (int64_t)warp * 256 + lane * 8; e < n; e += (blockDim.x / 32) * 256) {
         float a[8], b[8];
@@ -195,17 +197,24 @@ __global__ void __launch_bounds__(256) rope_kv_store_kernel(float * __restrict__
     pdl_trigger();
 }
 
-extern "C" int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff,
-                                  const int64_t * kv_ids, void * k_cache, void * v_cache, int kv_type, int64_t kv_row_stride,
-                                  int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_tok, const b200_rope_params * p, void * stream) {
-    if (!q || !k || !v || !pos || !kv_ids || !k_cache || !v_cache || !p) { b200_set_error("rope_kv_store: null pointer"); return B200_ERR_INVALID; }
+extern "C" int b200_rope_kv_store2(const float * q_src, float * q_dst, const float * k, const float * v, const int32_t * pos, const float * ff,
+                                   const int64_t * k_ids, const int64_t * v_ids, void * k_cache, void * v_cache, int kv_type,
+                                   int64_t k_row_stride, int64_t v_row_stride, int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_tok,
+                                   const b200_rope_params * p, void * stream) {
+    if (!q_src || !q_dst || !k || !v || !pos || !k_ids || !v_ids || !k_cache || !v_cache || !p) { b200_set_error("rope_kv_store: null pointer"); return B200_ERR_INVALID; }
     if (kv_type != B200_TYPE_F16 && kv_type != B200_TYPE_Q8_0) { b200_set_error("rope_kv_store: kv type %d unsupported", kv_type); return B200_ERR_UNSUPPORTED; }
     if (p->mode & ~2) { b200_set_error("rope_kv_store: only NORM/NEOX"); return B200_ERR_UNSUPPORTED; }
     if ((n_head_kv * hd) % 256 != 0 || p->n_dims > hd || (p->n_dims & 1)) { b200_set_error("rope_kv_store: n_head_kv*head_dim must be a multiple of 256"); return B200_ERR_INVALID; }
     if (n_tok <= 0) return B200_OK;
     const size_t smem = ((size_t)p->n_dims + (size_t)(n_head_kv * hd)) * sizeof(float);
-    rope_kv_store_kernel<<<(unsigned)n_tok, 256, smem, (cudaStream_t)stream>>>(q, k, v, pos, ff, kv_ids, k_cache, v_cache, kv_type, kv_row_stride,
+    rope_kv_store_kernel<<<(unsigned)n_tok, 256, smem, (cudaStream_t)stream>>>(q_src, q_dst, k, v, pos, ff, k_ids, v_ids, k_cache, v_cache, kv_type, k_row_stride, v_row_stride,
                                                                                hd, n_head, n_head_kv, rope_host_params(p));
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+extern "C" int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff,
+                                  const int64_t * kv_ids, void * k_cache, void * v_cache, int kv_type, int64_t kv_row_stride,
+                                  int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_tok, const b200_rope_params * p, void * stream) {
+    return b200_rope_kv_store2(q, q, k, v, pos, ff, kv_ids, kv_ids, k_cache, v_cache, kv_type, kv_row_stride, kv_row_stride, hd, n_head, n_head_kv, n_tok, p, stream);
 }

@@ -80,11 +80,15 @@ class Weights:
 
 
 class SyntheticLlama:
-    def __init__(self, cfg, ftype="Q4_K_M", n_ctx=4096, kv_type=G.F16, seed=1234, host_weights=None, n_layer=None):
+    def __init__(self, cfg, ftype="Q4_K_M", n_ctx=4096, kv_type=G.F16, seed=1234, host_weights=None, n_layer=None,
+                 layer_range=None, first=True, last=True, n_seq=1):
         c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
         if n_layer:
             c["n_layer"] = n_layer
         self.c, self.n_ctx, self.kv_type, self.ftype = c, n_ctx, kv_type, ftype
+        self.first, self.last, self.n_seq = first, last, n_seq
+        lo, hi = layer_range if layer_range else (0, c["n_layer"])
+        self.layer_ids = list(range(lo, hi))
         gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
         E, H, HK, D, FF, V, L = c["n_embd"], c["n_head"], c["n_head_kv"], c["head_dim"], c["n_ff"], c["n_vocab"], c["n_layer"]
         mix, out_t = type_mix(ftype, L)
@@ -98,7 +102,7 @@ class SyntheticLlama:
                 return torch.from_numpy(hw[name]).cuda()
             return (mean + 0.01 * torch.randn(n, device="cuda", generator=gen)).float()
         self.layers = []
-        for i in range(L):
+        for i in self.layer_ids:
             t = mix[i]
             ly = dict(attn_norm=vec(f"blk.{i}.attn_norm", E, 1.0), ffn_norm=vec(f"blk.{i}.ffn_norm", E, 1.0),
                       wq=W(f"blk.{i}.attn_q", t["wq"], H * D, E), wk=W(f"blk.{i}.attn_k", t["wk"], HK * D, E), wv=W(f"blk.{i}.attn_v", t["wv"], HK * D, E),
@@ -107,18 +111,21 @@ class SyntheticLlama:
             if c["qkv_bias"]:
                 ly.update(bq=vec(f"blk.{i}.bq", H * D, 0.0), bk=vec(f"blk.{i}.bk", HK * D, 0.0), bv=vec(f"blk.{i}.bv", HK * D, 0.0))
             kvrow = G.row_size(kv_type, HK * D)
-            ly["k_cache"] = torch.zeros(n_ctx * kvrow, dtype=torch.uint8, device="cuda")
-            ly["v_cache"] = torch.zeros(n_ctx * kvrow, dtype=torch.uint8, device="cuda")
+            ly["k_caches"] = [torch.zeros(n_ctx * kvrow, dtype=torch.uint8, device="cuda") for _ in range(n_seq)]
+            ly["v_caches"] = [torch.zeros(n_ctx * kvrow, dtype=torch.uint8, device="cuda") for _ in range(n_seq)]
+            ly["k_cache"], ly["v_cache"] = ly["k_caches"][0], ly["v_caches"][0]
             self.layers.append(ly)
-        self.output_norm = vec("output_norm", E, 1.0)
-        self.output = W("output", out_t, V, E)
-        self.tok_embd = torch.from_numpy(hw["token_embd"]).cuda() if "token_embd" in hw else (0.02 * torch.randn((V, E), device="cuda", generator=gen)).float()
+        self.output_norm = vec("output_norm", E, 1.0) if last else None
+        self.output = W("output", out_t, V, E) if last else None
+        self.tok_embd = None
+        if first:
+            self.tok_embd = torch.from_numpy(hw["token_embd"]).cuda() if "token_embd" in hw else (0.02 * torch.randn((V, E), device="cuda", generator=gen)).float()
         self.rope_ff = torch.from_numpy(hw["rope_freqs"]).cuda() if "rope_freqs" in hw else None
         self.bufs = {}
 
     # ---- bytes the decode step must stream from HBM: weights + norms + KV
     def streamed_weight_bytes(self):
-        b = self.output.nbytes + self.output_norm.numel() * 4
+        b = (self.output.nbytes + self.output_norm.numel() * 4) if self.last else 0
         for ly in self.layers:
             b += sum(ly[k].nbytes for k in ("wq", "wk", "wv", "wo", "gate", "up", "down")) + 2 * ly["attn_norm"].numel() * 4
         return b
@@ -132,7 +139,7 @@ class SyntheticLlama:
             self.bufs[key] = torch.zeros(shape, dtype=dtype, device="cuda")
         return self.bufs[key]
 
-    def build(self, n_tok, n_kv, want_all_logits=False):
+    def build(self, n_tok, n_kv, want_all_logits=False, seq=0):
         """node list for one ubatch of n_tok tokens attending to n_kv cache positions (n_kv % 256 == 0 with -fa).
         Inputs (device buffers the caller fills): tokens i32[n_tok], pos i32[n_tok], kv_idx i64[n_tok],
         mask f32[n_kv, pad64(n_tok)] (cast to f16 by a CPY node like llama-graph.cpp:1424), out_ids i32[n_out]."""
@@ -142,7 +149,8 @@ class SyntheticLlama:
         npad = (n_tok + 63) // 64 * 64
         n_out = n_tok if want_all_logits else 1
         io = dict(tokens=self._buf("tokens", [n_tok], torch.int32), pos=self._buf("pos", [n_tok], torch.int32), kv_idx=self._buf("kv_idx", [n_tok], torch.int64),
-                  mask=self._buf("mask", [npad, n_kv]), out_ids=self._buf("out_ids", [n_out], torch.int32), logits=self._buf("logits", [n_out, V]))
+                  mask=self._buf("mask", [npad, n_kv]), out_ids=self._buf("out_ids", [n_out], torch.int32), logits=self._buf("logits", [n_out, V]),
+                  hidden_in=self._buf("hidden_in", [n_tok, E]), hidden_out=self._buf("hidden_out", [n_tok, E]))
         f = lambda name, ne, dt=torch.float32: self._buf(name + f"@{n_tok}", list(reversed(ne)), dt)  # noqa: E731
         tT = lambda ten, t, ne: G.T(ten.data_ptr(), t, ne)  # noqa: E731
         pos_t, idx_t = tT(io["pos"], G.I32, [n_tok]), tT(io["kv_idx"], G.I64, [n_tok])
@@ -150,12 +158,15 @@ class SyntheticLlama:
         nl.add(G.OP_CPY, mask16, [mask32])
         # token embedding lookup: the reference runs it on the CPU (input layer, llama-model.cpp:1960-1962) and
         # uploads [n_embd, n_tok] f32; the resident-in-HBM harness gathers from an f32 table instead
-        inpL = nl.add(G.OP_GET_ROWS, tT(f("inp_embd", [E, n_tok]), G.F32, [E, n_tok]), [tT(self.tok_embd, G.F32, [E, V]), tT(io["tokens"], G.I32, [n_tok])])
+        if self.first:
+            inpL = nl.add(G.OP_GET_ROWS, tT(f("inp_embd", [E, n_tok]), G.F32, [E, n_tok]), [tT(self.tok_embd, G.F32, [E, V]), tT(io["tokens"], G.I32, [n_tok])])
+        else:
+            inpL = tT(io["hidden_in"], G.F32, [E, n_tok])          # handed over by the previous pipeline stage
         rope_params = [0, D, c["rope_mode"], 0, 8192, G.f32_bits(c["rope_base"]), G.f32_bits(1.0), G.f32_bits(0.0), G.f32_bits(1.0), G.f32_bits(32.0), G.f32_bits(1.0)]
         ff_t = tT(self.rope_ff, G.F32, [D // 2]) if self.rope_ff is not None else None
         kvrow = G.row_size(self.kv_type, HK * D); kvhead = G.row_size(self.kv_type, D)
         for il, ly in enumerate(self.layers):
-            last = il == len(self.layers) - 1
+            last = self.last and il == len(self.layers) - 1
             wT = lambda v, n=E: tT(v, G.F32, [n])  # noqa: E731
             # attn_norm
             t1 = nl.add(G.OP_RMS_NORM, tT(f(f"norm{il % 2}", [E, n_tok]), G.F32, [E, n_tok]), [inpL], [G.f32_bits(c["eps"])])
@@ -177,7 +188,7 @@ class SyntheticLlama:
             if c["qkv_bias"]:
                 v = nl.add(G.OP_ADD, tT(f("vb", [HK * D, n_tok]), G.F32, [HK * D, n_tok]), [v, wT(ly["bv"], HK * D)])
             # KV store (llama-kv-cache-unified.cpp:1103-1160)
-            kc = G.T(ly["k_cache"].data_ptr(), self.kv_type, [HK * D, self.n_ctx]); vc = G.T(ly["v_cache"].data_ptr(), self.kv_type, [HK * D, self.n_ctx])
+            kc = G.T(ly["k_caches"][seq].data_ptr(), self.kv_type, [HK * D, self.n_ctx]); vc = G.T(ly["v_caches"][seq].data_ptr(), self.kv_type, [HK * D, self.n_ctx])
             k2 = nl.view_op(kr.reshape([HK * D, n_tok]), kr)
             nl.add(G.OP_SET_ROWS, kc, [k2, idx_t])
             nl.add(G.OP_SET_ROWS, vc, [v, idx_t])
@@ -202,7 +213,11 @@ class SyntheticLlama:
             gate = nl.add(G.OP_MUL_MAT, tT(f("gate", [FF, nt]), G.F32, [FF, nt]), [ly["gate"].t, cur])
             h = nl.add(G.OP_GLU_SWIGLU, tT(f("h", [FF, nt]), G.F32, [FF, nt]), [gate, up], [2, 0])
             dn = nl.add(G.OP_MUL_MAT, tT(f("down", [E, nt]), G.F32, [E, nt]), [ly["down"].t, h])
-            inpL = nl.add(G.OP_ADD, tT(f(f"l_out{il % 2}", [E, nt]), G.F32, [E, nt]), [dn, ffn_inp])
+            final_stage_out = (not self.last) and il == len(self.layers) - 1
+            l_out = tT(io["hidden_out"], G.F32, [E, nt]) if final_stage_out else tT(f(f"l_out{il % 2}", [E, nt]), G.F32, [E, nt])
+            inpL = nl.add(G.OP_ADD, l_out, [dn, ffn_inp])
+        if not self.last:
+            return nl.build(), io
         nt = n_out
         t1 = nl.add(G.OP_RMS_NORM, tT(f("onorm", [E, nt]), G.F32, [E, nt]), [inpL], [G.f32_bits(c["eps"])])
         cur = nl.add(G.OP_MUL, tT(f("onormw", [E, nt]), G.F32, [E, nt]), [t1, tT(self.output_norm, G.F32, [E])])

@@ -29,6 +29,12 @@ class MmvDesc(C.Structure):
     _fields_ = [("W", vp), ("dst", vp), ("bias", vp), ("m", i64), ("type", C.c_int32), ("_pad", C.c_int32)]
 
 
+class MmvLaunch(C.Structure):
+    _fields_ = [("mats", MmvDesc * 4), ("residual", vp * 4), ("dst_col_stride", i64 * 4), ("n_mats", C.c_int32), ("swiglu", C.c_int32),
+                ("k", i64), ("ncols", i64), ("act_source", C.c_int32), ("eps", f32), ("act_q8K", vp), ("act_q80", vp),
+                ("x", vp), ("x_col_stride", i64), ("norm_w", vp), ("y_out", vp)]
+
+
 # name -> (restype, argtypes); must list every symbol include/b200_ops.h declares
 SIGNATURES = {
     "b200_abi_version": (i32, []),
@@ -50,6 +56,8 @@ SIGNATURES = {
     "b200_rms_norm_quantize": (i32, [vp, vp, vp, vp, i32, vp, i32, i64, i64, f32, vp]),
     "b200_mul_mat_vec_q": (i32, [i32, vp, vp, vp, i64, vp, vp, i64, i64, i64, vp]),
     "b200_mul_mat_vec_q_multi": (i32, [C.POINTER(MmvDesc), i32, vp, vp, i64, i64, vp]),
+    "b200_mul_mat_vec_q_launch": (i32, [C.POINTER(MmvLaunch), vp]),
+    "b200_rope_kv_store2": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, i64, C.POINTER(RopeParams), vp]),
     "b200_mul_mat_vec_q_swiglu": (i32, [i32, vp, i32, vp, vp, vp, vp, i64, i64, i64, vp]),
     "b200_mul_mat_q_workspace": (i64, [i32, i64, i64, i64]),
     "b200_mul_mat_q": (i32, [i32, vp, vp, i64, vp, i64, i64, i64, i64, vp, vp]),

@@ -189,6 +189,29 @@ def test_mmvq_swiglu(b200, tg, tu):
     assert np.abs(dst.cpu().numpy() - want).max() <= 3e-5 * max(np.abs(want).max(), 1e-6)
 
 
+@pytest.mark.parametrize("t,src", [(Q4_K, 2), (Q6_K, 2), (Q8_0, 2), (Q4_K, 1), (Q4_0, 1)])
+def test_mmvq_fused_activation_prologue(b200, t, src):
+    """rms_norm * w + quantise (act_source 2) or quantise only (1) inside the matvec kernel == oracle composition"""
+    rng = np.random.default_rng(31 + t + src)
+    m, k, n = 80, 4096, 2
+    W = rand_blocks(rng, t, m, k)
+    x = (rng.standard_normal((n, k)) * 2).astype(np.float32); w = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32)
+    resid = rng.standard_normal((n, m)).astype(np.float32)
+    xin = x
+    if src == 2:
+        xin = np.zeros_like(x); oracle().orc_rms_norm(ptr(x), ptr(w), ptr(xin), k, n, 1e-5)
+    want = orc_mul_mat(t, W, xin, m, n, k) + resid
+    L = b200.MmvLaunch()
+    Wd = padded_weights(b200, t, W); dst = torch.zeros((n, m), dtype=torch.float32, device="cuda")
+    xd, wd, rd = dev(x), dev(w), dev(resid)
+    L.n_mats = 1; L.k = k; L.ncols = n; L.act_source = src; L.eps = 1e-5
+    L.mats[0].W = Wd.data_ptr(); L.mats[0].dst = dst.data_ptr(); L.mats[0].m = m; L.mats[0].type = t
+    L.residual[0] = rd.data_ptr(); L.x = xd.data_ptr(); L.x_col_stride = k; L.norm_w = wd.data_ptr() if src == 2 else None
+    b200.check(b200.lib.b200_mul_mat_vec_q_launch(C.byref(L), b200.stream()))
+    got = dst.cpu().numpy()
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), np.abs(got - want).max()
+
+
 def test_mmvq_rejects_bad_shapes(b200):
     d = torch.zeros(4096, dtype=torch.uint8, device="cuda")
     assert b200.lib.b200_mul_mat_vec_q(Q4_K, b200.p(d), b200.p(d), b200.p(d), 8, None, None, 8, 100, 1, b200.stream()) < 0
