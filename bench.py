@@ -392,7 +392,7 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
     ex = G.Executor(local)
     flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION)
     n_kv_of = lambda pos: max(256, (pos + 1 + 255) // 256 * 256)  # noqa: E731
-    total_ticks = args.warmup + args.steps + world            # pipeline fill + timed region
+    total_ticks = args.warmup + world - 1 + args.steps        # pipeline fill + warm-up + timed region
     steps_per_seq = (total_ticks + world - 1) // world + 1
     assert n_kv_of(args.n_past + steps_per_seq) <= args.ctx
     stream = torch.cuda.current_stream()
@@ -408,6 +408,13 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
     tok = torch.ones(1, dtype=torch.int32, device="cuda")
     seq_pos = [args.n_past] * world
     handoff_ev = []
+
+    pending = [None]
+
+    def isend(x, dst):
+        if pending[0] is not None:
+            pending[0].wait()
+        pending[0] = dist.isend(x, dst=dst)
 
     def tick(t, timed):
         seq = (t - rank) % world
@@ -429,9 +436,9 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
         if last:
             ops.check(ops.lib.b200_argmax_f32(ops.p(io["logits"]), ops.p(tok), V, 1, st))
             if t + 1 < total_ticks:                                 # rank 0 stops receiving after the last tick
-                dist.send(tok, dst=0)
-        else:
-            dist.send(io["hidden_out"], dst=rank + 1)
+                isend(tok, 0)
+        elif t + 1 < total_ticks:                                   # rank r+1 consumes it at tick t + 1
+            isend(io["hidden_out"], rank + 1)
 
     for t in range(args.warmup + world - 1):
         tick(t, False)

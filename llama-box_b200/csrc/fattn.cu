@@ -273,14 +273,18 @@ static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_l
     return (int)((n_kv + len - 1) / len);
 }
 
-// workspace = split partials [(n_kv/32) splits][n_tok][n_head][dv + 2] f32, then one u32 counter per (token, head tile).
-// It must be zero-initialised ONCE by the caller (the counters clean themselves after every launch).
+// workspace = [FA_COUNTER_BYTES of u32 completion counters, one per (token, head tile)] [split partials
+// [splits][n_tok][n_head][dv + 2] f32].  The counter region sits at a FIXED offset so that calls with different shapes
+// never reinterpret old partials as counters; it must be zero-initialised ONCE by the caller (the counters clean
+// themselves after every launch).
+#define FA_COUNTER_BYTES (256 * 1024)
 static int64_t fa_partial_bytes(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
-    const int64_t maxs = (n_kv + 31) / 32;
+    int64_t maxs = (n_kv + 31) / 32;
+    if (maxs > FA_MAX_SPLITS) maxs = FA_MAX_SPLITS;
     return (maxs * n_tok * n_head * (dv + 2) * (int64_t)sizeof(float) + 255) & ~(int64_t)255;
 }
 extern "C" int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
-    return fa_partial_bytes(dv, n_head, n_tok, n_kv) + n_tok * n_head * (int64_t)sizeof(unsigned int) + 256;
+    return FA_COUNTER_BYTES + fa_partial_bytes(dv, n_head, n_tok, n_kv) + 256;
 }
 
 template <int D, int KVT, int G>
@@ -294,7 +298,8 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     const float m0 = powf(2.0f, -(max_bias) / (float)nh_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / (float)nh_log2);
     if (softcap != 0.0f) scale /= softcap;
     dim3 grid((unsigned)n_splits, (unsigned)n_tiles, (unsigned)n_tok);
-    unsigned int * counters = ws ? (unsigned int *)((uint8_t *)ws + fa_partial_bytes(D, n_head, n_tok, n_kv)) : nullptr;
+    unsigned int * counters = (unsigned int *)ws;
+    if (ws) ws = (float *)((uint8_t *)ws + FA_COUNTER_BYTES);
     fattn_vec_kernel<D, KVT, G><<<grid, FA_WARPS * 32, 0, st>>>(q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
         (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2);
     B200_LAUNCH_CHECK();
@@ -311,7 +316,7 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
     if (n_head_kv <= 0 || n_head % n_head_kv != 0 || n_tok <= 0 || n_kv <= 0) { b200_set_error("flash_attn: bad head counts"); return B200_ERR_INVALID; }
     if (((uintptr_t)q & 15) || (q_ts & 3) || (q_hs & 3)) { b200_set_error("flash_attn: q must be 16-byte aligned"); return B200_ERR_INVALID; }
     if (kv_type == B200_TYPE_F16 && ((((uintptr_t)k | (uintptr_t)v) & 15) || ((k_rs | k_hs | v_rs | v_hs) & 15))) { b200_set_error("flash_attn: f16 K/V rows must be 16-byte aligned"); return B200_ERR_INVALID; }
-    if (n_tok > 65535) { b200_set_error("flash_attn: n_tok too large for one launch"); return B200_ERR_UNSUPPORTED; }
+    if (n_tok > 65535 || n_tok * n_head * (int64_t)sizeof(unsigned int) > FA_COUNTER_BYTES) { b200_set_error("flash_attn: n_tok * n_head too large for one launch"); return B200_ERR_UNSUPPORTED; }
     const int64_t gq = n_head / n_head_kv;
     const int G = gq % 4 == 0 ? 4 : (gq % 2 == 0 ? 2 : 1);
     if (!workspace && (n_kv + 31) / 32 > 1) { b200_set_error("flash_attn: workspace required"); return B200_ERR_INVALID; }
