@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
+    ap.add_argument("--no-mega", action="store_true", help="per-op kernels instead of the persistent decode kernel")
     return ap.parse_args()
 
 
@@ -182,7 +183,7 @@ def run_b200(args):
             n = args.n_past * G.row_size(G.F16, c["n_head_kv"] * c["head_dim"]) // 2
             ly[key].view(torch.float16)[:n] = (torch.randn(n, device="cuda", generator=gen) * 0.5).half()
     ex = G.Executor(local)
-    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION)
+    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | (0 if (args.no_mega or args.no_fusion) else G.EXEC_MEGAKERNEL)
     stream = torch.cuda.Stream()
     total = args.warmup + args.steps
     pad = lambda p: (p + 256) // 256 * 256 if True else p  # noqa: E731
@@ -270,7 +271,7 @@ def run_b200(args):
             "dtype": "q4_K/q6_K x q8_K int8 dot (dp4a), f32 accumulate", "data": "synthetic",
             "config": {"workload": f"{args.model} {args.ftype} batch-1 decode, -c {args.ctx}, n_past {args.n_past}, F16 KV, flash-attn",
                        "n_layer": len(model.layers), "streamed_weight_bytes": model.streamed_weight_bytes(), "kv_bytes_per_pos": model.kv_bytes_per_pos(),
-                       "l2_policy": "inputs (4.6 GB of weights per step) larger than L2; no flush needed", "cuda_graphs": not args.no_graphs, "fusion": not args.no_fusion,
+                       "l2_policy": "inputs (4.6 GB of weights per step) larger than L2; no flush needed", "cuda_graphs": not args.no_graphs, "fusion": not args.no_fusion, "persistent_decode_kernel": not (args.no_mega or args.no_fusion),
                        "parallelism": "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernels_per_step": int(kernels_per_step),
             "graph_captures": int(ex.captures), "graph_replays": int(ex.replays), "roofline": roof, "cpu_baseline": cpu}
@@ -312,12 +313,19 @@ def mmvq_roofline(args, model, ops, G, stream, hbm_peak):
     with torch.cuda.stream(stream):
         for _ in range(3):
             nl = one_token()
+        stream.synchronize()
+        # replayed from a CUDA graph so the measurement is device-bound, as in the decode step itself
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            one_token()
+    with torch.cuda.stream(stream):
+        g.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         stream.synchronize()
         e0.record(stream)
         for _ in range(reps):
-            one_token()
+            g.replay()
         e1.record(stream)
         stream.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -390,7 +398,7 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
                 n = args.n_past * G.row_size(G.F16, c["n_head_kv"] * c["head_dim"]) // 2
                 cache.view(torch.float16)[:n] = (torch.randn(n, device="cuda", generator=gen) * 0.5).half()
     ex = G.Executor(local)
-    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION)
+    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | (0 if (args.no_mega or args.no_fusion) else G.EXEC_MEGAKERNEL)
     n_kv_of = lambda pos: max(256, (pos + 1 + 255) // 256 * 256)  # noqa: E731
     total_ticks = args.warmup + world - 1 + args.steps        # pipeline fill + warm-up + timed region
     steps_per_seq = (total_ticks + world - 1) // world + 1

@@ -65,6 +65,7 @@ typedef struct b200_node {
 enum {
     B200_EXEC_CUDA_GRAPHS = 1,   /* capture / replay (off: GGML_B200_DISABLE_GRAPHS, like GGML_CUDA_DISABLE_GRAPHS ggml-cuda.cu:2937) */
     B200_EXEC_FUSION      = 2,   /* cross-node fusion (off: GGML_B200_DISABLE_FUSION, like ggml-cuda.cu:2862)                          */
+    B200_EXEC_MEGAKERNEL  = 4,   /* decode lists: run the fused chain as ONE persistent kernel (needs FUSION; off: GGML_B200_DISABLE_MEGAKERNEL) */
 };
 
 typedef struct b200_executor b200_executor;
@@ -78,6 +79,9 @@ B200_API int            b200_executor_compute(b200_executor *ex, const b200_node
 /* counters for tests / bench: kernels launched by the last compute (inside a replayed graph too),
  * number of CUDA-graph captures and replays so far */
 B200_API int64_t        b200_executor_last_kernels(const b200_executor *ex);
+/* persistent decode kernel: launches recorded so far and phases they covered (recorded at capture time, not per replay) */
+B200_API int64_t        b200_executor_mk_launches(const b200_executor *ex);
+B200_API int64_t        b200_executor_mk_phases(const b200_executor *ex);
 B200_API int64_t        b200_executor_graph_captures(const b200_executor *ex);
 B200_API int64_t        b200_executor_graph_replays(const b200_executor *ex);
 

@@ -16,6 +16,20 @@ void b200_count_launch(int n = 1);
 int  b200_sm_count();                                     // SMs of the current device (cached)
 bool b200_pdl_enabled();                                  // programmatic dependent launch (off: GGML_B200_DISABLE_PDL)
 
+// launch with programmatic stream serialization (PDL) so that this kernel's launch latency and prologue overlap the
+// previous kernel's tail; every kernel of this library executes griddepcontrol.wait before touching dependent data
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t b200_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define B200_CUDA(expr) do { int _s = b200_check((expr), #expr); if (_s != B200_OK) return _s; } while (0)
 #define B200_LAUNCH_CHECK() do { b200_count_launch(); int _s = b200_check(cudaGetLastError(), "kernel launch"); if (_s != B200_OK) return _s; } while (0)
 

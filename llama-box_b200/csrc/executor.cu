@@ -5,6 +5,8 @@
 // other translation units and are reached through the same C-ABI the tests use (b200_ops.h).
 #include "common.cuh"
 #include "../../include/b200_graph.h"
+#include "mk.h"
+#include "ropeutil.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -139,7 +141,12 @@ struct b200_executor {
     std::unordered_map<uint64_t, int> seen;      // topology -> times seen before capture (first sighting runs eagerly)
     uint64_t tick = 0;
     int64_t last_kernels = 0, captures = 0, replays = 0;
-    bool env_no_graphs = false, env_no_fusion = false;
+    bool env_no_graphs = false, env_no_fusion = false, env_no_mega = false;
+    // persistent decode kernel (decode_mk.cu): compiled phase programs, resident on the device, keyed by content
+    struct DevProg { MkPhase * dev = nullptr; MkPhase * host = nullptr; int n = 0; };
+    std::unordered_map<uint64_t, DevProg> progs;
+    unsigned long long * mk_sync = nullptr;       // grid-barrier counters (zeroed once; the kernel cleans up after itself)
+    int64_t mk_launches = 0, mk_phases = 0;
 };
 
 namespace {
@@ -148,6 +155,112 @@ struct Runner {
     b200_executor * ex; const b200_node * nodes; int n; cudaStream_t st; bool fuse;
     std::vector<uint8_t> done;
     std::unordered_map<uint64_t, int> uses;
+    // ---- persistent decode kernel: phases recorded instead of launched, flushed as ONE launch ----------------
+    bool mega = false;
+    std::vector<MkPhase> pend;
+    struct RopePend { bool valid = false; const float * q_src; float * q_dst; const float * k, * v; const int32_t * pos; const float * ff;
+                      const int64_t * k_ids, * v_ids; void * k_cache, * v_cache; int kv_type; int64_t k_rs, v_rs, hd, nh, nhk; b200_rope_params p; } rope_pend;
+
+    int mk_flush() {
+        int s = B200_OK;
+        if (!pend.empty()) {
+            // content hash -> device-resident program (uploaded once; replayed graphs keep pointing at it)
+            uint64_t h = 0xcbf29ce484222325ull;
+            const uint64_t * w = (const uint64_t *)pend.data();
+            for (size_t i = 0; i < pend.size() * sizeof(MkPhase) / 8; i++) { h ^= w[i]; h *= 0x100000001b3ull; h ^= h >> 29; }
+            auto it = ex->progs.find(h);
+            if (it == ex->progs.end()) {
+                b200_executor::DevProg dp; dp.n = (int)pend.size();
+                const size_t bytes = pend.size() * sizeof(MkPhase);
+                B200_CUDA(cudaMallocHost((void **)&dp.host, bytes));
+                B200_CUDA(cudaMalloc((void **)&dp.dev, bytes));
+                memcpy(dp.host, pend.data(), bytes);
+                B200_CUDA(cudaMemcpyAsync(dp.dev, dp.host, bytes, cudaMemcpyHostToDevice, st));
+                it = ex->progs.emplace(h, dp).first;
+            }
+            if (!ex->mk_sync) { B200_CUDA(cudaMalloc((void **)&ex->mk_sync, 16)); B200_CUDA(cudaMemsetAsync(ex->mk_sync, 0, 16, st)); }
+            s = mk_launch(it->second.dev, it->second.n, ex->mk_sync, st);
+            ex->mk_launches++; ex->mk_phases += (int64_t)pend.size();
+            pend.clear();
+            if (s != B200_OK) return s;
+        }
+        if (rope_pend.valid) {
+            const RopePend & r = rope_pend;
+            rope_pend.valid = false;
+            s = b200_rope_kv_store2(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, r.k_rs, r.v_rs, r.hd, r.nh, r.nhk, 1, &r.p, st);
+        }
+        return s;
+    }
+    int mk_flush_rope_only() { return rope_pend.valid ? mk_flush() : B200_OK; }
+    // a decode matvec launch as a phase of the persistent kernel (Q4_K / Q6_K, one column, in-kernel activation)
+    bool mk_try_mmv(const b200_mmv_launch & L) {
+        if (!mega || L.ncols != 1 || (L.act_source != 1 && L.act_source != 2) || L.y_out || !mk_phase_ok_k(L.k) || L.n_mats < 1 || L.n_mats > MK_MAX_MATS) return false;
+        for (int q = 0; q < L.n_mats; q++) {
+            const b200_mmv_desc & d = L.mats[q];
+            if ((d.type != B200_TYPE_Q4_K && d.type != B200_TYPE_Q6_K) || d.m <= 0 || (d.m & 1) || d.m > 0x7fffffff || !d.W || !d.dst) return false;
+            if (((uintptr_t)d.dst & 7) || (L.residual[q] && ((uintptr_t)L.residual[q] & 3))) return false;
+        }
+        if (L.swiglu && (L.n_mats != 2 || L.mats[0].type != L.mats[1].type || L.mats[0].m != L.mats[1].m)) return false;
+        if (rope_pend.valid && mk_flush() != B200_OK) return false;
+        MkPhase ph; memset(&ph, 0, sizeof(ph));
+        ph.kind = MK_MMV;
+        ph.mmv.n_mats = L.n_mats; ph.mmv.swiglu = L.swiglu; ph.mmv.act_source = L.act_source; ph.mmv.k = (int32_t)L.k; ph.mmv.eps = L.eps;
+        ph.mmv.x = L.x; ph.mmv.norm_w = L.act_source == 2 ? L.norm_w : nullptr;
+        for (int q = 0; q < L.n_mats; q++) {
+            const b200_mmv_desc & d = L.mats[q];
+            MkMat & m = ph.mmv.mat[q];
+            m.W = (const uint8_t *)d.W; m.dst = d.dst; m.bias = d.bias; m.residual = L.residual[q];
+            m.rb = type_block_bytes(d.type) * (L.k / 256); m.m = (int32_t)d.m; m.type = d.type;
+        }
+        pend.push_back(ph);
+        return true;
+    }
+    int launch_mmv(const b200_mmv_launch & L) {
+        if (mk_try_mmv(L)) return B200_OK;
+        const int s = mk_flush();
+        if (s != B200_OK) return s;
+        return b200_mul_mat_vec_q_launch(&L, st);
+    }
+    // FLASH_ATTN_EXT right after the recorded rope + KV store of the same token: one fused attention phase
+    bool mk_try_attn(const b200_node & n) {
+        if (!mega || !rope_pend.valid) return false;
+        const RopePend & r = rope_pend;
+        const b200_tensor & q = n.src[0], & k = n.src[1], & v = n.src[2];
+        if (q.data != r.q_dst || q.ne[1] != 1 || q.ne[0] != r.hd || q.ne[2] != r.nh || q.nb[2] != r.hd * 4) return false;
+        if (k.data != r.k_cache || v.data != r.v_cache || k.type != r.kv_type || k.nb[1] != r.k_rs || v.nb[1] != r.v_rs || k.ne[2] != r.nhk) return false;
+        if (r.hd != 64 && r.hd != 128) return false;
+        const int64_t hs = r.kv_type == B200_TYPE_F16 ? r.hd * 2 : r.hd / 32 * 34;      // heads contiguous inside a cell, as SET_ROWS wrote them
+        if (k.nb[2] != hs || v.nb[2] != hs || n.dst.type != B200_TYPE_F32 || !contiguous(n.dst)) return false;
+        const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
+        const int64_t n_kv = k.ne[1];
+        const int64_t gq = r.nh / r.nhk;
+        const int G = gq % 4 == 0 ? 4 : (gq % 2 == 0 ? 2 : 1);
+        const int64_t n_tiles = r.nh / G;
+        int64_t want = b200_sm_count() / n_tiles; if (want < 1) want = 1;
+        int64_t maxs = (n_kv + 31) / 32; if (maxs > 64) maxs = 64;
+        if (want > maxs) want = maxs;
+        int64_t len = (n_kv + want - 1) / want; len = (len + 31) / 32 * 32;
+        const int64_t n_splits = (n_kv + len - 1) / len;
+        if (n_tiles * (int64_t)sizeof(unsigned int) > 256 * 1024) return false;
+        MkPhase ph; memset(&ph, 0, sizeof(ph));
+        ph.kind = MK_ATTN;
+        MkAttn & A = ph.attn;
+        A.q_src = r.q_src; A.q_dst = r.q_dst; A.k = r.k; A.v = r.v; A.pos = r.pos; A.ff = r.ff; A.k_ids = r.k_ids; A.v_ids = r.v_ids;
+        A.k_cache = (uint8_t *)r.k_cache; A.v_cache = (uint8_t *)r.v_cache; A.mask = (const uint16_t *)mask; A.dst = (float *)n.dst.data;
+        A.counters = (unsigned int *)(ex->ws + ex->off_fa); A.ws = (float *)(ex->ws + ex->off_fa + 256 * 1024);
+        A.k_rs = k.nb[1]; A.k_hs = k.nb[2]; A.v_rs = v.nb[1]; A.v_hs = v.nb[2];
+        A.kv_type = r.kv_type; A.hd = (int32_t)r.hd; A.n_head = (int32_t)r.nh; A.n_head_kv = (int32_t)r.nhk; A.n_kv = (int32_t)n_kv;
+        A.split_len = (int32_t)len; A.n_splits = (int32_t)n_splits;
+        float scale = f32_param(n, 0); const float max_bias = f32_param(n, 1), softcap = f32_param(n, 2);
+        A.nh_log2 = 1 << (int)floor(log2((double)r.nh));
+        A.m0 = powf(2.0f, -(max_bias) / (float)A.nh_log2); A.m1 = powf(2.0f, -(max_bias / 2.0f) / (float)A.nh_log2);
+        if (softcap != 0.0f) scale /= softcap;
+        A.scale = scale; A.max_bias = max_bias; A.softcap = softcap;
+        A.rp = rope_host_params(&r.p);
+        rope_pend.valid = false;
+        pend.push_back(ph);
+        return true;
+    }
 
     int use_count(const b200_tensor & t) const { auto it = uses.find(t.id); return it == uses.end() ? 0 : it->second; }
     int next_compute(int i) const { for (int j = i + 1; j < n; j++) if (!done[j] && nodes[j].op != B200_OP_NONE) return j; return -1; }
@@ -207,6 +320,7 @@ struct Runner {
                 if (c >= 0 && nodes[c].op == B200_OP_MUL_MAT && nodes[c].src[1].id == mu.dst.id && nodes[c].src[1].data == mu.dst.data &&
                     nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4) {
                     const int kind = b200_act_kind_for(nodes[c].src[0].type);
+                    { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
                     int s = b200_rms_norm_quantize((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, act_buf(kind), kind, nullptr, 0, ncols, nrows, eps, st);
                     if (s != B200_OK) return s;
                     invalidate_act(mu.dst);
@@ -214,10 +328,12 @@ struct Runner {
                     return B200_OK;
                 }
                 invalidate_act(mu.dst);
+                { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
                 return b200_rms_norm((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, ncols, nrows, ncols, ncols, eps, st);
             }
         }
         invalidate_act(n.dst);
+        { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
         return b200_rms_norm((const float *)x.data, nullptr, (float *)n.dst.data, ncols, nrows, ncols, ncols, eps, st);
     }
 
@@ -239,6 +355,7 @@ struct Runner {
         const b200_tensor & w = n.src[0], & x = n.src[1];
         const int64_t k = w.ne[0], m = w.ne[1], ncols = x.ne[1];
         if (ncols > 8) {
+            { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
             invalidate_act(n.dst);
             ex->act_id[0] = ex->act_id[1] = 0;           // the batched path owns the act buffers
             const int kind = b200_act_kind_for(w.type);
@@ -264,7 +381,7 @@ struct Runner {
                         L.mats[0] = { gate->src[0].data, (float *)G.dst.data, nullptr, m, gate->src[0].type, 0 };
                         L.mats[1] = { up->src[0].data, (float *)G.dst.data, nullptr, m, up->src[0].type, 0 };
                         done[j] = done[g] = 1;
-                        s = b200_mul_mat_vec_q_launch(&L, st);
+                        s = launch_mmv(L);
                         invalidate_act(G.dst);
                         return s;
                     }
@@ -297,7 +414,7 @@ struct Runner {
                         written[nw++] = &nodes[a].dst;
                     }
                 }
-                s = b200_mul_mat_vec_q_launch(&L, st);
+                s = launch_mmv(L);
                 for (int q = 0; q < nw; q++) invalidate_act(*written[q]);
                 return s;
             }
@@ -310,6 +427,7 @@ struct Runner {
                 const b200_node & A = nodes[a];
                 const b200_tensor * other = A.src[0].data == out->data ? &A.src[1] : (A.src[1].data == out->data ? &A.src[0] : nullptr);
                 if (!other || A.dst.nb[1] != out->nb[1] || !same_shape(A.dst, *out)) break;
+                if (overlaps(A.dst, x) || (ex->norm.out_id && ex->norm.out_id == x.id && overlaps(A.dst, ex->norm.x))) break;   // other CTAs still read the activation
                 if (!bias && !resid && nrows_of(*other) == 1 && other->ne[0] == m) bias = (const float *)other->data;
                 else if (!resid && same_shape(*other, *out) && other->nb[1] == out->nb[1]) resid = (const float *)other->data;
                 else break;
@@ -319,11 +437,13 @@ struct Runner {
             L.n_mats = 1;
             L.mats[0] = { w.data, (float *)out->data, bias, m, w.type, 0 };
             L.residual[0] = resid; L.dst_col_stride[0] = out->nb[1] / 4;
-            s = b200_mul_mat_vec_q_launch(&L, st);
+            s = launch_mmv(L);
             invalidate_act(*out);
             return s;
         }
         const int kind = b200_act_kind_for(w.type);
+        s = mk_flush();
+        if (s != B200_OK) return s;
         s = ensure_act(x, kind);
         if (s != B200_OK) return s;
         invalidate_act(n.dst);
@@ -364,9 +484,20 @@ struct Runner {
         p.freq_base = f32_param(rq, 5); p.freq_scale = f32_param(rq, 6); p.ext_factor = f32_param(rq, 7);
         p.attn_factor = f32_param(rq, 8); p.beta_fast = f32_param(rq, 9); p.beta_slow = f32_param(rq, 10);
         const float * ff = rq.n_src > 2 ? (const float *)rq.src[2].data : nullptr;
-        last_status = b200_rope_kv_store2((const float *)q.data, (float *)rq.dst.data, (const float *)k.data, (const float *)v.data, (const int32_t *)rq.src[1].data, ff,
-                                          (const int64_t *)SK.src[1].data, (const int64_t *)SV.src[1].data, SK.dst.data, SV.dst.data, SK.dst.type,
-                                          SK.dst.nb[1], SV.dst.nb[1], hd, nh, nhk, nt, &p, st);
+        if (mega && nt == 1 && (hd == 64 || hd == 128) && rq.dst.data && (p.mode & ~2) == 0 && p.n_dims <= hd && p.n_dims % 8 == 0 && (p.mode != 2 || p.n_dims % 16 == 0)) {
+            // decode token inside the persistent kernel: recorded, and merged with the FLASH_ATTN_EXT that follows
+            last_status = mk_flush_rope_only();
+            RopePend & r = rope_pend;
+            r.valid = true; r.q_src = (const float *)q.data; r.q_dst = (float *)rq.dst.data; r.k = (const float *)k.data; r.v = (const float *)v.data;
+            r.pos = (const int32_t *)rq.src[1].data; r.ff = ff; r.k_ids = (const int64_t *)SK.src[1].data; r.v_ids = (const int64_t *)SV.src[1].data;
+            r.k_cache = SK.dst.data; r.v_cache = SV.dst.data; r.kv_type = SK.dst.type; r.k_rs = SK.dst.nb[1]; r.v_rs = SV.dst.nb[1]; r.hd = hd; r.nh = nh; r.nhk = nhk; r.p = p;
+        } else {
+            last_status = mk_flush();
+            if (last_status == B200_OK)
+            last_status = b200_rope_kv_store2((const float *)q.data, (float *)rq.dst.data, (const float *)k.data, (const float *)v.data, (const int32_t *)rq.src[1].data, ff,
+                                              (const int64_t *)SK.src[1].data, (const int64_t *)SV.src[1].data, SK.dst.data, SV.dst.data, SK.dst.type,
+                                              SK.dst.nb[1], SV.dst.nb[1], hd, nh, nhk, nt, &p, st);
+        }
         done[j] = done[sk] = done[sv] = 1;
         invalidate_act(rq.dst);
         return true;
@@ -375,6 +506,9 @@ struct Runner {
 
     int run_node(int i) {
         const b200_node & n = nodes[i];
+        if (mega && n.op != B200_OP_NONE && n.op != B200_OP_MUL_MAT && n.op != B200_OP_ROPE && n.op != B200_OP_FLASH_ATTN_EXT && n.op != B200_OP_RMS_NORM) {
+            const int fs = mk_flush(); if (fs != B200_OK) return fs;            // everything else is an ordinary launch: keep program order
+        }
         switch (n.op) {
             case B200_OP_NONE: return B200_OK;
             case B200_OP_RMS_NORM: return run_rms_norm(i);
@@ -388,6 +522,7 @@ struct Runner {
             }
             case B200_OP_ROPE: {
                 if (fuse && try_rope_kv_store(i)) return last_status;
+                { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
                 invalidate_act(n.dst);
                 const b200_tensor & x = n.src[0];
                 b200_rope_params p; memset(&p, 0, sizeof(p));
@@ -414,6 +549,8 @@ struct Runner {
                 const b200_tensor & q = n.src[0], & k = n.src[1], & v = n.src[2];
                 const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
                 const int64_t mrs = mask ? n.src[3].nb[1] / 2 : 0;
+                if (mk_try_attn(n)) return B200_OK;
+                { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
                 return b200_flash_attn_ext((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
                                            (float *)n.dst.data, k.type, q.ne[0], v.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1],
                                            f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st);
@@ -440,12 +577,13 @@ struct Runner {
         for (int i = 0; i < n; i++) for (int s = 0; s < nodes[i].n_src && s < B200_MAX_SRC; s++) if (nodes[i].src[s].id) uses[nodes[i].src[s].id]++;
         ex->act_id[0] = ex->act_id[1] = 0;
         ex->norm.out_id = 0;
+        pend.clear(); rope_pend.valid = false;
         for (int i = 0; i < n; i++) {
             if (done[i]) continue;
             const int s = run_node(i);
             if (s != B200_OK) return s;
         }
-        return B200_OK;
+        return mk_flush();
     }
 };
 
@@ -506,6 +644,7 @@ extern "C" b200_executor * b200_executor_create(int device) {
     ex->device = device;
     ex->env_no_graphs = getenv("GGML_B200_DISABLE_GRAPHS") != nullptr;
     ex->env_no_fusion = getenv("GGML_B200_DISABLE_FUSION") != nullptr;
+    ex->env_no_mega   = getenv("GGML_B200_DISABLE_MEGAKERNEL") != nullptr;
     return ex;
 }
 
@@ -514,6 +653,8 @@ extern "C" void b200_executor_free(b200_executor * ex) {
     cudaSetDevice(ex->device);
     for (auto & g : ex->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     if (ex->ws) cudaFree(ex->ws);
+    for (auto & pr : ex->progs) { if (pr.second.dev) cudaFree(pr.second.dev); if (pr.second.host) cudaFreeHost(pr.second.host); }
+    if (ex->mk_sync) cudaFree(ex->mk_sync);
     delete ex;
 }
 
@@ -527,6 +668,7 @@ extern "C" int b200_executor_compute(b200_executor * ex, const b200_node * nodes
     if (s != B200_OK) return s;
     cudaStream_t st = (cudaStream_t)stream;
     Runner r{ ex, nodes, n_nodes, st, (flags & B200_EXEC_FUSION) && !ex->env_no_fusion, {}, {} };
+    r.mega = r.fuse && (flags & B200_EXEC_MEGAKERNEL) && !ex->env_no_mega;
 
     // CUDA graphs only pay for small-batch (decode / verify) lists; prefill lists are few big kernels
     bool small = true;
@@ -586,3 +728,5 @@ extern "C" int b200_executor_compute(b200_executor * ex, const b200_node * nodes
 extern "C" int64_t b200_executor_last_kernels(const b200_executor * ex)  { return ex ? ex->last_kernels : 0; }
 extern "C" int64_t b200_executor_graph_captures(const b200_executor * ex) { return ex ? ex->captures : 0; }
 extern "C" int64_t b200_executor_graph_replays(const b200_executor * ex)  { return ex ? ex->replays : 0; }
+extern "C" int64_t b200_executor_mk_launches(const b200_executor * ex)     { return ex ? ex->mk_launches : 0; }
+extern "C" int64_t b200_executor_mk_phases(const b200_executor * ex)       { return ex ? ex->mk_phases : 0; }

@@ -300,9 +300,9 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     dim3 grid((unsigned)n_splits, (unsigned)n_tiles, (unsigned)n_tok);
     unsigned int * counters = (unsigned int *)ws;
     if (ws) ws = (float *)((uint8_t *)ws + FA_COUNTER_BYTES);
-    fattn_vec_kernel<D, KVT, G><<<grid, FA_WARPS * 32, 0, st>>>(q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
-        (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2);
-    B200_LAUNCH_CHECK();
+    B200_CUDA(b200_launch_pdl(fattn_vec_kernel<D, KVT, G>, grid, dim3(FA_WARPS * 32), 0, st, q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
+        (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2));
+    b200_count_launch();
     return B200_OK;
 }
 

@@ -10,14 +10,10 @@
 //   * Q8_0 rows use the x86 oracle quantiser (RNE, id = 127/max), F16 rows use RNE conversion.
 // One CTA per token: the cos/sin table is built once in shared memory and reused by every head.
 #include "common.cuh"
+#include "ropeutil.cuh"
 #include <math.h>
 
-struct RopeDev {
-    int32_t n_dims, neox;
-    float theta_scale, freq_scale, ext_factor, mscale, corr_lo, corr_hi;
-};
-
-static RopeDev rope_host_params(const b200_rope_params * p) {
+RopeDev rope_host_params(const b200_rope_params * p) {
     RopeDev d;
     d.n_dims = p->n_dims;
     d.neox   = (p->mode & 2) != 0;
@@ -32,32 +28,6 @@ static RopeDev rope_host_params(const b200_rope_params * p) {
     d.corr_lo = lo < 0.0f ? 0.0f : lo;
     d.corr_hi = hi > (float)(p->n_dims - 1) ? (float)(p->n_dims - 1) : hi;
     return d;
-}
-
-// cs[2i] = cos, cs[2i+1] = sin for pair i of this token
-__device__ __forceinline__ void rope_table(float * cs, int32_t pos, const float * ff, const RopeDev & rp, int tid, int nthreads) {
-    for (int i = tid; i < rp.n_dims / 2; i += nthreads) {
-        float theta = (float)pos;
-        for (int j = 0; j < i; j++) theta = __fmul_rn(theta, rp.theta_scale);
-        const float extrap = ff ? __fdiv_rn(theta, ff[i]) : theta;
-        const float interp = __fmul_rn(rp.freq_scale, extrap);
-        float th = interp;
-        if (rp.ext_factor != 0.0f) {
-            const float y = __fdiv_rn((float)i - rp.corr_lo, fmaxf(0.001f, rp.corr_hi - rp.corr_lo));
-            const float ramp = __fmul_rn(1.0f - fminf(1.0f, fmaxf(0.0f, y)), rp.ext_factor);
-            th = __fadd_rn(__fmul_rn(interp, 1.0f - ramp), __fmul_rn(extrap, ramp));
-        }
-        cs[2 * i]     = __fmul_rn(cosf(th), rp.mscale);
-        cs[2 * i + 1] = __fmul_rn(sinf(th), rp.mscale);
-    }
-}
-
-__device__ __forceinline__ void rope_pair(const float * s, float * d, int i, const float * cs, const RopeDev & rp) {
-    const int a = rp.neox ? i : 2 * i, b = rp.neox ? i + rp.n_dims / 2 : 2 * i + 1;
-    const float c = cs[2 * i], sn = cs[2 * i + 1];
-    const float x0 = s[a], x1 = s[b];
-    d[a] = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
-    d[b] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
 }
 
 __global__ void __launch_bounds__(256) rope_kernel(const float * __restrict__ x, float * __restrict__ y, const int32_t * __restrict__ pos,
@@ -88,39 +58,6 @@ extern "C" int b200_rope(const float * x, float * y, const int32_t * pos, const 
     rope_kernel<<<(unsigned)n_tok, 256, (size_t)p->n_dims * sizeof(float), (cudaStream_t)stream>>>(x, y, pos, ff, hd, n_head, xhs, xts, yhs, yts, rope_host_params(p));
     B200_LAUNCH_CHECK();
     return B200_OK;
-}
-
-// ---- row converters -----------------------------------------------------------------------------
-// 8 consecutive floats per lane -> destination row of `type` at element offset e (multiple of 8)
-__device__ __forceinline__ void store8(void * drow, int type, int64_t e, const float (&v)[8], int lane, bool active = true) {
-    if (type == B200_TYPE_F32) {
-        if (!active) return;
-        *(float4 *)((float *)drow + e)     = make_float4(v[0], v[1], v[2], v[3]);
-        *(float4 *)((float *)drow + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else if (type == B200_TYPE_F16) {
-        if (!active) return;
-        uint4 pk;
-        pk.x = f2h_rn(v[0]) | ((uint32_t)f2h_rn(v[1]) << 16); pk.y = f2h_rn(v[2]) | ((uint32_t)f2h_rn(v[3]) << 16);
-        pk.z = f2h_rn(v[4]) | ((uint32_t)f2h_rn(v[5]) << 16); pk.w = f2h_rn(v[6]) | ((uint32_t)f2h_rn(v[7]) << 16);
-        *(uint4 *)((uint16_t *)drow + e) = pk;
-    } else { // Q8_0, native 34-byte blocks; 4 lanes per block (all 32 lanes of the warp must call)
-        float am = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 8; j++) am = fmaxf(am, fabsf(v[j]));
-        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
-        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
-        const float d  = __fdiv_rn(am, 127.0f);
-        const float id = am != 0.0f ? __fdiv_rn(127.0f, am) : 0.0f;
-        int q[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = __float2int_rn(__fmul_rn(v[j], id));
-        if (!active) return;
-        uint8_t * blk = (uint8_t *)drow + (e / 32) * 34;
-        uint16_t * o = (uint16_t *)(blk + 2 + (e % 32));
-        o[0] = (uint16_t)((q[0] & 0xff) | ((q[1] & 0xff) << 8)); o[1] = (uint16_t)((q[2] & 0xff) | ((q[3] & 0xff) << 8));
-        o[2] = (uint16_t)((q[4] & 0xff) | ((q[5] & 0xff) << 8)); o[3] = (uint16_t)((q[6] & 0xff) | ((q[7] & 0xff) << 8));
-        if ((lane & 3) == 0) *(uint16_t *)blk = f2h_rn(d);
-    }
 }
 
 __global__ void __launch_bounds__(128) set_rows_kernel(const float * __restrict__ src, int64_t src_row_stride, const int64_t * __restrict__ ids,
@@ -207,9 +144,9 @@ extern "C" int b200_rope_kv_store2(const float * q_src, float * q_dst, const flo
     if ((n_head_kv * hd) % 256 != 0 || p->n_dims > hd || (p->n_dims & 1)) { b200_set_error("rope_kv_store: n_head_kv*head_dim must be a multiple of 256"); return B200_ERR_INVALID; }
     if (n_tok <= 0) return B200_OK;
     const size_t smem = ((size_t)p->n_dims + (size_t)(n_head_kv * hd)) * sizeof(float);
-    rope_kv_store_kernel<<<(unsigned)n_tok, 256, smem, (cudaStream_t)stream>>>(q_src, q_dst, k, v, pos, ff, k_ids, v_ids, k_cache, v_cache, kv_type, k_row_stride, v_row_stride,
-                                                                               hd, n_head, n_head_kv, rope_host_params(p));
-    B200_LAUNCH_CHECK();
+    B200_CUDA(b200_launch_pdl(rope_kv_store_kernel, dim3((unsigned)n_tok), dim3(256), smem, (cudaStream_t)stream, q_src, q_dst, k, v, pos, ff, k_ids, v_ids, k_cache, v_cache,
+                              kv_type, k_row_stride, v_row_stride, hd, n_head, n_head_kv, rope_host_params(p)));
+    b200_count_launch();
     return B200_OK;
 }
 

@@ -10,7 +10,7 @@ from . import ops
 
 F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K, I32, I64 = 0, 1, 2, 8, 12, 13, 14, 26, 27
 OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY = range(11)
-EXEC_CUDA_GRAPHS, EXEC_FUSION = 1, 2
+EXEC_CUDA_GRAPHS, EXEC_FUSION, EXEC_MEGAKERNEL = 1, 2, 4
 MAX_SRC = 6
 ELEM_SIZE = {F32: 4, F16: 2, I32: 4, I64: 8}
 
@@ -28,10 +28,10 @@ _lib.b200_executor_create.restype = C.c_void_p; _lib.b200_executor_create.argtyp
 _lib.b200_executor_free.restype = None; _lib.b200_executor_free.argtypes = [C.c_void_p]
 _lib.b200_executor_supports.restype = C.c_int; _lib.b200_executor_supports.argtypes = [C.POINTER(Node)]
 _lib.b200_executor_compute.restype = C.c_int; _lib.b200_executor_compute.argtypes = [C.c_void_p, C.POINTER(Node), C.c_int, C.c_void_p, C.c_int]
-for _n in ("b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays"):
+for _n in ("b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays", "b200_executor_mk_launches", "b200_executor_mk_phases"):
     getattr(_lib, _n).restype = C.c_int64; getattr(_lib, _n).argtypes = [C.c_void_p]
 GRAPH_SYMBOLS = ["b200_executor_create", "b200_executor_free", "b200_executor_supports", "b200_executor_compute",
-                 "b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays"]
+                 "b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays", "b200_executor_mk_launches", "b200_executor_mk_phases"]
 
 _next_id = [1]
 
@@ -103,7 +103,7 @@ class Executor:
         if not self.h:
             raise ops.B200Error(_lib.b200_last_error().decode())
 
-    def compute(self, nodes, flags=EXEC_CUDA_GRAPHS | EXEC_FUSION, stream=None):
+    def compute(self, nodes, flags=EXEC_CUDA_GRAPHS | EXEC_FUSION | EXEC_MEGAKERNEL, stream=None):
         ops.check(_lib.b200_executor_compute(self.h, nodes, len(nodes), stream if stream is not None else ops.stream(), flags))
 
     def supports(self, node):
@@ -120,6 +120,14 @@ class Executor:
     @property
     def replays(self):
         return _lib.b200_executor_graph_replays(self.h)
+
+    @property
+    def mk_launches(self):
+        return _lib.b200_executor_mk_launches(self.h)
+
+    @property
+    def mk_phases(self):
+        return _lib.b200_executor_mk_phases(self.h)
 
     def close(self):
         if self.h:

@@ -67,11 +67,12 @@ def test_executor_vs_oracle_forward(ftype, kv, bias):
                          causal_mask(1, 256, pos).astype(np.float16).view(np.uint16))
         want.append(lg); wtoks.append(int(lg.argmax())); pos += 1
     results = {}
-    for name, flags in (("plain", 0), ("fused", G.EXEC_FUSION), ("fused+graphs", G.EXEC_FUSION | G.EXEC_CUDA_GRAPHS)):
+    for name, flags in (("plain", 0), ("fused", G.EXEC_FUSION), ("fused+graphs", G.EXEC_FUSION | G.EXEC_CUDA_GRAPHS),
+                        ("mega", G.EXEC_FUSION | G.EXEC_MEGAKERNEL), ("mega+graphs", G.EXEC_FUSION | G.EXEC_MEGAKERNEL | G.EXEC_CUDA_GRAPHS)):
         model = M.SyntheticLlama(cfg, ftype, n_ctx=n_ctx, kv_type=kv, host_weights=hw)
         ex = G.Executor(0)
         got, gtoks = run_steps(G, M, model, ex, flags, steps, prompt, len(prompt))
-        results[name] = (got, gtoks, ex.last_kernels, ex.captures, ex.replays)
+        results[name] = (got, gtoks, ex.last_kernels, ex.captures, ex.replays, ex.mk_launches, ex.mk_phases)
         # Q8_0 KV: the oracle accumulates V in f32 -> the north_star bar (1e-3 relative) applies directly.
         # F16 KV: the oracle's V accumulator is fp16 (ggml-cpu/ops.cpp:8278-8340, ~4e-4 relative noise per
         # attention output, see test_flash_attn_f16_closer_to_f64_than_oracle); on random weights that noise is
@@ -85,9 +86,18 @@ def test_executor_vs_oracle_forward(ftype, kv, bias):
     # fusion must cut launches, graphs must capture once and replay
     assert results["fused"][2] < results["plain"][2]
     assert results["fused+graphs"][3] >= 1 and results["fused+graphs"][4] >= 1
-    # the three execution modes agree with each other much more tightly than with the oracle
+    # the execution modes agree with each other much more tightly than with the oracle
     for a, b in zip(results["plain"][0], results["fused+graphs"][0]):
         assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+    if ftype == "Q4_K_M":
+        # the persistent decode kernel took the Q4_K / Q6_K decode steps (two launches per token: the chain is cut at
+        # the last layer's GET_ROWS) and agrees with the per-op path
+        assert results["mega"][5] >= 2 * steps and results["mega"][6] > results["mega"][5]
+        assert results["mega"][2] < results["fused"][2]
+        for a, b in zip(results["fused"][0], results["mega+graphs"][0]):
+            assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+    elif ftype == "Q8_0":
+        assert results["mega"][5] == 0          # other weight types stay on the per-op kernels (Q4_0 models still have a Q6_K output matrix)
 
 
 def test_executor_rejects_unsupported_node():
