@@ -22,17 +22,26 @@
 #include "mk.h"
 #include "ropeutil.cuh"
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
 
 namespace {
 
-struct PCache { int ngroups; int gbase[MK_MAX_MATS + 1]; int pstart[MK_MAX_MATS]; int pend[MK_MAX_MATS]; };
-struct Cur { int p, g, s, nsteps; };
+// One entry of the CTA's phase table: this SM's pair ranges per matrix + a shared-memory copy of the phase record (every
+// descriptor field on the refill path would otherwise be an L2 round trip per ring slot).  Entries are planned two phases
+// ahead by one warp (mk_plan), so neither the global read nor the partition arithmetic sits on anyone's critical path.
+struct PCache { int kind; int ngroups; int gbase[MK_MAX_MATS + 1]; int pstart[MK_MAX_MATS]; int pend[MK_MAX_MATS]; MkMmv m; };
+#define MK_TAB 4
+struct Cur { int p, g, s, nsteps, entered; };
+#define MK_TUNE_DEFAULT 0        // bit 4: no weight streaming across phase boundaries (debug)
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long * p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void grid_arrive(unsigned long long * bar) {
     __syncthreads();
     if (threadIdx.x == 0) { __threadfence(); atomicAdd(bar, 1ULL); }
@@ -66,107 +75,134 @@ __device__ __forceinline__ int ppg_of(int type) { return type == B200_TYPE_Q4_K 
 __device__ __forceinline__ int act_chunk(int idx, int sb) { return idx ^ (sb & 7) ^ ((idx & 8) >> 1); }
 
 // ---- activation vector: [rms_norm * w ->] q8_K exactly as the CPU oracle quantises (ggml-quants.c:2555-2592) ----
-__device__ __forceinline__ void mk_quant_block(const float (&v)[8], uint8_t * act, int k, int blk, int lane) {
+// 8 lanes per 256-element block, 32 consecutive elements per lane: the per-16 / per-32 sums and the packing are in-lane,
+// only the block maximum crosses lanes (3 shuffle rounds), and a warp quantises 4 blocks at once.  This sits on the
+// critical path right after every grid barrier.
+__device__ __forceinline__ void mk_quant32(const float (&v)[32], uint8_t * act, int k, int blk, int li) {
     const int nsb = k >> 8;
-    float am = 0.0f; int ai = 0;
+    const unsigned gm = 0xffu << ((threadIdx.x & 24));              // the 8 lanes of this block
+    float am = 0.0f, mv = 0.0f; int ai = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { const float a = fabsf(v[j]); if (a > am) { am = a; ai = lane * 8 + j; } }
+    for (int j = 0; j < 32; j++) { const float a = fabsf(v[j]); if (a > am) { am = a; mv = v[j]; ai = li * 32 + j; } }
+    // first index of the largest |x| (the reference scans sequentially with a strict '>')
 #pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) {
-        const float am2 = __shfl_xor_sync(0xffffffffu, am, o2);
-        const int   ai2 = __shfl_xor_sync(0xffffffffu, ai, o2);
-        if (am2 > am || (am2 == am && ai2 < ai)) { am = am2; ai = ai2; }
+    for (int o2 = 1; o2 < 8; o2 <<= 1) {
+        const float am2 = __shfl_xor_sync(gm, am, o2), mv2 = __shfl_xor_sync(gm, mv, o2);
+        const int   ai2 = __shfl_xor_sync(gm, ai, o2);
+        if (am2 > am || (am2 == am && ai2 < ai)) { am = am2; mv = mv2; ai = ai2; }
     }
-    float mine = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 8; j++) if ((ai & 7) == j) mine = v[j];
-    const float maxv = __shfl_sync(0xffffffffu, mine, ai >> 3);
-    int q[8]; int s = 0; float d = 0.0f;
+    uint32_t w[8]; int s16a = 0, s16b = 0; float d = 0.0f;
     if (am != 0.0f) {
-        const float iscale = __fdiv_rn(-127.0f, maxv);
+        const float iscale = __fdiv_rn(-127.0f, mv);
 #pragma unroll
-        for (int j = 0; j < 8; j++) { const int t = __float2int_rn(__fmul_rn(iscale, v[j])); q[j] = t > 127 ? 127 : t; s += q[j]; }
+        for (int j = 0; j < 32; j++) {
+            int t = __float2int_rn(__fmul_rn(iscale, v[j])); t = t > 127 ? 127 : t;
+            if (j < 16) s16a += t; else s16b += t;
+            if ((j & 3) == 0) w[j >> 2] = (uint32_t)(t & 0xff); else w[j >> 2] |= (uint32_t)(t & 0xff) << (8 * (j & 3));
+        }
         d = __fdiv_rn(1.0f, iscale);
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = 0;
+        for (int j = 0; j < 8; j++) w[j] = 0;
     }
-    uint2 pk;
-    pk.x = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((q[3] & 0xff) << 24);
-    pk.y = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((q[7] & 0xff) << 24);
-    *(uint2 *)(act + blk * 256 + act_chunk(lane >> 1, blk) * 16 + (lane & 1) * 8) = pk;
-    const int s16 = s + __shfl_xor_sync(0xffffffffu, s, 1);
-    const int s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 2);
-    int16_t * b16 = (int16_t *)(act + k + 4 * nsb);
-    int16_t * b32 = (int16_t *)(act + k + 36 * nsb);
-    if ((lane & 1) == 0) b16[blk * 16 + (lane >> 1)] = (int16_t)s16;
-    if ((lane & 3) == 0) b32[blk * 8 + (lane >> 2)]  = (int16_t)s32;
-    if (lane == 0) ((float *)(act + k))[blk] = d;
+    uint8_t * qb = act + blk * 256;
+    *(uint4 *)(qb + act_chunk(2 * li, blk) * 16)     = make_uint4(w[0], w[1], w[2], w[3]);
+    *(uint4 *)(qb + act_chunk(2 * li + 1, blk) * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+    *(uint32_t *)(act + k + 4 * nsb + blk * 32 + li * 4) = (uint32_t)(s16a & 0xffff) | ((uint32_t)(s16b & 0xffff) << 16);
+    ((int16_t *)(act + k + 36 * nsb))[blk * 8 + li] = (int16_t)(s16a + s16b);
+    if (li == 0) ((float *)(act + k))[blk] = d;
 }
 
-__device__ __forceinline__ void mk_build_act(const MkMmv * M, uint8_t * act, double * red, float * s_scale, int warp, int lane, int nw) {
+__device__ __forceinline__ void mk_load32(const float * p, float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { const float4 t = __ldcg((const float4 *)(p + 4 * j)); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
+}
+
+__device__ __noinline__ void mk_build_act(const MkMmv * M, uint8_t * act, double * red, int warp, int lane, int nw) {
     const int k = M->k, nsb = k >> 8;
     const float * x = M->x;
-    float scale = 1.0f;
+    const int lg = lane >> 3, li = lane & 7;
     if (M->act_source == 2) {
-        double a2 = 0.0;                                        // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
-        for (int blk = warp; blk < nsb; blk += nw) {
-            const float4 a = __ldcg((const float4 *)(x + blk * 256 + lane * 8)), b = __ldcg((const float4 *)(x + blk * 256 + lane * 8 + 4));
-            a2 += (double)__fmul_rn(a.x, a.x); a2 += (double)__fmul_rn(a.y, a.y); a2 += (double)__fmul_rn(a.z, a.z); a2 += (double)__fmul_rn(a.w, a.w);
-            a2 += (double)__fmul_rn(b.x, b.x); a2 += (double)__fmul_rn(b.y, b.y); a2 += (double)__fmul_rn(b.z, b.z); a2 += (double)__fmul_rn(b.w, b.w);
+        // rms_norm (ggml-cpu/ops.cpp:4164-4183: f32 squares summed in double) — one block per lane group: k <= 4 * nw * 256
+        const int blk = warp * 4 + lg;
+        const bool on = blk < nsb;
+        float v[32];
+        if (on) mk_load32(x + blk * 256 + li * 32, v);
+        else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = 0.0f;
         }
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) { a0 += (double)__fmul_rn(v[j], v[j]); a1 += (double)__fmul_rn(v[j + 1], v[j + 1]); }
+        double a2 = a0 + a1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
         if (lane == 0) red[warp] = a2;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int i = 0; i < nw; i++) t += red[i];
-            *s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)k), M->eps)));
+        const float * nwp = M->norm_w;
+        float4 wv[8];
+        if (nwp && on) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) wv[j] = *(const float4 *)(nwp + blk * 256 + li * 32 + 4 * j);
         }
         __syncthreads();
-        scale = *s_scale;
-    }
-    const float * nwp = M->norm_w;
-    for (int blk = warp; blk < nsb; blk += nw) {
-        const int i = blk * 256 + lane * 8;
-        const float4 a = __ldcg((const float4 *)(x + i)), b = __ldcg((const float4 *)(x + i + 4));
-        float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-        if (M->act_source == 2) {
+        double t = 0.0;
+        for (int i = 0; i < nw; i++) t += red[i];                  // every thread: same order, same value
+        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)k), M->eps)));
+        if (on) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) v[j] = __fmul_rn(v[j], scale);
+            for (int j = 0; j < 32; j++) v[j] = __fmul_rn(v[j], scale);
             if (nwp) {
-                const float4 wa = *(const float4 *)(nwp + i), wb = *(const float4 *)(nwp + i + 4);
-                v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
-                v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { v[4 * j] = __fmul_rn(v[4 * j], wv[j].x); v[4 * j + 1] = __fmul_rn(v[4 * j + 1], wv[j].y); v[4 * j + 2] = __fmul_rn(v[4 * j + 2], wv[j].z); v[4 * j + 3] = __fmul_rn(v[4 * j + 3], wv[j].w); }
             }
         }
-        mk_quant_block(v, act, k, blk, lane);
+        if (on) mk_quant32(v, act, k, blk, li);                   // shuffles stay inside the 8-lane group
+    } else {
+        for (int b0 = warp * 4; b0 < nsb; b0 += nw * 4) {
+            const int blk = b0 + lg;
+            if (blk < nsb) {                                        // nsb % 8 == 0: a lane group is on or off as a whole; shuffles stay inside it
+                float v[32];
+                mk_load32(x + blk * 256 + li * 32, v);
+                mk_quant32(v, act, k, blk, li);
+            }
+        }
     }
     __syncthreads();
 }
 
-// ---- this SM's share of a matvec phase ----------------------------------------------------------------------------
-__device__ __forceinline__ void mk_partition(const MkMmv * M, PCache * pc, int lane) {
-    // pairs: two consecutive rows of one matrix, or (gate row r, up row r)
-    const int nm = M->swiglu ? 1 : M->n_mats;
-    long long total = 0;
-    for (int i = 0; i < nm; i++) total += M->swiglu ? M->mat[0].m : (M->mat[i].m >> 1);
-    const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
-    long long off = 0; int gb = 0;
-    for (int i = 0; i < MK_MAX_MATS; i++) {
-        int ps = 0, pe = 0;
-        if (i < nm) {
-            const long long n = M->swiglu ? M->mat[0].m : (M->mat[i].m >> 1);
-            const long long s = lo > off ? lo : off, e = hi < off + n ? hi : off + n;
-            if (e > s) { ps = (int)(s - off); pe = (int)(e - off); }
-            off += n;
+// ---- this SM's share of a matvec phase: planned into the CTA's phase table by ONE warp, two phases ahead -----------
+__device__ __noinline__ void mk_plan(const MkPhase * prog, int q, PCache * tab, volatile int * tab_phase, int lane) {
+    PCache * pc = &tab[q % MK_TAB];
+    const int kind = __ldg(&prog[q].kind);
+    if (kind == MK_MMV) {
+        const uint32_t * src = (const uint32_t *)&prog[q].mmv; uint32_t * dst = (uint32_t *)&pc->m;
+        for (int i = lane; i < (int)(sizeof(MkMmv) / 4); i += 32) dst[i] = __ldg(src + i);
+        __syncwarp();
+        const MkMmv * M = &pc->m;
+        // pairs: two consecutive rows of one matrix, or (gate row r, up row r)
+        const int nm = M->swiglu ? 1 : M->n_mats;
+        long long total = 0;
+        for (int i = 0; i < nm; i++) total += M->swiglu ? M->mat[0].m : (M->mat[i].m >> 1);
+        const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+        long long off = 0; int gb = 0;
+        for (int i = 0; i < MK_MAX_MATS; i++) {
+            int ps = 0, pe = 0;
+            if (i < nm) {
+                const long long n = M->swiglu ? M->mat[0].m : (M->mat[i].m >> 1);
+                const long long s = lo > off ? lo : off, e = hi < off + n ? hi : off + n;
+                if (e > s) { ps = (int)(s - off); pe = (int)(e - off); }
+                off += n;
+            }
+            if (lane == 0) { pc->gbase[i] = gb; pc->pstart[i] = ps; pc->pend[i] = pe; }
+            if (i < nm) { const int ppg = ppg_of(M->mat[i].type); gb += (pe - ps + ppg - 1) / ppg; }
         }
-        if (lane == 0) { pc->gbase[i] = gb; pc->pstart[i] = ps; pc->pend[i] = pe; }
-        if (i < nm) { const int ppg = ppg_of(M->mat[i].type); gb += (pe - ps + ppg - 1) / ppg; }
+        if (lane == 0) { pc->gbase[MK_MAX_MATS] = gb; pc->ngroups = gb; }
     }
-    if (lane == 0) { pc->gbase[MK_MAX_MATS] = gb; pc->ngroups = gb; }
+    if (lane == 0) pc->kind = kind;
     __syncwarp();
+    __threadfence_block();
+    if (lane == 0) tab_phase[q % MK_TAB] = q;
 }
 
 struct Grp { int i, type, pair0, np; };
@@ -210,22 +246,34 @@ __device__ __forceinline__ void mk_issue(const MkMmv * M, const PCache * pc, int
     }
 }
 
-__device__ __forceinline__ void cur_enter(Cur & c, const MkPhase * prog, int n_phases, PCache * pc, int warp, int lane) {
+// position the issue cursor on this warp's next ring slot; false: the phase it would enter is not planned yet
+__device__ __forceinline__ bool cur_seek(Cur & c, int n_phases, const PCache * tab, const volatile int * tab_phase, int warp) {
     while (c.p < n_phases) {
-        const MkPhase * ph = prog + c.p;
-        if (ph->kind == MK_MMV) {
-            mk_partition(&ph->mmv, pc, lane);
-            if (warp < pc->ngroups) { c.g = warp; c.s = 0; c.nsteps = ph->mmv.k >> 11; return; }
-        }
+        if (tab_phase[c.p % MK_TAB] != c.p) return false;
+        const PCache * pc = &tab[c.p % MK_TAB];
+        if (pc->kind == MK_MMV && warp < pc->ngroups) { c.g = warp; c.s = 0; c.nsteps = pc->m.k >> 11; c.entered = 1; return true; }
         c.p++;
     }
+    return false;
 }
-__device__ __forceinline__ void cur_next(Cur & c, const MkPhase * prog, int n_phases, PCache * pc, int warp, int lane, int nw) {
+__device__ __forceinline__ void cur_advance(Cur & c, const PCache * pc, int nw) {
     if (++c.s < c.nsteps) return;
     c.s = 0; c.g += nw;
     if (c.g < pc->ngroups) return;
-    c.p++;
-    cur_enter(c, prog, n_phases, pc, warp, lane);
+    c.p++; c.entered = 0;
+}
+// keep this warp's two ring slots busy: issue the next slots of its sequence (possibly of later phases) while there is room
+__device__ __forceinline__ void mk_pump(Cur & ic, int & nissued, int ncons, int plimit, int n_phases, const PCache * tab, const volatile int * tab_phase,
+                                        uint8_t * ring, uint64_t * full, int warp, int lane, int nw) {
+    while (nissued - ncons < 2) {
+        if (!ic.entered && !cur_seek(ic, n_phases, tab, tab_phase, warp)) break;
+        if (ic.p > plimit) break;
+        const PCache * pc = &tab[ic.p % MK_TAB];
+        const int ipos = nissued & 1;
+        mk_issue(&pc->m, pc, ic.g, ic.s, ring + ipos * MK_SLOT_BYTES, &full[ipos], lane);
+        cur_advance(ic, pc, nw);
+        nissued++;
+    }
 }
 
 // ---- Q4_K: lane = (pair lg = lane>>3, super-block sb = lane&7) of the slot; both rows of the pair ------------------
@@ -323,27 +371,28 @@ __device__ __forceinline__ void mk_dot_q6K(const uint8_t * slot, const uint8_t *
 }
 
 // ---- one matvec phase, consumer side ----------------------------------------------------------------------------------
-__device__ __forceinline__ void mk_mmv_phase(const MkPhase * prog, int n_phases, int p, const uint8_t * act, uint8_t * ring, uint64_t * full,
-                                             PCache * cpc, PCache * ipc, Cur & ic, int & ncons, int warp, int lane, int nw) {
-    const MkMmv * M = &prog[p].mmv;
+__device__ __forceinline__ void mk_mmv_phase(int n_phases, int p, const uint8_t * act, uint8_t * ring, uint64_t * full, const PCache * tab, const volatile int * tab_phase,
+                                             Cur & ic, int & ncons, int & nissued, int plimit, int warp, int lane, int nw, unsigned int * stats) {
+    const PCache * cpc = &tab[p % MK_TAB];
+    const MkMmv * M = &cpc->m;                                      // shared-memory copy
     const int k = M->k, nsteps = k >> 11;
-    mk_partition(M, cpc, lane);
     const int ng = cpc->ngroups;
     for (int g = warp; g < ng; g += nw) {
         const Grp gr = mk_locate(M, cpc, g);
         float acc0 = 0.0f, acc1 = 0.0f;
         for (int step = 0; step < nsteps; step++) {
             const int pos = ncons & 1;
+            const long long c0 = stats ? clock64() : 0;
             mbar_wait(&full[pos], (uint32_t)((ncons >> 1) & 1));
+            const long long c1 = stats ? clock64() : 0;
             uint8_t * slot = ring + pos * MK_SLOT_BYTES;
             if (gr.type == B200_TYPE_Q4_K) mk_dot_q4K(slot, act, k, step, lane, acc0, acc1);
             else                           mk_dot_q6K(slot, act, k, step, lane, acc0, acc1);
             __syncwarp();                                           // every lane is done reading the slot
+            const long long c2 = stats ? clock64() : 0;
             ncons++;
-            if (ic.p < n_phases) {                                  // refill it with the next slot of this warp's sequence
-                mk_issue(&prog[ic.p].mmv, ipc, ic.g, ic.s, slot, &full[pos], lane);
-                cur_next(ic, prog, n_phases, ipc, warp, lane, nw);
-            }
+            mk_pump(ic, nissued, ncons, plimit, n_phases, tab, tab_phase, ring, full, warp, lane, nw);   // refill it
+            if (stats && lane == 0) { atomicAdd(stats + 0, (unsigned int)(c1 - c0)); atomicAdd(stats + 1, (unsigned int)(c2 - c1)); atomicAdd(stats + 2, (unsigned int)(clock64() - c2)); atomicAdd(stats + 3, 1u); }
         }
         // reduce over the lanes of each pair, then bias / residual / SwiGLU
         const int lgw = gr.type == B200_TYPE_Q4_K ? 8 : 16;
@@ -411,7 +460,7 @@ __device__ __forceinline__ void load_roped8(const float * head, int e0, const fl
 }
 
 template <int D, int KVT, int G>
-__device__ void mk_attn(const MkAttn * Ap, uint8_t * scr, int nw) {
+__device__ __noinline__ void mk_attn(const MkAttn * Ap, uint8_t * scr, int nw) {
     constexpr int LP = D / 8, PPW = 32 / LP;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sg = lane / LP, dl = lane % LP;
@@ -642,12 +691,13 @@ __device__ __forceinline__ void mk_attn_g(const MkAttn * A, uint8_t * scr, int n
     else mk_attn<D, KVT, 1>(A, scr, nw);
 }
 
-__global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase * __restrict__ prog, int n_phases, unsigned long long * sync) {
+__global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase * __restrict__ prog, int n_phases, unsigned long long * sync, unsigned long long * trace, int tune) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MK_MAX_WARPS][2];
-    __shared__ PCache pcs[MK_MAX_WARPS][2];
+    __shared__ PCache tab[MK_TAB];
+    __shared__ volatile int tab_phase[MK_TAB];
     __shared__ double red[MK_MAX_WARPS];
-    __shared__ float s_scale;
+    __shared__ unsigned int wstats[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     uint8_t * act  = smem;
     uint8_t * ring = smem + MK_AREG_BYTES + (size_t)warp * 2 * MK_SLOT_BYTES;
@@ -655,26 +705,38 @@ __global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase 
     mbar_fence_init();
     __syncthreads();
 
-    // issue cursor: runs two slots ahead of consumption, across phase boundaries (weights are independent of activations)
-    Cur ic; ic.p = 0; ic.g = 0; ic.s = 0; ic.nsteps = 1;
-    PCache * ipc = &pcs[warp][0], * cpc = &pcs[warp][1];
-    cur_enter(ic, prog, n_phases, ipc, warp, lane);
-    for (int s = 0; s < 2 && ic.p < n_phases; s++) {
-        mk_issue(&prog[ic.p].mmv, ipc, ic.g, ic.s, ring + s * MK_SLOT_BYTES, &full_bar[warp][s], lane);
-        cur_next(ic, prog, n_phases, ipc, warp, lane, nw);
-    }
-    int ncons = 0;
+    // phase table: entries 0..2 now, entry p+2 at the start of phase p (by warp p % nw)
+    if (tid < MK_TAB) tab_phase[tid] = -1;
+    __syncthreads();
+    if (warp < 3 && warp < n_phases) mk_plan(prog, warp, tab, tab_phase, lane);
+    __syncthreads();
+    // issue cursor: runs up to two ring slots ahead of consumption, across phase boundaries (weights do not depend on activations)
+    Cur ic; ic.p = 0; ic.g = 0; ic.s = 0; ic.nsteps = 1; ic.entered = 0;
+    int ncons = 0, nissued = 0;
+    const bool xphase = !(tune & 16);
+    if (xphase) mk_pump(ic, nissued, ncons, n_phases, n_phases, tab, tab_phase, ring, full_bar[warp], warp, lane, nw);
     for (int p = 0; p < n_phases; p++) {
+        if (trace && tid == 0) { trace[((size_t)blockIdx.x * n_phases + p) * 4 + 0] = gtimer(); wstats[0] = wstats[1] = wstats[2] = wstats[3] = 0; }
         if (p > 0) grid_wait(sync, (unsigned long long)p * gridDim.x);
-        const MkPhase * ph = prog + p;
-        if (ph->kind == MK_MMV) {
-            mk_build_act(&ph->mmv, act, red, &s_scale, warp, lane, nw);
-            mk_mmv_phase(prog, n_phases, p, act, ring, full_bar[warp], cpc, ipc, ic, ncons, warp, lane, nw);
+        if (trace && tid == 0) trace[((size_t)blockIdx.x * n_phases + p) * 4 + 1] = gtimer();
+        const int plimit = xphase ? n_phases : p;
+        const PCache * cpc = &tab[p % MK_TAB];
+        // first this warp's own refills (phase p is planned), then the planning of phase p + 2 by one warp
+        mk_pump(ic, nissued, ncons, plimit, n_phases, tab, tab_phase, ring, full_bar[warp], warp, lane, nw);
+        if (p > 0 && p + 2 < n_phases && warp == p % nw) mk_plan(prog, p + 2, tab, tab_phase, lane);
+        if (cpc->kind == MK_MMV) {
+            mk_build_act(&cpc->m, act, red, warp, lane, nw);
+            if (trace && tid == 0) trace[((size_t)blockIdx.x * n_phases + p) * 4 + 2] = gtimer();
+            mk_mmv_phase(n_phases, p, act, ring, full_bar[warp], tab, tab_phase, ic, ncons, nissued, plimit, warp, lane, nw, trace ? wstats : nullptr);
         } else {
-            const MkAttn * A = &ph->attn;
+            if (trace && tid == 0) trace[((size_t)blockIdx.x * n_phases + p) * 4 + 2] = gtimer();
+            const MkAttn * A = &prog[p].attn;
             if (A->hd == 128) { if (A->kv_type == B200_TYPE_F16) mk_attn_g<128, B200_TYPE_F16>(A, act, nw); else mk_attn_g<128, B200_TYPE_Q8_0>(A, act, nw); }
             else              { if (A->kv_type == B200_TYPE_F16) mk_attn_g<64,  B200_TYPE_F16>(A, act, nw); else mk_attn_g<64,  B200_TYPE_Q8_0>(A, act, nw); }
         }
+        if (trace) { __syncthreads(); if (tid == 0) { trace[((size_t)blockIdx.x * n_phases + p) * 4 + 3] = gtimer();
+            unsigned long long * ext = trace + (size_t)gridDim.x * 512 * 4 + ((size_t)blockIdx.x * n_phases + p) * 4;
+            ext[0] = wstats[0]; ext[1] = wstats[1]; ext[2] = wstats[2]; ext[3] = wstats[3]; } }
         if (p + 1 < n_phases) grid_arrive(sync);
     }
     // the last CTA out resets the barrier for the next launch
@@ -686,14 +748,65 @@ __global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase 
 
 } // namespace
 
-int mk_phase_ok_k(int64_t k) { return k > 0 && k % 2048 == 0 && mk_act_bytes(k) <= MK_AREG_BYTES; }
+int mk_phase_ok_k(int64_t k, int act_source) {
+    // rms_norm phases keep their block in registers: one 256-element block per 8-lane group
+    return k > 0 && k % 2048 == 0 && mk_act_bytes(k) <= MK_AREG_BYTES && (act_source != 2 || k <= (int64_t)4 * MK_MAX_WARPS * 256);
+}
+
+// GGML_B200_MK_TRACE=1: per-phase timestamps of every CTA of the most recent launch, printed by b200_mk_trace_dump()
+static unsigned long long * g_trace = nullptr; static int g_trace_phases = 0; static std::vector<int> g_trace_kinds;
+static const size_t TRACE_MAX_PHASES = 512;
 
 int mk_launch(const MkPhase * dev_prog, int n_phases, unsigned long long * dev_sync, void * stream) {
     if (!dev_prog || n_phases <= 0 || !dev_sync) { b200_set_error("mk_launch: bad arguments"); return B200_ERR_INVALID; }
     const size_t smem = MK_AREG_BYTES + (size_t)MK_MAX_WARPS * 2 * MK_SLOT_BYTES;
     static bool attr = false;
+    static const bool want_trace = getenv("GGML_B200_MK_TRACE") != nullptr;
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    mk_kernel<<<(unsigned)b200_sm_count(), MK_MAX_WARPS * 32, smem, (cudaStream_t)stream>>>(dev_prog, n_phases, dev_sync);
+    unsigned long long * trace = nullptr;
+    if (want_trace && (size_t)n_phases <= TRACE_MAX_PHASES && n_phases >= 8) {
+        if (!g_trace) B200_CUDA(cudaMalloc((void **)&g_trace, (size_t)b200_sm_count() * TRACE_MAX_PHASES * 4 * 8 * 2));
+        trace = g_trace; g_trace_phases = n_phases;
+    }
+    static const int tune = getenv("GGML_B200_MK_TUNE") ? atoi(getenv("GGML_B200_MK_TUNE")) : MK_TUNE_DEFAULT;
+    mk_kernel<<<(unsigned)b200_sm_count(), MK_MAX_WARPS * 32, smem, (cudaStream_t)stream>>>(dev_prog, n_phases, dev_sync, trace, tune);
     B200_LAUNCH_CHECK();
     return B200_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void b200_mk_trace_dump(const MkPhase * dev_prog_or_null) {
+    (void)dev_prog_or_null;
+    if (!g_trace || g_trace_phases <= 0) { fprintf(stderr, "mk trace: nothing recorded (set GGML_B200_MK_TRACE=1)\n"); return; }
+    cudaDeviceSynchronize();
+    const int G = b200_sm_count(), P = g_trace_phases;
+    std::vector<unsigned long long> t((size_t)G * P * 4), x((size_t)G * P * 4);
+    cudaMemcpy(t.data(), g_trace, t.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(x.data(), g_trace + (size_t)G * 512 * 4, x.size() * 8, cudaMemcpyDeviceToHost);
+    const unsigned long long t0 = t[0];
+    const bool verbose = atoi(getenv("GGML_B200_MK_TRACE")) > 1;
+    const int period = getenv("GGML_B200_MK_TRACE_PERIOD") ? atoi(getenv("GGML_B200_MK_TRACE_PERIOD")) : 5;
+    std::vector<double> agg((size_t)period * 6, 0.0), sagg((size_t)period * 4, 0.0); std::vector<int> cnt(period, 0);
+    double t_end = 0;
+    for (int p = 0; p < P; p++) {
+        double wmin = 1e30, wmax = 0, cmin = 1e30, cmax = 0, csum = 0, first = 1e30, last = 0;
+        for (int b = 0; b < G; b++) {
+            const unsigned long long * r = &t[((size_t)b * P + p) * 4];
+            const double w = (r[1] - r[0]) * 1e-3, c = (r[3] - r[1]) * 1e-3;
+            wmin = w < wmin ? w : wmin; wmax = w > wmax ? w : wmax; cmin = c < cmin ? c : cmin; cmax = c > cmax ? c : cmax; csum += c;
+            const double s0 = (r[1] - t0) * 1e-3, e = (r[3] - t0) * 1e-3; first = s0 < first ? s0 : first; last = e > last ? e : last;
+        }
+        const unsigned long long * r0 = &t[(size_t)p * 4];
+        const double actb = (r0[2] - r0[1]) * 1e-3;
+        if (verbose) fprintf(stderr, "  phase %3d  start %8.1f  wait %5.1f/%5.1f  act %5.1f  compute %5.1f/%5.1f/%5.1f  end(all) %8.1f\n", p, first, wmin, wmax, actb, cmin, csum / G, cmax, last);
+        if (p >= period && p < P - period) { double * a = &agg[(size_t)(p % period) * 6]; a[0] += wmin; a[1] += wmax; a[2] += actb; a[3] += cmin; a[4] += csum / G; a[5] += cmax; cnt[p % period]++; }
+        t_end = last;
+        if (p >= period && p < P - period) for (int b = 0; b < G; b++) for (int q = 0; q < 4; q++) sagg[(size_t)(p % period) * 4 + q] += (double)x[((size_t)b * P + p) * 4 + q];
+    }
+    fprintf(stderr, "mk trace: %d phases, %d CTAs, %.1f us total; mean per phase slot (p %% %d): barrier wait min/max | act build (CTA0) | phase time min/avg/max\n", P, G, t_end, period);
+    for (int q = 0; q < period; q++) if (cnt[q]) {
+        const double * a = &agg[(size_t)q * 6]; const double n = cnt[q];
+        const double * sg = &sagg[(size_t)q * 4]; const double ns = sg[3] > 0 ? sg[3] : 1;
+        fprintf(stderr, "  slot %d: wait %5.1f/%5.1f  act %5.1f  time %5.1f/%5.1f/%5.1f | per ring slot (cycles): data wait %7.0f  dot %6.0f  refill %6.0f  (%.1f slots per SM)\n", q, a[0] / n, a[1] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n,
+                sg[0] / ns, sg[1] / ns, sg[2] / ns, sg[3] / n / G);
+    }
 }

@@ -64,5 +64,5 @@ struct MkPhase {
 static inline int64_t mk_act_bytes(int64_t k) { return k + 52 * (k / 256); }   // qs | d f32 | sums16 | sums32
 
 // host entry points (decode_mk.cu)
-int  mk_phase_ok_k(int64_t k);
+int  mk_phase_ok_k(int64_t k, int act_source);
 int  mk_launch(const MkPhase * dev_prog, int n_phases, unsigned long long * dev_sync, void * stream);
