@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-fusion", action="store_true")
-    ap.add_argument("--no-mega", action="store_true", help="per-op kernels instead of the persistent decode kernel")
+    ap.add_argument("--mega", action="store_true", help="experimental: attention as a phase of the persistent decode kernel")
+    ap.add_argument("--mega-mmv", action="store_true", help="experimental: attention and the matvecs inside the persistent decode kernel")
     return ap.parse_args()
 
 
@@ -183,7 +184,7 @@ def run_b200(args):
             n = args.n_past * G.row_size(G.F16, c["n_head_kv"] * c["head_dim"]) // 2
             ly[key].view(torch.float16)[:n] = (torch.randn(n, device="cuda", generator=gen) * 0.5).half()
     ex = G.Executor(local)
-    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | (0 if (args.no_mega or args.no_fusion) else G.EXEC_MEGAKERNEL)
+    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | ((G.EXEC_MEGAKERNEL if (args.mega or args.mega_mmv) else 0) | (G.EXEC_MEGA_MMV if args.mega_mmv else 0) if not args.no_fusion else 0)
     stream = torch.cuda.Stream()
     total = args.warmup + args.steps
     pad = lambda p: (p + 256) // 256 * 256 if True else p  # noqa: E731
@@ -271,7 +272,7 @@ def run_b200(args):
             "dtype": "q4_K/q6_K x q8_K int8 dot (dp4a), f32 accumulate", "data": "synthetic",
             "config": {"workload": f"{args.model} {args.ftype} batch-1 decode, -c {args.ctx}, n_past {args.n_past}, F16 KV, flash-attn",
                        "n_layer": len(model.layers), "streamed_weight_bytes": model.streamed_weight_bytes(), "kv_bytes_per_pos": model.kv_bytes_per_pos(),
-                       "l2_policy": "inputs (4.6 GB of weights per step) larger than L2; no flush needed", "cuda_graphs": not args.no_graphs, "fusion": not args.no_fusion, "persistent_decode_kernel": not (args.no_mega or args.no_fusion),
+                       "l2_policy": "inputs (4.6 GB of weights per step) larger than L2; no flush needed", "cuda_graphs": not args.no_graphs, "fusion": not args.no_fusion, "persistent_decode_kernel": ("attention+matvec" if args.mega_mmv else ("attention" if args.mega else "off")),
                        "parallelism": "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernels_per_step": int(kernels_per_step),
             "graph_captures": int(ex.captures), "graph_replays": int(ex.replays), "roofline": roof, "cpu_baseline": cpu}
@@ -398,7 +399,7 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
                 n = args.n_past * G.row_size(G.F16, c["n_head_kv"] * c["head_dim"]) // 2
                 cache.view(torch.float16)[:n] = (torch.randn(n, device="cuda", generator=gen) * 0.5).half()
     ex = G.Executor(local)
-    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | (0 if (args.no_mega or args.no_fusion) else G.EXEC_MEGAKERNEL)
+    flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | ((G.EXEC_MEGAKERNEL if (args.mega or args.mega_mmv) else 0) | (G.EXEC_MEGA_MMV if args.mega_mmv else 0) if not args.no_fusion else 0)
     n_kv_of = lambda pos: max(256, (pos + 1 + 255) // 256 * 256)  # noqa: E731
     total_ticks = args.warmup + world - 1 + args.steps        # pipeline fill + warm-up + timed region
     steps_per_seq = (total_ticks + world - 1) // world + 1

@@ -65,7 +65,10 @@ typedef struct b200_node {
 enum {
     B200_EXEC_CUDA_GRAPHS = 1,   /* capture / replay (off: GGML_B200_DISABLE_GRAPHS, like GGML_CUDA_DISABLE_GRAPHS ggml-cuda.cu:2937) */
     B200_EXEC_FUSION      = 2,   /* cross-node fusion (off: GGML_B200_DISABLE_FUSION, like ggml-cuda.cu:2862)                          */
-    B200_EXEC_MEGAKERNEL  = 4,   /* decode lists: run the fused chain as ONE persistent kernel (needs FUSION; off: GGML_B200_DISABLE_MEGAKERNEL) */
+    B200_EXEC_MEGAKERNEL  = 4,   /* decode lists: phases of the persistent decode kernel — rope + KV store + attention as one launch
+                                    (needs FUSION; also GGML_B200_MEGAKERNEL=1; off: GGML_B200_DISABLE_MEGAKERNEL).  Experimental: the default
+                                    decode path is per-op kernels with the attention fused into one launch (b200_rope_kv_flash_attn) */
+    B200_EXEC_MEGA_MMV    = 8,   /* ... and the Q4_K / Q6_K matvecs of the chain in the same launch (also: GGML_B200_MEGA_MMV=1)        */
 };
 
 typedef struct b200_executor b200_executor;

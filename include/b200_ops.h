@@ -205,6 +205,17 @@ B200_API int b200_flash_attn_ext(const float *q, int64_t q_tok_stride, int64_t q
                                  int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap,
                                  void *workspace, void *stream);
 
+/* decode token (n_tok = 1): ROPE(q), ROPE(k) -> K cache cell k_ids[0], v -> V cache cell v_ids[0] and FLASH_ATTN_EXT over
+ * n_kv cells in ONE launch (replaces rope x2 + set_rows x2 + flash_attn_vec + combine of the reference: ggml-cuda/rope.cu,
+ * set-rows.cu, fattn.cu).  q_src/k_new/v_new: this token's projections, f32 [n_head|n_head_kv][hd]; q_dst receives the roped
+ * query (a declared graph output); caches as in b200_flash_attn_ext with heads contiguous inside a cell. */
+B200_API int b200_rope_kv_flash_attn(const float *q_src, float *q_dst, const float *k_new, const float *v_new, const int32_t *pos,
+                                     const float *freq_factors_or_null, const int64_t *k_ids, const int64_t *v_ids,
+                                     void *k_cache, void *v_cache, int kv_type, int64_t k_cell_stride, int64_t k_head_stride,
+                                     int64_t v_cell_stride, int64_t v_head_stride, const void *mask_f16_or_null, float *dst,
+                                     int64_t head_dim, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params *p,
+                                     float scale, float max_bias, float softcap, void *workspace, void *stream);
+
 /* ---- glue (replaces binbcast.cu, unary.cu:291, getrows.cu, cpy.cu) ----------------------- */
 B200_API int b200_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows, void *stream);
 B200_API int b200_mul(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows, void *stream);

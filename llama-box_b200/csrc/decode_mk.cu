@@ -31,9 +31,9 @@ namespace {
 // One entry of the CTA's phase table: this SM's pair ranges per matrix + a shared-memory copy of the phase record (every
 // descriptor field on the refill path would otherwise be an L2 round trip per ring slot).  Entries are planned two phases
 // ahead by one warp (mk_plan), so neither the global read nor the partition arithmetic sits on anyone's critical path.
-struct PCache { int kind; int ngroups; int gbase[MK_MAX_MATS + 1]; int pstart[MK_MAX_MATS]; int pend[MK_MAX_MATS]; MkMmv m; };
+struct PCache { alignas(16) MkPhase ph; int ngroups; int gbase[MK_MAX_MATS + 1]; int pstart[MK_MAX_MATS]; int pend[MK_MAX_MATS]; int pad[2]; };
 #define MK_TAB 4
-struct Cur { int p, g, s, nsteps, entered; };
+struct Cur { int p, g, s, entered; };
 #define MK_TUNE_DEFAULT 0        // bit 4: no weight streaming across phase boundaries (debug)
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long * p) {
@@ -68,7 +68,12 @@ __device__ __forceinline__ int prmt(uint32_t a, uint32_t b, uint32_t sel) {     
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
-__device__ __forceinline__ int ppg_of(int type) { return type == B200_TYPE_Q4_K ? 4 : 2; }
+// Slot geometry.  A ring slot always holds 64 (Q4_K) / 32 (Q6_K) super-blocks: S super-blocks of each row of `ppg` row
+// pairs.  When a whole row fits (S == nsb: k = 2048, 4096 and, for Q4_K, 8192) the rows of a group are ONE contiguous byte
+// range -> one bulk copy per slot (two for a gate/up pair); otherwise S = 8 and a row is walked in nsb/8 steps.
+__device__ __forceinline__ int S_of(int type, int nsb) { return (nsb == 16 || (nsb == 32 && type == B200_TYPE_Q4_K)) ? nsb : 8; }
+__device__ __forceinline__ int ppg_of(int type, int nsb) { return (type == B200_TYPE_Q4_K ? 32 : 16) / S_of(type, nsb); }
+__device__ __forceinline__ int rowbytes_of(int type, int S) { return S * (type == B200_TYPE_Q4_K ? 144 : 210); }
 
 // swizzled position of 16-byte chunk `idx` (0..15) of super-block sb in the activation vector: lanes that read the same
 // chunk of 8 consecutive super-blocks (Q4_K mapping), or different chunks of 4 (Q6_K mapping), hit 8 distinct bank groups
@@ -172,14 +177,20 @@ __device__ __noinline__ void mk_build_act(const MkMmv * M, uint8_t * act, double
 }
 
 // ---- this SM's share of a matvec phase: planned into the CTA's phase table by ONE warp, two phases ahead -----------
-__device__ __noinline__ void mk_plan(const MkPhase * prog, int q, PCache * tab, volatile int * tab_phase, int lane) {
+// plan_begin: fire-and-forget copy of the phase record (cp.async, 16 lanes x 16 bytes) at the start of phase q - 3;
+// plan_finish: at the end of that phase the same warp waits for it (long since landed), partitions and publishes.
+__device__ __forceinline__ void mk_plan_begin(const MkPhase * prog, int q, PCache * tab, int lane) {
+    if (lane < 16) {
+        const uint32_t dst = smem_u32((uint8_t *)&tab[q % MK_TAB].ph + lane * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"((const uint8_t *)(prog + q) + lane * 16) : "memory");
+    }
+}
+__device__ __noinline__ void mk_plan_finish(int q, PCache * tab, volatile int * tab_phase, int lane) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
     PCache * pc = &tab[q % MK_TAB];
-    const int kind = __ldg(&prog[q].kind);
-    if (kind == MK_MMV) {
-        const uint32_t * src = (const uint32_t *)&prog[q].mmv; uint32_t * dst = (uint32_t *)&pc->m;
-        for (int i = lane; i < (int)(sizeof(MkMmv) / 4); i += 32) dst[i] = __ldg(src + i);
-        __syncwarp();
-        const MkMmv * M = &pc->m;
+    if (pc->ph.kind == MK_MMV) {
+        const MkMmv * M = &pc->ph.mmv;
         // pairs: two consecutive rows of one matrix, or (gate row r, up row r)
         const int nm = M->swiglu ? 1 : M->n_mats;
         long long total = 0;
@@ -195,53 +206,69 @@ __device__ __noinline__ void mk_plan(const MkPhase * prog, int q, PCache * tab, 
                 off += n;
             }
             if (lane == 0) { pc->gbase[i] = gb; pc->pstart[i] = ps; pc->pend[i] = pe; }
-            if (i < nm) { const int ppg = ppg_of(M->mat[i].type); gb += (pe - ps + ppg - 1) / ppg; }
+            if (i < nm) { const int ppg = ppg_of(M->mat[i].type, M->k >> 8); gb += (pe - ps + ppg - 1) / ppg; }
         }
         if (lane == 0) { pc->gbase[MK_MAX_MATS] = gb; pc->ngroups = gb; }
     }
-    if (lane == 0) pc->kind = kind;
     __syncwarp();
     __threadfence_block();
     if (lane == 0) tab_phase[q % MK_TAB] = q;
 }
 
-struct Grp { int i, type, pair0, np; };
+struct Grp { int i, type, pair0, np, S, ppg; };
 __device__ __forceinline__ Grp mk_locate(const MkMmv * M, const PCache * pc, int g) {
     Grp r; r.i = 0;
 #pragma unroll
     for (int i = 1; i < MK_MAX_MATS; i++) if (g >= pc->gbase[i]) r.i = i;
     // gbase[] is non-decreasing (empty matrices repeat the next base): the last i with gbase[i] <= g owns group g
     r.type = M->mat[r.i].type;
-    const int ppg = ppg_of(r.type);
-    r.pair0 = pc->pstart[r.i] + (g - pc->gbase[r.i]) * ppg;
-    r.np = pc->pend[r.i] - r.pair0; if (r.np > ppg) r.np = ppg;
+    r.S = S_of(r.type, M->k >> 8);
+    r.ppg = (r.type == B200_TYPE_Q4_K ? 32 : 16) / r.S;
+    r.pair0 = pc->pstart[r.i] + (g - pc->gbase[r.i]) * r.ppg;
+    r.np = pc->pend[r.i] - r.pair0; if (r.np > r.ppg) r.np = r.ppg;
     return r;
 }
 
-// one ring slot = the 2048-element step `step` of every row of group g, rows packed at 1152 (Q4_K) / 1680 (Q6_K) bytes
+// one ring slot = step `step` (S super-blocks) of every row of group g.  Rows sit at rowbytes = S*144 (Q4_K) or S*210
+// (Q6_K, as ql[S*128] | qh[S*64] | scales[S*16] | d[S*2]); pair j's rows are slot rows 2j, 2j+1 — or j and ppg + j for a
+// gate/up pair, so that each matrix's rows stay one contiguous range.
 __device__ __forceinline__ void mk_issue(const MkMmv * M, const PCache * pc, int g, int step, uint8_t * slot, uint64_t * bar, int lane) {
     const Grp gr = mk_locate(M, pc, g);
     const int rows = 2 * gr.np;
     const int nb = M->k >> 8;
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(rows * (gr.type == B200_TYPE_Q4_K ? 1152 : 1680)));
+    const int rowbytes = rowbytes_of(gr.type, gr.S);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(rows * rowbytes));
     __syncwarp();
+    if (gr.S == nb) {
+        // whole rows: the group's rows are contiguous in the matrix
+        if (M->swiglu) {
+            if (lane < 2) bulk_g2s(slot + lane * gr.ppg * rowbytes, M->mat[lane].W + (int64_t)gr.pair0 * M->mat[lane].rb, (uint32_t)(gr.np * rowbytes), bar);
+        } else if (lane == 0) {
+            bulk_g2s(slot, M->mat[gr.i].W + (int64_t)(2 * gr.pair0) * M->mat[gr.i].rb, (uint32_t)(rows * rowbytes), bar);
+        }
+        return;
+    }
     if (gr.type == B200_TYPE_Q4_K) {
         if (lane < rows) {
-            const MkMat & mt = M->swiglu ? M->mat[lane & 1] : M->mat[gr.i];
-            const int64_t row = M->swiglu ? gr.pair0 + (lane >> 1) : 2 * gr.pair0 + lane;
-            bulk_g2s(slot + lane * 1152, mt.W + row * mt.rb + (int64_t)step * 1152, 1152, bar);
+            const int pj = lane >> 1, rr = lane & 1;
+            const MkMat & mt = M->swiglu ? M->mat[rr] : M->mat[gr.i];
+            const int64_t row = M->swiglu ? gr.pair0 + pj : 2 * gr.pair0 + lane;
+            const int srow = M->swiglu ? pj + rr * gr.ppg : lane;
+            bulk_g2s(slot + srow * 1152, mt.W + row * mt.rb + (int64_t)step * 1152, 1152, bar);
         }
     } else {
         if (lane < rows * 4) {
             const int r = lane >> 2, part = lane & 3;
-            const MkMat & mt = M->swiglu ? M->mat[r & 1] : M->mat[gr.i];
-            const int64_t row = M->swiglu ? gr.pair0 + (r >> 1) : 2 * gr.pair0 + r;
+            const int pj = r >> 1, rr = r & 1;
+            const MkMat & mt = M->swiglu ? M->mat[rr] : M->mat[gr.i];
+            const int64_t row = M->swiglu ? gr.pair0 + pj : 2 * gr.pair0 + r;
+            const int srow = M->swiglu ? pj + rr * gr.ppg : r;
             const uint8_t * rb = mt.W + row * mt.rb;
             // repacked Q6_K row: ql[nb*128] | qh[nb*64] | scales[nb*16] | d[nb*2]   (repack.cu)
             const int64_t soff = part == 0 ? (int64_t)step * 1024 : part == 1 ? (int64_t)nb * 128 + step * 512 : part == 2 ? (int64_t)nb * 192 + step * 128 : (int64_t)nb * 208 + step * 16;
             const int doff = part == 0 ? 0 : part == 1 ? 1024 : part == 2 ? 1536 : 1664;
             const uint32_t bytes = part == 0 ? 1024u : part == 1 ? 512u : part == 2 ? 128u : 16u;
-            bulk_g2s(slot + r * 1680 + doff, rb + soff, bytes, bar);
+            bulk_g2s(slot + srow * 1680 + doff, rb + soff, bytes, bar);
         }
     }
 }
@@ -251,13 +278,13 @@ __device__ __forceinline__ bool cur_seek(Cur & c, int n_phases, const PCache * t
     while (c.p < n_phases) {
         if (tab_phase[c.p % MK_TAB] != c.p) return false;
         const PCache * pc = &tab[c.p % MK_TAB];
-        if (pc->kind == MK_MMV && warp < pc->ngroups) { c.g = warp; c.s = 0; c.nsteps = pc->m.k >> 11; c.entered = 1; return true; }
+        if (pc->ph.kind == MK_MMV && warp < pc->ngroups) { c.g = warp; c.s = 0; c.entered = 1; return true; }
         c.p++;
     }
     return false;
 }
-__device__ __forceinline__ void cur_advance(Cur & c, const PCache * pc, int nw) {
-    if (++c.s < c.nsteps) return;
+__device__ __forceinline__ void cur_advance(Cur & c, const PCache * pc, int nsteps, int nw) {
+    if (++c.s < nsteps) return;
     c.s = 0; c.g += nw;
     if (c.g < pc->ngroups) return;
     c.p++; c.entered = 0;
@@ -270,24 +297,29 @@ __device__ __forceinline__ void mk_pump(Cur & ic, int & nissued, int ncons, int 
         if (ic.p > plimit) break;
         const PCache * pc = &tab[ic.p % MK_TAB];
         const int ipos = nissued & 1;
-        mk_issue(&pc->m, pc, ic.g, ic.s, ring + ipos * MK_SLOT_BYTES, &full[ipos], lane);
-        cur_advance(ic, pc, nw);
+        mk_issue(&pc->ph.mmv, pc, ic.g, ic.s, ring + ipos * MK_SLOT_BYTES, &full[ipos], lane);
+        { const Grp gi = mk_locate(&pc->ph.mmv, pc, ic.g); cur_advance(ic, pc, (pc->ph.mmv.k >> 8) / gi.S, nw); }
         nissued++;
     }
 }
 
 // ---- Q4_K: lane = (pair lg = lane>>3, super-block sb = lane&7) of the slot; both rows of the pair ------------------
-__device__ __forceinline__ void mk_dot_q4K(const uint8_t * slot, const uint8_t * act, int k, int step, int lane, float & acc0, float & acc1) {
-    const int lg = lane >> 3, sb = lane & 7;
-    const int nsb = k >> 8, gsb = step * 8 + sb;
-    const uint8_t * r0 = slot + (2 * lg) * 1152 + sb * 144;
+// S super-blocks per slot row (8 | 16 | 32); the pair's second row sits `rstride` bytes after the first (row-interleaved
+// pairs: one row; gate/up pairs: ppg rows)
+template <int S>
+__device__ __forceinline__ void mk_dot_q4K(const uint8_t * slot, const uint8_t * act, int k, int step, int lane, bool glu, float & acc0, float & acc1) {
+    constexpr int RB = S * 144, PPG = 32 / S;
+    const int lg = lane / S, sb = lane % S;
+    const int nsb = k >> 8, gsb = step * S + sb;
+    const int rstride = glu ? PPG * RB : RB;
+    const uint8_t * r0 = slot + (glu ? lg : 2 * lg) * RB + sb * 144;
     const uint8_t * aq = act + gsb * 256;
     const float da = ((const float *)(act + k))[gsb];
     const uint4 s32 = *(const uint4 *)(act + k + 36 * nsb + gsb * 16);
     uint32_t sc03[2], sc47[2], mn03[2], mn47[2]; float dw[2], dm[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const uint4 hdr = *(const uint4 *)(r0 + r * 1152);
+        const uint4 hdr = *(const uint4 *)(r0 + r * rstride);
         const uint32_t y = hdr.y, z = hdr.z, w = hdr.w;              // 6-bit scales / mins (ggml-quants.c:703-711), SIMD decode
         sc03[r] = y & 0x3f3f3f3fu; mn03[r] = z & 0x3f3f3f3fu;
         sc47[r] = (w & 0x0f0f0f0fu) | ((y >> 2) & 0x30303030u);
@@ -299,10 +331,10 @@ __device__ __forceinline__ void mk_dot_q4K(const uint8_t * slot, const uint8_t *
     for (int g = 0; g < 4; g++) {
         uint4 a[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { const int idx = 4 * g + j; a[j] = *(const uint4 *)(aq + (((idx ^ ((idx & 8) >> 1)) ^ sb) << 4)); }
+        for (int j = 0; j < 4; j++) { const int idx = 4 * g + j; a[j] = *(const uint4 *)(aq + (((idx ^ ((idx & 8) >> 1)) ^ (sb & 7)) << 4)); }
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            const uint8_t * rr = r0 + r * 1152 + 16 + 32 * g;
+            const uint8_t * rr = r0 + r * rstride + 16 + 32 * g;
             const uint4 q0 = *(const uint4 *)rr, q1 = *(const uint4 *)(rr + 16);
             int dl = dot16m(q0, a[0], 0x0F0F0F0Fu, 0); dl = dot16m(q1, a[1], 0x0F0F0F0Fu, dl);
             int dh = dot16m(q0, a[2], 0xF0F0F0F0u, 0); dh = dot16m(q1, a[3], 0xF0F0F0F0u, dh);
@@ -324,35 +356,38 @@ __device__ __forceinline__ void mk_dot_q4K(const uint8_t * slot, const uint8_t *
 }
 
 // ---- Q6_K: lane = (pair lg = lane>>4, super-block sb = (lane>>1)&7, half h = lane&1) ---------------------------------
-__device__ __forceinline__ void mk_dot_q6K(const uint8_t * slot, const uint8_t * act, int k, int step, int lane, float & acc0, float & acc1) {
-    const int lg = lane >> 4, sb = (lane >> 1) & 7, h = lane & 1;
-    const int nsb = k >> 8, gsb = step * 8 + sb;
+template <int S>
+__device__ __forceinline__ void mk_dot_q6K(const uint8_t * slot, const uint8_t * act, int k, int step, int lane, bool glu, float & acc0, float & acc1) {
+    constexpr int RB = S * 210, PPG = 16 / S;
+    const int lg = lane / (2 * S), sb = (lane >> 1) % S, h = lane & 1;
+    const int nsb = k >> 8, gsb = step * S + sb;
     const int rot = (0x78 >> (2 * (sb & 3))) & 3;                   // chunk order differs per lane: conflict-free LDS.128
-    const uint8_t * rb0 = slot + (2 * lg) * 1680;
+    const int rstride = glu ? PPG * RB : RB;
+    const uint8_t * rb0 = slot + (glu ? lg : 2 * lg) * RB;
     const uint8_t * aq = act + gsb * 256;
     const float da = ((const float *)(act + k))[gsb];
     const uint4 b16 = *(const uint4 *)(act + k + 4 * nsb + gsb * 32 + h * 16);
     uint2 scw[2]; float dw[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        scw[r] = *(const uint2 *)(rb0 + r * 1680 + 1536 + sb * 16 + h * 8);
-        dw[r]  = h2f(*(const uint16_t *)(rb0 + r * 1680 + 1664 + sb * 2));
+        scw[r] = *(const uint2 *)(rb0 + r * rstride + S * 192 + sb * 16 + h * 8);
+        dw[r]  = h2f(*(const uint16_t *)(rb0 + r * rstride + S * 208 + sb * 2));
     }
     int isum[2] = { 0, 0 };
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const int cp = c ^ rot, which = cp >> 1;
         const int ilo = 8 * h + cp;
-        const uint4 Alo = *(const uint4 *)(aq + ((ilo ^ sb ^ (4 * h)) << 4));
-        const uint4 Ahi = *(const uint4 *)(aq + (((ilo + 4) ^ sb ^ (4 * h)) << 4));
+        const uint4 Alo = *(const uint4 *)(aq + ((ilo ^ (sb & 7) ^ (4 * h)) << 4));
+        const uint4 Ahi = *(const uint4 *)(aq + (((ilo + 4) ^ (sb & 7) ^ (4 * h)) << 4));
         const int shl = 2 * which;
         const uint32_t mlo = 0x03030303u << shl, mhi = mlo << 4;
         const uint32_t sel_lo = (uint32_t)cp | ((uint32_t)(cp | 8) * 0x1110u), sel_hi = sel_lo + 0x4444u;   // sign-extending byte select
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            const uint8_t * rb = rb0 + r * 1680;
+            const uint8_t * rb = rb0 + r * rstride;
             const uint4 QL = *(const uint4 *)(rb + sb * 128 + h * 64 + cp * 16);
-            const uint4 QH = *(const uint4 *)(rb + 1024 + sb * 64 + h * 32 + (cp & 1) * 16);
+            const uint4 QH = *(const uint4 *)(rb + S * 128 + sb * 64 + h * 32 + (cp & 1) * 16);
             const int dlo = dot16m(QL, Alo, 0x0F0F0F0Fu, 0), dloh = dot16m(QH, Alo, mlo, 0) >> shl;
             const int dhi = dot16m(QL, Ahi, 0xF0F0F0F0u, 0) >> 4, dhih = dot16m(QH, Ahi, mhi, 0) >> (shl + 4);
             const int sclo = prmt(scw[r].x, scw[r].y, sel_lo), schi = prmt(scw[r].x, scw[r].y, sel_hi);
@@ -374,11 +409,13 @@ __device__ __forceinline__ void mk_dot_q6K(const uint8_t * slot, const uint8_t *
 __device__ __forceinline__ void mk_mmv_phase(int n_phases, int p, const uint8_t * act, uint8_t * ring, uint64_t * full, const PCache * tab, const volatile int * tab_phase,
                                              Cur & ic, int & ncons, int & nissued, int plimit, int warp, int lane, int nw, unsigned int * stats) {
     const PCache * cpc = &tab[p % MK_TAB];
-    const MkMmv * M = &cpc->m;                                      // shared-memory copy
-    const int k = M->k, nsteps = k >> 11;
+    const MkMmv * M = &cpc->ph.mmv;                                 // shared-memory copy
+    const int k = M->k;
     const int ng = cpc->ngroups;
+    const bool glu = M->swiglu != 0;
     for (int g = warp; g < ng; g += nw) {
         const Grp gr = mk_locate(M, cpc, g);
+        const int nsteps = (k >> 8) / gr.S;
         float acc0 = 0.0f, acc1 = 0.0f;
         for (int step = 0; step < nsteps; step++) {
             const int pos = ncons & 1;
@@ -386,8 +423,14 @@ __device__ __forceinline__ void mk_mmv_phase(int n_phases, int p, const uint8_t 
             mbar_wait(&full[pos], (uint32_t)((ncons >> 1) & 1));
             const long long c1 = stats ? clock64() : 0;
             uint8_t * slot = ring + pos * MK_SLOT_BYTES;
-            if (gr.type == B200_TYPE_Q4_K) mk_dot_q4K(slot, act, k, step, lane, acc0, acc1);
-            else                           mk_dot_q6K(slot, act, k, step, lane, acc0, acc1);
+            if (gr.type == B200_TYPE_Q4_K) {
+                if (gr.S == 8) mk_dot_q4K<8>(slot, act, k, step, lane, glu, acc0, acc1);
+                else if (gr.S == 16) mk_dot_q4K<16>(slot, act, k, step, lane, glu, acc0, acc1);
+                else mk_dot_q4K<32>(slot, act, k, step, lane, glu, acc0, acc1);
+            } else {
+                if (gr.S == 8) mk_dot_q6K<8>(slot, act, k, step, lane, glu, acc0, acc1);
+                else mk_dot_q6K<16>(slot, act, k, step, lane, glu, acc0, acc1);
+            }
             __syncwarp();                                           // every lane is done reading the slot
             const long long c2 = stats ? clock64() : 0;
             ncons++;
@@ -395,11 +438,11 @@ __device__ __forceinline__ void mk_mmv_phase(int n_phases, int p, const uint8_t 
             if (stats && lane == 0) { atomicAdd(stats + 0, (unsigned int)(c1 - c0)); atomicAdd(stats + 1, (unsigned int)(c2 - c1)); atomicAdd(stats + 2, (unsigned int)(clock64() - c2)); atomicAdd(stats + 3, 1u); }
         }
         // reduce over the lanes of each pair, then bias / residual / SwiGLU
-        const int lgw = gr.type == B200_TYPE_Q4_K ? 8 : 16;
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
-        if (lgw == 16) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, 8); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8); }
+        const int lgw = 32 / gr.ppg;                              // lanes per pair: 8, 16 or 32
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            if (o < lgw) { acc0 += __shfl_xor_sync(0xffffffffu, acc0, o); acc1 += __shfl_xor_sync(0xffffffffu, acc1, o); }
+        }
         const int pl = lane / lgw;
         if ((lane & (lgw - 1)) == 0 && pl < gr.np) {
             const int pair = gr.pair0 + pl;
@@ -547,58 +590,80 @@ __device__ __noinline__ void mk_attn(const MkAttn * Ap, uint8_t * scr, int nw) {
         const unsigned gmask = (LP == 32 ? 0xffffffffu : ((1u << LP) - 1u)) << (sg * LP);
         const int p_begin = split * split_len;
         const int p_end   = min(n_kv, p_begin + split_len);
-        for (int p = p_begin + warp * PPW + sg; p < p_end; p += nw * PPW) {
-            const float mraw = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
-            if (mraw == -INFINITY && max_bias <= 0.0f) continue;
-            const uint8_t * krow = p == kcell ? newk : kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
-            const uint8_t * vrow = p == vcell ? newv : vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
-            float kf[8], vf[8]; int kq[2]; float kd = 0.0f;
-            if (KVT == B200_TYPE_F16) {
-                unpack_h8(p == kcell ? *(const uint4 *)(krow + dl * 16) : ldg_stream16(krow + dl * 16), kf);
-                unpack_h8(p == vcell ? *(const uint4 *)(vrow + dl * 16) : ldg_stream16(vrow + dl * 16), vf);
-            } else {
-                load_q80_8(krow, dl, kq, kd);
-                int vq[2]; float vd;
-                load_q80_8(vrow, dl, vq, vd);
+        // positions are visited in chunks of MAXIT per lane group: all loads of a chunk (mask, K, V) are issued before any
+        // arithmetic, so a chunk costs ONE memory round trip (the phase sits on the token's critical path, and under full
+        // weight streaming a DRAM round trip is several microseconds).  K/V of masked positions are loaded but never used.
+        constexpr int MAXIT = 4;
+        const int pstride = nw * PPW;
+        for (int base = p_begin + warp * PPW + sg; base < p_end; base += pstride * MAXIT) {
+            float mraw[MAXIT]; uint4 kraw[MAXIT], vraw[MAXIT]; float kdv[MAXIT], vdv[MAXIT];
 #pragma unroll
-                for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)((vq[e >> 2] >> (8 * (e & 3))) & 0xff), vd);
-            }
-            float s[G];
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (KVT == B200_TYPE_F16) {
-                    float a = 0.0f;
-#pragma unroll
-                    for (int e = 0; e < 8; e++) a = fmaf(kf[e], qf[g][e], a);
-#pragma unroll
-                    for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
-                    s[g] = a;
-                } else {
-                    int is = dp4a_s(kq[0], qi[g][0], 0);
-                    is = dp4a_s(kq[1], qi[g][1], is);
-                    is += __shfl_xor_sync(gmask, is, 1, LP);
-                    is += __shfl_xor_sync(gmask, is, 2, LP);
-                    float a = __fmul_rn((float)is, __fmul_rn(kd, qd[g]));      // ggml-cpu/quants.c:305-333
-                    a = (dl & 3) == 0 ? a : 0.0f;
-#pragma unroll
-                    for (int o = LP / 2; o >= 4; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
-                    s[g] = __shfl_sync(gmask, a, 0, LP);
+            for (int it = 0; it < MAXIT; it++) {
+                const int p = base + it * pstride;
+                mraw[it] = -INFINITY; kraw[it] = make_uint4(0, 0, 0, 0); vraw[it] = kraw[it]; kdv[it] = 0.0f; vdv[it] = 0.0f;
+                if (p < p_end) {
+                    mraw[it] = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
+                    const uint8_t * krow = p == kcell ? newk : kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
+                    const uint8_t * vrow = p == vcell ? newv : vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
+                    if (KVT == B200_TYPE_F16) {
+                        kraw[it] = p == kcell ? *(const uint4 *)(krow + dl * 16) : ldg_stream16(krow + dl * 16);
+                        vraw[it] = p == vcell ? *(const uint4 *)(vrow + dl * 16) : ldg_stream16(vrow + dl * 16);
+                    } else {
+                        int q2[2];
+                        load_q80_8(krow, dl, q2, kdv[it]); kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1];
+                        load_q80_8(vrow, dl, q2, vdv[it]); vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1];
+                    }
                 }
             }
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                float sv = s[g] * scale;
-                if (softcap != 0.0f) sv = softcap * tanhf(sv);
-                sv += slope[g] * mraw;
-                if (sv == -INFINITY) continue;
-                float ms = 1.0f, vs = 1.0f;
-                if (sv > M[g]) { ms = expf(M[g] - sv); M[g] = sv;
+            for (int it = 0; it < MAXIT; it++) {
+                if (mraw[it] == -INFINITY && max_bias <= 0.0f) continue;            // masked or beyond the split (uniform inside the lane group)
+                if (base + it * pstride >= p_end) continue;
+                float kf[8], vf[8];
+                if (KVT == B200_TYPE_F16) {
+                    unpack_h8(kraw[it], kf);
+                    unpack_h8(vraw[it], vf);
+                } else {
 #pragma unroll
-                    for (int e = 0; e < 8; e++) acc[g][e] *= ms;
-                } else vs = expf(sv - M[g]);
+                    for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)(((e < 4 ? vraw[it].x : vraw[it].y) >> (8 * (e & 3))) & 0xff), vdv[it]);
+                }
+                float s[G];
 #pragma unroll
-                for (int e = 0; e < 8; e++) acc[g][e] = fmaf(vf[e], vs, acc[g][e]);
-                L[g] = L[g] * ms + vs;
+                for (int g = 0; g < G; g++) {
+                    if (KVT == B200_TYPE_F16) {
+                        float a = 0.0f;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) a = fmaf(kf[e], qf[g][e], a);
+#pragma unroll
+                        for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
+                        s[g] = a;
+                    } else {
+                        int is = dp4a_s((int)kraw[it].x, qi[g][0], 0);
+                        is = dp4a_s((int)kraw[it].y, qi[g][1], is);
+                        is += __shfl_xor_sync(gmask, is, 1, LP);
+                        is += __shfl_xor_sync(gmask, is, 2, LP);
+                        float a = __fmul_rn((float)is, __fmul_rn(kdv[it], qd[g]));      // ggml-cpu/quants.c:305-333
+                        a = (dl & 3) == 0 ? a : 0.0f;
+#pragma unroll
+                        for (int o = LP / 2; o >= 4; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
+                        s[g] = __shfl_sync(gmask, a, 0, LP);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    float sv = s[g] * scale;
+                    if (softcap != 0.0f) sv = softcap * tanhf(sv);
+                    sv += slope[g] * mraw[it];
+                    if (sv == -INFINITY) continue;
+                    float ms = 1.0f, vs = 1.0f;
+                    if (sv > M[g]) { ms = expf(M[g] - sv); M[g] = sv;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) acc[g][e] *= ms;
+                    } else vs = expf(sv - M[g]);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) acc[g][e] = fmaf(vf[e], vs, acc[g][e]);
+                    L[g] = L[g] * ms + vs;
+                }
             }
         }
         // merge the position groups of the warp, then the warps
@@ -650,9 +715,11 @@ __device__ __noinline__ void mk_attn(const MkAttn * Ap, uint8_t * scr, int nw) {
             __syncthreads();
             if (*s_last) {
                 __threadfence();
+                float * s_l = sA;                                   // [n_splits][G] partial sums (the merge buffer is free now)
                 for (int idx = threadIdx.x; idx < n_splits * G; idx += nw * 32) {
                     const int sp = idx / G, g = idx % G;
-                    s_sc[sp * G + g] = __ldcg(ws + ((int64_t)sp * n_head + h0 + g) * (D + 2) + D);
+                    const float2 ml = __ldcg((const float2 *)(ws + ((int64_t)sp * n_head + h0 + g) * (D + 2) + D));   // all (m, l) pairs in one round trip
+                    s_sc[sp * G + g] = ml.x; s_l[sp * G + g] = ml.y;
                 }
                 __syncthreads();
                 if (threadIdx.x < G) {
@@ -663,7 +730,7 @@ __device__ __noinline__ void mk_attn(const MkAttn * Ap, uint8_t * scr, int nw) {
                     for (int sp = 0; sp < n_splits; sp++) {
                         const float m = s_sc[sp * G + g];
                         const float sc = m == -INFINITY ? 0.0f : expf(m - Mn);
-                        l += __ldcg(ws + ((int64_t)sp * n_head + h0 + g) * (D + 2) + D + 1) * sc;
+                        l += s_l[sp * G + g] * sc;
                         s_sc[sp * G + g] = sc;
                     }
                     s_inv[g] = 1.0f / l;
@@ -686,9 +753,13 @@ __device__ __noinline__ void mk_attn(const MkAttn * Ap, uint8_t * scr, int nw) {
 template <int D, int KVT>
 __device__ __forceinline__ void mk_attn_g(const MkAttn * A, uint8_t * scr, int nw) {
     const int gq = A->n_head / A->n_head_kv;
+#ifdef MK_SLIM        // experiment: only the Llama-3-8B variant (code-size / instruction-cache study)
+    mk_attn<D, KVT, 4>(A, scr, nw);
+#else
     if (gq % 4 == 0) mk_attn<D, KVT, 4>(A, scr, nw);
     else if (gq % 2 == 0) mk_attn<D, KVT, 2>(A, scr, nw);
     else mk_attn<D, KVT, 1>(A, scr, nw);
+#endif
 }
 
 __global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase * __restrict__ prog, int n_phases, unsigned long long * sync, unsigned long long * trace, int tune) {
@@ -705,13 +776,13 @@ __global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase 
     mbar_fence_init();
     __syncthreads();
 
-    // phase table: entries 0..2 now, entry p+2 at the start of phase p (by warp p % nw)
+    // phase table: entries 0..2 now; entry p + 3 is fetched at the start of phase p and finished at its end (last warp)
     if (tid < MK_TAB) tab_phase[tid] = -1;
     __syncthreads();
-    if (warp < 3 && warp < n_phases) mk_plan(prog, warp, tab, tab_phase, lane);
+    if (warp < 3 && warp < n_phases) { mk_plan_begin(prog, warp, tab, lane); mk_plan_finish(warp, tab, tab_phase, lane); }
     __syncthreads();
     // issue cursor: runs up to two ring slots ahead of consumption, across phase boundaries (weights do not depend on activations)
-    Cur ic; ic.p = 0; ic.g = 0; ic.s = 0; ic.nsteps = 1; ic.entered = 0;
+    Cur ic; ic.p = 0; ic.g = 0; ic.s = 0; ic.entered = 0;
     int ncons = 0, nissued = 0;
     const bool xphase = !(tune & 16);
     if (xphase) mk_pump(ic, nissued, ncons, n_phases, n_phases, tab, tab_phase, ring, full_bar[warp], warp, lane, nw);
@@ -721,19 +792,39 @@ __global__ void __launch_bounds__(MK_MAX_WARPS * 32, 1) mk_kernel(const MkPhase 
         if (trace && tid == 0) trace[((size_t)blockIdx.x * n_phases + p) * 4 + 1] = gtimer();
         const int plimit = xphase ? n_phases : p;
         const PCache * cpc = &tab[p % MK_TAB];
-        // first this warp's own refills (phase p is planned), then the planning of phase p + 2 by one warp
+        // first this warp's own refills (phases up to p + 2 are planned)
         mk_pump(ic, nissued, ncons, plimit, n_phases, tab, tab_phase, ring, full_bar[warp], warp, lane, nw);
-        if (p > 0 && p + 2 < n_phases && warp == p % nw) mk_plan(prog, p + 2, tab, tab_phase, lane);
-        if (cpc->kind == MK_MMV) {
-            mk_build_act(&cpc->m, act, red, warp, lane, nw);
+        const bool planner = warp == nw - 1 && p + 3 < n_phases;
+        if (planner) mk_plan_begin(prog, p + 3, tab, lane);
+        // the KV rows the NEXT phase (attention) will read: each CTA warms its share of the range in L2 now, one phase early
+        if (warp == nw - 2 && lane < 2 && p + 1 < n_phases && cpc->ph.kind == MK_MMV && tab_phase[(p + 1) % MK_TAB] == p + 1 && tab[(p + 1) % MK_TAB].ph.kind == MK_ATTN) {
+            const MkAttn * An = &tab[(p + 1) % MK_TAB].ph.attn;
+            const int64_t rs = lane == 0 ? An->k_rs : An->v_rs;
+            const uint8_t * base = lane == 0 ? An->k_cache : An->v_cache;
+            const int64_t total = (int64_t)An->n_kv * rs;
+            const int64_t share = ((total + gridDim.x - 1) / gridDim.x + 15) & ~(int64_t)15;
+            const int64_t lo = share * blockIdx.x;
+            if (lo < total && (((uintptr_t)base | (uintptr_t)rs) & 15) == 0) {
+                int64_t n = total - lo < share ? total - lo : share;
+                n &= ~(int64_t)15;
+                if (n > 0) bulk_prefetch_l2(base + lo, (uint32_t)n);
+            }
+        }
+        if (cpc->ph.kind == MK_MMV) {
+            mk_build_act(&cpc->ph.mmv, act, red, warp, lane, nw);
             if (trace && tid == 0) trace[((size_t)blockIdx.x * n_phases + p) * 4 + 2] = gtimer();
             mk_mmv_phase(n_phases, p, act, ring, full_bar[warp], tab, tab_phase, ic, ncons, nissued, plimit, warp, lane, nw, trace ? wstats : nullptr);
         } else {
             if (trace && tid == 0) trace[((size_t)blockIdx.x * n_phases + p) * 4 + 2] = gtimer();
-            const MkAttn * A = &prog[p].attn;
+            const MkAttn * A = &cpc->ph.attn;                     // shared-memory copy
+#ifdef MK_SLIM
+            mk_attn_g<128, B200_TYPE_F16>(A, act, nw);
+#else
             if (A->hd == 128) { if (A->kv_type == B200_TYPE_F16) mk_attn_g<128, B200_TYPE_F16>(A, act, nw); else mk_attn_g<128, B200_TYPE_Q8_0>(A, act, nw); }
             else              { if (A->kv_type == B200_TYPE_F16) mk_attn_g<64,  B200_TYPE_F16>(A, act, nw); else mk_attn_g<64,  B200_TYPE_Q8_0>(A, act, nw); }
+#endif
         }
+        if (planner) mk_plan_finish(p + 3, tab, tab_phase, lane);
         if (trace) { __syncthreads(); if (tid == 0) { trace[((size_t)blockIdx.x * n_phases + p) * 4 + 3] = gtimer();
             unsigned long long * ext = trace + (size_t)gridDim.x * 512 * 4 + ((size_t)blockIdx.x * n_phases + p) * 4;
             ext[0] = wstats[0]; ext[1] = wstats[1]; ext[2] = wstats[2]; ext[3] = wstats[3]; } }

@@ -141,7 +141,7 @@ struct b200_executor {
     std::unordered_map<uint64_t, int> seen;      // topology -> times seen before capture (first sighting runs eagerly)
     uint64_t tick = 0;
     int64_t last_kernels = 0, captures = 0, replays = 0;
-    bool env_no_graphs = false, env_no_fusion = false, env_no_mega = false;
+    bool env_no_graphs = false, env_no_fusion = false, env_no_mega = false, env_mega = false, env_mega_mmv = false;
     // persistent decode kernel (decode_mk.cu): compiled phase programs, resident on the device, keyed by content
     struct DevProg { MkPhase * dev = nullptr; MkPhase * host = nullptr; int n = 0; };
     std::unordered_map<uint64_t, DevProg> progs;
@@ -156,7 +156,7 @@ struct Runner {
     std::vector<uint8_t> done;
     std::unordered_map<uint64_t, int> uses;
     // ---- persistent decode kernel: phases recorded instead of launched, flushed as ONE launch ----------------
-    bool mega = false;
+    bool mega = false, mega_mmv = false;
     std::vector<MkPhase> pend;
     struct RopePend { bool valid = false; const float * q_src; float * q_dst; const float * k, * v; const int32_t * pos; const float * ff;
                       const int64_t * k_ids, * v_ids; void * k_cache, * v_cache; int kv_type; int64_t k_rs, v_rs, hd, nh, nhk; b200_rope_params p; } rope_pend;
@@ -194,7 +194,7 @@ struct Runner {
     int mk_flush_rope_only() { return rope_pend.valid ? mk_flush() : B200_OK; }
     // a decode matvec launch as a phase of the persistent kernel (Q4_K / Q6_K, one column, in-kernel activation)
     bool mk_try_mmv(const b200_mmv_launch & L) {
-        if (!mega || L.ncols != 1 || (L.act_source != 1 && L.act_source != 2) || L.y_out || !mk_phase_ok_k(L.k, L.act_source) || L.n_mats < 1 || L.n_mats > MK_MAX_MATS) return false;
+        if (!mega || !mega_mmv || L.ncols != 1 || (L.act_source != 1 && L.act_source != 2) || L.y_out || !mk_phase_ok_k(L.k, L.act_source) || L.n_mats < 1 || L.n_mats > MK_MAX_MATS) return false;
         for (int q = 0; q < L.n_mats; q++) {
             const b200_mmv_desc & d = L.mats[q];
             if ((d.type != B200_TYPE_Q4_K && d.type != B200_TYPE_Q6_K) || d.m <= 0 || (d.m & 1) || d.m > 0x7fffffff || !d.W || !d.dst) return false;
@@ -221,9 +221,9 @@ struct Runner {
         if (s != B200_OK) return s;
         return b200_mul_mat_vec_q_launch(&L, st);
     }
-    // FLASH_ATTN_EXT right after the recorded rope + KV store of the same token: one fused attention phase
-    bool mk_try_attn(const b200_node & n) {
-        if (!mega || !rope_pend.valid) return false;
+    // does this FLASH_ATTN_EXT consume exactly what the recorded rope + KV store of the same token produces?
+    bool attn_matches(const b200_node & n) const {
+        if (!rope_pend.valid) return false;
         const RopePend & r = rope_pend;
         const b200_tensor & q = n.src[0], & k = n.src[1], & v = n.src[2];
         if (q.data != r.q_dst || q.ne[1] != 1 || q.ne[0] != r.hd || q.ne[2] != r.nh || q.nb[2] != r.hd * 4) return false;
@@ -231,6 +231,23 @@ struct Runner {
         if (r.hd != 64 && r.hd != 128) return false;
         const int64_t hs = r.kv_type == B200_TYPE_F16 ? r.hd * 2 : r.hd / 32 * 34;      // heads contiguous inside a cell, as SET_ROWS wrote them
         if (k.nb[2] != hs || v.nb[2] != hs || n.dst.type != B200_TYPE_F32 || !contiguous(n.dst)) return false;
+        return true;
+    }
+    // ... as one launch of the split-KV attention kernel (fattn.cu, FaFuse)
+    int launch_fused_attn(const b200_node & n) {
+        const RopePend r = rope_pend;
+        rope_pend.valid = false;
+        const int fs = mk_flush(); if (fs != B200_OK) return fs;
+        const b200_tensor & k = n.src[1], & v = n.src[2];
+        const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
+        return b200_rope_kv_flash_attn(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, k.nb[1], k.nb[2], v.nb[1], v.nb[2],
+                                       mask, (float *)n.dst.data, r.hd, r.nh, r.nhk, k.ne[1], &r.p, f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st);
+    }
+    // ... or as a phase of the persistent kernel
+    bool mk_try_attn(const b200_node & n) {
+        if (!mega || !attn_matches(n)) return false;
+        const RopePend & r = rope_pend;
+        const b200_tensor & k = n.src[1], & v = n.src[2];
         const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
         const int64_t n_kv = k.ne[1];
         const int64_t gq = r.nh / r.nhk;
@@ -239,7 +256,7 @@ struct Runner {
         int64_t want = b200_sm_count() / n_tiles; if (want < 1) want = 1;
         int64_t maxs = (n_kv + 31) / 32; if (maxs > 64) maxs = 64;
         if (want > maxs) want = maxs;
-        int64_t len = (n_kv + want - 1) / want; len = (len + 31) / 32 * 32;
+        int64_t len = (n_kv + want - 1) / want; len = (len + 3) / 4 * 4;
         const int64_t n_splits = (n_kv + len - 1) / len;
         if (n_tiles * (int64_t)sizeof(unsigned int) > 256 * 1024) return false;
         MkPhase ph; memset(&ph, 0, sizeof(ph));
@@ -484,8 +501,8 @@ struct Runner {
         p.freq_base = f32_param(rq, 5); p.freq_scale = f32_param(rq, 6); p.ext_factor = f32_param(rq, 7);
         p.attn_factor = f32_param(rq, 8); p.beta_fast = f32_param(rq, 9); p.beta_slow = f32_param(rq, 10);
         const float * ff = rq.n_src > 2 ? (const float *)rq.src[2].data : nullptr;
-        if (mega && nt == 1 && (hd == 64 || hd == 128) && rq.dst.data && (p.mode & ~2) == 0 && p.n_dims <= hd && p.n_dims % 8 == 0 && (p.mode != 2 || p.n_dims % 16 == 0)) {
-            // decode token inside the persistent kernel: recorded, and merged with the FLASH_ATTN_EXT that follows
+        if (nt == 1 && (hd == 64 || hd == 128) && rq.dst.data && (p.mode & ~2) == 0 && p.n_dims <= hd && p.n_dims % 8 == 0 && (p.mode != 2 || p.n_dims % 16 == 0)) {
+            // decode token: recorded, and merged with the FLASH_ATTN_EXT that follows (one fused launch, or a phase of the persistent kernel)
             last_status = mk_flush_rope_only();
             RopePend & r = rope_pend;
             r.valid = true; r.q_src = (const float *)q.data; r.q_dst = (float *)rq.dst.data; r.k = (const float *)k.data; r.v = (const float *)v.data;
@@ -550,6 +567,7 @@ struct Runner {
                 const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
                 const int64_t mrs = mask ? n.src[3].nb[1] / 2 : 0;
                 if (mk_try_attn(n)) return B200_OK;
+                if (attn_matches(n)) return launch_fused_attn(n);
                 { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
                 return b200_flash_attn_ext((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
                                            (float *)n.dst.data, k.type, q.ne[0], v.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1],
@@ -645,6 +663,8 @@ extern "C" b200_executor * b200_executor_create(int device) {
     ex->env_no_graphs = getenv("GGML_B200_DISABLE_GRAPHS") != nullptr;
     ex->env_no_fusion = getenv("GGML_B200_DISABLE_FUSION") != nullptr;
     ex->env_no_mega   = getenv("GGML_B200_DISABLE_MEGAKERNEL") != nullptr;
+    ex->env_mega      = getenv("GGML_B200_MEGAKERNEL") != nullptr;       // opt-in for callers that cannot pass flags (the ggml plug-in)
+    ex->env_mega_mmv  = getenv("GGML_B200_MEGA_MMV") != nullptr;
     return ex;
 }
 
@@ -668,7 +688,8 @@ extern "C" int b200_executor_compute(b200_executor * ex, const b200_node * nodes
     if (s != B200_OK) return s;
     cudaStream_t st = (cudaStream_t)stream;
     Runner r{ ex, nodes, n_nodes, st, (flags & B200_EXEC_FUSION) && !ex->env_no_fusion, {}, {} };
-    r.mega = r.fuse && (flags & B200_EXEC_MEGAKERNEL) && !ex->env_no_mega;
+    r.mega = r.fuse && ((flags & B200_EXEC_MEGAKERNEL) || ex->env_mega) && !ex->env_no_mega;
+    r.mega_mmv = r.mega && ((flags & B200_EXEC_MEGA_MMV) || ex->env_mega_mmv);
 
     // CUDA graphs only pay for small-batch (decode / verify) lists; prefill lists are few big kernels
     bool small = true;

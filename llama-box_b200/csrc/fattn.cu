@@ -13,7 +13,9 @@
 // writes (m, l, acc) partials that a second kernel merges.  HBM-bound: bytes = K+V rows once per
 // head tile.
 #include "common.cuh"
+#include "ropeutil.cuh"
 #include <math.h>
+#include <string.h>
 
 #define FA_WARPS 4
 #define FA_MAX_SPLITS 64
@@ -34,6 +36,52 @@ __device__ __forceinline__ void load_q80_8(const uint8_t * row, int dl, int (&q)
     q[1] = (int)((uint32_t)__ldg(p + 2) | ((uint32_t)__ldg(p + 3) << 16));
 }
 
+// ---- decode fusion: ROPE(q), ROPE(k) -> K cache, v -> V cache and the attention itself in ONE launch ----------------
+// (replaces rope_norm/rope_neox x2 + k_set_rows x2 + flash_attn_vec + combine: ggml-cuda/rope.cu, set-rows.cu, fattn.cu).
+// Every CTA ropes the query heads of its tile on the fly and stages this token's K (roped) / V for its kv head in shared
+// memory in cache format; positions equal to the token's cell are read from there, so no CTA depends on another CTA's
+// cache write.  One CTA per kv head also writes the cell (and the roped Q, which the graph declares as an output).
+struct FaFuse {
+    const float * q_src; float * q_dst; const float * k_new; const float * v_new;
+    const int32_t * pos; const float * ff; const int64_t * k_ids; const int64_t * v_ids;
+    RopeDev rp; int enabled;
+};
+// elements e0..e0+7 of one head, roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled)
+__device__ __forceinline__ void load_roped8(const float * head, int e0, const float * cs, const RopeDev & rp, float (&v)[8]) {
+    const float4 a = *(const float4 *)(head + e0), b = *(const float4 *)(head + e0 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if (e0 >= rp.n_dims) return;
+    if (!rp.neox) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = (e0 >> 1) + j;
+            const float c = cs[2 * i], sn = cs[2 * i + 1], x0 = v[2 * j], x1 = v[2 * j + 1];
+            v[2 * j]     = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
+            v[2 * j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
+        }
+    } else {
+        const int half = rp.n_dims >> 1;
+        const bool first = e0 < half;
+        const int po = first ? e0 + half : e0 - half;
+        const float4 pa = *(const float4 *)(head + po), pb = *(const float4 *)(head + po + 4);
+        const float o[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int i = first ? e0 + j : e0 - half + j;
+            const float c = cs[2 * i], sn = cs[2 * i + 1];
+            v[j] = first ? __fsub_rn(__fmul_rn(v[j], c), __fmul_rn(o[j], sn)) : __fadd_rn(__fmul_rn(o[j], sn), __fmul_rn(v[j], c));
+        }
+    }
+}
+// 8 int8 of a q8_0 row in shared memory (34-byte blocks) + the block scale
+__device__ __forceinline__ void lds_q80_8(const uint8_t * row, int dl, int (&q)[2], float & d) {
+    const uint8_t * blk = row + (dl >> 2) * 34;
+    const uint16_t * p = (const uint16_t *)(blk + 2 + (dl & 3) * 8);
+    d = h2f(*(const uint16_t *)blk);
+    q[0] = (int)((uint32_t)p[0] | ((uint32_t)p[1] << 16));
+    q[1] = (int)((uint32_t)p[2] | ((uint32_t)p[3] << 16));
+}
+
 template <int D, int KVT, int G>
 __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         const float * __restrict__ q, int64_t q_ts, int64_t q_hs,
@@ -42,7 +90,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         const uint16_t * __restrict__ mask, int64_t mask_rs,
         float * __restrict__ dst, float * __restrict__ ws, unsigned int * __restrict__ counters,
         int n_head, int n_head_kv, int n_kv, int split_len, int n_splits,
-        float scale, float max_bias, float softcap, float m0, float m1, int nh_log2) {
+        float scale, float max_bias, float softcap, float m0, float m1, int nh_log2, const FaFuse fu) {
     constexpr int LP  = D / 8;          // lanes per position
     constexpr int PPW = 32 / LP;        // positions per warp step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -51,16 +99,50 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     const int gq = n_head / n_head_kv;                  // query heads per kv head
     const int h0 = tile * G;                            // first query head of this tile
     const int hk = h0 / gq;
+    __shared__ __align__(16) float s_cs[D];
+    __shared__ __align__(16) uint8_t s_newk[D * 2 + 32], s_newv[D * 2 + 32];
     pdl_wait();
+    int kcell = -1, vcell = -1;
+    if (fu.enabled) {
+        // (n_tok == 1) rope table, then this token's K / V slice for kv head hk in cache format
+        kcell = (int)fu.k_ids[0]; vcell = (int)fu.v_ids[0];
+        rope_table(s_cs, fu.pos[0], fu.ff, fu.rp, threadIdx.x, FA_WARPS * 32);
+        __syncthreads();
+        if (warp < 2) {
+            const int e = lane * 8; const bool on = e < D;
+            float a[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+            const bool storer = split == 0 && (h0 % gq) == 0;
+            if (warp == 0) {
+                if (on) load_roped8(fu.k_new + (int64_t)hk * D, e, s_cs, fu.rp, a);
+                store8(s_newk, KVT, e, a, lane, on);
+                if (storer) store8((uint8_t *)kc + (int64_t)kcell * k_rs + (int64_t)hk * k_hs, KVT, e, a, lane, on);
+            } else {
+                if (on) { const float4 x = *(const float4 *)(fu.v_new + (int64_t)hk * D + e), y = *(const float4 *)(fu.v_new + (int64_t)hk * D + e + 4);
+                          a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w; }
+                store8(s_newv, KVT, e, a, lane, on);
+                if (storer) store8((uint8_t *)vc + (int64_t)vcell * v_rs + (int64_t)hk * v_hs, KVT, e, a, lane, on);
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- query slices: q8[g][8] as f32 (f16-rounded) or int8 + scale -------------------------
     float qf[G][8]; int qi[G][2]; float qd[G]; float slope[G];
 #pragma unroll
     for (int g = 0; g < G; g++) {
         const int h = h0 + g;
-        const float * qp = q + (int64_t)tok * q_ts + (int64_t)h * q_hs + dl * 8;
-        const float4 a = *(const float4 *)qp, b = *(const float4 *)(qp + 4);
-        float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+        float v[8];
+        if (fu.enabled) {
+            load_roped8(fu.q_src + (int64_t)h * D, dl * 8, s_cs, fu.rp, v);
+            if (split == 0 && warp == 0 && sg == 0) {
+                *(float4 *)(fu.q_dst + (int64_t)h * D + dl * 8)     = make_float4(v[0], v[1], v[2], v[3]);
+                *(float4 *)(fu.q_dst + (int64_t)h * D + dl * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        } else {
+            const float * qp = q + (int64_t)tok * q_ts + (int64_t)h * q_hs + dl * 8;
+            const float4 a = *(const float4 *)qp, b = *(const float4 *)(qp + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
         if (KVT == B200_TYPE_F16) {
 #pragma unroll
             for (int e = 0; e < 8; e++) qf[g][e] = __half2float(__float2half_rn(v[e]));
@@ -102,12 +184,12 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
         float kf[8], vf[8]; int kq[2]; float kd = 0.0f;
         if (KVT == B200_TYPE_F16) {
-            unpack_h8(ldg_stream16(krow + dl * 16), kf);
-            unpack_h8(ldg_stream16(vrow + dl * 16), vf);
+            unpack_h8(p == kcell ? *(const uint4 *)(s_newk + dl * 16) : ldg_stream16(krow + dl * 16), kf);
+            unpack_h8(p == vcell ? *(const uint4 *)(s_newv + dl * 16) : ldg_stream16(vrow + dl * 16), vf);
         } else {
-            load_q80_8(krow, dl, kq, kd);
+            if (p == kcell) lds_q80_8(s_newk, dl, kq, kd); else load_q80_8(krow, dl, kq, kd);
             int vq[2]; float vd;
-            load_q80_8(vrow, dl, vq, vd);
+            if (p == vcell) lds_q80_8(s_newv, dl, vq, vd); else load_q80_8(vrow, dl, vq, vd);
 #pragma unroll
             for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)((vq[e >> 2] >> (8 * (e & 3))) & 0xff), vd);
         }
@@ -209,9 +291,11 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
             __shared__ float s_sc[FA_MAX_SPLITS][G];
             __shared__ float s_inv[G];
             const int n_rows = gridDim.z * n_head;
+            __shared__ float s_l[FA_MAX_SPLITS][G];
             for (int idx = threadIdx.x; idx < n_splits * G; idx += FA_WARPS * 32) {
                 const int sp = idx / G, g = idx % G;
-                s_sc[sp][g] = __ldcg(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D);
+                const float2 ml = __ldcg((const float2 *)(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D));   // every (m, l) pair in one round trip
+                s_sc[sp][g] = ml.x; s_l[sp][g] = ml.y;
             }
             __syncthreads();
             if (threadIdx.x < G) {
@@ -222,7 +306,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
                 for (int sp = 0; sp < n_splits; sp++) {
                     const float m = s_sc[sp][g];
                     const float sc = m == -INFINITY ? 0.0f : expf(m - Mn);
-                    l += __ldcg(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D + 1) * sc;
+                    l += s_l[sp][g] * sc;
                     s_sc[sp][g] = sc;
                 }
                 s_inv[g] = 1.0f / l;
@@ -290,7 +374,7 @@ extern "C" int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t
 template <int D, int KVT, int G>
 static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
                      const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst, float * ws,
-                     int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float softcap, cudaStream_t st) {
+                     int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float softcap, cudaStream_t st, const FaFuse & fu) {
     int split_len = 0;
     const int n_tiles = (int)(n_head / G);
     const int n_splits = fa_splits(n_tiles, n_tok, n_kv, &split_len);
@@ -301,15 +385,15 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     unsigned int * counters = (unsigned int *)ws;
     if (ws) ws = (float *)((uint8_t *)ws + FA_COUNTER_BYTES);
     B200_CUDA(b200_launch_pdl(fattn_vec_kernel<D, KVT, G>, grid, dim3(FA_WARPS * 32), 0, st, q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
-        (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2));
+        (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2, fu));
     b200_count_launch();
     return B200_OK;
 }
 
-extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
+static int fa_dispatch(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
                                    const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst,
                                    int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
-                                   float scale, float max_bias, float softcap, void * workspace, void * stream) {
+                                   float scale, float max_bias, float softcap, void * workspace, void * stream, const FaFuse & fu) {
     if (!q || !k || !v || !dst) { b200_set_error("flash_attn: null pointer"); return B200_ERR_INVALID; }
     if (dk != dv || (dk != 64 && dk != 128)) { b200_set_error("flash_attn: head size %lld/%lld unsupported (64 or 128)", (long long)dk, (long long)dv); return B200_ERR_UNSUPPORTED; }
     if (kv_type != B200_TYPE_F16 && kv_type != B200_TYPE_Q8_0) { b200_set_error("flash_attn: kv type %d unsupported", kv_type); return B200_ERR_UNSUPPORTED; }
@@ -321,7 +405,7 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
     const int G = gq % 4 == 0 ? 4 : (gq % 2 == 0 ? 2 : 1);
     if (!workspace && (n_kv + 31) / 32 > 1) { b200_set_error("flash_attn: workspace required"); return B200_ERR_INVALID; }
     cudaStream_t st = (cudaStream_t)stream; float * ws = (float *)workspace;
-#define FA_CASE(DD, KK, GG) return fa_launch<DD, KK, GG>(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, ws, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, st)
+#define FA_CASE(DD, KK, GG) return fa_launch<DD, KK, GG>(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, ws, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, st, fu)
     if (dk == 128) {
         if (kv_type == B200_TYPE_F16) { if (G == 4) FA_CASE(128, B200_TYPE_F16, 4); if (G == 2) FA_CASE(128, B200_TYPE_F16, 2); FA_CASE(128, B200_TYPE_F16, 1); }
         else                          { if (G == 4) FA_CASE(128, B200_TYPE_Q8_0, 4); if (G == 2) FA_CASE(128, B200_TYPE_Q8_0, 2); FA_CASE(128, B200_TYPE_Q8_0, 1); }
@@ -331,4 +415,30 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
     }
 #undef FA_CASE
     return B200_ERR_UNSUPPORTED;
+}
+
+extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
+                                   const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst,
+                                   int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
+                                   float scale, float max_bias, float softcap, void * workspace, void * stream) {
+    FaFuse fu; memset(&fu, 0, sizeof(fu));
+    return fa_dispatch(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, kv_type, dk, dv, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, workspace, stream, fu);
+}
+
+// decode token: rope(q), rope(k) -> K cache cell, v -> V cache cell, attention over n_kv cells — one launch (see FaFuse)
+extern "C" int b200_rope_kv_flash_attn(const float * q_src, float * q_dst, const float * k_new, const float * v_new, const int32_t * pos, const float * ff,
+                                       const int64_t * k_ids, const int64_t * v_ids, void * k_cache, void * v_cache, int kv_type,
+                                       int64_t k_rs, int64_t k_hs, int64_t v_rs, int64_t v_hs, const void * mask, float * dst,
+                                       int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params * p,
+                                       float scale, float max_bias, float softcap, void * workspace, void * stream) {
+    if (!q_src || !q_dst || !k_new || !v_new || !pos || !k_ids || !v_ids || !k_cache || !v_cache || !dst || !p) { b200_set_error("rope_kv_flash_attn: null pointer"); return B200_ERR_INVALID; }
+    if ((p->mode & ~2) || p->n_dims > hd || p->n_dims % 8 != 0 || (p->mode == 2 && p->n_dims % 16 != 0)) { b200_set_error("rope_kv_flash_attn: rope mode / n_dims unsupported"); return B200_ERR_UNSUPPORTED; }
+    const int64_t hs = kv_type == B200_TYPE_F16 ? hd * 2 : hd / 32 * 34;
+    if (k_hs != hs || v_hs != hs) { b200_set_error("rope_kv_flash_attn: heads must be contiguous inside a cache cell"); return B200_ERR_INVALID; }
+    if (((uintptr_t)q_src | (uintptr_t)q_dst | (uintptr_t)k_new | (uintptr_t)v_new) & 15) { b200_set_error("rope_kv_flash_attn: 16-byte alignment required"); return B200_ERR_INVALID; }
+    FaFuse fu; memset(&fu, 0, sizeof(fu));
+    fu.q_src = q_src; fu.q_dst = q_dst; fu.k_new = k_new; fu.v_new = v_new; fu.pos = pos; fu.ff = ff; fu.k_ids = k_ids; fu.v_ids = v_ids;
+    fu.rp = rope_host_params(p); fu.enabled = 1;
+    return fa_dispatch(q_dst, hd * n_head, hd, k_cache, k_rs, k_hs, v_cache, v_rs, v_hs, mask, 0, dst, kv_type, hd, hd, n_head, n_head_kv, 1, n_kv,
+                       scale, max_bias, softcap, workspace, stream, fu);
 }

@@ -52,10 +52,12 @@ struct MkAttn {
     MkRope rp;
 };
 
-struct MkPhase {
+struct MkPhase {                 // 256 bytes: copied into shared memory with 16 cp.async of 16 bytes
     int32_t kind; int32_t pad;
     union { MkMmv mmv; MkAttn attn; };
+    uint8_t pad2[16];
 };
+static_assert(sizeof(MkPhase) == 256, "MkPhase must be 256 bytes");
 
 // geometry shared by host and device
 #define MK_SLOT_BYTES   9216            // one ring slot: 8 rows x 8 super-blocks of Q4_K (4 rows x 8 of Q6_K = 6720)

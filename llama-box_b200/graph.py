@@ -10,7 +10,7 @@ from . import ops
 
 F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K, I32, I64 = 0, 1, 2, 8, 12, 13, 14, 26, 27
 OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY = range(11)
-EXEC_CUDA_GRAPHS, EXEC_FUSION, EXEC_MEGAKERNEL = 1, 2, 4
+EXEC_CUDA_GRAPHS, EXEC_FUSION, EXEC_MEGAKERNEL, EXEC_MEGA_MMV = 1, 2, 4, 8
 MAX_SRC = 6
 ELEM_SIZE = {F32: 4, F16: 2, I32: 4, I64: 8}
 
@@ -103,7 +103,7 @@ class Executor:
         if not self.h:
             raise ops.B200Error(_lib.b200_last_error().decode())
 
-    def compute(self, nodes, flags=EXEC_CUDA_GRAPHS | EXEC_FUSION | EXEC_MEGAKERNEL, stream=None):
+    def compute(self, nodes, flags=EXEC_CUDA_GRAPHS | EXEC_FUSION, stream=None):
         ops.check(_lib.b200_executor_compute(self.h, nodes, len(nodes), stream if stream is not None else ops.stream(), flags))
 
     def supports(self, node):

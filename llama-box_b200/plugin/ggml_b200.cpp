@@ -299,7 +299,7 @@ static enum ggml_status be_graph_compute(ggml_backend_t b, struct ggml_cgraph * 
             }
         }
     }
-    const int st = b200_executor_compute(c->ex, c->nodes.data(), n, c->stream, B200_EXEC_CUDA_GRAPHS | B200_EXEC_FUSION | B200_EXEC_MEGAKERNEL);
+    const int st = b200_executor_compute(c->ex, c->nodes.data(), n, c->stream, B200_EXEC_CUDA_GRAPHS | B200_EXEC_FUSION);
     if (st != B200_OK) { fprintf(stderr, "ggml-b200: graph_compute failed: %s\n", b200_last_error()); return GGML_STATUS_FAILED; }
     return GGML_STATUS_SUCCESS;
 }

@@ -68,7 +68,8 @@ def test_executor_vs_oracle_forward(ftype, kv, bias):
         want.append(lg); wtoks.append(int(lg.argmax())); pos += 1
     results = {}
     for name, flags in (("plain", 0), ("fused", G.EXEC_FUSION), ("fused+graphs", G.EXEC_FUSION | G.EXEC_CUDA_GRAPHS),
-                        ("mega", G.EXEC_FUSION | G.EXEC_MEGAKERNEL), ("mega+graphs", G.EXEC_FUSION | G.EXEC_MEGAKERNEL | G.EXEC_CUDA_GRAPHS)):
+                        ("mega-attn", G.EXEC_FUSION | G.EXEC_MEGAKERNEL | G.EXEC_CUDA_GRAPHS),
+                        ("mega", G.EXEC_FUSION | G.EXEC_MEGAKERNEL | G.EXEC_MEGA_MMV), ("mega+graphs", G.EXEC_FUSION | G.EXEC_MEGAKERNEL | G.EXEC_MEGA_MMV | G.EXEC_CUDA_GRAPHS)):
         model = M.SyntheticLlama(cfg, ftype, n_ctx=n_ctx, kv_type=kv, host_weights=hw)
         ex = G.Executor(0)
         got, gtoks = run_steps(G, M, model, ex, flags, steps, prompt, len(prompt))
@@ -88,6 +89,10 @@ def test_executor_vs_oracle_forward(ftype, kv, bias):
     assert results["fused+graphs"][3] >= 1 and results["fused+graphs"][4] >= 1
     # the execution modes agree with each other much more tightly than with the oracle
     for a, b in zip(results["plain"][0], results["fused+graphs"][0]):
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+    # attention-only programs: one launch per layer and token, each a single phase
+    assert results["mega-attn"][5] == results["mega-attn"][6] and results["mega-attn"][5] >= cfg["n_layer"]
+    for a, b in zip(results["fused"][0], results["mega-attn"][0]):
         assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
     if ftype == "Q4_K_M":
         # the persistent decode kernel took the Q4_K / Q6_K decode steps (two launches per token: the chain is cut at

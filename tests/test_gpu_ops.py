@@ -398,6 +398,46 @@ def test_flash_attn(b200, kvt, dk, nh, nhkv, nt, nkv):
         assert np.abs(got - want).max() <= 5e-2 * sc, (np.abs(got - want).max(), sc)
 
 
+@pytest.mark.parametrize("kvt", [F16, Q8_0])
+@pytest.mark.parametrize("hd,nh,nhkv,nkv,pos,mode", [(128, 32, 8, 768, 517, 0), (128, 8, 2, 256, 3, 2), (64, 32, 4, 256, 255, 0), (128, 4, 4, 1024, 600, 2)])
+def test_rope_kv_flash_attn_equals_separate_kernels(b200, kvt, hd, nh, nhkv, nkv, pos, mode):
+    """the fused decode launch (rope q/k, KV store, attention) against b200_rope_kv_store2 + b200_flash_attn_ext, which are
+    each checked against the oracle above: identical cache bytes, identical roped Q, identical attention output"""
+    rng = np.random.default_rng(hd + nh + nkv + kvt + mode)
+    tot = nkv + 8
+    q = rng.standard_normal((1, nh, hd)).astype(np.float32); k = rng.standard_normal((1, nhkv, hd)).astype(np.float32)
+    v = rng.standard_normal((1, nhkv, hd)).astype(np.float32)
+    rb_row = row_bytes(kvt, nhkv * hd); rb_head = row_bytes(kvt, hd)
+    kf = rng.standard_normal((tot, nhkv * hd)).astype(np.float32); vf = rng.standard_normal((tot, nhkv * hd)).astype(np.float32)
+    kc = np.zeros((tot, rb_row), np.uint8); vc = np.zeros((tot, rb_row), np.uint8)
+    ids_all = np.arange(tot, dtype=np.int64)
+    oracle().orc_set_rows(ptr(kf), ptr(ids_all), ptr(kc), kvt, nhkv * hd, tot, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids_all), ptr(vc), kvt, nhkv * hd, tot, rb_row)
+    mask = np.full((64, nkv), -np.inf, np.float32); mask[0, :pos + 1] = 0
+    mask16 = mask.astype(np.float16).view(np.uint16)
+    posd, idsd = dev(np.array([pos], np.int32)), dev(np.array([pos], np.int64))
+    c = dict(ROPE_CASES[0]); prm = rope_params(b200, c); prm.mode = mode
+    scale = 1.0 / np.sqrt(hd)
+    wsb = max(16, b200.lib.b200_flash_attn_workspace(hd, nh, 1, nkv))
+    # reference: two launches
+    q1 = dev(q); qr1 = torch.zeros_like(q1); kc1, vc1 = dev(kc), dev(vc); ws1 = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+    d1 = torch.full((1, nh, hd), float("nan"), dtype=torch.float32, device="cuda")
+    b200.check(b200.lib.b200_rope_kv_store2(b200.p(q1), b200.p(qr1), b200.p(dev(k)), b200.p(dev(v)), b200.p(posd), None, b200.p(idsd), b200.p(idsd),
+                                            b200.p(kc1), b200.p(vc1), kvt, rb_row, rb_row, hd, nh, nhkv, 1, C.byref(prm), b200.stream()))
+    b200.check(b200.lib.b200_flash_attn_ext(b200.p(qr1), nh * hd, hd, b200.p(kc1), rb_row, rb_head, b200.p(vc1), rb_row, rb_head, b200.p(dev(mask16)), nkv,
+                                            b200.p(d1), kvt, hd, hd, nh, nhkv, 1, nkv, scale, 0.0, 0.0, b200.p(ws1), b200.stream()))
+    # fused: one launch
+    q2 = dev(q); qr2 = torch.zeros_like(q2); kc2, vc2 = dev(kc), dev(vc); ws2 = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+    d2 = torch.full((1, nh, hd), float("nan"), dtype=torch.float32, device="cuda")
+    b200.check(b200.lib.b200_rope_kv_flash_attn(b200.p(q2), b200.p(qr2), b200.p(dev(k)), b200.p(dev(v)), b200.p(posd), None, b200.p(idsd), b200.p(idsd),
+                                                b200.p(kc2), b200.p(vc2), kvt, rb_row, rb_head, rb_row, rb_head, b200.p(dev(mask16)), b200.p(d2),
+                                                hd, nh, nhkv, nkv, C.byref(prm), scale, 0.0, 0.0, b200.p(ws2), b200.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+    assert torch.equal(qr1, qr2)
+    assert torch.isfinite(d2).all() and torch.equal(d1, d2)
+
+
 def test_flash_attn_f16_closer_to_f64_than_oracle(b200):
     """With F16 V the oracle accumulates in fp16; our f32 accumulation must be at least as close to an
     f64 evaluation of the same attention (same f16-rounded Q, K, V) as the oracle is."""
