@@ -177,58 +177,82 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     const int p_end   = min(n_kv, p_begin + split_len);
     const uint16_t * mrow = mask ? mask + (int64_t)tok * mask_rs : nullptr;
 
-    for (int p = p_begin + warp * PPW + sg; p < p_end; p += FA_WARPS * PPW) {
-        const float mraw = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
-        if (mraw == -INFINITY && max_bias <= 0.0f) continue;     // masked (uniform inside the LP-lane group)
-        const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
-        const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
-        float kf[8], vf[8]; int kq[2]; float kd = 0.0f;
-        if (KVT == B200_TYPE_F16) {
-            unpack_h8(p == kcell ? *(const uint4 *)(s_newk + dl * 16) : ldg_stream16(krow + dl * 16), kf);
-            unpack_h8(p == vcell ? *(const uint4 *)(s_newv + dl * 16) : ldg_stream16(vrow + dl * 16), vf);
-        } else {
-            if (p == kcell) lds_q80_8(s_newk, dl, kq, kd); else load_q80_8(krow, dl, kq, kd);
-            int vq[2]; float vd;
-            if (p == vcell) lds_q80_8(s_newv, dl, vq, vd); else load_q80_8(vrow, dl, vq, vd);
+    // positions are visited in chunks of MAXIT per lane group: every load of a chunk (mask, K, V) is issued before any
+    // arithmetic, so a chunk costs one memory round trip instead of MAXIT (decode attention is latency-bound: a split is
+    // a few dozen positions).  K/V of masked positions are loaded but never used.
+    constexpr int MAXIT = 4;
+    constexpr int pstride = FA_WARPS * PPW;
+    for (int base = p_begin + warp * PPW + sg; base < p_end; base += pstride * MAXIT) {
+        float mraw[MAXIT]; uint4 kraw[MAXIT], vraw[MAXIT]; float kdv[MAXIT], vdv[MAXIT];
 #pragma unroll
-            for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)((vq[e >> 2] >> (8 * (e & 3))) & 0xff), vd);
-        }
-        float s[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            if (KVT == B200_TYPE_F16) {
-                float a = 0.0f;
-#pragma unroll
-                for (int e = 0; e < 8; e++) a = fmaf(kf[e], qf[g][e], a);
-#pragma unroll
-                for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
-                s[g] = a;
-            } else {
-                int is = dp4a_s(kq[0], qi[g][0], 0);
-                is = dp4a_s(kq[1], qi[g][1], is);
-                is += __shfl_xor_sync(gmask, is, 1, LP);          // whole 32-element block
-                is += __shfl_xor_sync(gmask, is, 2, LP);
-                float a = __fmul_rn((float)is, __fmul_rn(kd, qd[g]));   // ggml-cpu/quants.c:305-333
-                a = (dl & 3) == 0 ? a : 0.0f;
-#pragma unroll
-                for (int o = LP / 2; o >= 4; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
-                s[g] = __shfl_sync(gmask, a, 0, LP);
+        for (int it = 0; it < MAXIT; it++) {
+            const int p = base + it * pstride;
+            mraw[it] = -INFINITY; kraw[it] = make_uint4(0, 0, 0, 0); vraw[it] = kraw[it]; kdv[it] = 0.0f; vdv[it] = 0.0f;
+            if (p < p_end) {
+                mraw[it] = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
+                const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
+                const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
+                if (KVT == B200_TYPE_F16) {
+                    kraw[it] = p == kcell ? *(const uint4 *)(s_newk + dl * 16) : ldg_stream16(krow + dl * 16);
+                    vraw[it] = p == vcell ? *(const uint4 *)(s_newv + dl * 16) : ldg_stream16(vrow + dl * 16);
+                } else {
+                    int q2[2];
+                    if (p == kcell) lds_q80_8(s_newk, dl, q2, kdv[it]); else load_q80_8(krow, dl, q2, kdv[it]);
+                    kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1];
+                    if (p == vcell) lds_q80_8(s_newv, dl, q2, vdv[it]); else load_q80_8(vrow, dl, q2, vdv[it]);
+                    vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1];
+                }
             }
         }
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            float sv = s[g] * scale;
-            if (softcap != 0.0f) sv = softcap * tanhf(sv);
-            sv += slope[g] * mraw;
-            if (sv == -INFINITY) continue;
-            float ms = 1.0f, vs = 1.0f;
-            if (sv > M[g]) { ms = expf(M[g] - sv); M[g] = sv;
+        for (int it = 0; it < MAXIT; it++) {
+            if (mraw[it] == -INFINITY && max_bias <= 0.0f) continue;       // masked, or beyond the split (uniform inside the LP-lane group)
+            if (base + it * pstride >= p_end) continue;
+            float kf[8], vf[8];
+            if (KVT == B200_TYPE_F16) {
+                unpack_h8(kraw[it], kf);
+                unpack_h8(vraw[it], vf);
+            } else {
 #pragma unroll
-                for (int e = 0; e < 8; e++) acc[g][e] *= ms;
-            } else vs = expf(sv - M[g]);
+                for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)(((e < 4 ? vraw[it].x : vraw[it].y) >> (8 * (e & 3))) & 0xff), vdv[it]);
+            }
+            float s[G];
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[g][e] = fmaf(vf[e], vs, acc[g][e]);
-            L[g] = L[g] * ms + vs;
+            for (int g = 0; g < G; g++) {
+                if (KVT == B200_TYPE_F16) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) a = fmaf(kf[e], qf[g][e], a);
+#pragma unroll
+                    for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
+                    s[g] = a;
+                } else {
+                    int is = dp4a_s((int)kraw[it].x, qi[g][0], 0);
+                    is = dp4a_s((int)kraw[it].y, qi[g][1], is);
+                    is += __shfl_xor_sync(gmask, is, 1, LP);          // whole 32-element block
+                    is += __shfl_xor_sync(gmask, is, 2, LP);
+                    float a = __fmul_rn((float)is, __fmul_rn(kdv[it], qd[g]));   // ggml-cpu/quants.c:305-333
+                    a = (dl & 3) == 0 ? a : 0.0f;
+#pragma unroll
+                    for (int o = LP / 2; o >= 4; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
+                    s[g] = __shfl_sync(gmask, a, 0, LP);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                float sv = s[g] * scale;
+                if (softcap != 0.0f) sv = softcap * tanhf(sv);
+                sv += slope[g] * mraw[it];
+                if (sv == -INFINITY) continue;
+                float ms = 1.0f, vs = 1.0f;
+                if (sv > M[g]) { ms = expf(M[g] - sv); M[g] = sv;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) acc[g][e] *= ms;
+                } else vs = expf(sv - M[g]);
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc[g][e] = fmaf(vf[e], vs, acc[g][e]);
+                L[g] = L[g] * ms + vs;
+            }
         }
     }
 

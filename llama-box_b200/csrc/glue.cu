@@ -100,7 +100,24 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float * __restrict__
     pdl_wait();
     const float * row = x + (int64_t)blockIdx.x * n;
     float best = -INFINITY; int bi = 0x7fffffff;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float v = row[i]; if (v > best || (v == best && (int)i < bi)) { best = v; bi = (int)i; } }
+    // one row is ~0.5 MB for a 128k vocabulary and a single CTA scans it: keep 8 independent 16-byte loads in flight per thread
+    if ((((uintptr_t)row) & 15) == 0 && (n & 3) == 0) {
+        const int64_t n4 = n >> 2;
+        for (int64_t i0 = threadIdx.x; i0 < n4; i0 += (int64_t)blockDim.x * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int64_t i = i0 + (int64_t)u * blockDim.x; v[u] = i < n4 ? __ldg((const float4 *)row + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int e = (int)((i0 + (int64_t)u * blockDim.x) * 4);
+                const float f[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+                for (int c = 0; c < 4; c++) if (f[c] > best || (f[c] == best && e + c < bi)) { best = f[c]; bi = e + c; }
+            }
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float v = row[i]; if (v > best || (v == best && (int)i < bi)) { best = v; bi = (int)i; } }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float v2 = __shfl_xor_sync(0xffffffffu, best, o); const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);

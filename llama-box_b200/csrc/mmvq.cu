@@ -500,6 +500,12 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
 
     // prime the ring: weights do not depend on the previous kernel (PDL overlap)
     if (lane == 0) for (int s = 0; s < S && ig < total; s++) issue_next();
+    // norm weights are parameters too: fetch this warp's first block before waiting for the previous kernel (otherwise a
+    // cold DRAM access sits between the rms_norm reduction and the quantisation, on every CTA's critical path)
+    float4 nwa = make_float4(1.0f, 1.0f, 1.0f, 1.0f), nwb = nwa;
+    if (args.act_source == 2 && args.norm_w && warp < (int)(args.k >> 8)) {
+        nwa = __ldg((const float4 *)(args.norm_w + warp * 256 + lane * 8)); nwb = __ldg((const float4 *)(args.norm_w + warp * 256 + lane * 8 + 4));
+    }
     pdl_trigger();
     pdl_wait();
     if (args.act_source == 0) {
@@ -513,7 +519,6 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
         // every CTA builds the quantised activation vector itself, straight into shared memory:
         // [rms_norm * w ->] q8_K / q8_0 exactly as the CPU oracle quantises (no separate kernels, no HBM round trip)
         __shared__ double red[MMV_WARPS];
-        __shared__ float s_scale;
         const int nblk = (int)(args.k >> 8);
         for (int col = 0; col < args.ncols; col++) {
             const float * xc = args.x + (int64_t)col * args.x_col_stride;
@@ -529,13 +534,9 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
                 for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
                 if (lane == 0) red[warp] = acc2;
                 __syncthreads();
-                if (tid == 0) {
-                    double t = 0.0;
-                    for (int i = 0; i < MMV_WARPS; i++) t += red[i];
-                    s_scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k), args.eps)));
-                }
-                __syncthreads();
-                scale = s_scale;
+                double t = 0.0;
+                for (int i = 0; i < MMV_WARPS; i++) t += red[i];    // every thread: same order, same value — no second barrier
+                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k), args.eps)));
             }
             for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                 const int64_t i = (int64_t)blk * 256 + lane * 8;
@@ -545,7 +546,8 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 8; j++) v[j] = __fmul_rn(v[j], scale);
                     if (args.norm_w) {
-                        const float4 wa = *(const float4 *)(args.norm_w + i), wb = *(const float4 *)(args.norm_w + i + 4);
+                        const bool pre = blk == warp;
+                        const float4 wa = pre ? nwa : *(const float4 *)(args.norm_w + i), wb = pre ? nwb : *(const float4 *)(args.norm_w + i + 4);
                         v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
                         v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
                     }

@@ -416,7 +416,7 @@ def test_rope_kv_flash_attn_equals_separate_kernels(b200, kvt, hd, nh, nhkv, nkv
     mask = np.full((64, nkv), -np.inf, np.float32); mask[0, :pos + 1] = 0
     mask16 = mask.astype(np.float16).view(np.uint16)
     posd, idsd = dev(np.array([pos], np.int32)), dev(np.array([pos], np.int64))
-    c = dict(ROPE_CASES[0]); prm = rope_params(b200, c); prm.mode = mode
+    c = dict(ROPE_CASES[0]); prm = rope_params(b200, c); prm.mode = mode; prm.n_dims = hd
     scale = 1.0 / np.sqrt(hd)
     wsb = max(16, b200.lib.b200_flash_attn_workspace(hd, nh, 1, nkv))
     # reference: two launches
