@@ -20,7 +20,8 @@ flash-attention over an F16 KV cache), run by the graph executor on hand-written
 N > 1 (torchrun): layer split as the reference's default LLAMA_SPLIT_MODE_LAYER does it — rank r owns a
 contiguous range of layers (and its KV), the hidden state is handed to rank r+1 with one NCCL send/recv;
 N sequences are kept in flight so every GPU streams its slice of the weights once per pipeline tick
-(weak scaling: per-GPU work per tick is fixed at 1/N of the model... see DESIGN.md §multi-GPU).
+("scaling": "strong" — the work per counted unit, one token through all layers, is fixed while N grows; each GPU
+streams 1/N of it per tick.  See DESIGN.md, multi-GPU).
 """
 import argparse
 import ctypes as C
@@ -60,12 +61,12 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
 
     def __init__(self, gpu_index=0):
-        self.proc, self.lines, self.gpu = None, [], gpu_index
+        self.proc, self.lines, self.gpu, self.t_begin = None, [], gpu_index, None
 
     def start(self):
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -73,14 +74,24 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        """the sampler is started before the warm-up (nvidia-smi needs ~0.1 s to produce its first line); samples taken
+        from here on are the ones inside the timed region"""
+        self.t_begin = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time()
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if self.t_begin is None or self.t_begin <= t <= t_end + 0.02]
+        window = "timed region"
+        if not inside:                                   # region shorter than the sampling period: fall back to the loaded warm-up samples
+            inside = [ln for (t, ln) in self.lines][-3:]; window = "warm-up (timed region shorter than one sample)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -92,7 +103,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def peaks():
@@ -145,7 +156,7 @@ def run_reference_arm(args):
         return
     tps, threads, sample, raw = res
     line = {"metric": "decode tok/s Llama-3-8B Q4_K_M bs=1", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 / tps if tps else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "q4_K x q8_K int8 dot, f32 accumulate",
+            "ms_per_step": 1000.0 / tps if tps else None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "q4_K x q8_K int8 dot, f32 accumulate",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": f"{args.model} {args.ftype} batch-1 decode, -c {args.ctx}, n_past {args.n_past}, F16 KV", "backend": "ggml-cpu (unmodified reference build)"},
             "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": threads, "kind": "reference", "sample": sample},
@@ -225,10 +236,11 @@ def run_b200(args):
             mask_dev[i] = mask_row(args.n_past + i, n_kv_of(args.n_past + i)).cuda()
         nodes, io = nodes_for(n_kv_of(args.n_past))
         io["tokens"].fill_(1); io["out_ids"].fill_(0)
+        sampler = ClockSampler(local); sampler.start()
         for i in range(args.warmup):
             device_step(i)
         stream.synchronize()
-        sampler = ClockSampler(local); sampler.start()
+        sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ops.lib.b200_kernel_launches()
         torch.cuda.synchronize()
@@ -268,7 +280,7 @@ def run_b200(args):
             cpu = {"value": None, "unit": "tok/s", "cores": 0, "kind": "reference", "sample": "unavailable: oracle/_ref not present on this box"}
 
     line = {"metric": "decode tok/s Llama-3-8B Q4_K_M bs=1", "value": tps, "unit": "tok/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "q4_K/q6_K x q8_K int8 dot (dp4a), f32 accumulate", "data": "synthetic",
             "config": {"workload": f"{args.model} {args.ftype} batch-1 decode, -c {args.ctx}, n_past {args.n_past}, F16 KV, flash-attn",
                        "n_layer": len(model.layers), "streamed_weight_bytes": model.streamed_weight_bytes(), "kv_bytes_per_pos": model.kv_bytes_per_pos(),
@@ -332,8 +344,12 @@ def mmvq_roofline(args, model, ops, G, stream, hbm_peak):
     ms = e0.elapsed_time(e1) / reps
     wbytes = sum(sum(ly[k].nbytes for k in ("wq", "wk", "wv", "wo", "gate", "up", "down")) for ly in model.layers) + model.output.nbytes
     ach = wbytes / (ms * 1e-3) / 1e9
+    # DRAM bytes per algorithmic byte of the QKV / wo / gate+up / down launches in the round's `ncu --set full` capture
+    # (profiles/r1_mmvq_ncu_full_metrics.tsv: 123.60 MB moved for 122.68 MB of weights; the surplus is activations + outputs)
+    dram_per_alg = 1.0075
     return {"bound": "hbm", "kernel": "mmvq_kernel (quantised matvec, all %d launches of one token)" % nl, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-            "frac": ach / hbm_peak, "frac_of_8TBs": ach / 8000.0, "traffic": None, "bytes_per_token": wbytes, "launches_per_token": nl,
+            "frac": ach / hbm_peak, "frac_of_8TBs": ach / 8000.0, "traffic": int(wbytes * dram_per_alg), "traffic_source": "ncu dram__bytes_read+write ratio x bytes_per_token (profiles/)",
+            "bytes_per_token": wbytes, "launches_per_token": nl,
             "avg_launch_us": ms * 1e3 / nl, "ms_per_token_matvec_only": ms}
 
 
@@ -401,7 +417,8 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
     ex = G.Executor(local)
     flags = (0 if args.no_graphs else G.EXEC_CUDA_GRAPHS) | (0 if args.no_fusion else G.EXEC_FUSION) | ((G.EXEC_MEGAKERNEL if (args.mega or args.mega_mmv) else 0) | (G.EXEC_MEGA_MMV if args.mega_mmv else 0) if not args.no_fusion else 0)
     n_kv_of = lambda pos: max(256, (pos + 1 + 255) // 256 * 256)  # noqa: E731
-    total_ticks = args.warmup + world - 1 + args.steps        # pipeline fill + warm-up + timed region
+    e2e_steps = 0 if args.no_e2e else args.steps
+    total_ticks = args.warmup + world - 1 + args.steps + e2e_steps   # pipeline fill + warm-up + timed region (+ the e2e leg)
     steps_per_seq = (total_ticks + world - 1) // world + 1
     assert n_kv_of(args.n_past + steps_per_seq) <= args.ctx
     stream = torch.cuda.current_stream()
@@ -425,7 +442,14 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
             pending[0].wait()
         pending[0] = dist.isend(x, dst=dst)
 
-    def tick(t, timed):
+    import numpy as np
+    n_kv_cap = n_kv_of(args.n_past + steps_per_seq)
+    host_in = dict(pos=torch.zeros(1, dtype=torch.int32).pin_memory(), idx=torch.zeros(1, dtype=torch.int64).pin_memory(),
+                   mask=torch.zeros(n_kv_cap, dtype=torch.float32).pin_memory(), tok=torch.ones(1, dtype=torch.int32).pin_memory())
+    host_logits = torch.zeros(V, dtype=torch.float32).pin_memory() if last else None
+    io_bytes = [0, 0]
+
+    def tick(t, timed, e2e=False):
         seq = (t - rank) % world
         if t < rank:
             return                                                  # pipeline fill
@@ -438,21 +462,36 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
             io["tokens"].copy_(tok)
         else:
             dist.recv(io["hidden_in"], src=rank - 1)
-        io["pos"].fill_(pos); io["kv_idx"].fill_(pos)
-        m = neg[:n_kv].clone(); m[:pos + 1] = 0
-        io["mask"][0].copy_(m)
+        if e2e:
+            # the caller's side of the boundary: this tick's inputs come from pinned host memory ...
+            host_in["pos"][0] = pos; host_in["idx"][0] = pos
+            host_in["mask"][:n_kv].fill_(float("-inf")); host_in["mask"][:pos + 1] = 0
+            io["pos"].copy_(host_in["pos"], non_blocking=True); io["kv_idx"].copy_(host_in["idx"], non_blocking=True)
+            io["mask"][0].copy_(host_in["mask"][:n_kv], non_blocking=True)
+            io_bytes[0] = 4 + 8 + 4 * n_kv + (4 if first else 0)
+        else:
+            io["pos"].fill_(pos); io["kv_idx"].fill_(pos)
+            m = neg[:n_kv].clone(); m[:pos + 1] = 0
+            io["mask"][0].copy_(m)
         ex.compute(nodes, flags, stream=st)
         if last:
             ops.check(ops.lib.b200_argmax_f32(ops.p(io["logits"]), ops.p(tok), V, 1, st))
+            if e2e:
+                # ... and the logits go back to the host, which picks the token (llama_get_logits + greedy sampling)
+                host_logits.copy_(io["logits"][0], non_blocking=True)
+                stream.synchronize()
+                host_in["tok"][0] = int(np.argmax(host_logits.numpy()))
+                io_bytes[1] = 4 * V
             if t + 1 < total_ticks:                                 # rank 0 stops receiving after the last tick
                 isend(tok, 0)
         elif t + 1 < total_ticks:                                   # rank r+1 consumes it at tick t + 1
             isend(io["hidden_out"], rank + 1)
 
+    sampler = ClockSampler(local); sampler.start()
     for t in range(args.warmup + world - 1):
         tick(t, False)
     torch.cuda.synchronize(); dist.barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ops.lib.b200_kernel_launches()
     e0.record(stream)
@@ -466,18 +505,38 @@ def run_b200_pipeline(args, G, M, ops, rank, world, local):
     launches = torch.tensor([ops.lib.b200_kernel_launches() - l0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches)
     clocks = sampler.stop()
-    # drain: the last stage still owes rank 0 nothing (sends are matched tick by tick)
+    # ---- e2e leg: same ticks, host buffers on both sides of the boundary
+    e2e = None
+    if e2e_steps:
+        t_base = args.warmup + world - 1 + args.steps
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record(stream)
+        for t in range(t_base, t_base + e2e_steps):
+            tick(t, True, e2e=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        iob = torch.tensor(io_bytes, device="cuda", dtype=torch.int64)
+        dist.barrier()
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX); dist.all_reduce(iob)
+        e2e = {"value": 1000.0 * e2e_steps / float(ms2.item()), "unit": "tok/s", "h2d_bytes_per_step": int(iob[0].item()), "d2h_bytes_per_step": int(iob[1].item()),
+               "ms_per_step": float(ms2.item()) / e2e_steps, "api": "b200_executor_compute per pipeline stage, pinned host inputs on every stage, logits D2H + host argmax on the last"}
+    wb = torch.tensor([model.streamed_weight_bytes() + n_kv_of(args.n_past + args.steps // world) * model.kv_bytes_per_pos()], device="cuda", dtype=torch.int64)
+    dist.all_reduce(wb)
     if rank == 0:
         ms_per_step = float(ms.item()) / args.steps
         hbm_peak, peak_src = peaks()
         wbytes = None
         line = {"metric": "decode tok/s Llama-3-8B Q4_K_M bs=1", "value": 1000.0 / ms_per_step, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "q4_K/q6_K x q8_K int8 dot (dp4a), f32 accumulate", "data": "synthetic",
                 "config": {"workload": f"{args.model} {args.ftype} batch-1 decode per sequence, {world} sequences in flight (one per pipeline stage), -c {args.ctx}, n_past {args.n_past}, F16 KV",
                            "parallelism": f"layer split over {world} GPUs (--tensor-split {','.join(['1'] * world)}), NCCL send/recv hidden-state handoff",
                            "l2_policy": "inputs larger than L2"},
-                "clocks": clocks, "e2e": None, "gpu_launches": int(launches.item()), "roofline": None, "cpu_baseline": None,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
+                "roofline": {"bound": "hbm", "kernel": "whole pipeline tick (all stages run concurrently, each streams its layer range)", "achieved": int(wb.item()) / (ms_per_step * 1e-3) / 1e9,
+                             "peak": hbm_peak * world, "unit": "GB/s", "frac": int(wb.item()) / (ms_per_step * 1e-3) / 1e9 / (hbm_peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
+                "cpu_baseline": None,
                 "note": "a step = one pipeline tick: every GPU streams its 1/N slice of the weights for one sequence; one token leaves the last stage per tick"}
         print(json.dumps(line))
     dist.barrier()
