@@ -523,10 +523,12 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
         for (int col = 0; col < args.ncols; col++) {
             const float * xc = args.x + (int64_t)col * args.x_col_stride;
             float scale = 1.0f;
+            float4 xa0 = make_float4(0.f, 0.f, 0.f, 0.f), xb0 = xa0;     // this warp's first block stays in registers between the two passes
             if (args.act_source == 2) {
                 double acc2 = 0.0;                                  // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
                 for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                     const float4 a = *(const float4 *)(xc + blk * 256 + lane * 8), b = *(const float4 *)(xc + blk * 256 + lane * 8 + 4);
+                    if (blk == warp) { xa0 = a; xb0 = b; }
                     acc2 += (double)__fmul_rn(a.x, a.x); acc2 += (double)__fmul_rn(a.y, a.y); acc2 += (double)__fmul_rn(a.z, a.z); acc2 += (double)__fmul_rn(a.w, a.w);
                     acc2 += (double)__fmul_rn(b.x, b.x); acc2 += (double)__fmul_rn(b.y, b.y); acc2 += (double)__fmul_rn(b.z, b.z); acc2 += (double)__fmul_rn(b.w, b.w);
                 }
@@ -540,7 +542,8 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
             }
             for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                 const int64_t i = (int64_t)blk * 256 + lane * 8;
-                const float4 a = *(const float4 *)(xc + i), b = *(const float4 *)(xc + i + 4);
+                const bool kept = args.act_source == 2 && blk == warp;
+                const float4 a = kept ? xa0 : *(const float4 *)(xc + i), b = kept ? xb0 : *(const float4 *)(xc + i + 4);
                 float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
                 if (args.act_source == 2) {
 #pragma unroll

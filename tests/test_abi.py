@@ -41,3 +41,29 @@ def test_no_cpu_fallback_without_cuda(b200):
     buf = (C.c_float * 1024)()
     st = b200.lib.b200_rms_norm(C.addressof(buf), None, C.addressof(buf), 1024, 1, 1024, 1024, 1e-5, None)
     assert st == -3 and b"CUDA" in b200.lib.b200_last_error()
+
+
+def test_b200_graph_exports_every_declared_symbol(b200):
+    """include/b200_graph.h (executor C-ABI): every declared entry point is exported and mirrored in graph.py"""
+    import importlib
+    G = importlib.import_module("llama_box_b200.graph")
+    names = declared_symbols("b200_graph.h")
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(b200.lib, n), n
+    assert set(names) == set(G.GRAPH_SYMBOLS), set(names) ^ set(G.GRAPH_SYMBOLS)
+
+
+def test_ggml_plugin_exports_backend_entry_points():
+    """include/ggml_b200.h: the dynamic-backend entry points ggml's loader dlsym()s (ggml-backend-reg.cpp:243-274).
+    The plug-in links against the reference's libggml-base, so it only exists where oracle/_ref was built."""
+    so = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")
+    if not os.path.exists(so):
+        import pytest
+        pytest.skip("libggml-b200.so not built (needs oracle/_ref)")
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    for n in declared_symbols("ggml_b200.h"):
+        assert n in exported, n
+    assert {"ggml_backend_init", "ggml_backend_score"} <= exported
