@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     __shared__ __align__(16) float s_cs[D];
     __shared__ __align__(16) uint8_t s_newk[D * 2 + 32], s_newv[D * 2 + 32];
     pdl_wait();
-    if (fu.early_trigger) pdl_trigger();      // the next kernel (the wo matvec) may start priming its weight ring now; its own griddepcontrol.wait orders the data
+    if (fu.early_trigger & 1) pdl_trigger();  // the next kernel (the wo matvec) may start priming its weight ring now; its own griddepcontrol.wait orders the data
     // ---- every independent load of the prologue is issued here, together: token position / cells, this token's K and V
     //      slices, the query slices, and mask + K + V of the first chunk of positions.  Decode attention is a chain of
     //      dependent memory round trips; done one after the other (table -> K staging -> Q -> K/V) they were the kernel.
@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         }
     };
     const int base0 = p_begin + warp * PPW + sg;
-    load_chunk(base0);                                              // (the new token's cell is patched from shared memory below)
+    const bool hoist = !(fu.early_trigger & 2);
+    if (hoist) load_chunk(base0);                                   // (the new token's cell is patched from shared memory below)
 
     if (fu.enabled) {
         // (n_tok == 1) rope table, then this token's K / V slice for kv head hk in cache format
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     // arithmetic, so a chunk costs one memory round trip instead of MAXIT (a decode split is a few dozen positions: usually
     // ONE chunk, already in flight since the top of the kernel).  K/V of masked positions are loaded but never used.
     for (int base = base0; base < p_end; base += pstride * MAXIT) {
-        if (base != base0) load_chunk(base);
+        if (base != base0 || !hoist) load_chunk(base);
         patch_chunk(base);
 #pragma unroll
         for (int it = 0; it < MAXIT; it++) {
@@ -387,8 +388,8 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
             const int n_rows = gridDim.z * n_head;
             __shared__ float s_l[FA_MAX_SPLITS][G];
             // every load of the merge is issued before the first barrier: the (m, l) pairs and — per output element — the
-            // partial accumulators of up to 32 splits (one round trip instead of three)
-            constexpr int PRE = 32;
+            // partial accumulators of the first 8 splits
+            constexpr int PRE = 8;
             float av[(G * D + FA_WARPS * 32 - 1) / (FA_WARPS * 32)][PRE];
 #pragma unroll
             for (int u = 0; u < (G * D + FA_WARPS * 32 - 1) / (FA_WARPS * 32); u++) {
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
             }
         }
     }
-    if (!fu.early_trigger) pdl_trigger();
+    if (!(fu.early_trigger & 1)) pdl_trigger();
 }
 
 template <int D>
