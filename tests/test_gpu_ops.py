@@ -189,11 +189,11 @@ def test_mmvq_swiglu(b200, tg, tu):
     assert np.abs(dst.cpu().numpy() - want).max() <= 3e-5 * max(np.abs(want).max(), 1e-6)
 
 
-@pytest.mark.parametrize("t,src", [(Q4_K, 2), (Q6_K, 2), (Q8_0, 2), (Q4_K, 1), (Q4_0, 1)])
-def test_mmvq_fused_activation_prologue(b200, t, src):
+@pytest.mark.parametrize("t,src,k", [(Q4_K, 2, 4096), (Q6_K, 2, 4096), (Q8_0, 2, 4096), (Q4_K, 1, 4096), (Q4_0, 1, 4096), (Q4_K, 1, 14336), (Q6_K, 1, 14336)])
+def test_mmvq_fused_activation_prologue(b200, t, src, k):
     """rms_norm * w + quantise (act_source 2) or quantise only (1) inside the matvec kernel == oracle composition"""
     rng = np.random.default_rng(31 + t + src)
-    m, k, n = 80, 4096, 2
+    m, n = 80, (2 if k == 4096 else 1)
     W = rand_blocks(rng, t, m, k)
     x = (rng.standard_normal((n, k)) * 2).astype(np.float32); w = (1 + 0.1 * rng.standard_normal(k)).astype(np.float32)
     resid = rng.standard_normal((n, m)).astype(np.float32)
@@ -210,6 +210,15 @@ def test_mmvq_fused_activation_prologue(b200, t, src):
     b200.check(b200.lib.b200_mul_mat_vec_q_launch(C.byref(L), b200.stream()))
     got = dst.cpu().numpy()
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), np.abs(got - want).max()
+
+
+def test_mmvq_group_quant_opt_in():
+    """B200_MMV_TUNE=1 (8 lanes per block for long activation vectors, read once per process): same results"""
+    import os, subprocess, sys
+    env = dict(os.environ, B200_MMV_TUNE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", "fused_activation_prologue or mmvq_bias_residual"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
 
 
 def test_mmvq_rejects_bad_shapes(b200):
