@@ -212,6 +212,7 @@ def test_mmvq_fused_activation_prologue(b200, t, src, k):
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), np.abs(got - want).max()
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_OPT_IN"), reason="opt-in kernel variant not yet measured on the GPU (set B200_TEST_OPT_IN=1)")
 def test_mmvq_group_quant_opt_in():
     """B200_MMV_TUNE=1 (8 lanes per block for long activation vectors, read once per process): same results"""
     import os, subprocess, sys
