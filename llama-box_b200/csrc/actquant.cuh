@@ -75,39 +75,3 @@ __device__ __forceinline__ void warp_quant_q80(const float (&v)[8], ActOut o, in
     }
 }
 
-
-// q8_K with 8 lanes per 256-element block (32 consecutive elements per lane): per-16 sums and packing are in-lane, only the
-// block maximum crosses lanes (3 shuffle rounds inside the 8-lane group), and a warp quantises 4 blocks at once — the
-// quantisation of a long activation vector (ffn_down: k = 14336) sits between the PDL wait and the first dot product of
-// every CTA.  Same arithmetic as warp_quant_q8K (first index of the largest |x|, iscale = -127/max, RNE, clamp 127).
-__device__ __forceinline__ void group_quant_q8K(const float (&v)[32], ActOut o, int64_t blk, int li) {
-    const unsigned gm = 0xffu << (threadIdx.x & 24);                // the 8 lanes of this block
-    float am = 0.0f, mv = 0.0f; int ai = 0;
-#pragma unroll
-    for (int j = 0; j < 32; j++) { const float a = fabsf(v[j]); if (a > am) { am = a; mv = v[j]; ai = li * 32 + j; } }
-#pragma unroll
-    for (int o2 = 1; o2 < 8; o2 <<= 1) {
-        const float am2 = __shfl_xor_sync(gm, am, o2), mv2 = __shfl_xor_sync(gm, mv, o2);
-        const int   ai2 = __shfl_xor_sync(gm, ai, o2);
-        if (am2 > am || (am2 == am && ai2 < ai)) { am = am2; mv = mv2; ai = ai2; }
-    }
-    uint32_t w[8]; int s16a = 0, s16b = 0; float d = 0.0f;
-    if (am != 0.0f) {
-        const float iscale = __fdiv_rn(-127.0f, mv);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            int t = __float2int_rn(__fmul_rn(iscale, v[j])); t = t > 127 ? 127 : t;
-            if (j < 16) s16a += t; else s16b += t;
-            if ((j & 3) == 0) w[j >> 2] = (uint32_t)(t & 0xff); else w[j >> 2] |= (uint32_t)(t & 0xff) << (8 * (j & 3));
-        }
-        d = __fdiv_rn(1.0f, iscale);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) w[j] = 0;
-    }
-    int8_t * qb = o.qs + blk * 256 + li * 32;
-    *(uint4 *)qb        = make_uint4(w[0], w[1], w[2], w[3]);
-    *(uint4 *)(qb + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-    *(uint32_t *)(o.bs + blk * 16 + li * 2) = (uint32_t)(s16a & 0xffff) | ((uint32_t)(s16b & 0xffff) << 16);
-    if (li == 0) o.d[blk] = d;
-}

@@ -16,7 +16,6 @@
 #include "ropeutil.cuh"
 #include <math.h>
 #include <string.h>
-#include <stdlib.h>
 
 #define FA_WARPS 4
 #define FA_MAX_SPLITS 64
@@ -45,44 +44,9 @@ __device__ __forceinline__ void load_q80_8(const uint8_t * row, int dl, int (&q)
 struct FaFuse {
     const float * q_src; float * q_dst; const float * k_new; const float * v_new;
     const int32_t * pos; const float * ff; const int64_t * k_ids; const int64_t * v_ids;
-    RopeDev rp; int enabled; int early_trigger;
+    RopeDev rp; int enabled;
 };
-// elements e0..e0+7 of one head (+ the 8 partner elements NEOX pairs them with): raw loads, issued early
-struct Raw8 { float4 a, b, pa, pb; };
-__device__ __forceinline__ Raw8 load_raw8(const float * head, int e0, const RopeDev & rp) {
-    Raw8 r;
-    r.a = *(const float4 *)(head + e0); r.b = *(const float4 *)(head + e0 + 4);
-    r.pa = r.a; r.pb = r.b;
-    if (rp.neox && e0 < rp.n_dims) {
-        const int half = rp.n_dims >> 1, po = e0 < half ? e0 + half : e0 - half;
-        r.pa = *(const float4 *)(head + po); r.pb = *(const float4 *)(head + po + 4);
-    }
-    return r;
-}
-// ... roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled)
-__device__ __forceinline__ void rope_raw8(const Raw8 & r, int e0, const float * cs, const RopeDev & rp, float (&v)[8]) {
-    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
-    if (e0 >= rp.n_dims) return;
-    if (!rp.neox) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int i = (e0 >> 1) + j;
-            const float c = cs[2 * i], sn = cs[2 * i + 1], x0 = v[2 * j], x1 = v[2 * j + 1];
-            v[2 * j]     = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, sn));
-            v[2 * j + 1] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
-        }
-    } else {
-        const int half = rp.n_dims >> 1;
-        const bool first = e0 < half;
-        const float o[8] = { r.pa.x, r.pa.y, r.pa.z, r.pa.w, r.pb.x, r.pb.y, r.pb.z, r.pb.w };
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int i = first ? e0 + j : e0 - half + j;
-            const float c = cs[2 * i], sn = cs[2 * i + 1];
-            v[j] = first ? __fsub_rn(__fmul_rn(v[j], c), __fmul_rn(o[j], sn)) : __fadd_rn(__fmul_rn(o[j], sn), __fmul_rn(v[j], c));
-        }
-    }
-}
+// elements e0..e0+7 of one head, roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled)
 __device__ __forceinline__ void load_roped8(const float * head, int e0, const float * cs, const RopeDev & rp, float (&v)[8]) {
     const float4 a = *(const float4 *)(head + e0), b = *(const float4 *)(head + e0 + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -138,90 +102,29 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     __shared__ __align__(16) float s_cs[D];
     __shared__ __align__(16) uint8_t s_newk[D * 2 + 32], s_newv[D * 2 + 32];
     pdl_wait();
-    if (fu.early_trigger & 1) pdl_trigger();  // the next kernel (the wo matvec) may start priming its weight ring now; its own griddepcontrol.wait orders the data
-    // ---- every independent load of the prologue is issued here, together: token position / cells, this token's K and V
-    //      slices, the query slices, and mask + K + V of the first chunk of positions.  Decode attention is a chain of
-    //      dependent memory round trips; done one after the other (table -> K staging -> Q -> K/V) they were the kernel.
-    constexpr int MAXIT = 4;
-    constexpr int pstride = FA_WARPS * PPW;
-    const int p_begin = split * split_len;
-    const int p_end   = min(n_kv, p_begin + split_len);
-    const uint16_t * mrow = mask ? mask + (int64_t)tok * mask_rs : nullptr;
-    int kcell = -1, vcell = -1, pos0 = 0;
-    Raw8 qraw[G]; Raw8 knew; float4 vna = make_float4(0.f, 0.f, 0.f, 0.f), vnb = vna;
-    const int e_kv = lane * 8; const bool on_kv = e_kv < D;
-    if (fu.enabled) {
-        kcell = (int)fu.k_ids[0]; vcell = (int)fu.v_ids[0]; pos0 = fu.pos[0];
-        if (warp == 0 && on_kv) knew = load_raw8(fu.k_new + (int64_t)hk * D, e_kv, fu.rp);
-        if (warp == 1 && on_kv) { vna = *(const float4 *)(fu.v_new + (int64_t)hk * D + e_kv); vnb = *(const float4 *)(fu.v_new + (int64_t)hk * D + e_kv + 4); }
-#pragma unroll
-        for (int g = 0; g < G; g++) qraw[g] = load_raw8(fu.q_src + (int64_t)(h0 + g) * D, dl * 8, fu.rp);
-    } else {
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            const float * qp = q + (int64_t)tok * q_ts + (int64_t)(h0 + g) * q_hs + dl * 8;
-            qraw[g].a = *(const float4 *)qp; qraw[g].b = *(const float4 *)(qp + 4);
-        }
-    }
-    float mraw[MAXIT]; uint4 kraw[MAXIT], vraw[MAXIT]; float kdv[MAXIT], vdv[MAXIT];
-    auto load_chunk = [&](int base) {
-#pragma unroll
-        for (int it = 0; it < MAXIT; it++) {
-            const int p = base + it * pstride;
-            mraw[it] = -INFINITY; kraw[it] = make_uint4(0, 0, 0, 0); vraw[it] = kraw[it]; kdv[it] = 0.0f; vdv[it] = 0.0f;
-            if (p < p_end) {
-                mraw[it] = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
-                const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
-                const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
-                if (KVT == B200_TYPE_F16) {
-                    kraw[it] = ldg_stream16(krow + dl * 16);
-                    vraw[it] = ldg_stream16(vrow + dl * 16);
-                } else {
-                    int q2[2];
-                    load_q80_8(krow, dl, q2, kdv[it]); kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1];
-                    load_q80_8(vrow, dl, q2, vdv[it]); vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1];
-                }
-            }
-        }
-    };
-    const int base0 = p_begin + warp * PPW + sg;
-    const bool hoist = !(fu.early_trigger & 2);
-    if (hoist) load_chunk(base0);                                   // (the new token's cell is patched from shared memory below)
-
+    int kcell = -1, vcell = -1;
     if (fu.enabled) {
         // (n_tok == 1) rope table, then this token's K / V slice for kv head hk in cache format
-        rope_table(s_cs, pos0, fu.ff, fu.rp, threadIdx.x, FA_WARPS * 32);
+        kcell = (int)fu.k_ids[0]; vcell = (int)fu.v_ids[0];
+        rope_table(s_cs, fu.pos[0], fu.ff, fu.rp, threadIdx.x, FA_WARPS * 32);
         __syncthreads();
         if (warp < 2) {
+            const int e = lane * 8; const bool on = e < D;
             float a[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
             const bool storer = split == 0 && (h0 % gq) == 0;
             if (warp == 0) {
-                if (on_kv) rope_raw8(knew, e_kv, s_cs, fu.rp, a);
-                store8(s_newk, KVT, e_kv, a, lane, on_kv);
-                if (storer) store8((uint8_t *)kc + (int64_t)kcell * k_rs + (int64_t)hk * k_hs, KVT, e_kv, a, lane, on_kv);
+                if (on) load_roped8(fu.k_new + (int64_t)hk * D, e, s_cs, fu.rp, a);
+                store8(s_newk, KVT, e, a, lane, on);
+                if (storer) store8((uint8_t *)kc + (int64_t)kcell * k_rs + (int64_t)hk * k_hs, KVT, e, a, lane, on);
             } else {
-                if (on_kv) { a[0] = vna.x; a[1] = vna.y; a[2] = vna.z; a[3] = vna.w; a[4] = vnb.x; a[5] = vnb.y; a[6] = vnb.z; a[7] = vnb.w; }
-                store8(s_newv, KVT, e_kv, a, lane, on_kv);
-                if (storer) store8((uint8_t *)vc + (int64_t)vcell * v_rs + (int64_t)hk * v_hs, KVT, e_kv, a, lane, on_kv);
+                if (on) { const float4 x = *(const float4 *)(fu.v_new + (int64_t)hk * D + e), y = *(const float4 *)(fu.v_new + (int64_t)hk * D + e + 4);
+                          a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w; }
+                store8(s_newv, KVT, e, a, lane, on);
+                if (storer) store8((uint8_t *)vc + (int64_t)vcell * v_rs + (int64_t)hk * v_hs, KVT, e, a, lane, on);
             }
         }
         __syncthreads();
     }
-    // the cell of this token comes from shared memory, whatever the cache held
-    auto patch_chunk = [&](int base) {
-#pragma unroll
-        for (int it = 0; it < MAXIT; it++) {
-            const int p = base + it * pstride;
-            if (p == kcell) {
-                if (KVT == B200_TYPE_F16) kraw[it] = *(const uint4 *)(s_newk + dl * 16);
-                else { int q2[2]; lds_q80_8(s_newk, dl, q2, kdv[it]); kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1]; }
-            }
-            if (p == vcell) {
-                if (KVT == B200_TYPE_F16) vraw[it] = *(const uint4 *)(s_newv + dl * 16);
-                else { int q2[2]; lds_q80_8(s_newv, dl, q2, vdv[it]); vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1]; }
-            }
-        }
-    };
 
     // ---- query slices: q8[g][8] as f32 (f16-rounded) or int8 + scale -------------------------
     float qf[G][8]; int qi[G][2]; float qd[G]; float slope[G];
@@ -230,13 +133,15 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         const int h = h0 + g;
         float v[8];
         if (fu.enabled) {
-            rope_raw8(qraw[g], dl * 8, s_cs, fu.rp, v);
+            load_roped8(fu.q_src + (int64_t)h * D, dl * 8, s_cs, fu.rp, v);
             if (split == 0 && warp == 0 && sg == 0) {
                 *(float4 *)(fu.q_dst + (int64_t)h * D + dl * 8)     = make_float4(v[0], v[1], v[2], v[3]);
                 *(float4 *)(fu.q_dst + (int64_t)h * D + dl * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
             }
         } else {
-            v[0] = qraw[g].a.x; v[1] = qraw[g].a.y; v[2] = qraw[g].a.z; v[3] = qraw[g].a.w; v[4] = qraw[g].b.x; v[5] = qraw[g].b.y; v[6] = qraw[g].b.z; v[7] = qraw[g].b.w;
+            const float * qp = q + (int64_t)tok * q_ts + (int64_t)h * q_hs + dl * 8;
+            const float4 a = *(const float4 *)qp, b = *(const float4 *)(qp + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         }
         if (KVT == B200_TYPE_F16) {
 #pragma unroll
@@ -268,13 +173,37 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
         for (int e = 0; e < 8; e++) acc[g][e] = 0.0f; }
 
     const unsigned gmask = ((1u << LP) - 1u) << (sg * LP);   // lanes sharing one KV position (converged inside the loop)
+    const int p_begin = split * split_len;
+    const int p_end   = min(n_kv, p_begin + split_len);
+    const uint16_t * mrow = mask ? mask + (int64_t)tok * mask_rs : nullptr;
 
     // positions are visited in chunks of MAXIT per lane group: every load of a chunk (mask, K, V) is issued before any
-    // arithmetic, so a chunk costs one memory round trip instead of MAXIT (a decode split is a few dozen positions: usually
-    // ONE chunk, already in flight since the top of the kernel).  K/V of masked positions are loaded but never used.
-    for (int base = base0; base < p_end; base += pstride * MAXIT) {
-        if (base != base0 || !hoist) load_chunk(base);
-        patch_chunk(base);
+    // arithmetic, so a chunk costs one memory round trip instead of MAXIT (decode attention is latency-bound: a split is
+    // a few dozen positions).  K/V of masked positions are loaded but never used.
+    constexpr int MAXIT = 4;
+    constexpr int pstride = FA_WARPS * PPW;
+    for (int base = p_begin + warp * PPW + sg; base < p_end; base += pstride * MAXIT) {
+        float mraw[MAXIT]; uint4 kraw[MAXIT], vraw[MAXIT]; float kdv[MAXIT], vdv[MAXIT];
+#pragma unroll
+        for (int it = 0; it < MAXIT; it++) {
+            const int p = base + it * pstride;
+            mraw[it] = -INFINITY; kraw[it] = make_uint4(0, 0, 0, 0); vraw[it] = kraw[it]; kdv[it] = 0.0f; vdv[it] = 0.0f;
+            if (p < p_end) {
+                mraw[it] = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
+                const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
+                const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
+                if (KVT == B200_TYPE_F16) {
+                    kraw[it] = p == kcell ? *(const uint4 *)(s_newk + dl * 16) : ldg_stream16(krow + dl * 16);
+                    vraw[it] = p == vcell ? *(const uint4 *)(s_newv + dl * 16) : ldg_stream16(vrow + dl * 16);
+                } else {
+                    int q2[2];
+                    if (p == kcell) lds_q80_8(s_newk, dl, q2, kdv[it]); else load_q80_8(krow, dl, q2, kdv[it]);
+                    kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1];
+                    if (p == vcell) lds_q80_8(s_newv, dl, q2, vdv[it]); else load_q80_8(vrow, dl, q2, vdv[it]);
+                    vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1];
+                }
+            }
+        }
 #pragma unroll
         for (int it = 0; it < MAXIT; it++) {
             if (mraw[it] == -INFINITY && max_bias <= 0.0f) continue;       // masked, or beyond the split (uniform inside the LP-lane group)
@@ -387,20 +316,9 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
             __shared__ float s_inv[G];
             const int n_rows = gridDim.z * n_head;
             __shared__ float s_l[FA_MAX_SPLITS][G];
-            // every load of the merge is issued before the first barrier: the (m, l) pairs and — per output element — the
-            // partial accumulators of the first 8 splits
-            constexpr int PRE = 8;
-            float av[(G * D + FA_WARPS * 32 - 1) / (FA_WARPS * 32)][PRE];
-#pragma unroll
-            for (int u = 0; u < (G * D + FA_WARPS * 32 - 1) / (FA_WARPS * 32); u++) {
-                const int idx = threadIdx.x + u * FA_WARPS * 32;
-                const int row = tok * n_head + h0 + idx / D, e = idx % D;
-#pragma unroll
-                for (int sp = 0; sp < PRE; sp++) av[u][sp] = (sp < n_splits && idx < G * D) ? __ldcg(ws + ((int64_t)sp * n_rows + row) * (D + 2) + e) : 0.0f;
-            }
             for (int idx = threadIdx.x; idx < n_splits * G; idx += FA_WARPS * 32) {
                 const int sp = idx / G, g = idx % G;
-                const float2 ml = __ldcg((const float2 *)(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D));
+                const float2 ml = __ldcg((const float2 *)(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D));   // every (m, l) pair in one round trip
                 s_sc[sp][g] = ml.x; s_l[sp][g] = ml.y;
             }
             __syncthreads();
@@ -418,23 +336,18 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
                 s_inv[g] = 1.0f / l;
             }
             __syncthreads();
-            // phase 2: scale and sum (same order as before: split 0 first)
-#pragma unroll
-            for (int u = 0; u < (G * D + FA_WARPS * 32 - 1) / (FA_WARPS * 32); u++) {
-                const int idx = threadIdx.x + u * FA_WARPS * 32;
-                if (idx < G * D) {
-                    const int g = idx / D, e = idx % D;
-                    const int row = tok * n_head + h0 + g;
-                    float a = 0.0f;
-#pragma unroll
-                    for (int sp = 0; sp < PRE; sp++) if (sp < n_splits) a = fmaf(av[u][sp], s_sc[sp][g], a);
-                    for (int sp = PRE; sp < n_splits; sp++) a = fmaf(__ldcg(ws + ((int64_t)sp * n_rows + row) * (D + 2) + e), s_sc[sp][g], a);
-                    dst[(int64_t)row * D + e] = a * s_inv[g];
-                }
+            // phase 2: independent, coalesced loads of the partial accumulators
+            for (int idx = threadIdx.x; idx < G * D; idx += FA_WARPS * 32) {
+                const int g = idx / D, e = idx % D;
+                const int row = tok * n_head + h0 + g;
+                float a = 0.0f;
+#pragma unroll 8
+                for (int sp = 0; sp < n_splits; sp++) a = fmaf(__ldcg(ws + ((int64_t)sp * n_rows + row) * (D + 2) + e), s_sc[sp][g], a);
+                dst[(int64_t)row * D + e] = a * s_inv[g];
             }
         }
     }
-    if (!(fu.early_trigger & 1)) pdl_trigger();
+    pdl_trigger();
 }
 
 template <int D>
@@ -501,7 +414,6 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     return B200_OK;
 }
 
-static int fa_early_trigger() { static const int v = getenv("B200_FA_EARLY_TRIGGER") ? atoi(getenv("B200_FA_EARLY_TRIGGER")) : 0; return v; }
 static int fa_dispatch(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
                                    const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst,
                                    int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
@@ -534,7 +446,6 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
                                    int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
                                    float scale, float max_bias, float softcap, void * workspace, void * stream) {
     FaFuse fu; memset(&fu, 0, sizeof(fu));
-    fu.early_trigger = fa_early_trigger();
     return fa_dispatch(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, kv_type, dk, dv, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, workspace, stream, fu);
 }
 
@@ -551,7 +462,7 @@ extern "C" int b200_rope_kv_flash_attn(const float * q_src, float * q_dst, const
     if (((uintptr_t)q_src | (uintptr_t)q_dst | (uintptr_t)k_new | (uintptr_t)v_new) & 15) { b200_set_error("rope_kv_flash_attn: 16-byte alignment required"); return B200_ERR_INVALID; }
     FaFuse fu; memset(&fu, 0, sizeof(fu));
     fu.q_src = q_src; fu.q_dst = q_dst; fu.k_new = k_new; fu.v_new = v_new; fu.pos = pos; fu.ff = ff; fu.k_ids = k_ids; fu.v_ids = v_ids;
-    fu.rp = rope_host_params(p); fu.enabled = 1; fu.early_trigger = fa_early_trigger();
+    fu.rp = rope_host_params(p); fu.enabled = 1;
     return fa_dispatch(q_dst, hd * n_head, hd, k_cache, k_rs, k_hs, v_cache, v_rs, v_hs, mask, 0, dst, kv_type, hd, hd, n_head, n_head_kv, 1, n_kv,
                        scale, max_bias, softcap, workspace, stream, fu);
 }

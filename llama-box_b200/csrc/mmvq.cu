@@ -18,7 +18,6 @@
 // Rows of Q4_0/Q8_0/Q6_K are repacked at load time so every part of a segment is 16-byte aligned
 // (repack.cu); Q4_K/Q5_K keep the GGUF layout.
 #include "common.cuh"
-#include <stdlib.h>
 #include "actquant.cuh"
 
 #define MMV_WARPS 16
@@ -64,7 +63,7 @@ struct MmvArgs {
     float *       y_out;        // optional f32 copy of the (normalised) activations, written by CTA 0
     int64_t       x_col_stride;
     float         eps;
-    int32_t       tune;         // bit 0: 8-lanes-per-block quantisation of long activation vectors
+    int32_t       _pad2;
 };
 
 // ---- activation view in shared memory --------------------------------------------------------
@@ -524,12 +523,10 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
         for (int col = 0; col < args.ncols; col++) {
             const float * xc = args.x + (int64_t)col * args.x_col_stride;
             float scale = 1.0f;
-            float4 xa0 = make_float4(0.f, 0.f, 0.f, 0.f), xb0 = xa0;     // this warp's first block stays in registers between the two passes
             if (args.act_source == 2) {
                 double acc2 = 0.0;                                  // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
                 for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                     const float4 a = *(const float4 *)(xc + blk * 256 + lane * 8), b = *(const float4 *)(xc + blk * 256 + lane * 8 + 4);
-                    if (blk == warp) { xa0 = a; xb0 = b; }
                     acc2 += (double)__fmul_rn(a.x, a.x); acc2 += (double)__fmul_rn(a.y, a.y); acc2 += (double)__fmul_rn(a.z, a.z); acc2 += (double)__fmul_rn(a.w, a.w);
                     acc2 += (double)__fmul_rn(b.x, b.x); acc2 += (double)__fmul_rn(b.y, b.y); acc2 += (double)__fmul_rn(b.z, b.z); acc2 += (double)__fmul_rn(b.w, b.w);
                 }
@@ -541,25 +538,9 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
                 for (int i = 0; i < MMV_WARPS; i++) t += red[i];    // every thread: same order, same value — no second barrier
                 scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k), args.eps)));
             }
-            if ((args.tune & 1) && args.act_source == 1 && args.act_bytes[0] && !args.act_bytes[1] && !args.y_out && nblk > MMV_WARPS) {
-                // long vector, q8_K only (wo / ffn_down of K-quant models): 8 lanes per block, 4 blocks per warp at once
-                const int lg = lane >> 3, li = lane & 7;
-                const ActOut o = act_sections(act_s0, 0, args.k, col);
-                for (int b0 = warp * 4; b0 < nblk; b0 += MMV_WARPS * 4) {
-                    const int blk = b0 + lg;
-                    if (blk < nblk) {                              // nblk % 8 == 0 on this path: a lane group is on or off as a whole
-                        float v[32];
-                        const float * xp = xc + (int64_t)blk * 256 + li * 32;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) { const float4 t = *(const float4 *)(xp + 4 * j); v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w; }
-                        group_quant_q8K(v, o, blk, li);
-                    }
-                }
-            } else
             for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                 const int64_t i = (int64_t)blk * 256 + lane * 8;
-                const bool kept = args.act_source == 2 && blk == warp;
-                const float4 a = kept ? xa0 : *(const float4 *)(xc + i), b = kept ? xb0 : *(const float4 *)(xc + i + 4);
+                const float4 a = *(const float4 *)(xc + i), b = *(const float4 *)(xc + i + 4);
                 float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
                 if (args.act_source == 2) {
 #pragma unroll
@@ -676,8 +657,6 @@ template <int NCOLS> static int mmv_launch_n(const MmvArgs & a, int mode, size_t
 static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
     if (ncols < 1 || ncols > 8) { b200_set_error("mmvq: ncols must be 1..8"); return B200_ERR_INVALID; }
     a.ncols = (int32_t)ncols;
-    static const int tune = getenv("B200_MMV_TUNE") ? atoi(getenv("B200_MMV_TUNE")) : 0;     // until verified on the GPU: opt-in
-    a.tune = tune;
     if (a.act_source != 0 && (!a.x || ((uintptr_t)a.x & 15) || (a.x_col_stride & 3) || ((uintptr_t)a.norm_w & 15))) { b200_set_error("mmvq: f32 activation source must be 16-byte aligned"); return B200_ERR_INVALID; }
     bool need[2] = { false, false };
     for (int i = 0; i < a.n_mats; i++) {

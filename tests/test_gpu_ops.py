@@ -212,16 +212,6 @@ def test_mmvq_fused_activation_prologue(b200, t, src, k):
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), np.abs(got - want).max()
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("B200_TEST_OPT_IN"), reason="opt-in kernel variant not yet measured on the GPU (set B200_TEST_OPT_IN=1)")
-def test_mmvq_group_quant_opt_in():
-    """B200_MMV_TUNE=1 (8 lanes per block for long activation vectors, read once per process): same results"""
-    import os, subprocess, sys
-    env = dict(os.environ, B200_MMV_TUNE="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", "fused_activation_prologue or mmvq_bias_residual"],
-                       capture_output=True, text=True, env=env, timeout=900)
-    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
-
-
 def test_mmvq_rejects_bad_shapes(b200):
     d = torch.zeros(4096, dtype=torch.uint8, device="cuda")
     assert b200.lib.b200_mul_mat_vec_q(Q4_K, b200.p(d), b200.p(d), b200.p(d), 8, None, None, 8, 100, 1, b200.stream()) < 0
