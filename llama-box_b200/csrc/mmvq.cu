@@ -382,6 +382,16 @@ __device__ __forceinline__ void slot_dispatch(int t0, int t1, const uint8_t * s0
             case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
             default:             slot_dot<B200_TYPE_Q8_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
         }
+    } else if (TT == -2) {
+        // the launch mixes Q4_K and Q6_K matrices only (QKV of a Q4_K_M model: attn_v is Q6_K in half of the layers):
+        // two types' worth of code instead of five — these 10-microsecond kernels feel every instruction-cache miss
+        if (t0 == B200_TYPE_Q4_K) {
+            if (segc == 64) slot_dot_q4K_fast<NCOLS, NR>(s0, s1, nb0, lseg, seg, a0, k, lane, acc);
+            else slot_dot<B200_TYPE_Q4_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc);
+        } else {
+            if (segc == 64) slot_dot_q6K_fast<NCOLS, NR>(s0, s1, nb0, lseg, seg, a0, k, lane, acc);
+            else slot_dot<B200_TYPE_Q6_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc);
+        }
     } else if (t0 == t1) {
         slot_one_type<NCOLS, NR>(t0, s0, s1, nb0, segc, lseg, seg, a0, a1, k, lane, acc);
     } else {
@@ -650,7 +660,12 @@ template <int NCOLS> static int mmv_launch_n(const MmvArgs & a, int mode, size_t
         case B200_TYPE_Q4_K: return mmv_launch_nt<NCOLS, B200_TYPE_Q4_K>(a, mode, smem, grid, st);
         case B200_TYPE_Q5_K: return mmv_launch_nt<NCOLS, B200_TYPE_Q5_K>(a, mode, smem, grid, st);
         case B200_TYPE_Q6_K: return mmv_launch_nt<NCOLS, B200_TYPE_Q6_K>(a, mode, smem, grid, st);
-        default:             return mmv_launch_nt<NCOLS, -1>(a, mode, smem, grid, st);
+        default: {
+            bool k46 = mode != MMV_MODE_SWIGLU;
+            for (int i = 0; i < a.n_mats; i++) if (a.mat[i].type != B200_TYPE_Q4_K && a.mat[i].type != B200_TYPE_Q6_K) k46 = false;
+            if (k46) return mmv_launch_ntm<NCOLS, -2, MMV_MODE_PLAIN>(a, smem, grid, st);
+            return mmv_launch_nt<NCOLS, -1>(a, mode, smem, grid, st);
+        }
     }
 }
 
