@@ -350,22 +350,6 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     pdl_trigger();
 }
 
-template <int D>
-__global__ void __launch_bounds__(D) fattn_combine_kernel(const float * __restrict__ ws, float * __restrict__ dst, int n_splits, int n_rows) {
-    pdl_wait();
-    const int row = blockIdx.x, e = threadIdx.x;           // row = tok*n_head + head
-    float Mn = -INFINITY;
-    for (int s = 0; s < n_splits; s++) Mn = fmaxf(Mn, ws[((int64_t)s * n_rows + row) * (D + 2) + D]);
-    float a = 0.0f, l = 0.0f;
-    for (int s = 0; s < n_splits; s++) {
-        const float * wp = ws + ((int64_t)s * n_rows + row) * (D + 2);
-        const float sc = wp[D] == -INFINITY ? 0.0f : expf(wp[D] - Mn);
-        a += wp[e] * sc; l += wp[D + 1] * sc;
-    }
-    dst[(int64_t)row * D + e] = a * (1.0f / l);
-    pdl_trigger();
-}
-
 // KV splits: ~2 CTAs of 128 threads per SM, at least 32 positions per split, at most FA_MAX_SPLITS
 static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_len) {
     const int sms = b200_sm_count();
