@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "ropeutil.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define FA_WARPS 4
@@ -354,13 +355,15 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
 static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_len) {
     const int sms = b200_sm_count();
     int64_t base = n_tiles * n_tok;
-    int64_t want = (2 * (int64_t)sms + base - 1) / base;
-    int64_t maxs = (n_kv + 31) / 32;
+    static const int factor = getenv("B200_FA_SPLIT_FACTOR") ? atoi(getenv("B200_FA_SPLIT_FACTOR")) : 2;   // CTAs per SM aimed for
+    int64_t want = ((int64_t)factor * sms + base - 1) / base;
+    static const int minlen = getenv("B200_FA_MIN_SPLIT") ? atoi(getenv("B200_FA_MIN_SPLIT")) : 32;     // positions per split, at least
+    int64_t maxs = (n_kv + minlen - 1) / minlen;
     if (maxs > FA_MAX_SPLITS) maxs = FA_MAX_SPLITS;
     if (want > maxs) want = maxs;
     if (want < 1) want = 1;
     int64_t len = (n_kv + want - 1) / want;
-    len = (len + 31) / 32 * 32;
+    len = (len + minlen - 1) / minlen * minlen;
     *split_len = (int)len;
     return (int)((n_kv + len - 1) / len);
 }
@@ -371,8 +374,8 @@ static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_l
 // themselves after every launch).
 #define FA_COUNTER_BYTES (256 * 1024)
 static int64_t fa_partial_bytes(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
-    int64_t maxs = (n_kv + 31) / 32;
-    if (maxs > FA_MAX_SPLITS) maxs = FA_MAX_SPLITS;
+    int sl = 0;
+    int64_t maxs = fa_splits((n_head + 3) / 4, n_tok, n_kv, &sl);      // fewest head tiles (G = 4) -> most splits: an upper bound
     return (maxs * n_tok * n_head * (dv + 2) * (int64_t)sizeof(float) + 255) & ~(int64_t)255;
 }
 extern "C" int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
