@@ -19,6 +19,9 @@
 #include <string.h>
 
 #define FA_WARPS 4
+#ifndef FA_MIN_CTAS
+#define FA_MIN_CTAS 1      // (4 = at most 128 registers, so that a CTA fits next to a resident matvec CTA: measured no gain)
+#endif
 #define FA_MAX_SPLITS 64
 
 
@@ -45,7 +48,7 @@ __device__ __forceinline__ void load_q80_8(const uint8_t * row, int dl, int (&q)
 struct FaFuse {
     const float * q_src; float * q_dst; const float * k_new; const float * v_new;
     const int32_t * pos; const float * ff; const int64_t * k_ids; const int64_t * v_ids;
-    RopeDev rp; int enabled;
+    RopeDev rp; int enabled; int early_trigger;
 };
 // elements e0..e0+7 of one head, roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled)
 __device__ __forceinline__ void load_roped8(const float * head, int e0, const float * cs, const RopeDev & rp, float (&v)[8]) {
@@ -84,7 +87,7 @@ __device__ __forceinline__ void lds_q80_8(const uint8_t * row, int dl, int (&q)[
 }
 
 template <int D, int KVT, int G>
-__global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
+__global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         const float * __restrict__ q, int64_t q_ts, int64_t q_hs,
         const uint8_t * __restrict__ kc, int64_t k_rs, int64_t k_hs,
         const uint8_t * __restrict__ vc, int64_t v_rs, int64_t v_hs,
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
     const int hk = h0 / gq;
     __shared__ __align__(16) float s_cs[D];
     __shared__ __align__(16) uint8_t s_newk[D * 2 + 32], s_newv[D * 2 + 32];
+    if (fu.early_trigger) pdl_trigger();      // B200_FA_EARLY_TRIGGER=1: the next kernel may prime its weight ring during the attention — measured slower (its burst delays our loads)
     pdl_wait();
     int kcell = -1, vcell = -1;
     if (fu.enabled) {
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fattn_vec_kernel(
             }
         }
     }
-    pdl_trigger();
+    if (!fu.early_trigger) pdl_trigger();
 }
 
 // KV splits: ~2 CTAs of 128 threads per SM, at least 32 positions per split, at most FA_MAX_SPLITS
@@ -401,6 +405,7 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     return B200_OK;
 }
 
+static int fa_early_trigger() { static const int v = getenv("B200_FA_EARLY_TRIGGER") ? atoi(getenv("B200_FA_EARLY_TRIGGER")) : 0; return v; }
 static int fa_dispatch(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
                                    const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst,
                                    int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
@@ -433,6 +438,7 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
                                    int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
                                    float scale, float max_bias, float softcap, void * workspace, void * stream) {
     FaFuse fu; memset(&fu, 0, sizeof(fu));
+    fu.early_trigger = fa_early_trigger();
     return fa_dispatch(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, kv_type, dk, dv, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, workspace, stream, fu);
 }
 
@@ -449,7 +455,7 @@ extern "C" int b200_rope_kv_flash_attn(const float * q_src, float * q_dst, const
     if (((uintptr_t)q_src | (uintptr_t)q_dst | (uintptr_t)k_new | (uintptr_t)v_new) & 15) { b200_set_error("rope_kv_flash_attn: 16-byte alignment required"); return B200_ERR_INVALID; }
     FaFuse fu; memset(&fu, 0, sizeof(fu));
     fu.q_src = q_src; fu.q_dst = q_dst; fu.k_new = k_new; fu.v_new = v_new; fu.pos = pos; fu.ff = ff; fu.k_ids = k_ids; fu.v_ids = v_ids;
-    fu.rp = rope_host_params(p); fu.enabled = 1;
+    fu.rp = rope_host_params(p); fu.enabled = 1; fu.early_trigger = fa_early_trigger();
     return fa_dispatch(q_dst, hd * n_head, hd, k_cache, k_rs, k_hs, v_cache, v_rs, v_hs, mask, 0, dst, kv_type, hd, hd, n_head, n_head_kv, 1, n_kv,
                        scale, max_bias, softcap, workspace, stream, fu);
 }
