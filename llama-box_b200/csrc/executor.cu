@@ -370,6 +370,111 @@ struct Runner {
         return true;
     }
 
+    // ---- the whole attention block of a decode token as TWO launches, even when the graph allocator recycles buffers -------
+    // libllama's graph reuses the buffer of the un-roped Q for K and V (llama-graph allocations), which forbids hoisting the
+    // K / V projections next to Q's — and with that every later fusion.  All intermediates of the block (Q/K/V before rope,
+    // roped K) have exactly one consumer inside the block, so they are never materialised in the graph's buffers at all: the
+    // three projections go to executor scratch in one launch, the fused rope + KV-store + attention launch reads them there.
+    //   MUL_MAT(q)[+bias] ROPE  MUL_MAT(k)[+bias] ROPE  MUL_MAT(v)[+bias]  SET_ROWS(k) SET_ROWS(v) [CPY mask] FLASH_ATTN_EXT
+    // (llama-model.cpp:6004-6043, llama-kv-cache-unified.cpp:1103-1160, llama-graph.cpp:1236-1265)
+    int sole_consumer(int from, const b200_tensor & t, const b200_tensor ** as_seen) const {
+        uint64_t id = t.id;
+        for (int hop = 0; hop < 5; hop++) {
+            auto it = uses.find(id);
+            if (it == uses.end() || it->second != 1) return -1;
+            int c = -1, sidx = -1;
+            for (int q = from + 1; q < n && c < 0; q++) for (int sx = 0; sx < nodes[q].n_src && sx < B200_MAX_SRC; sx++) if (nodes[q].src[sx].id == id) { c = q; sidx = sx; break; }
+            if (c < 0) return -1;
+            if (nodes[c].op != B200_OP_NONE) { *as_seen = &nodes[c].src[sidx]; return c; }
+            id = nodes[c].dst.id; from = c;
+        }
+        return -1;
+    }
+    bool try_attn_block(int i, int & status) {
+        const b200_node & mq = nodes[i];
+        const b200_tensor & x = mq.src[1];
+        if (x.ne[1] != 1 || !ex->ws) return false;
+        struct Proj { int mm = -1, add = -1; const b200_tensor * out = nullptr; const float * bias = nullptr; } P[3];
+        int rope[2] = { -1, -1 };
+        int cur = i;
+        for (int j = 0; j < 3; j++) {
+            if (j > 0) { cur = next_compute(cur); if (cur < 0 || nodes[cur].op != B200_OP_MUL_MAT) return false; }
+            const b200_node & mm = nodes[cur];
+            if (mm.src[1].id != x.id || mm.src[1].data != x.data || mm.src[0].ne[0] != mq.src[0].ne[0] || mm.dst.nb[1] != mm.src[0].ne[1] * 4) return false;
+            P[j].mm = cur; P[j].out = &mm.dst;
+            const int a = next_compute(cur);
+            if (a >= 0 && nodes[a].op == B200_OP_ADD && use_count(mm.dst) == 1 && nodes[a].src[0].data == mm.dst.data && nrows_of(nodes[a].src[1]) == 1 &&
+                nodes[a].src[1].ne[0] == mm.src[0].ne[1] && nodes[a].dst.nb[1] == mm.src[0].ne[1] * 4) {
+                P[j].add = a; P[j].out = &nodes[a].dst; P[j].bias = (const float *)nodes[a].src[1].data; cur = a;
+            }
+            if (j < 2) {
+                const b200_tensor * seen = nullptr;
+                const int r = sole_consumer(cur, *P[j].out, &seen);
+                if (r < 0 || nodes[r].op != B200_OP_ROPE || r != next_compute(cur)) return false;
+                rope[j] = r; cur = r;
+            }
+        }
+        const b200_node & rq = nodes[rope[0]], & rk = nodes[rope[1]];
+        if (memcmp(rq.op_params, rk.op_params, sizeof(rq.op_params)) != 0 || rq.src[1].data != rk.src[1].data) return false;
+        if ((rq.n_src > 2 ? rq.src[2].data : nullptr) != (rk.n_src > 2 ? rk.src[2].data : nullptr)) return false;
+        const b200_tensor & q3 = rq.src[0], & k3 = rk.src[0];
+        const int64_t hd = q3.ne[0], nh = q3.ne[1], nhk = k3.ne[1];
+        auto dense3 = [&](const b200_tensor & t) { return t.nb[0] == 4 && t.nb[1] == t.ne[0] * 4 && t.nb[2] == t.ne[0] * t.ne[1] * 4; };
+        if (q3.ne[2] != 1 || k3.ne[2] != 1 || k3.ne[0] != hd || !dense3(q3) || !dense3(k3) || !dense3(rq.dst) || (hd != 64 && hd != 128)) return false;
+        if (nh * hd != nodes[P[0].mm].src[0].ne[1] || nhk * hd != nodes[P[1].mm].src[0].ne[1] || nhk * hd != nodes[P[2].mm].src[0].ne[1] || (nhk * hd) % 256 != 0) return false;
+        // KV stores: K consumes exactly the roped K, V exactly the V projection (through views), each once
+        const b200_tensor * seen = nullptr;
+        const int sk = sole_consumer(rope[1], rk.dst, &seen);
+        if (sk < 0 || nodes[sk].op != B200_OP_SET_ROWS || seen != &nodes[sk].src[0] || seen->ne[0] != nhk * hd || seen->ne[1] != 1) return false;
+        const int sv = sole_consumer(P[2].add >= 0 ? P[2].add : P[2].mm, *P[2].out, &seen);
+        if (sv < 0 || nodes[sv].op != B200_OP_SET_ROWS || seen != &nodes[sv].src[0] || seen->ne[0] != nhk * hd || seen->ne[1] != 1) return false;
+        if (sk != next_compute(P[2].add >= 0 ? P[2].add : P[2].mm) || sv != next_compute(sk)) return false;
+        const b200_node & SK = nodes[sk], & SV = nodes[sv];
+        if (SK.dst.type != SV.dst.type || (SK.dst.type != B200_TYPE_F16 && SK.dst.type != B200_TYPE_Q8_0) || SK.dst.ne[2] != 1 || SV.dst.ne[2] != 1) return false;
+        // the roped Q goes to FLASH_ATTN_EXT only; mask casts in between are independent of the block and run first
+        const int fa = sole_consumer(rope[0], rq.dst, &seen);
+        if (fa < 0 || nodes[fa].op != B200_OP_FLASH_ATTN_EXT || seen != &nodes[fa].src[0]) return false;
+        for (int q = next_compute(sv); q >= 0 && q < fa; q = next_compute(q)) if (nodes[q].op != B200_OP_CPY) return false;
+        b200_rope_params p; memset(&p, 0, sizeof(p));
+        p.n_dims = rq.op_params[1]; p.mode = rq.op_params[2]; p.n_ctx_orig = rq.op_params[4];
+        p.freq_base = f32_param(rq, 5); p.freq_scale = f32_param(rq, 6); p.ext_factor = f32_param(rq, 7);
+        p.attn_factor = f32_param(rq, 8); p.beta_fast = f32_param(rq, 9); p.beta_slow = f32_param(rq, 10);
+        if ((p.mode & ~2) || p.n_dims > hd || p.n_dims % 8 != 0 || (p.mode == 2 && p.n_dims % 16 != 0)) return false;
+        const b200_node & F = nodes[fa];
+        // executor scratch behind the attention workspace: q | k | v projections of this token
+        const size_t fa_ws = (size_t)b200_flash_attn_workspace(hd, nh, 1, F.src[1].ne[1]);
+        if (ex->off_fa + fa_ws + (size_t)(nh + 2 * nhk) * hd * 4 + 256 > ex->ws_bytes) return false;
+        float * sq = (float *)(ex->ws + ex->off_fa + ((fa_ws + 255) & ~(size_t)255));
+        float * skn = sq + nh * hd, * svn = skn + nhk * hd;
+        RopePend r;
+        r.valid = true; r.q_src = sq; r.q_dst = (float *)rq.dst.data; r.k = skn; r.v = svn; r.pos = (const int32_t *)rq.src[1].data;
+        r.ff = rq.n_src > 2 ? (const float *)rq.src[2].data : nullptr; r.k_ids = (const int64_t *)SK.src[1].data; r.v_ids = (const int64_t *)SV.src[1].data;
+        r.k_cache = SK.dst.data; r.v_cache = SV.dst.data; r.kv_type = SK.dst.type; r.k_rs = SK.dst.nb[1]; r.v_rs = SV.dst.nb[1]; r.hd = hd; r.nh = nh; r.nhk = nhk; r.p = p;
+        rope_pend = r;
+        if (!attn_matches(F)) { rope_pend.valid = false; return false; }
+        rope_pend.valid = false;
+        // ---- commit: the projections (they read the pending norm / x NOW), then independent mask casts that sat between the
+        //      KV stores and the attention (their output may recycle x's buffer), then the attention launch
+        b200_mmv_launch L; memset(&L, 0, sizeof(L));
+        L.k = mq.src[0].ne[0]; L.ncols = 1; L.n_mats = 3;
+        fill_act_source(L, x);
+        float * outs[3] = { sq, skn, svn };
+        for (int j = 0; j < 3; j++) {
+            const b200_node & mm = nodes[P[j].mm];
+            L.mats[j] = { mm.src[0].data, outs[j], P[j].bias, mm.src[0].ne[1], mm.src[0].type, 0 };
+            if (j) done[P[j].mm] = 1;
+            if (P[j].add >= 0) done[P[j].add] = 1;
+        }
+        status = launch_mmv(L);
+        done[rope[0]] = done[rope[1]] = done[sk] = done[sv] = done[fa] = 1;
+        if (status != B200_OK) return true;
+        for (int q = next_compute(sv); q >= 0 && q < fa; q = next_compute(q)) { status = run_node(q); done[q] = 1; if (status != B200_OK) return true; }
+        rope_pend = r;
+        status = launch_fused_attn(F);
+        invalidate_act(rq.dst); invalidate_act(F.dst);
+        return true;
+    }
+
     int run_mul_mat(int i) {
         const b200_node & n = nodes[i];
         const b200_tensor & w = n.src[0], & x = n.src[1];
@@ -382,6 +487,7 @@ struct Runner {
             return b200_mul_mat_q(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, ncols, act_buf(kind), st);
         }
         int s = B200_OK;
+        if (fuse && !mega && ncols == 1 && try_attn_block(i, s)) return s;
         b200_mmv_launch L; memset(&L, 0, sizeof(L));
         L.k = k; L.ncols = ncols;
         if (fuse) {
@@ -636,7 +742,8 @@ int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
         } else if (nd.op == B200_OP_RMS_NORM) {
             for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(8 * act_col_bytes(kd, (nd.src[0].ne[0] + 255) / 256 * 256)); if (b > act[kd]) act[kd] = b; }
         } else if (nd.op == B200_OP_FLASH_ATTN_EXT) {
-            const size_t b = (size_t)b200_flash_attn_workspace(nd.src[2].ne[0], nd.src[0].ne[2], nd.src[0].ne[1], nd.src[1].ne[1]);
+            size_t b = (size_t)b200_flash_attn_workspace(nd.src[2].ne[0], nd.src[0].ne[2], nd.src[0].ne[1], nd.src[1].ne[1]);
+            if (nd.src[0].ne[1] == 1) b = ((b + 255) & ~(size_t)255) + (size_t)(nd.src[0].ne[2] + 2 * nd.src[1].ne[2]) * nd.src[0].ne[0] * 4 + 512;   // + q|k|v scratch of try_attn_block
             if (b > fa) fa = b;
         }
     }

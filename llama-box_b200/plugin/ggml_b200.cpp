@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -229,10 +230,13 @@ static bool node_to_b200(const ggml_tensor * t, b200_node & n) {
 // backend = one stream (ggml_backend_i, ggml-backend-impl.h:87-124)
 // ------------------------------------------------------------------------------------------------
 static const char * be_name(ggml_backend_t b) { return ((b200_backend_ctx *)b->context)->name.c_str(); }
+static bool g_timing_flag(); static long g_calls_ref(); static long g_nodes_ref(); static long g_kernels_ref(); static double g_conv_ref(); static double g_exec_ref();
 static void be_free(ggml_backend_t b) {
     b200_backend_ctx * c = (b200_backend_ctx *)b->context;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (g_timing_flag() && g_calls_ref()) fprintf(stderr, "ggml-b200 timing: %ld graph_compute calls, %.1f nodes and %.1f kernels per call, host: %.1f us translate + %.1f us executor per call; graph captures %lld replays %lld\n",
+                                      g_calls_ref(), (double)g_nodes_ref() / g_calls_ref(), (double)g_kernels_ref() / g_calls_ref(), g_conv_ref() / g_calls_ref(), g_exec_ref() / g_calls_ref(), (long long)b200_executor_graph_captures(c->ex), (long long)b200_executor_graph_replays(c->ex));
     b200_executor_free(c->ex);
     cudaStreamDestroy(c->stream);
     delete c; delete b;
@@ -278,9 +282,18 @@ static void be_synchronize(ggml_backend_t b) {
     CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
+// GGML_B200_TIMING=1: host-side cost of graph_compute (node translation / executor call), printed when the backend is freed
+static bool g_timing = getenv("GGML_B200_TIMING") != nullptr;
+static double g_t_conv = 0, g_t_exec = 0; static long g_calls = 0, g_nodes = 0, g_kernels = 0;
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static bool g_timing_flag() { return g_timing; } static long g_calls_ref() { return g_calls; } static long g_nodes_ref() { return g_nodes; } static long g_kernels_ref() { return g_kernels; }
+static double g_conv_ref() { return g_t_conv; } static double g_exec_ref() { return g_t_exec; }
+
 static enum ggml_status be_graph_compute(ggml_backend_t b, struct ggml_cgraph * cgraph) {
     b200_backend_ctx * c = (b200_backend_ctx *)b->context;
     cudaSetDevice(c->device);
+    const double t0 = g_timing ? now_us() : 0;
     const int n = ggml_graph_n_nodes(cgraph);
     c->nodes.resize(n);
     for (int i = 0; i < n; i++) {
@@ -299,7 +312,18 @@ static enum ggml_status be_graph_compute(ggml_backend_t b, struct ggml_cgraph * 
             }
         }
     }
+    static int dumped = 0;
+    if (getenv("GGML_B200_DUMP_GRAPH") && n > 200 && dumped < 1) {           // debugging: the node list as the executor sees it
+        dumped++;
+        for (int i = 0; i < n && i < 140; i++) {
+            ggml_tensor * t = ggml_graph_node(cgraph, i);
+            fprintf(stderr, "node %3d %-14s %-22s [%lld,%lld,%lld] nb1=%lld src0=%s(%s) src1=%s data=%p\n", i, ggml_op_name(t->op), t->name, (long long)t->ne[0], (long long)t->ne[1], (long long)t->ne[2], (long long)t->nb[1],
+                    t->src[0] ? t->src[0]->name : "-", t->src[0] ? ggml_type_name(t->src[0]->type) : "", t->src[1] ? t->src[1]->name : "-", t->data);
+        }
+    }
+    const double t1 = g_timing ? now_us() : 0;
     const int st = b200_executor_compute(c->ex, c->nodes.data(), n, c->stream, B200_EXEC_CUDA_GRAPHS | B200_EXEC_FUSION);
+    if (g_timing) { const double t2 = now_us(); g_t_conv += t1 - t0; g_t_exec += t2 - t1; g_calls++; g_nodes += n; g_kernels += b200_executor_last_kernels(c->ex); }
     if (st != B200_OK) { fprintf(stderr, "ggml-b200: graph_compute failed: %s\n", b200_last_error()); return GGML_STATUS_FAILED; }
     return GGML_STATUS_SUCCESS;
 }
