@@ -145,6 +145,28 @@ def cpu_reference(args, gen=16, prompt_len=None):
     return out["decode_tps"], threads, f"{gen - 1} greedy decode tokens after a {prompt_len}-token prompt, {args.model} {args.ftype} synthetic GGUF, ggml-cpu {threads} threads of {cores} cores", out
 
 
+def libllama_plugin(args, gen=65):
+    """the drop-in path proper: the unmodified reference libllama (llama_decode loop of oracle/drivers/llama_drv.cpp) driving
+    libggml-b200.so through ggml's backend C-ABI on the same synthetic GGUF, flash attention on, F16 KV.  Informational
+    (`e2e_libllama`); runs after the timed legs, in its own process.  None where oracle/_ref or the plug-in are absent."""
+    drv = os.path.join(REF_DIR, "llama_drv"); plugin = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    path = os.path.join(shm, f"b200_bench_{args.model}_{args.ftype}{'_L%d' % args.layers if args.layers else ''}.gguf")
+    if not (os.path.exists(drv) and os.path.exists(plugin) and os.path.exists(path)):
+        return None
+    env = dict(os.environ, LD_LIBRARY_PATH=REF_DIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), GGML_BACKEND_PATH=plugin)
+    try:
+        r = subprocess.run([drv, "--model", path, "--plugin", plugin, "--ngl", "99", "--fa", "--ctx", str(args.ctx), "--prompt-len", str(min(args.n_past, 512)), "--gen", str(gen)],
+                           capture_output=True, text=True, env=env, timeout=600)
+        if r.returncode != 0:
+            return {"value": None, "unit": "tok/s", "error": (r.stderr or r.stdout)[-300:]}
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": out["decode_tps"], "unit": "tok/s", "prefill_tok_s": out["prefill_tps"],
+                "api": "llama_decode of the unmodified reference libllama + libggml-b200.so (ggml backend C-ABI), greedy, %d tokens after a %d-token prompt" % (gen - 1, out["prompt_len"])}
+    except Exception as e:  # noqa: BLE001 — informational leg, never fails the bench
+        return {"value": None, "unit": "tok/s", "error": str(e)[:300]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -288,6 +310,8 @@ def run_b200(args):
                        "parallelism": "single GPU"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "kernels_per_step": int(kernels_per_step),
             "graph_captures": int(ex.captures), "graph_replays": int(ex.replays), "roofline": roof, "cpu_baseline": cpu}
+    if not args.no_cpu_baseline:
+        line["e2e_libllama"] = libllama_plugin(args)   # own process, own copy of the model (4.9 GB more HBM)
     if args.layers:
         line["config"]["INVALID"] = "layer count overridden (debug run)"
     print(json.dumps(line))
