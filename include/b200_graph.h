@@ -79,6 +79,9 @@ B200_API void           b200_executor_free(b200_executor *ex);
 B200_API int            b200_executor_supports(const b200_node *node);
 /* run the list in order on `stream`; asynchronous.  Returns b200_status. */
 B200_API int            b200_executor_compute(b200_executor *ex, const b200_node *nodes, int n_nodes, void *stream, int flags);
+/* dry run: how many kernel launches the executor would issue for this list with these flags (no device is touched, so the
+ * fusion logic is testable on a CPU-only host); negative b200_status on unsupported nodes */
+B200_API int64_t        b200_executor_plan(const b200_node *nodes, int n_nodes, int flags);
 /* counters for tests / bench: kernels launched by the last compute (inside a replayed graph too),
  * number of CUDA-graph captures and replays so far */
 B200_API int64_t        b200_executor_last_kernels(const b200_executor *ex);

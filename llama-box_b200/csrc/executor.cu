@@ -8,6 +8,7 @@
 #include "mk.h"
 #include "ropeutil.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
@@ -151,18 +152,24 @@ struct b200_executor {
 
 namespace {
 
+// a kernel launch — or, in a dry run, just its count
+#define KL(call) (dry ? (plan_note(#call), (int)B200_OK) : (int)(call))
+
 struct Runner {
     b200_executor * ex; const b200_node * nodes; int n; cudaStream_t st; bool fuse;
     std::vector<uint8_t> done;
     std::unordered_map<uint64_t, int> uses;
     // ---- persistent decode kernel: phases recorded instead of launched, flushed as ONE launch ----------------
     bool mega = false, mega_mmv = false;
+    bool dry = false; int64_t planned = 0;      // dry run (b200_executor_plan): walk the list, count launches, touch no device
+    void plan_note(const char * what) { planned++; static const bool dbg = getenv("B200_PLAN_DEBUG") != nullptr; if (dbg) fprintf(stderr, "plan %3lld: %.40s\n", (long long)planned, what); }
     std::vector<MkPhase> pend;
     struct RopePend { bool valid = false; const float * q_src; float * q_dst; const float * k, * v; const int32_t * pos; const float * ff;
                       const int64_t * k_ids, * v_ids; void * k_cache, * v_cache; int kv_type; int64_t k_rs, v_rs, hd, nh, nhk; b200_rope_params p; } rope_pend;
 
     int mk_flush() {
         int s = B200_OK;
+        if (dry && !pend.empty()) { plan_note("mk_launch(persistent kernel program)"); pend.clear(); }
         if (!pend.empty()) {
             // content hash -> device-resident program (uploaded once; replayed graphs keep pointing at it)
             uint64_t h = 0xcbf29ce484222325ull;
@@ -187,7 +194,7 @@ struct Runner {
         if (rope_pend.valid) {
             const RopePend & r = rope_pend;
             rope_pend.valid = false;
-            s = b200_rope_kv_store2(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, r.k_rs, r.v_rs, r.hd, r.nh, r.nhk, 1, &r.p, st);
+            s = KL(b200_rope_kv_store2(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, r.k_rs, r.v_rs, r.hd, r.nh, r.nhk, 1, &r.p, st));
         }
         return s;
     }
@@ -222,7 +229,7 @@ struct Runner {
         if (mk_try_mmv(L)) return B200_OK;
         const int s = mk_flush();
         if (s != B200_OK) return s;
-        return b200_mul_mat_vec_q_launch(&L, st);
+        return KL(b200_mul_mat_vec_q_launch(&L, st));
     }
     // does this FLASH_ATTN_EXT consume exactly what the recorded rope + KV store of the same token produces?
     bool attn_matches(const b200_node & n) const {
@@ -243,8 +250,8 @@ struct Runner {
         const int fs = mk_flush(); if (fs != B200_OK) return fs;
         const b200_tensor & k = n.src[1], & v = n.src[2];
         const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
-        return b200_rope_kv_flash_attn(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, k.nb[1], k.nb[2], v.nb[1], v.nb[2],
-                                       mask, (float *)n.dst.data, r.hd, r.nh, r.nhk, k.ne[1], &r.p, f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st);
+        return KL(b200_rope_kv_flash_attn(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, k.nb[1], k.nb[2], v.nb[1], v.nb[2],
+                                       mask, (float *)n.dst.data, r.hd, r.nh, r.nhk, k.ne[1], &r.p, f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st));
     }
     // ... or as a phase of the persistent kernel
     bool mk_try_attn(const b200_node & n) {
@@ -303,7 +310,7 @@ struct Runner {
     // make sure the act buffer of `kind` holds the quantised form of x (n cols of k)
     int ensure_act(const b200_tensor & x, int kind) {
         if (ex->act_id[kind] == x.id && x.id != 0 && ex->act_ptr[kind] == x.data && ex->act_cols[kind] == x.ne[1]) return B200_OK;
-        int s = b200_quantize_act(kind, (const float *)x.data, x.nb[1] / 4, act_buf(kind), x.ne[0], x.ne[1], st);
+        int s = KL(b200_quantize_act(kind, (const float *)x.data, x.nb[1] / 4, act_buf(kind), x.ne[0], x.ne[1], st));
         if (s != B200_OK) return s;
         ex->act_id[kind] = x.id; ex->act_ptr[kind] = x.data; ex->act_cols[kind] = x.ne[1];
         return B200_OK;
@@ -341,7 +348,7 @@ struct Runner {
                     nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4) {
                     const int kind = b200_act_kind_for(nodes[c].src[0].type);
                     { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
-                    int s = b200_rms_norm_quantize((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, act_buf(kind), kind, nullptr, 0, ncols, nrows, eps, st);
+                    int s = KL(b200_rms_norm_quantize((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, act_buf(kind), kind, nullptr, 0, ncols, nrows, eps, st));
                     if (s != B200_OK) return s;
                     invalidate_act(mu.dst);
                     ex->act_id[kind] = mu.dst.id; ex->act_ptr[kind] = mu.dst.data; ex->act_cols[kind] = nrows;
@@ -349,12 +356,12 @@ struct Runner {
                 }
                 invalidate_act(mu.dst);
                 { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
-                return b200_rms_norm((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, ncols, nrows, ncols, ncols, eps, st);
+                return KL(b200_rms_norm((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, ncols, nrows, ncols, ncols, eps, st));
             }
         }
         invalidate_act(n.dst);
         { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
-        return b200_rms_norm((const float *)x.data, nullptr, (float *)n.dst.data, ncols, nrows, ncols, ncols, eps, st);
+        return KL(b200_rms_norm((const float *)x.data, nullptr, (float *)n.dst.data, ncols, nrows, ncols, ncols, eps, st));
     }
 
     // may node j (a later MUL_MAT of the same activation) be executed now, at position i?
@@ -393,7 +400,7 @@ struct Runner {
     bool try_attn_block(int i, int & status) {
         const b200_node & mq = nodes[i];
         const b200_tensor & x = mq.src[1];
-        if (x.ne[1] != 1 || !ex->ws) return false;
+        if (x.ne[1] != 1 || (!dry && !ex->ws)) return false;
         struct Proj { int mm = -1, add = -1; const b200_tensor * out = nullptr; const float * bias = nullptr; } P[3];
         int rope[2] = { -1, -1 };
         int cur = i;
@@ -443,8 +450,8 @@ struct Runner {
         const b200_node & F = nodes[fa];
         // executor scratch behind the attention workspace: q | k | v projections of this token
         const size_t fa_ws = (size_t)b200_flash_attn_workspace(hd, nh, 1, F.src[1].ne[1]);
-        if (ex->off_fa + fa_ws + (size_t)(nh + 2 * nhk) * hd * 4 + 256 > ex->ws_bytes) return false;
-        float * sq = (float *)(ex->ws + ex->off_fa + ((fa_ws + 255) & ~(size_t)255));
+        if (!dry && ex->off_fa + fa_ws + (size_t)(nh + 2 * nhk) * hd * 4 + 256 > ex->ws_bytes) return false;
+        float * sq = dry ? (float *)(uintptr_t)0x10000 : (float *)(ex->ws + ex->off_fa + ((fa_ws + 255) & ~(size_t)255));
         float * skn = sq + nh * hd, * svn = skn + nhk * hd;
         RopePend r;
         r.valid = true; r.q_src = sq; r.q_dst = (float *)rq.dst.data; r.k = skn; r.v = svn; r.pos = (const int32_t *)rq.src[1].data;
@@ -470,7 +477,7 @@ struct Runner {
         if (status != B200_OK) return true;
         for (int q = next_compute(sv); q >= 0 && q < fa; q = next_compute(q)) { status = run_node(q); done[q] = 1; if (status != B200_OK) return true; }
         rope_pend = r;
-        status = launch_fused_attn(F);
+        status = (mega && mk_try_attn(F)) ? (int)B200_OK : launch_fused_attn(F);      // a phase of the persistent kernel, or its own launch
         invalidate_act(rq.dst); invalidate_act(F.dst);
         return true;
     }
@@ -484,10 +491,10 @@ struct Runner {
             invalidate_act(n.dst);
             ex->act_id[0] = ex->act_id[1] = 0;           // the batched path owns the act buffers
             const int kind = b200_act_kind_for(w.type);
-            return b200_mul_mat_q(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, ncols, act_buf(kind), st);
+            return KL(b200_mul_mat_q(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, ncols, act_buf(kind), st));
         }
         int s = B200_OK;
-        if (fuse && !mega && ncols == 1 && try_attn_block(i, s)) return s;
+        if (fuse && ncols == 1 && try_attn_block(i, s)) return s;
         b200_mmv_launch L; memset(&L, 0, sizeof(L));
         L.k = k; L.ncols = ncols;
         if (fuse) {
@@ -573,7 +580,7 @@ struct Runner {
         s = ensure_act(x, kind);
         if (s != B200_OK) return s;
         invalidate_act(n.dst);
-        return b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)n.dst.data, n.dst.nb[1] / 4, nullptr, nullptr, m, k, ncols, st);
+        return KL(b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)n.dst.data, n.dst.nb[1] / 4, nullptr, nullptr, m, k, ncols, st));
     }
     static constexpr int MAX_GROUP = 4;
     int last_status = B200_OK;
@@ -620,9 +627,9 @@ struct Runner {
         } else {
             last_status = mk_flush();
             if (last_status == B200_OK)
-            last_status = b200_rope_kv_store2((const float *)q.data, (float *)rq.dst.data, (const float *)k.data, (const float *)v.data, (const int32_t *)rq.src[1].data, ff,
+            last_status = KL(b200_rope_kv_store2((const float *)q.data, (float *)rq.dst.data, (const float *)k.data, (const float *)v.data, (const int32_t *)rq.src[1].data, ff,
                                               (const int64_t *)SK.src[1].data, (const int64_t *)SV.src[1].data, SK.dst.data, SV.dst.data, SK.dst.type,
-                                              SK.dst.nb[1], SV.dst.nb[1], hd, nh, nhk, nt, &p, st);
+                                              SK.dst.nb[1], SV.dst.nb[1], hd, nh, nhk, nt, &p, st));
         }
         done[j] = done[sk] = done[sv] = 1;
         invalidate_act(rq.dst);
@@ -643,8 +650,8 @@ struct Runner {
                 invalidate_act(n.dst);
                 const b200_tensor & a = n.src[0], & b = n.src[1];
                 const int64_t rows = nrows_of(a), brows = same_shape(a, b) ? rows : b.ne[1];
-                return n.op == B200_OP_ADD ? b200_add((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st)
-                                           : b200_mul((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st);
+                return KL(n.op == B200_OP_ADD ? b200_add((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st)
+                                              : b200_mul((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st));
             }
             case B200_OP_ROPE: {
                 if (fuse && try_rope_kv_store(i)) return last_status;
@@ -656,16 +663,16 @@ struct Runner {
                 p.freq_base = f32_param(n, 5); p.freq_scale = f32_param(n, 6); p.ext_factor = f32_param(n, 7);
                 p.attn_factor = f32_param(n, 8); p.beta_fast = f32_param(n, 9); p.beta_slow = f32_param(n, 10);
                 const float * ff = n.n_src > 2 ? (const float *)n.src[2].data : nullptr;
-                return b200_rope((const float *)x.data, (float *)n.dst.data, (const int32_t *)n.src[1].data, ff, x.ne[0], x.ne[1], x.ne[2],
-                                 x.nb[1] / 4, x.nb[2] / 4, n.dst.nb[1] / 4, n.dst.nb[2] / 4, &p, st);
+                return KL(b200_rope((const float *)x.data, (float *)n.dst.data, (const int32_t *)n.src[1].data, ff, x.ne[0], x.ne[1], x.ne[2],
+                                    x.nb[1] / 4, x.nb[2] / 4, n.dst.nb[1] / 4, n.dst.nb[2] / 4, &p, st));
             }
             case B200_OP_SET_ROWS: {
                 const b200_tensor & s = n.src[0], & ids = n.src[1];
                 for (int64_t i3 = 0; i3 < s.ne[3]; i3++) for (int64_t i2 = 0; i2 < s.ne[2]; i2++) {
                     const int64_t i11 = i2 % ids.ne[1], i12 = i3 % ids.ne[2];
-                    const int r = b200_set_rows((const float *)((const char *)s.data + i2 * s.nb[2] + i3 * s.nb[3]), s.nb[1] / 4,
+                    const int r = KL(b200_set_rows((const float *)((const char *)s.data + i2 * s.nb[2] + i3 * s.nb[3]), s.nb[1] / 4,
                                                 (const int64_t *)((const char *)ids.data + i11 * ids.nb[1] + i12 * ids.nb[2]),
-                                                (char *)n.dst.data + i2 * n.dst.nb[2] + i3 * n.dst.nb[3], n.dst.type, n.dst.nb[1], s.ne[0], s.ne[1], st);
+                                                (char *)n.dst.data + i2 * n.dst.nb[2] + i3 * n.dst.nb[3], n.dst.type, n.dst.nb[1], s.ne[0], s.ne[1], st));
                     if (r != B200_OK) return r;
                 }
                 return B200_OK;
@@ -678,20 +685,20 @@ struct Runner {
                 if (mk_try_attn(n)) return B200_OK;
                 if (attn_matches(n)) return launch_fused_attn(n);
                 { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
-                return b200_flash_attn_ext((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
+                return KL(b200_flash_attn_ext((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
                                            (float *)n.dst.data, k.type, q.ne[0], v.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1],
-                                           f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st);
+                                           f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st));
             }
             case B200_OP_GLU_SWIGLU:
                 invalidate_act(n.dst);
-                return b200_swiglu((const float *)n.src[0].data, (const float *)n.src[1].data, (float *)n.dst.data, nelem(n.dst), st);
+                return KL(b200_swiglu((const float *)n.src[0].data, (const float *)n.src[1].data, (float *)n.dst.data, nelem(n.dst), st));
             case B200_OP_GET_ROWS:
                 invalidate_act(n.dst);
-                return b200_get_rows_f32((const float *)n.src[0].data, n.src[0].nb[1] / 4, (const int32_t *)n.src[1].data, (float *)n.dst.data, n.src[0].ne[0], n.src[1].ne[0], st);
+                return KL(b200_get_rows_f32((const float *)n.src[0].data, n.src[0].nb[1] / 4, (const int32_t *)n.src[1].data, (float *)n.dst.data, n.src[0].ne[0], n.src[1].ne[0], st));
             case B200_OP_CPY:
                 invalidate_act(n.dst);
-                if (n.dst.type == B200_TYPE_F16) return b200_cpy_f32_f16((const float *)n.src[0].data, n.dst.data, nelem(n.dst), st);
-                return b200_check(cudaMemcpyAsync(n.dst.data, n.src[0].data, (size_t)nelem(n.dst) * 4, cudaMemcpyDeviceToDevice, st), "cpy f32");
+                if (n.dst.type == B200_TYPE_F16) return KL(b200_cpy_f32_f16((const float *)n.src[0].data, n.dst.data, nelem(n.dst), st));
+                return KL(b200_check(cudaMemcpyAsync(n.dst.data, n.src[0].data, (size_t)nelem(n.dst) * 4, cudaMemcpyDeviceToDevice, st), "cpy f32"));
             default:
                 b200_set_error("executor: op %d not supported", n.op);
                 return B200_ERR_UNSUPPORTED;
@@ -854,6 +861,17 @@ extern "C" int b200_executor_compute(b200_executor * ex, const b200_node * nodes
     b200_count_launch((int)it->second.kernels);
     B200_CUDA(cudaGraphLaunch(it->second.exec, st));
     return B200_OK;
+}
+
+extern "C" int64_t b200_executor_plan(const b200_node * nodes, int n_nodes, int flags) {
+    if ((!nodes && n_nodes > 0) || n_nodes < 0) { b200_set_error("executor_plan: bad arguments"); return B200_ERR_INVALID; }
+    for (int i = 0; i < n_nodes; i++) if (!node_ok(nodes[i])) { b200_set_error("executor_plan: node %d (op %d) is not supported", i, nodes[i].op); return B200_ERR_UNSUPPORTED; }
+    b200_executor tmp;                                   // never touches a device
+    Runner r{ &tmp, nodes, n_nodes, nullptr, (flags & B200_EXEC_FUSION) != 0, {}, {} };
+    r.mega = r.fuse && (flags & B200_EXEC_MEGAKERNEL); r.mega_mmv = r.mega && (flags & B200_EXEC_MEGA_MMV);
+    r.dry = true;
+    const int s = r.run_all();
+    return s == B200_OK ? r.planned : (int64_t)s;
 }
 
 extern "C" int64_t b200_executor_last_kernels(const b200_executor * ex)  { return ex ? ex->last_kernels : 0; }

@@ -27,10 +27,11 @@ _lib = ops.lib
 _lib.b200_executor_create.restype = C.c_void_p; _lib.b200_executor_create.argtypes = [C.c_int]
 _lib.b200_executor_free.restype = None; _lib.b200_executor_free.argtypes = [C.c_void_p]
 _lib.b200_executor_supports.restype = C.c_int; _lib.b200_executor_supports.argtypes = [C.POINTER(Node)]
+_lib.b200_executor_plan.restype = C.c_int64; _lib.b200_executor_plan.argtypes = [C.POINTER(Node), C.c_int, C.c_int]
 _lib.b200_executor_compute.restype = C.c_int; _lib.b200_executor_compute.argtypes = [C.c_void_p, C.POINTER(Node), C.c_int, C.c_void_p, C.c_int]
 for _n in ("b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays", "b200_executor_mk_launches", "b200_executor_mk_phases"):
     getattr(_lib, _n).restype = C.c_int64; getattr(_lib, _n).argtypes = [C.c_void_p]
-GRAPH_SYMBOLS = ["b200_executor_create", "b200_executor_free", "b200_executor_supports", "b200_executor_compute",
+GRAPH_SYMBOLS = ["b200_executor_plan", "b200_executor_create", "b200_executor_free", "b200_executor_supports", "b200_executor_compute",
                  "b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays", "b200_executor_mk_launches", "b200_executor_mk_phases"]
 
 _next_id = [1]
@@ -95,6 +96,11 @@ class NodeList:
             for i, p in enumerate(params):
                 n.op_params[i] = p
         return arr
+
+
+def plan(nodes, flags=EXEC_CUDA_GRAPHS | EXEC_FUSION):
+    """launches the executor would issue for this node list (dry run, no device)"""
+    return int(_lib.b200_executor_plan(nodes, len(nodes), flags))
 
 
 class Executor:
