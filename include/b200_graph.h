@@ -44,12 +44,13 @@ enum b200_op {
 };
 
 #define B200_MAX_SRC 6
+#define B200_TENSOR_FLAG_OUTPUT 2   /* == GGML_TENSOR_FLAG_OUTPUT: never elided, never fused away (ggml-impl.h:565) */
 
 typedef struct b200_tensor {
     uint64_t id;             /* identity for dependency analysis (plug-in: the ggml_tensor address); 0 = absent */
     void    *data;           /* device pointer                                                          */
     int32_t  type;           /* ggml_type value                                                         */
-    int32_t  flags;          /* reserved                                                                */
+    int32_t  flags;          /* ggml's tensor flags (ggml.h:602-607); B200_TENSOR_FLAG_OUTPUT = the caller reads this tensor  */
     int64_t  ne[4];
     int64_t  nb[4];
 } b200_tensor;

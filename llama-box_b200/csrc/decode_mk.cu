@@ -851,9 +851,10 @@ static const size_t TRACE_MAX_PHASES = 512;
 int mk_launch(const MkPhase * dev_prog, int n_phases, unsigned long long * dev_sync, void * stream) {
     if (!dev_prog || n_phases <= 0 || !dev_sync) { b200_set_error("mk_launch: bad arguments"); return B200_ERR_INVALID; }
     const size_t smem = MK_AREG_BYTES + (size_t)MK_MAX_WARPS * 2 * MK_SLOT_BYTES;
-    static bool attr = false;
+    static bool attr[64] = { false };                   // the opt-in is per device (single-process --tensor-split uses several)
+    int dev = 0; cudaGetDevice(&dev);
     static const bool want_trace = getenv("GGML_B200_MK_TRACE") != nullptr;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    if (!attr[dev & 63]) { B200_CUDA(cudaFuncSetAttribute(mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr[dev & 63] = true; }
     unsigned long long * trace = nullptr;
     if (want_trace && (size_t)n_phases <= TRACE_MAX_PHASES && n_phases >= 8) {
         if (!g_trace) B200_CUDA(cudaMalloc((void **)&g_trace, (size_t)b200_sm_count() * TRACE_MAX_PHASES * 4 * 8 * 2));

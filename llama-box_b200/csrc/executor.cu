@@ -32,6 +32,7 @@ inline bool contiguous(const b200_tensor & t) {
 }
 inline bool same_shape(const b200_tensor & a, const b200_tensor & b) { return a.ne[0] == b.ne[0] && a.ne[1] == b.ne[1] && a.ne[2] == b.ne[2] && a.ne[3] == b.ne[3]; }
 inline bool aligned16(const void * p) { return ((uintptr_t)p & 15) == 0; }
+inline bool is_output(const b200_tensor & t) { return (t.flags & B200_TENSOR_FLAG_OUTPUT) != 0; }   // the caller reads it: never elide or fuse away
 inline float f32_param(const b200_node & n, int i) { float f; memcpy(&f, &n.op_params[i], 4); return f; }
 
 inline size_t tensor_bytes(const b200_tensor & t) {
@@ -332,13 +333,24 @@ struct Runner {
                 done[j] = 1;
                 // all consumers are decode-shaped quantised MUL_MATs of this tensor: no kernel at all, the matvec
                 // prologue normalises and quantises (b200_mul_mat_vec_q_launch act_source = 2)
-                if (nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4 && x.nb[1] == ncols * 4) {
+                if (nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4 && x.nb[1] == ncols * 4 && !is_output(n.dst) && !is_output(mu.dst)) {
                     int consumers = 0, mm = 0;
                     for (int q = j + 1; q < this->n; q++) for (int sidx = 0; sidx < nodes[q].n_src && sidx < B200_MAX_SRC; sidx++)
                         if (nodes[q].src[sidx].id == mu.dst.id) { consumers++; if (nodes[q].op == B200_OP_MUL_MAT && sidx == 1 && !done[q] && nodes[q].src[1].ne[1] <= 8) mm++; }
                     if (consumers > 0 && consumers == mm) {
                         ex->norm.out_id = mu.dst.id; ex->norm.out_data = mu.dst.data; ex->norm.x = x; ex->norm.out = mu.dst;
                         ex->norm.w = (const float *)w->data; ex->norm.eps = eps;
+                        // a normalised tensor that no later node overwrites is still there when the graph ends, and the caller may
+                        // read it (libllama fetches result_norm as the embeddings output without flagging it: llama-context.cpp:1115-1151):
+                        // materialise it as well — the matvec prologue still recomputes it, so the weight stream is not delayed
+                        // (only the LAST norm of a list can be that tensor: it feeds the output matrix)
+                        bool survives = true;
+                        for (int q = j + 1; q < this->n && survives; q++)
+                            if (nodes[q].op == B200_OP_RMS_NORM || (nodes[q].op != B200_OP_NONE && overlaps(nodes[q].dst, mu.dst))) survives = false;
+                        if (survives) {
+                            { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+                            return KL(b200_rms_norm((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, ncols, nrows, ncols, ncols, eps, st));
+                        }
                         return B200_OK;
                     }
                 }
@@ -408,6 +420,7 @@ struct Runner {
             if (j > 0) { cur = next_compute(cur); if (cur < 0 || nodes[cur].op != B200_OP_MUL_MAT) return false; }
             const b200_node & mm = nodes[cur];
             if (mm.src[1].id != x.id || mm.src[1].data != x.data || mm.src[0].ne[0] != mq.src[0].ne[0] || mm.dst.nb[1] != mm.src[0].ne[1] * 4) return false;
+            if (is_output(mm.dst)) return false;
             P[j].mm = cur; P[j].out = &mm.dst;
             const int a = next_compute(cur);
             if (a >= 0 && nodes[a].op == B200_OP_ADD && use_count(mm.dst) == 1 && nodes[a].src[0].data == mm.dst.data && nrows_of(nodes[a].src[1]) == 1 &&
@@ -424,6 +437,7 @@ struct Runner {
         const b200_node & rq = nodes[rope[0]], & rk = nodes[rope[1]];
         if (memcmp(rq.op_params, rk.op_params, sizeof(rq.op_params)) != 0 || rq.src[1].data != rk.src[1].data) return false;
         if ((rq.n_src > 2 ? rq.src[2].data : nullptr) != (rk.n_src > 2 ? rk.src[2].data : nullptr)) return false;
+        if (is_output(*P[0].out) || is_output(*P[1].out) || is_output(*P[2].out) || is_output(rk.dst)) return false;   // never materialised by the fused launches
         const b200_tensor & q3 = rq.src[0], & k3 = rk.src[0];
         const int64_t hd = q3.ne[0], nh = q3.ne[1], nhk = k3.ne[1];
         auto dense3 = [&](const b200_tensor & t) { return t.nb[0] == 4 && t.nb[1] == t.ne[0] * 4 && t.nb[2] == t.ne[0] * t.ne[1] * 4; };
@@ -502,8 +516,9 @@ struct Runner {
             const int j = next_compute(i);
             if (j >= 0 && nodes[j].op == B200_OP_MUL_MAT && nodes[j].src[1].id == x.id && nodes[j].src[1].data == x.data && nodes[j].src[0].ne[1] == m && nodes[j].src[1].ne[1] == ncols) {
                 const int g = next_compute(j);
+                const bool x_live = g >= 0 && (overlaps(nodes[g].dst, x) || (ex->norm.out_id && ex->norm.out_id == x.id && overlaps(nodes[g].dst, ex->norm.x)));   // late CTAs still quantise x in their prologue
                 if (g >= 0 && nodes[g].op == B200_OP_GLU_SWIGLU && use_count(n.dst) == 1 && use_count(nodes[j].dst) == 1 &&
-                    n.dst.nb[1] == m * 4 && nodes[j].dst.nb[1] == m * 4) {
+                    n.dst.nb[1] == m * 4 && nodes[j].dst.nb[1] == m * 4 && !x_live && !is_output(n.dst) && !is_output(nodes[j].dst)) {
                     const b200_node & G = nodes[g];
                     const b200_node * gate = nullptr, * up = nullptr;
                     if (G.src[0].data == nodes[j].dst.data && G.src[1].data == n.dst.data) { gate = &nodes[j]; up = &n; }
@@ -528,6 +543,7 @@ struct Runner {
                 const b200_node & o = nodes[j2];
                 if (o.src[1].id != x.id || o.src[1].data != x.data || o.src[1].ne[1] != ncols || o.src[0].ne[0] != k) continue;
                 if (o.dst.nb[1] != o.src[0].ne[1] * 4 || !can_hoist(i, j2)) continue;
+                if (overlaps(o.dst, x) || (ex->norm.out_id && ex->norm.out_id == x.id && overlaps(o.dst, ex->norm.x))) continue;
                 group[ng++] = j2;
             }
             if (ng > 1 && n.dst.nb[1] == m * 4) {
@@ -541,8 +557,9 @@ struct Runner {
                     written[nw++] = &o.dst;
                     // bias ADD right after the projection (Qwen2 QKV bias, llama-model.cpp:6006-6020)
                     const int a = next_compute(group[q]);
-                    if (a >= 0 && nodes[a].op == B200_OP_ADD && use_count(o.dst) == 1 && nodes[a].src[0].data == o.dst.data && nrows_of(nodes[a].src[1]) == 1 &&
-                        nodes[a].src[1].ne[0] == o.src[0].ne[1] && nodes[a].dst.nb[1] == o.src[0].ne[1] * 4 && (q == 0 || can_hoist(i, a))) {
+                    if (a >= 0 && nodes[a].op == B200_OP_ADD && use_count(o.dst) == 1 && !is_output(o.dst) && nodes[a].src[0].data == o.dst.data && nrows_of(nodes[a].src[1]) == 1 &&
+                        nodes[a].src[1].ne[0] == o.src[0].ne[1] && nodes[a].dst.nb[1] == o.src[0].ne[1] * 4 && (q == 0 || can_hoist(i, a)) &&
+                        !overlaps(nodes[a].dst, x) && !(ex->norm.out_id && ex->norm.out_id == x.id && overlaps(nodes[a].dst, ex->norm.x))) {
                         L.mats[q].bias = (const float *)nodes[a].src[1].data; L.mats[q].dst = (float *)nodes[a].dst.data; done[a] = 1;
                         written[nw++] = &nodes[a].dst;
                     }
@@ -556,7 +573,7 @@ struct Runner {
             int cur = i;
             for (int step = 0; step < 2; step++) {
                 const int a = next_compute(cur);
-                if (a < 0 || nodes[a].op != B200_OP_ADD || use_count(*out) != 1) break;
+                if (a < 0 || nodes[a].op != B200_OP_ADD || use_count(*out) != 1 || is_output(*out)) break;
                 const b200_node & A = nodes[a];
                 const b200_tensor * other = A.src[0].data == out->data ? &A.src[1] : (A.src[1].data == out->data ? &A.src[0] : nullptr);
                 if (!other || A.dst.nb[1] != out->nb[1] || !same_shape(A.dst, *out)) break;
@@ -603,7 +620,7 @@ struct Runner {
         // K store consumes exactly the roped K (through a reshape view), V store a dense [n_embd_v, n_tok] f32 tensor
         if (SK.src[0].data != rk.dst.data || SK.src[0].ne[0] != nhk * hd || SK.src[0].ne[1] != nt || SK.src[0].nb[1] != nhk * hd * 4) return false;
         if (v.ne[0] != nhk * hd || v.ne[1] != nt || v.nb[1] != nhk * hd * 4 || v.ne[2] != 1 || SK.src[0].ne[2] != 1 || SK.dst.ne[2] != 1 || SV.dst.ne[2] != 1) return false;
-        if (SK.dst.type != SV.dst.type || (SK.dst.type != B200_TYPE_F16 && SK.dst.type != B200_TYPE_Q8_0)) return false;
+        if (SK.dst.type != SV.dst.type || (SK.dst.type != B200_TYPE_F16 && SK.dst.type != B200_TYPE_Q8_0) || is_output(rk.dst)) return false;
         // the roped K must have no other reader: it feeds SET_ROWS directly or through exactly one view node
         // (identity by tensor id — buffers are recycled by the graph allocator, pointers are not identities)
         if (SK.src[0].id != rk.dst.id) {
@@ -637,8 +654,24 @@ struct Runner {
     }
     int n_limit(int i) const { return i + 24 < n ? i + 24 : n; }
 
+    // does this node read or write anything the recorded (not yet launched) rope + KV store produces or consumes?
+    bool touches_rope_pend(const b200_node & n) const {
+        const RopePend & r = rope_pend;
+        auto range = [](const void * p, int64_t bytes) { b200_tensor t; memset(&t, 0, sizeof(t)); t.data = (void *)p; t.type = B200_TYPE_F32; t.ne[0] = bytes / 4; t.ne[1] = t.ne[2] = t.ne[3] = 1; t.nb[0] = 4; t.nb[1] = t.nb[2] = t.nb[3] = bytes; return t; };
+        const b200_tensor qd = range(r.q_dst, r.nh * r.hd * 4), qs = range(r.q_src, r.nh * r.hd * 4), kn = range(r.k, r.nhk * r.hd * 4), vn = range(r.v, r.nhk * r.hd * 4);
+        for (int s = 0; s < n.n_src && s < B200_MAX_SRC; s++) {
+            const b200_tensor & t = n.src[s];
+            if (!t.data) continue;
+            if (overlaps(t, qd) || t.data == r.k_cache || t.data == r.v_cache) return true;      // reads the roped Q or the KV cells
+        }
+        return overlaps(n.dst, qd) || overlaps(n.dst, qs) || overlaps(n.dst, kn) || overlaps(n.dst, vn) || n.dst.data == r.k_cache || n.dst.data == r.v_cache;
+    }
+
     int run_node(int i) {
         const b200_node & n = nodes[i];
+        if (rope_pend.valid && n.op != B200_OP_NONE && n.op != B200_OP_FLASH_ATTN_EXT && touches_rope_pend(n)) {
+            const int fs = mk_flush(); if (fs != B200_OK) return fs;
+        }
         if (mega && n.op != B200_OP_NONE && n.op != B200_OP_MUL_MAT && n.op != B200_OP_ROPE && n.op != B200_OP_FLASH_ATTN_EXT && n.op != B200_OP_RMS_NORM) {
             const int fs = mk_flush(); if (fs != B200_OK) return fs;            // everything else is an ordinary launch: keep program order
         }

@@ -117,8 +117,9 @@ static int launch_rms(const float * x, const float * w, float * y, void * act0, 
     const size_t smem = (size_t)ncols * sizeof(float);
     if (smem > 200 * 1024) { b200_set_error("rms_norm: row of %lld floats exceeds shared memory", (long long)ncols); return B200_ERR_UNSUPPORTED; }
     if (ncols >= 2048) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(rms_norm_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        static bool attr[64] = { false };               // per device
+        int dev = 0; cudaGetDevice(&dev);
+        if (!attr[dev & 63]) { cudaFuncSetAttribute(rms_norm_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr[dev & 63] = true; }
         rms_norm_kernel<512><<<(unsigned)nrows, 512, smem, st>>>(x, w, y, act0, kind0, act1, kind1, ncols, xs, ys, eps);
     } else {
         rms_norm_kernel<128><<<(unsigned)nrows, 128, smem, st>>>(x, w, y, act0, kind0, act1, kind1, ncols, xs, ys, eps);

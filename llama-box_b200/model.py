@@ -139,8 +139,11 @@ class SyntheticLlama:
             self.bufs[key] = torch.zeros(shape, dtype=dtype, device="cuda")
         return self.bufs[key]
 
-    def build(self, n_tok, n_kv, want_all_logits=False, seq=0):
+    def build(self, n_tok, n_kv, want_all_logits=False, seq=0, skip_attention=False):
         """node list for one ubatch of n_tok tokens attending to n_kv cache positions (n_kv % 256 == 0 with -fa).
+        skip_attention (bench roofline leg only): leave out ROPE / SET_ROWS / FLASH_ATTN_EXT and feed the Q projection
+        straight into wo, so that the list holds exactly the step's matvec launches with their in-situ prologues
+        (rms_norm + quantise inside the kernel, residual epilogues, lm_head) and nothing else.
         Inputs (device buffers the caller fills): tokens i32[n_tok], pos i32[n_tok], kv_idx i64[n_tok],
         mask f32[n_kv, pad64(n_tok)] (cast to f16 by a CPY node like llama-graph.cpp:1424), out_ids i32[n_out]."""
         c = self.c
@@ -177,28 +180,34 @@ class SyntheticLlama:
                 q = nl.add(G.OP_ADD, tT(f("qb", [H * D, n_tok]), G.F32, [H * D, n_tok]), [q, wT(ly["bq"], H * D)])
             q3 = nl.view_op(q.reshape([D, H, n_tok]), q)
             srcs = [q3, pos_t] + ([ff_t] if ff_t else [])
-            qr = nl.add(G.OP_ROPE, tT(f("qr", [D, H, n_tok]), G.F32, [D, H, n_tok]), srcs, rope_params)
+            if not skip_attention:
+                qr = nl.add(G.OP_ROPE, tT(f("qr", [D, H, n_tok]), G.F32, [D, H, n_tok]), srcs, rope_params)
             k = nl.add(G.OP_MUL_MAT, tT(f("k", [HK * D, n_tok]), G.F32, [HK * D, n_tok]), [ly["wk"].t, cur])
             if c["qkv_bias"]:
                 k = nl.add(G.OP_ADD, tT(f("kb", [HK * D, n_tok]), G.F32, [HK * D, n_tok]), [k, wT(ly["bk"], HK * D)])
             k3 = nl.view_op(k.reshape([D, HK, n_tok]), k)
             srcs = [k3, pos_t] + ([ff_t] if ff_t else [])
-            kr = nl.add(G.OP_ROPE, tT(f("kr", [D, HK, n_tok]), G.F32, [D, HK, n_tok]), srcs, rope_params)
+            if not skip_attention:
+                kr = nl.add(G.OP_ROPE, tT(f("kr", [D, HK, n_tok]), G.F32, [D, HK, n_tok]), srcs, rope_params)
             v = nl.add(G.OP_MUL_MAT, tT(f("v", [HK * D, n_tok]), G.F32, [HK * D, n_tok]), [ly["wv"].t, cur])
             if c["qkv_bias"]:
                 v = nl.add(G.OP_ADD, tT(f("vb", [HK * D, n_tok]), G.F32, [HK * D, n_tok]), [v, wT(ly["bv"], HK * D)])
-            # KV store (llama-kv-cache-unified.cpp:1103-1160)
-            kc = G.T(ly["k_caches"][seq].data_ptr(), self.kv_type, [HK * D, self.n_ctx]); vc = G.T(ly["v_caches"][seq].data_ptr(), self.kv_type, [HK * D, self.n_ctx])
-            k2 = nl.view_op(kr.reshape([HK * D, n_tok]), kr)
-            nl.add(G.OP_SET_ROWS, kc, [k2, idx_t])
-            nl.add(G.OP_SET_ROWS, vc, [v, idx_t])
-            # attention (llama-graph.cpp:1236-1265; views llama-kv-cache-unified.cpp:1056-1101)
-            qp = nl.view_op(qr.view([D, n_tok, H], [4, 4 * D * H, 4 * D, 4 * D * H * n_tok]), qr)
-            kv = nl.view_op(kc.view([D, n_kv, HK], [G.ELEM_SIZE.get(self.kv_type, 34), kvrow, kvhead, kvrow * n_kv]), kc)
-            vv = nl.view_op(vc.view([D, n_kv, HK], [G.ELEM_SIZE.get(self.kv_type, 34), kvrow, kvhead, kvrow * n_kv]), vc)
-            att = nl.add(G.OP_FLASH_ATTN_EXT, tT(f("att", [D, H, n_tok]), G.F32, [D, H, n_tok]), [qp, kv, vv, mask16],
-                         [G.f32_bits(1.0 / math.sqrt(D)), G.f32_bits(0.0), G.f32_bits(0.0), 10])
-            att2 = nl.view_op(att.reshape([H * D, n_tok]), att)
+            if skip_attention:
+                assert H * D == E
+                att2 = q
+            else:
+                # KV store (llama-kv-cache-unified.cpp:1103-1160)
+                kc = G.T(ly["k_caches"][seq].data_ptr(), self.kv_type, [HK * D, self.n_ctx]); vc = G.T(ly["v_caches"][seq].data_ptr(), self.kv_type, [HK * D, self.n_ctx])
+                k2 = nl.view_op(kr.reshape([HK * D, n_tok]), kr)
+                nl.add(G.OP_SET_ROWS, kc, [k2, idx_t])
+                nl.add(G.OP_SET_ROWS, vc, [v, idx_t])
+                # attention (llama-graph.cpp:1236-1265; views llama-kv-cache-unified.cpp:1056-1101)
+                qp = nl.view_op(qr.view([D, n_tok, H], [4, 4 * D * H, 4 * D, 4 * D * H * n_tok]), qr)
+                kv = nl.view_op(kc.view([D, n_kv, HK], [G.ELEM_SIZE.get(self.kv_type, 34), kvrow, kvhead, kvrow * n_kv]), kc)
+                vv = nl.view_op(vc.view([D, n_kv, HK], [G.ELEM_SIZE.get(self.kv_type, 34), kvrow, kvhead, kvrow * n_kv]), vc)
+                att = nl.add(G.OP_FLASH_ATTN_EXT, tT(f("att", [D, H, n_tok]), G.F32, [D, H, n_tok]), [qp, kv, vv, mask16],
+                             [G.f32_bits(1.0 / math.sqrt(D)), G.f32_bits(0.0), G.f32_bits(0.0), 10])
+                att2 = nl.view_op(att.reshape([H * D, n_tok]), att)
             cur = nl.add(G.OP_MUL_MAT, tT(f("wo", [E, n_tok]), G.F32, [E, n_tok]), [ly["wo"].t, att2])
             inpSA, nt = inpL, n_tok
             if last and not want_all_logits:

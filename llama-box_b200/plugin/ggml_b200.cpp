@@ -15,6 +15,7 @@
 #include "ggml.h"
 #include "ggml-backend.h"
 #include "ggml-backend-impl.h"
+#include "ggml-impl.h"
 
 #include "../../include/b200_graph.h"
 
@@ -52,9 +53,11 @@ struct b200_device_ctx {
 struct b200_buffer_ctx {
     int    device;
     void * base;
-    // weight tensors whose rows currently are in the kernels' repacked layout (see b200_repack_rows);
-    // keyed by tensor->data.  Weights are uploaded in ggml's layout and repacked lazily, in place, the first
-    // time a MUL_MAT consumes them; set/get_tensor convert back so ggml never sees the private layout.
+    // weight tensors whose rows currently are in the kernels' repacked layout (see b200_repack_rows), keyed by
+    // tensor->data.  Whole-tensor uploads into a WEIGHTS buffer (what llama_model_loader does, llama-model-loader.cpp:1060,
+    // 1095) are repacked right there, synchronously, at load time; anything uploaded in pieces is repacked the first time
+    // a MUL_MAT consumes it, under `mu` and followed by a stream sync, so that no other stream or backend can observe a
+    // half-converted tensor.  get_tensor / partial set_tensor convert back first: ggml never sees the private layout.
     std::mutex mu;
     std::unordered_set<const void *> repacked;
 };
@@ -62,10 +65,17 @@ struct b200_buffer_ctx {
 struct b200_backend_ctx {
     int device;
     cudaStream_t stream = nullptr;
+    cudaEvent_t  copy_event = nullptr;     // reused for every hidden-state handoff issued by this backend (as ggml-cuda does, ggml-cuda.cu:2566-2575)
     b200_executor * ex = nullptr;
     std::vector<b200_node> nodes;
     std::string name;
 };
+
+// ---- statistics of the inter-device handoff (row a11), readable through reg->get_proc_address("ggml_b200_handoff_stats")
+struct b200_handoff_stats { int64_t copies; int64_t bytes; double device_us; double host_us; };
+static std::mutex g_stat_mu;
+static b200_handoff_stats g_handoff = { 0, 0, 0.0, 0.0 };
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_handoff_pending;   // timing event pairs not yet read back
 
 static b200_device_ctx   g_dev[B200_MAX_DEVICES];
 static ggml_backend_device g_devices[B200_MAX_DEVICES];
@@ -89,17 +99,27 @@ static void * buf_get_base(ggml_backend_buffer_t buffer) { return ((b200_buffer_
 
 static enum ggml_status buf_init_tensor(ggml_backend_buffer_t, struct ggml_tensor *) { return GGML_STATUS_SUCCESS; }
 
-static bool tensor_is_repacked(b200_buffer_ctx * c, const ggml_tensor * t) {
-    std::lock_guard<std::mutex> lk(c->mu);
-    return c->repacked.count(t->data) != 0;
-}
 // bring a weight tensor back to ggml's layout (before ggml reads or partially writes it)
 static void ensure_native(b200_buffer_ctx * c, const ggml_tensor * t) {
-    if (!is_repack_type(t->type) || !tensor_is_repacked(c, t)) return;
-    b200_unpack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], nullptr);
-    CUDA_OK(cudaStreamSynchronize(nullptr));
+    if (!is_repack_type(t->type)) return;
     std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->repacked.count(t->data)) return;
+    cudaSetDevice(c->device);
+    CUDA_OK(cudaDeviceSynchronize());                    // compute streams are non-blocking: order against every reader of the tensor
+    b200_unpack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread);
+    CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
     c->repacked.erase(t->data);
+}
+static bool repack_k_ok(const ggml_tensor * t) { return t->ne[0] % 256 == 0 && (t->type != GGML_TYPE_Q6_K || t->ne[0] % 2048 == 0) && ggml_is_contiguous(t); }
+// convert a weight tensor to the kernels' layout, exactly once, visible to every stream when this returns
+static bool ensure_repacked(b200_buffer_ctx * c, const ggml_tensor * t) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->repacked.count(t->data)) return true;
+    cudaSetDevice(c->device);
+    if (b200_repack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread) != B200_OK) return false;
+    if (!CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread))) return false;
+    c->repacked.insert(t->data);
+    return true;
 }
 
 static void buf_memset_tensor(ggml_backend_buffer_t buffer, struct ggml_tensor * tensor, uint8_t value, size_t offset, size_t size) {
@@ -113,6 +133,9 @@ static void buf_set_tensor(ggml_backend_buffer_t buffer, struct ggml_tensor * te
     cudaSetDevice(c->device);
     ensure_native(c, tensor);
     CUDA_OK(cudaMemcpy((char *)tensor->data + offset, data, size, cudaMemcpyHostToDevice));
+    // load-time repack: a whole quantised weight tensor has just arrived (llama_model_loader::load_all_data)
+    if (buffer->usage == GGML_BACKEND_BUFFER_USAGE_WEIGHTS && is_repack_type(tensor->type) && offset == 0 && size == ggml_nbytes(tensor) &&
+        !tensor->view_src && repack_k_ok(tensor)) ensure_repacked(c, tensor);
 }
 static void buf_get_tensor(ggml_backend_buffer_t buffer, const struct ggml_tensor * tensor, void * data, size_t offset, size_t size) {
     b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context;
@@ -194,7 +217,7 @@ static bool hbuft_is_host(ggml_backend_buffer_type_t) { return true; }
 static void to_b200(const ggml_tensor * t, b200_tensor & o) {
     memset(&o, 0, sizeof(o));
     if (!t) return;
-    o.id = (uint64_t)(uintptr_t)t; o.data = t->data; o.type = (int32_t)t->type;
+    o.id = (uint64_t)(uintptr_t)t; o.data = t->data; o.type = (int32_t)t->type; o.flags = t->flags;   // GGML_TENSOR_FLAG_OUTPUT etc. (ggml.h:602-607)
     for (int i = 0; i < 4; i++) { o.ne[i] = t->ne[i]; o.nb[i] = (int64_t)t->nb[i]; }
 }
 // false = this op is not one the hot path handles
@@ -230,6 +253,7 @@ static bool node_to_b200(const ggml_tensor * t, b200_node & n) {
 // backend = one stream (ggml_backend_i, ggml-backend-impl.h:87-124)
 // ------------------------------------------------------------------------------------------------
 static const char * be_name(ggml_backend_t b) { return ((b200_backend_ctx *)b->context)->name.c_str(); }
+static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static bool g_timing_flag(); static long g_calls_ref(); static long g_nodes_ref(); static long g_kernels_ref(); static double g_conv_ref(); static double g_exec_ref();
 static void be_free(ggml_backend_t b) {
     b200_backend_ctx * c = (b200_backend_ctx *)b->context;
@@ -238,6 +262,7 @@ static void be_free(ggml_backend_t b) {
     if (g_timing_flag() && g_calls_ref()) fprintf(stderr, "ggml-b200 timing: %ld graph_compute calls, %.1f nodes and %.1f kernels per call, host: %.1f us translate + %.1f us executor per call; graph captures %lld replays %lld\n",
                                       g_calls_ref(), (double)g_nodes_ref() / g_calls_ref(), (double)g_kernels_ref() / g_calls_ref(), g_conv_ref() / g_calls_ref(), g_exec_ref() / g_calls_ref(), (long long)b200_executor_graph_captures(c->ex), (long long)b200_executor_graph_replays(c->ex));
     b200_executor_free(c->ex);
+    if (c->copy_event) cudaEventDestroy(c->copy_event);
     cudaStreamDestroy(c->stream);
     delete c; delete b;
 }
@@ -262,19 +287,57 @@ static bool be_cpy_tensor_async(ggml_backend_t bsrc, ggml_backend_t bdst, const 
     ggml_backend_buffer_t sb = src->view_src ? src->view_src->buffer : src->buffer, db = dst->view_src ? dst->view_src->buffer : dst->buffer;
     if (!is_b200_buffer(sb) || !is_b200_buffer(db)) return false;
     b200_backend_ctx * cs = (b200_backend_ctx *)bsrc->context, * cd = (b200_backend_ctx *)bdst->context;
+    if (((b200_buffer_ctx *)sb->context)->device != cs->device || ((b200_buffer_ctx *)db->context)->device != cd->device) return false;
     if (cs == cd) {
         cudaSetDevice(cs->device);
         return CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(dst), cudaMemcpyDeviceToDevice, cs->stream));
     }
+    const double h0 = now_us();
     cudaSetDevice(cs->device);
-    if (!CUDA_OK(cudaMemcpyPeerAsync(dst->data, cd->device, src->data, cs->device, ggml_nbytes(dst), cs->stream))) return false;
-    cudaEvent_t ev;
-    if (!CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming))) return false;
-    CUDA_OK(cudaEventRecord(ev, cs->stream));
+    // GGML_B200_TIMING / handoff statistics: timing events around the peer copy on the source stream
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    static const bool timed = g_timing_flag() || getenv("GGML_B200_HANDOFF_TIMING") != nullptr;
+    if (timed) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, cs->stream); }
+    bool ok;
+    if (cs->device == cd->device) ok = CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(dst), cudaMemcpyDeviceToDevice, cs->stream));
+    else                          ok = CUDA_OK(cudaMemcpyPeerAsync(dst->data, cd->device, src->data, cs->device, ggml_nbytes(dst), cs->stream));
+    if (!ok) return false;
+    if (timed) cudaEventRecord(t1, cs->stream);
+    if (!cs->copy_event && !CUDA_OK(cudaEventCreateWithFlags(&cs->copy_event, cudaEventDisableTiming))) return false;
+    CUDA_OK(cudaEventRecord(cs->copy_event, cs->stream));
     cudaSetDevice(cd->device);
-    CUDA_OK(cudaStreamWaitEvent(cd->stream, ev, 0));
-    CUDA_OK(cudaEventDestroy(ev));                          // released once the wait has consumed it
+    CUDA_OK(cudaStreamWaitEvent(cd->stream, cs->copy_event, 0));
+    {
+        std::lock_guard<std::mutex> lk(g_stat_mu);
+        g_handoff.copies++; g_handoff.bytes += (int64_t)ggml_nbytes(dst); g_handoff.host_us += now_us() - h0;
+        if (timed) g_handoff_pending.emplace_back(t0, t1);
+    }
     return true;
+}
+// drain finished timing pairs into the statistics (called with every stream idle, or lazily when the list grows)
+static void handoff_collect(bool all) {
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    size_t keep = 0;
+    for (auto & pr : g_handoff_pending) {
+        if (all) cudaEventSynchronize(pr.second);
+        if (cudaEventQuery(pr.second) == cudaSuccess) {
+            float ms = 0; if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) g_handoff.device_us += ms * 1e3;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        } else g_handoff_pending[keep++] = pr;
+    }
+    g_handoff_pending.resize(keep);
+    cudaGetLastError();
+}
+extern "C" void ggml_b200_handoff_stats(int64_t * copies, int64_t * bytes, double * device_us, double * host_us) {
+    handoff_collect(true);
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    if (copies) *copies = g_handoff.copies; if (bytes) *bytes = g_handoff.bytes;
+    if (device_us) *device_us = g_handoff.device_us; if (host_us) *host_us = g_handoff.host_us;
+}
+extern "C" void ggml_b200_handoff_reset(void) {
+    handoff_collect(true);
+    std::lock_guard<std::mutex> lk(g_stat_mu);
+    g_handoff = { 0, 0, 0.0, 0.0 };
 }
 static void be_synchronize(ggml_backend_t b) {
     b200_backend_ctx * c = (b200_backend_ctx *)b->context;
@@ -285,7 +348,6 @@ static void be_synchronize(ggml_backend_t b) {
 // GGML_B200_TIMING=1: host-side cost of graph_compute (node translation / executor call), printed when the backend is freed
 static bool g_timing = getenv("GGML_B200_TIMING") != nullptr;
 static double g_t_conv = 0, g_t_exec = 0; static long g_calls = 0, g_nodes = 0, g_kernels = 0;
-static double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static bool g_timing_flag() { return g_timing; } static long g_calls_ref() { return g_calls; } static long g_nodes_ref() { return g_nodes; } static long g_kernels_ref() { return g_kernels; }
 static double g_conv_ref() { return g_t_conv; } static double g_exec_ref() { return g_t_exec; }
@@ -299,17 +361,14 @@ static enum ggml_status be_graph_compute(ggml_backend_t b, struct ggml_cgraph * 
     for (int i = 0; i < n; i++) {
         ggml_tensor * t = ggml_graph_node(cgraph, i);
         if (!node_to_b200(t, c->nodes[i])) { fprintf(stderr, "ggml-b200: op %s is not supported (node %s)\n", ggml_op_name(t->op), t->name); return GGML_STATUS_FAILED; }
-        // lazily repack weights consumed by MUL_MAT (once per tensor, outside any CUDA-graph capture)
+        // weights that did not arrive as one whole-tensor upload (chunked --no-mmap loads) are converted here, once, with the
+        // buffer mutex held across check + conversion + mark and a stream sync before anyone may read them
         if (t->op == GGML_OP_MUL_MAT && is_repack_type(t->src[0]->type)) {
             const ggml_tensor * w = t->src[0];
             ggml_backend_buffer_t wb = w->view_src ? w->view_src->buffer : w->buffer;
-            if (!is_b200_buffer(wb)) return GGML_STATUS_FAILED;
-            b200_buffer_ctx * bc = (b200_buffer_ctx *)wb->context;
-            if (!tensor_is_repacked(bc, w)) {
-                if (b200_repack_rows((int)w->type, w->data, ggml_nrows(w), w->ne[0], c->stream) != B200_OK) { fprintf(stderr, "ggml-b200: repack failed: %s\n", b200_last_error()); return GGML_STATUS_FAILED; }
-                std::lock_guard<std::mutex> lk(bc->mu);
-                bc->repacked.insert(w->data);
-            }
+            if (!is_b200_buffer(wb)) { fprintf(stderr, "ggml-b200: MUL_MAT weight %s is not in a B200 buffer\n", w->name); return GGML_STATUS_FAILED; }
+            if (!ensure_repacked((b200_buffer_ctx *)wb->context, w)) { fprintf(stderr, "ggml-b200: repack failed: %s\n", b200_last_error()); return GGML_STATUS_FAILED; }
+            cudaSetDevice(c->device);
         }
     }
     static int dumped = 0;
@@ -379,9 +438,11 @@ static ggml_backend_t dev_init_backend(ggml_backend_dev_t d, const char *) {
     c->ex = b200_executor_create(dc->device);
     if (!c->ex) { cudaStreamDestroy(c->stream); delete c; return nullptr; }
     // NVLink peer access for the hidden-state handoff, enabled once (ggml-cuda enables it lazily per batch size)
-    for (int j = 0; j < g_ndev; j++) if (j != dc->device) {
+    for (int j = 0; j < g_ndev; j++) {
+        const int peer = g_dev[j].device;                    // CUDA ordinal of plug-in device j (they differ on mixed boxes)
+        if (peer == dc->device) continue;
         int can = 0;
-        if (cudaDeviceCanAccessPeer(&can, dc->device, j) == cudaSuccess && can) { cudaError_t e = cudaDeviceEnablePeerAccess(j, 0); if (e != cudaSuccess) cudaGetLastError(); }
+        if (cudaDeviceCanAccessPeer(&can, dc->device, peer) == cudaSuccess && can) { cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0); if (e != cudaSuccess) cudaGetLastError(); }
     }
     ggml_backend_t be = new ggml_backend{ &g_guid, b200_backend_iface, d, c };
     return be;
@@ -391,6 +452,15 @@ static ggml_backend_buffer_type_t dev_host_buft(ggml_backend_dev_t d) { return &
 
 static bool dev_supports_op(ggml_backend_dev_t, const struct ggml_tensor * op) {
     b200_node n;
+    if (op->op == GGML_OP_SOFT_MAX) {
+        // attention without -fa (SOFT_MAX + batched KQ / KQV matmuls, llama-graph.cpp:1267-1330) is not on this backend's hot
+        // path: ggml's scheduler will run those nodes on the CPU backend.  Say so once, loudly — llama-box only turns flash
+        // attention on with -fa (llama-box/engine_param.hpp:772-779).
+        static std::once_flag warned;
+        std::call_once(warned, [] { GGML_LOG_WARN("ggml-b200: this graph uses non-flash attention (SOFT_MAX); the B200 backend implements FLASH_ATTN_EXT only — "
+                                                  "start llama-box / llama.cpp with -fa (--flash-attn) or attention will run on the CPU backend\n"); });
+        return false;
+    }
     if (!node_to_b200(op, n)) return false;
     if (op->op == GGML_OP_CPY) {
         // only the contiguous f32 -> f16/f32 casts of the mask / KV path
@@ -412,8 +482,11 @@ static bool dev_supports_op(ggml_backend_dev_t, const struct ggml_tensor * op) {
     return ok;
 }
 static bool dev_supports_buft(ggml_backend_dev_t d, ggml_backend_buffer_type_t buft) {
+    // own device memory only, like ggml-cuda on discrete GPUs (ggml-cuda.cu:3538-3547): tensors living in the pinned host
+    // buffer type (CPU-resident layers with -ngl below the layer count, llama-model.cpp:321-333) belong to the CPU backend;
+    // the scheduler copies the activations across the boundary
     b200_device_ctx * dc = (b200_device_ctx *)d->context;
-    return buft == &dc->buft || buft->iface.get_name == hbuft_name;
+    return buft == &dc->buft;
 }
 static bool dev_offload_op(ggml_backend_dev_t, const struct ggml_tensor *) { return false; }
 static ggml_backend_event_t dev_event_new(ggml_backend_dev_t d) {
@@ -436,7 +509,12 @@ static const ggml_backend_device_i b200_device_iface = {
 static const char * reg_name(ggml_backend_reg_t) { return "B200"; }
 static size_t reg_dev_count(ggml_backend_reg_t) { return (size_t)g_ndev; }
 static ggml_backend_dev_t reg_get_dev(ggml_backend_reg_t, size_t i) { return i < (size_t)g_ndev ? &g_devices[i] : nullptr; }
-static void * reg_proc(ggml_backend_reg_t, const char *) { return nullptr; }   // no split buffers / n_threads / extra bufts (NULL is legal)
+// no split buffers / n_threads / extra bufts (NULL is legal); two diagnostic entry points of our own
+static void * reg_proc(ggml_backend_reg_t, const char * name) {
+    if (!strcmp(name, "ggml_b200_handoff_stats")) return (void *)ggml_b200_handoff_stats;
+    if (!strcmp(name, "ggml_b200_handoff_reset")) return (void *)ggml_b200_handoff_reset;
+    return nullptr;
+}
 
 static int count_blackwell(int * ids) {
     int n = 0, nd = 0;

@@ -43,6 +43,26 @@ def layer_types(ftype, i, n):
     return {k: t for k in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")}
 
 
+def gauss_quantized(t, m, k, seed):
+    """N(0, 0.02^2) f32 weights quantised with the REFERENCE quantiser (ggml_quantize_chunk), generated and converted in
+    row chunks on several threads (each chunk has its own counter-based stream, so the file does not depend on the thread count)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from refutil import ptr, ref
+    base, _ = ref()
+    out = np.zeros((m, row_bytes(t, k)), dtype=np.uint8)
+    rows = max(1, (1 << 22) // k)
+
+    def work(r0):
+        r1 = min(m, r0 + rows)
+        g = np.random.Generator(np.random.Philox(key=seed, counter=r0))
+        w = g.standard_normal((r1 - r0, k), dtype=np.float32) * np.float32(0.02)
+        base.ggml_quantize_chunk(t, ptr(w), ptr(out[r0:r1]), 0, r1 - r0, k, None)
+    nthr = max(1, min(32, len(os.sched_getaffinity(0))))
+    with ThreadPoolExecutor(nthr) as tp:
+        list(tp.map(work, range(0, m, rows)))
+    return out
+
+
 def main():
     import gguf
     ap = argparse.ArgumentParser()
@@ -85,8 +105,7 @@ def main():
         key = (t, m, k)
         if key not in cache or a.weights == "gauss":
             if a.weights == "gauss":
-                from refutil import ref_quantize_weights
-                cache[key] = ref_quantize_weights(t, (rng.standard_normal((m, k)) * 0.02).astype(np.float32))
+                cache[key] = gauss_quantized(t, m, k, int(rng.integers(1 << 31)))
             else:
                 cache[key] = rand_blocks(rng, t, m, k, a.scale_mul)
         return cache[key]

@@ -156,7 +156,19 @@ def ref_quantize_weights(t, w):
     w = np.ascontiguousarray(w, dtype=np.float32)
     m, k = w.shape
     out = np.zeros((m, row_bytes(t, k)), dtype=np.uint8)
-    base.ggml_quantize_chunk(t, ptr(w), ptr(out), 0, m, k, None)
+    if m * k < (1 << 22):
+        base.ggml_quantize_chunk(t, ptr(w), ptr(out), 0, m, k, None)
+        return out
+    # big tensors (BASELINE-shaped vocab / ffn matrices): row chunks on a few threads (ctypes releases the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    nthr = max(1, min(16, len(os.sched_getaffinity(0))))
+    step = (m + nthr - 1) // nthr
+
+    def work(r0):
+        r1 = min(m, r0 + step)
+        base.ggml_quantize_chunk(t, ptr(w[r0:r1]), ptr(out[r0:r1]), 0, r1 - r0, k, None)
+    with ThreadPoolExecutor(nthr) as tp:
+        list(tp.map(work, range(0, m, step)))
     return out
 
 

@@ -1,0 +1,172 @@
+"""GPU: the product boundary on BASELINE-shaped models — the north-star bar, end to end.
+
+The UNMODIFIED reference libllama (oracle/_ref/llama_drv: llama_decode + greedy sampling) drives libggml-b200.so through
+ggml's backend C-ABI on synthetic GGUFs whose tensor SHAPES are the BASELINE.json configs' (layer count reduced — the
+per-layer arithmetic is what is under test) and whose weights are N(0, 0.02^2) quantised with the reference quantiser.
+Against the reference's own ggml-cpu run of the same file and prompt:
+    * identical greedy token IDs for every one of >= 32 steps,
+    * logits within 1e-3 relative (max |a-b| / max |b|) at EVERY step,
+for batch-1 decode (configs 1, 2), Q8_0 weights with a Q8_0 KV cache and 2..8-token speculative-verify batches (config 5),
+partial offload (-ngl below the layer count), the embeddings output, and — when the box has more than one GPU — the same
+run with --tensor-split over 2 / all devices, which must reproduce the 1-GPU tokens and logits.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from refutil import REF_DIR, ROOT, have_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")]
+PLUGIN = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")
+ENV = dict(os.environ, LD_LIBRARY_PATH=REF_DIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+ENV.pop("GGML_BACKEND_PATH", None)
+N_STEPS = 33
+
+
+def n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+_models = {}
+
+
+def model_file(tmp_path_factory, config, ftype, layers):
+    key = (config, ftype, layers)
+    if key not in _models:
+        d = tmp_path_factory.getbasetemp()
+        shm = "/dev/shm" if os.access("/dev/shm", os.W_OK) else str(d)
+        path = os.path.join(shm, f"b200_test_{config}_{ftype}_L{layers}_{os.getpid()}.gguf")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "make_gguf.py"), "--config", config, "--ftype", ftype, "--weights", "gauss", "--layers", str(layers), "--out", path],
+                           capture_output=True, text=True, env=ENV)
+        assert r.returncode == 0, r.stderr[-2000:]
+        _models[key] = path
+    return _models[key]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cleanup():
+    yield
+    for p in _models.values():
+        try:
+            os.remove(p)
+        except OSError:
+            pass
+
+
+def drv(gguf, out_prefix, plugin, kv="f16", prompt_len=24, gen=N_STEPS, verify=1, ngl=99, ts=None, embeddings=False, ctx=1024):
+    logits = out_prefix + ".logits"
+    cmd = [os.path.join(REF_DIR, "llama_drv"), "--model", gguf, "--ctx", str(ctx), "--prompt-len", str(prompt_len), "--gen", str(gen), "--logits-out", logits, "--fa",
+           "--ctk", kv, "--ctv", kv, "--verify-batch", str(verify)]
+    if plugin:
+        cmd += ["--plugin", PLUGIN, "--ngl", str(ngl)]
+        if ts:
+            cmd += ["--ts", ts]
+    else:
+        cmd += ["--ngl", "0", "--threads", str(min(32, len(os.sched_getaffinity(0)))), "--no-repack"]
+    if embeddings:
+        cmd += ["--embeddings", out_prefix + ".embd"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=ENV, timeout=1800)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    res["logits"] = np.fromfile(logits, np.float32).reshape(-1, res["n_vocab"])
+    if embeddings:
+        res["embd"] = np.fromfile(out_prefix + ".embd", np.float32)
+    res["stderr"] = r.stderr
+    return res
+
+
+def assert_north_star(gpu, cpu, what):
+    """identical greedy tokens at every step, logits within 1e-3 relative at every step"""
+    assert gpu["logits"].shape == cpu["logits"].shape
+    worst = 0.0
+    for i in range(cpu["logits"].shape[0]):
+        a, b = gpu["logits"][i], cpu["logits"][i]
+        rel = float(np.abs(a - b).max() / np.abs(b).max())
+        worst = max(worst, rel)
+        assert rel <= 1e-3, f"{what}: logits row {i}: rel {rel:.3e}"
+    assert gpu["tokens"] == cpu["tokens"], f"{what}: tokens differ: {gpu['tokens']} vs {cpu['tokens']}"
+    return worst
+
+
+CASES = [
+    # config, ftype, layers, kv, verify batch
+    ("llama3-8b", "Q4_K_M", 2, "f16", 1),          # BASELINE config 2: 8B shapes (n_ff 14336, vocab 128256), Q4_K + Q6_K mix
+    ("tinyllama-1.1b", "Q4_0", 2, "f16", 1),       # config 1 / the config-5 draft: head_dim 64, Q4_0
+    ("llama3-8b", "Q8_0", 2, "q8_0", 1),           # config 5 target, batch 1
+    ("llama3-8b", "Q8_0", 2, "q8_0", 2),           # config 5: speculative verify batches
+    ("llama3-8b", "Q8_0", 2, "q8_0", 5),
+    ("llama3-8b", "Q8_0", 2, "q8_0", 8),
+    ("llama3-8b", "Q4_K_M", 2, "q8_0", 4),
+]
+
+
+@pytest.mark.parametrize("config,ftype,layers,kv,verify", CASES)
+def test_baseline_shape_token_and_logit_parity(tmp_path, tmp_path_factory, config, ftype, layers, kv, verify):
+    gguf = model_file(tmp_path_factory, config, ftype, layers)
+    cpu = drv(gguf, str(tmp_path / "cpu"), False, kv=kv, verify=verify)
+    gpu = drv(gguf, str(tmp_path / "gpu"), True, kv=kv, verify=verify)
+    assert len(cpu["tokens"]) == N_STEPS
+    worst = assert_north_star(gpu, cpu, f"{config} {ftype} kv={kv} verify={verify}")
+    print(f"worst relative logit deviation over {cpu['logits'].shape[0]} rows: {worst:.2e}")
+
+
+def test_prefill_ubatch_then_decode_parity(tmp_path, tmp_path_factory):
+    """a 600-token prompt (one full 512-token ubatch through the batched MUL_MAT + multi-token attention path, then an 88-token
+    one) followed by decode, 8B shapes"""
+    gguf = model_file(tmp_path_factory, "llama3-8b", "Q4_K_M", 2)
+    cpu = drv(gguf, str(tmp_path / "cpu"), False, prompt_len=600, gen=9)
+    gpu = drv(gguf, str(tmp_path / "gpu"), True, prompt_len=600, gen=9)
+    assert_north_star(gpu, cpu, "prefill 600 + decode")
+
+
+@pytest.mark.parametrize("ngl", [0, 1, 2])
+def test_partial_offload(tmp_path, tmp_path_factory, ngl):
+    """-ngl below the layer count: CPU-resident layers live in the plug-in's pinned host buffer type and must run on the CPU
+    backend (supports_buft is true for device memory only, like ggml-cuda.cu:3538-3547); 3-layer model, 0 / 1 / 2 offloaded"""
+    gguf = model_file(tmp_path_factory, "tinyllama-1.1b", "Q4_0", 3)
+    cpu = drv(gguf, str(tmp_path / "cpu"), False, gen=9)
+    gpu = drv(gguf, str(tmp_path / "gpu"), True, gen=9, ngl=ngl)
+    assert_north_star(gpu, cpu, f"ngl={ngl}")
+
+
+def test_embeddings_output(tmp_path, tmp_path_factory):
+    """cparams.embeddings: libllama reads result_norm from the backend although nothing flags it as an output
+    (llama-context.cpp:1115-1151) — the executor must not elide it"""
+    gguf = model_file(tmp_path_factory, "tinyllama-1.1b", "Q4_0", 3)
+    cpu = drv(gguf, str(tmp_path / "cpu"), False, gen=5, embeddings=True)
+    gpu = drv(gguf, str(tmp_path / "gpu"), True, gen=5, embeddings=True)
+    assert gpu["embd"].shape == cpu["embd"].shape and cpu["embd"].size > 0
+    rel = float(np.abs(gpu["embd"] - cpu["embd"]).max() / np.abs(cpu["embd"]).max())
+    assert rel <= 1e-3, rel
+    assert gpu["tokens"] == cpu["tokens"]
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs >= 2 GPUs in one box")
+@pytest.mark.parametrize("split", ["2", "all"])
+def test_tensor_split_reproduces_single_gpu(tmp_path, tmp_path_factory, split):
+    """--tensor-split over 2 / all devices of the box (LLAMA_SPLIT_MODE_LAYER through the plug-in's cpy_tensor_async +
+    events): the same kernels run in the same order, so tokens AND logits must equal the 1-GPU run; and the 1-GPU run
+    meets the north-star bar against ggml-cpu"""
+    n = n_gpus()
+    k = 2 if split == "2" else n
+    if split == "all" and n == 2:
+        pytest.skip("'all' == '2' on this box")
+    layers = max(4, k)
+    gguf = model_file(tmp_path_factory, "llama3-8b", "Q4_K_M", layers)
+    one = drv(gguf, str(tmp_path / "one"), True, ts=",".join(["1"] + ["0"] * (n - 1)))
+    many = drv(gguf, str(tmp_path / "many"), True, ts=",".join(["1"] * k + ["0"] * (n - k)))
+    assert many["handoff"]["copies"] > 0, "no inter-device handoff happened: the split did not take effect"
+    assert many["tokens"] == one["tokens"]
+    d = float(np.abs(many["logits"] - one["logits"]).max() / np.abs(one["logits"]).max())
+    assert d <= 1e-6, d
+    cpu = drv(gguf, str(tmp_path / "cpu"), False)
+    assert_north_star(many, cpu, f"--ts over {k} devices")
+    print(f"handoff: {many['handoff']}")
