@@ -249,7 +249,9 @@ def product_decode(args, ts, n_past, steps, warmup, prefill_probe=0):
         V = d.n_vocab
         prompt = rng.integers(0, V, size=max(1, n_past)).tolist()
         t0 = time.perf_counter()
-        d.decode(prompt); lg = d.logits()
+        for i in range(0, len(prompt), 2048):
+            d.decode(prompt[i:i + 2048])
+        lg = d.logits()
         tok = int(np.argmax(lg))
         prefill_s = time.perf_counter() - t0
         for _ in range(warmup):
@@ -280,7 +282,9 @@ def product_decode(args, ts, n_past, steps, warmup, prefill_probe=0):
             pp = rng.integers(0, V, size=prefill_probe).tolist()
             d.decode(pp[:512]); d.sync(); d.reset()       # warm-up ubatch (graph shapes, workspace growth)
             t0 = time.perf_counter()
-            d.decode(pp); d.logits()
+            for i in range(0, len(pp), 2048):
+                d.decode(pp[i:i + 2048])
+            d.logits()
             out["prefill_probe"] = {"n_tokens": prefill_probe, "tok_s": prefill_probe / (time.perf_counter() - t0), "ubatch": 512}
         return out
     finally:

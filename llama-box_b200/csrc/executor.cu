@@ -105,6 +105,7 @@ bool fattn_ok(const b200_node & n) {
 }
 
 bool node_ok(const b200_node & n) {
+    if (n.op > B200_OP_NONE && n.op < B200_OP_COUNT && nelem(n.dst) == 0) return true;   // empty result (a ubatch without outputs): nothing to run, like ggml_is_empty nodes in ggml-cuda.cu:2858
     switch (n.op) {
         case B200_OP_NONE:     return true;
         case B200_OP_MUL_MAT:  return n.n_src >= 2 && mul_mat_ok(n);
@@ -349,6 +350,9 @@ struct Runner {
                             if (nodes[q].op == B200_OP_RMS_NORM || (nodes[q].op != B200_OP_NONE && overlaps(nodes[q].dst, mu.dst))) survives = false;
                         if (survives) {
                             { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+                            // ggml-alloc may have placed the normalised tensor IN PLACE over x: then it cannot be both written now and
+                            // recomputed from x later — the consumers quantise the materialised tensor instead (act_source 1)
+                            if (overlaps(mu.dst, x)) ex->norm.out_id = 0;
                             return KL(b200_rms_norm((const float *)x.data, (const float *)w->data, (float *)mu.dst.data, ncols, nrows, ncols, ncols, eps, st));
                         }
                         return B200_OK;
@@ -746,7 +750,7 @@ struct Runner {
         ex->norm.out_id = 0;
         pend.clear(); rope_pend.valid = false;
         for (int i = 0; i < n; i++) {
-            if (done[i]) continue;
+            if (done[i] || nelem(nodes[i].dst) == 0) continue;       // empty tensors (prompt ubatches that request no logits) are skipped
             const int s = run_node(i);
             if (s != B200_OK) return s;
         }
