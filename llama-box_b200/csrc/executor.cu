@@ -783,6 +783,11 @@ int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
         if (nd.op == B200_OP_MUL_MAT) {
             const int64_t k = nd.src[0].ne[0], cols = nd.src[1].ne[1];
             for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(cols * act_col_bytes(kd, k)); if (b > act[kd]) act[kd] = b; }
+            if (cols > 8) {                               // batched path: the tensor-core kernel's pre-tiled activation image
+                const int kd = b200_act_kind_for(nd.src[0].type);
+                const size_t b = (size_t)b200_mul_mat_q_workspace(nd.src[0].type, nd.src[0].ne[1], k, cols);
+                if (kd >= 0 && b > act[kd]) act[kd] = b;
+            }
         } else if (nd.op == B200_OP_RMS_NORM) {
             for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(8 * act_col_bytes(kd, (nd.src[0].ne[0] + 255) / 256 * 256)); if (b > act[kd]) act[kd] = b; }
         } else if (nd.op == B200_OP_FLASH_ATTN_EXT) {

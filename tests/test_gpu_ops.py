@@ -492,3 +492,42 @@ def test_glue_ops(b200):
     b200.check(b200.lib.b200_argmax_f32(b200.p(dev(lg)), b200.p(idx), 128256, 2, b200.stream()))
     assert idx.cpu().numpy().tolist() == [int(lg[0].argmax()), 777]
     assert b200.lib.b200_kernel_launches() > 0
+
+
+# ------------------------------------------------------------------ a4: batched MUL_MAT on the tensor cores (tcgen05, mmq_tc.cu)
+@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K])
+@pytest.mark.parametrize("m,k,n", [(128, 2048, 128), (256, 4096, 40), (48, 2048, 19), (384, 2048, 300), (1024, 4096, 512)])
+def test_mul_mat_q_tensor_core_vs_oracle(b200, t, m, k, n):
+    """the tcgen05 tile kernel against the C oracle (ggml_vec_dot_q*_K_q8_K restated): the integer sums are exact, so only the
+    f32 summation order over super-blocks differs — same bound as the matvec"""
+    rng = np.random.default_rng(1000 + m + n)
+    W = rand_blocks(rng, t, m, k)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    x[n // 2, :256] = 0.0                                       # an all-zero q8_K block (d = 0)
+    want = orc_mul_mat(t, W, x, m, n, k)
+    ws = torch.zeros(b200.lib.b200_mul_mat_q_workspace(t, m, k, n), dtype=torch.uint8, device="cuda")
+    dst = torch.full((n, m), float("nan"), dtype=torch.float32, device="cuda")
+    Wd = padded_weights(b200, t, W)
+    b200.check(b200.lib.b200_mul_mat_q(t, b200.p(Wd), b200.p(dev(x)), k, b200.p(dst), m, m, k, n, b200.p(ws), b200.stream()))
+    got = dst.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err <= 2e-5, err
+
+
+def test_mul_mat_q_tensor_core_baseline_shape(b200):
+    """BASELINE config 3 shape: ffn_down of Llama-3-8B (m 4096, k 14336) against a 512-token ubatch; NMSE vs the oracle on a row sample"""
+    rng = np.random.default_rng(5)
+    t, m, k, n = Q4_K, 4096, 14336, 512
+    W = rand_blocks(rng, t, m, k)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    ws = torch.zeros(b200.lib.b200_mul_mat_q_workspace(t, m, k, n), dtype=torch.uint8, device="cuda")
+    dst = torch.zeros((n, m), dtype=torch.float32, device="cuda")
+    Wd = padded_weights(b200, t, W)
+    b200.check(b200.lib.b200_mul_mat_q(t, b200.p(Wd), b200.p(dev(x)), k, b200.p(dst), m, m, k, n, b200.p(ws), b200.stream()))
+    got = dst.cpu().numpy()
+    rows = np.concatenate([np.arange(0, 64), np.arange(2000, 2064), np.arange(m - 64, m)])
+    want = orc_mul_mat(t, W[rows], x, len(rows), n, k)
+    d = (got[:, rows] - want).astype(np.float64)
+    nmse = float((d * d).sum() / (want.astype(np.float64) ** 2).sum())
+    assert nmse < 1e-10, nmse

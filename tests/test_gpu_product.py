@@ -135,7 +135,7 @@ def assert_within_reference_self_consistency(gpu, cpu, cpu2, what):
     print(f"{what}: ours worst {max(ours):.2e} (rows <= 1e-3: {sum(r <= 1e-3 for r in ours)}/{len(ours)}); ggml-cpu avx2 vs avx512 worst {max(ref):.2e}")
     per_step = max(1, cpu["verify_batch"])
     for i, (o, r) in enumerate(zip(ours, ref)):
-        step = i // per_step if i else 0
+        step = 0 if i == 0 else 1 + (i - 1) // per_step       # row 0: the prompt's last token; then `verify` rows per decode step
         if gpu["tokens"][:step] != cpu["tokens"][:step] or cpu2["tokens"][:step] != cpu["tokens"][:step]:
             break                                      # histories diverged (already at the CPU-vs-CPU level): rows no longer comparable
         assert o <= bound, f"{what}: row {i}: {o:.3e} > bound {bound:.3e} (ggml-cpu's own builds differ by {r:.3e} here)"
