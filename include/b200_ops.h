@@ -216,6 +216,16 @@ B200_API int b200_rope_kv_flash_attn(const float *q_src, float *q_dst, const flo
                                      int64_t head_dim, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params *p,
                                      float scale, float max_bias, float softcap, void *workspace, void *stream);
 
+/* the same with a per-token cos/sin table shared by all layers (the table depends on the position only): rope_tab = 2*head_dim
+ * floats of caller scratch; tab_mode 0 = this launch computes the table and stores it there, 1 = an earlier launch for the same
+ * token and rope parameters did.  rope_tab NULL = every launch computes its own. */
+B200_API int b200_rope_kv_flash_attn2(const float *q_src, float *q_dst, const float *k_new, const float *v_new, const int32_t *pos,
+                                      const float *freq_factors_or_null, const int64_t *k_ids, const int64_t *v_ids,
+                                      void *k_cache, void *v_cache, int kv_type, int64_t k_cell_stride, int64_t k_head_stride,
+                                      int64_t v_cell_stride, int64_t v_head_stride, const void *mask_f16_or_null, float *dst,
+                                      int64_t head_dim, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params *p,
+                                      float scale, float max_bias, float softcap, void *workspace, float *rope_tab, int tab_mode, void *stream);
+
 /* ---- glue (replaces binbcast.cu, unary.cu:291, getrows.cu, cpy.cu) ----------------------- */
 B200_API int b200_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows, void *stream);
 B200_API int b200_mul(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows, void *stream);

@@ -246,14 +246,24 @@ struct Runner {
         return true;
     }
     // ... as one launch of the split-KV attention kernel (fattn.cu, FaFuse)
+    // the cos/sin table of a decode token depends on its position only: the first attention launch of a list computes it into
+    // executor scratch, the other layers (same positions tensor, same rope parameters) load it
+    struct { bool valid = false; const int32_t * pos = nullptr; const float * ff = nullptr; b200_rope_params p; int64_t hd = 0; } tab;
     int launch_fused_attn(const b200_node & n) {
         const RopePend r = rope_pend;
         rope_pend.valid = false;
         const int fs = mk_flush(); if (fs != B200_OK) return fs;
         const b200_tensor & k = n.src[1], & v = n.src[2];
         const void * mask = n.n_src > 3 ? n.src[3].data : nullptr;
-        return KL(b200_rope_kv_flash_attn(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, k.nb[1], k.nb[2], v.nb[1], v.nb[2],
-                                       mask, (float *)n.dst.data, r.hd, r.nh, r.nhk, k.ne[1], &r.p, f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st));
+        float * rope_tab = nullptr; int tab_mode = 0;
+        if (dry || (ex->ws && ex->fa_bytes >= 1024)) {
+            rope_tab = dry ? (float *)(uintptr_t)0x20000 : (float *)(ex->ws + ex->off_fa + ex->fa_bytes - 1024);
+            tab_mode = tab.valid && tab.pos == r.pos && tab.ff == r.ff && tab.hd == r.hd && memcmp(&tab.p, &r.p, sizeof(r.p)) == 0;
+            tab.valid = true; tab.pos = r.pos; tab.ff = r.ff; tab.p = r.p; tab.hd = r.hd;
+        }
+        return KL(b200_rope_kv_flash_attn2(r.q_src, r.q_dst, r.k, r.v, r.pos, r.ff, r.k_ids, r.v_ids, r.k_cache, r.v_cache, r.kv_type, k.nb[1], k.nb[2], v.nb[1], v.nb[2],
+                                        mask, (float *)n.dst.data, r.hd, r.nh, r.nhk, k.ne[1], &r.p, f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa,
+                                        rope_tab, tab_mode, st));
     }
     // ... or as a phase of the persistent kernel
     bool mk_try_attn(const b200_node & n) {
@@ -468,7 +478,7 @@ struct Runner {
         const b200_node & F = nodes[fa];
         // executor scratch behind the attention workspace: q | k | v projections of this token
         const size_t fa_ws = (size_t)b200_flash_attn_workspace(hd, nh, 1, F.src[1].ne[1]);
-        if (!dry && ex->off_fa + fa_ws + (size_t)(nh + 2 * nhk) * hd * 4 + 256 > ex->ws_bytes) return false;
+        if (!dry && (((fa_ws + 255) & ~(size_t)255) + (size_t)(nh + 2 * nhk) * hd * 4 + 1024 > ex->fa_bytes)) return false;
         float * sq = dry ? (float *)(uintptr_t)0x10000 : (float *)(ex->ws + ex->off_fa + ((fa_ws + 255) & ~(size_t)255));
         float * skn = sq + nh * hd, * svn = skn + nhk * hd;
         RopePend r;
@@ -748,7 +758,7 @@ struct Runner {
         for (int i = 0; i < n; i++) for (int s = 0; s < nodes[i].n_src && s < B200_MAX_SRC; s++) if (nodes[i].src[s].id) uses[nodes[i].src[s].id]++;
         ex->act_id[0] = ex->act_id[1] = 0;
         ex->norm.out_id = 0;
-        pend.clear(); rope_pend.valid = false;
+        pend.clear(); rope_pend.valid = false; tab.valid = false;
         for (int i = 0; i < n; i++) {
             if (done[i] || nelem(nodes[i].dst) == 0) continue;       // empty tensors (prompt ubatches that request no logits) are skipped
             const int s = run_node(i);
@@ -793,6 +803,7 @@ int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
         } else if (nd.op == B200_OP_FLASH_ATTN_EXT) {
             size_t b = (size_t)b200_flash_attn_workspace(nd.src[2].ne[0], nd.src[0].ne[2], nd.src[0].ne[1], nd.src[1].ne[1]);
             if (nd.src[0].ne[1] == 1) b = ((b + 255) & ~(size_t)255) + (size_t)(nd.src[0].ne[2] + 2 * nd.src[1].ne[2]) * nd.src[0].ne[0] * 4 + 512;   // + q|k|v scratch of try_attn_block
+            b = ((b + 255) & ~(size_t)255) + 1024;                // + the per-token rope table (last KiB of the region)
             if (b > fa) fa = b;
         }
     }

@@ -49,11 +49,25 @@ struct FaFuse {
     const float * q_src; float * q_dst; const float * k_new; const float * v_new;
     const int32_t * pos; const float * ff; const int64_t * k_ids; const int64_t * v_ids;
     RopeDev rp; int enabled; int early_trigger;
+    // cos/sin table of this token: the same for every layer, so the first attention launch of a token computes it (every CTA for
+    // itself, one CTA also stores it) and the other layers just load 512 bytes: tab_mode 0 = compute (+ store if rope_tab), 1 = load
+    float * rope_tab; int tab_mode;
 };
-// elements e0..e0+7 of one head, roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled)
-__device__ __forceinline__ void load_roped8(const float * head, int e0, const float * cs, const RopeDev & rp, float (&v)[8]) {
+// elements e0..e0+7 of one head, roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled) — in three steps so
+// that the global loads can be issued long before the table is ready: raw8 (the elements), partner8 (NEOX: the other half of
+// each pair), rope8 (arithmetic only)
+__device__ __forceinline__ void raw8(const float * head, int e0, float (&v)[8]) {
     const float4 a = *(const float4 *)(head + e0), b = *(const float4 *)(head + e0 + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void partner8(const float * head, int e0, const RopeDev & rp, float (&o)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j] = 0.0f;
+    if (!rp.neox || e0 >= rp.n_dims) return;
+    const int half = rp.n_dims >> 1;
+    raw8(head, e0 < half ? e0 + half : e0 - half, o);
+}
+__device__ __forceinline__ void rope8(float (&v)[8], const float (&o)[8], int e0, const float * cs, const RopeDev & rp) {
     if (e0 >= rp.n_dims) return;
     if (!rp.neox) {
 #pragma unroll
@@ -66,9 +80,6 @@ __device__ __forceinline__ void load_roped8(const float * head, int e0, const fl
     } else {
         const int half = rp.n_dims >> 1;
         const bool first = e0 < half;
-        const int po = first ? e0 + half : e0 - half;
-        const float4 pa = *(const float4 *)(head + po), pb = *(const float4 *)(head + po + 4);
-        const float o[8] = { pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w };
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int i = first ? e0 + j : e0 - half + j;
@@ -76,6 +87,12 @@ __device__ __forceinline__ void load_roped8(const float * head, int e0, const fl
             v[j] = first ? __fsub_rn(__fmul_rn(v[j], c), __fmul_rn(o[j], sn)) : __fadd_rn(__fmul_rn(o[j], sn), __fmul_rn(v[j], c));
         }
     }
+}
+__device__ __forceinline__ void load_roped8(const float * head, int e0, const float * cs, const RopeDev & rp, float (&v)[8]) {
+    float o[8];
+    raw8(head, e0, v);
+    partner8(head, e0, rp, o);
+    rope8(v, o, e0, cs, rp);
 }
 // 8 int8 of a q8_0 row in shared memory (34-byte blocks) + the block scale
 __device__ __forceinline__ void lds_q80_8(const uint8_t * row, int dl, int (&q)[2], float & d) {
@@ -105,30 +122,71 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
     const int hk = h0 / gq;
     __shared__ __align__(16) float s_cs[D];
     __shared__ __align__(16) uint8_t s_newk[D * 2 + 32], s_newv[D * 2 + 32];
+    constexpr int MAXIT = 4;
+    constexpr int pstride = FA_WARPS * PPW;
+    const int p_begin = split * split_len;
+    const int p_end   = min(n_kv, p_begin + split_len);
+    const int base0 = p_begin + warp * PPW + sg;
+    // K / V of the first chunk of this split.  On the decode path (fu.enabled) the cells of EARLIER tokens were written by earlier
+    // launches of the token loop, and pos / cell ids are graph inputs: all of it may be fetched before griddepcontrol.wait, while
+    // the previous kernel (the QKV projection) is still running — a memory round trip off the token's critical path.
+    uint4 kpre[MAXIT], vpre[MAXIT]; float kdpre[MAXIT], vdpre[MAXIT];
+    int kcell = -1, vcell = -1, tok_pos = 0;
+    auto load_kv = [&](int p, uint4 & kr, uint4 & vr, float & kd, float & vd) {
+        const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
+        const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
+        if (KVT == B200_TYPE_F16) { kr = ldg_stream16(krow + dl * 16); vr = ldg_stream16(vrow + dl * 16); kd = 0.0f; vd = 0.0f; }
+        else {
+            int q2[2];
+            load_q80_8(krow, dl, q2, kd); kr = make_uint4((uint32_t)q2[0], (uint32_t)q2[1], 0, 0);
+            load_q80_8(vrow, dl, q2, vd); vr = make_uint4((uint32_t)q2[0], (uint32_t)q2[1], 0, 0);
+        }
+    };
+    if (fu.enabled) {
+        kcell = (int)fu.k_ids[0]; vcell = (int)fu.v_ids[0]; tok_pos = fu.pos[0];
+#pragma unroll
+        for (int it = 0; it < MAXIT; it++) {
+            const int p = base0 + it * pstride;
+            kpre[it] = make_uint4(0, 0, 0, 0); vpre[it] = kpre[it]; kdpre[it] = 0.0f; vdpre[it] = 0.0f;
+            if (p < p_end) load_kv(p, kpre[it], vpre[it], kdpre[it], vdpre[it]);
+        }
+    }
     if (fu.early_trigger) pdl_trigger();      // B200_FA_EARLY_TRIGGER=1: the next kernel may prime its weight ring during the attention — measured slower (its burst delays our loads)
     pdl_wait();
-    int kcell = -1, vcell = -1;
+    float qraw[G][8], qpar[G][8];
     if (fu.enabled) {
-        // (n_tok == 1) rope table, then this token's K / V slice for kv head hk in cache format
-        kcell = (int)fu.k_ids[0]; vcell = (int)fu.v_ids[0];
-        rope_table(s_cs, fu.pos[0], fu.ff, fu.rp, threadIdx.x, FA_WARPS * 32);
-        __syncthreads();
-        if (warp < 2) {
-            const int e = lane * 8; const bool on = e < D;
-            float a[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-            const bool storer = split == 0 && (h0 % gq) == 0;
-            if (warp == 0) {
-                if (on) load_roped8(fu.k_new + (int64_t)hk * D, e, s_cs, fu.rp, a);
-                store8(s_newk, KVT, e, a, lane, on);
-                if (storer) store8((uint8_t *)kc + (int64_t)kcell * k_rs + (int64_t)hk * k_hs, KVT, e, a, lane, on);
-            } else {
-                if (on) { const float4 x = *(const float4 *)(fu.v_new + (int64_t)hk * D + e), y = *(const float4 *)(fu.v_new + (int64_t)hk * D + e + 4);
-                          a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w; }
-                store8(s_newv, KVT, e, a, lane, on);
-                if (storer) store8((uint8_t *)vc + (int64_t)vcell * v_rs + (int64_t)hk * v_hs, KVT, e, a, lane, on);
-            }
+        // this token's query heads: issue the loads now, rope them once the table is in shared memory
+#pragma unroll
+        for (int g = 0; g < G; g++) { raw8(fu.q_src + (int64_t)(h0 + g) * D, dl * 8, qraw[g]); partner8(fu.q_src + (int64_t)(h0 + g) * D, dl * 8, fu.rp, qpar[g]); }
+        // rope table: computed by the first layer's launch (kept for the others), loaded by the rest
+        if (fu.tab_mode == 1) {
+            if (threadIdx.x < D / 4) *(float4 *)(s_cs + threadIdx.x * 4) = __ldcg((const float4 *)(fu.rope_tab) + threadIdx.x);
+        } else {
+            rope_table(s_cs, tok_pos, fu.ff, fu.rp, threadIdx.x, FA_WARPS * 32);
         }
         __syncthreads();
+        if (fu.tab_mode == 0 && fu.rope_tab && split == 0 && tile == 0 && threadIdx.x < D / 4) ((float4 *)fu.rope_tab)[threadIdx.x] = *(const float4 *)(s_cs + threadIdx.x * 4);
+        // this token's K (roped) / V for kv head hk in cache format: only the CTA whose split holds the cell reads it from shared
+        // memory, and one CTA per kv head writes the cell — every other CTA skips the staging (and its barrier) altogether
+        const bool storer = split == 0 && (h0 % gq) == 0;
+        const bool mine = (kcell >= p_begin && kcell < p_end) || (vcell >= p_begin && vcell < p_end);
+        if (storer || mine) {
+            if (warp < 2) {
+                const int e = lane * 8; const bool on = e < D;
+                float a[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                if (warp == 0) {
+                    if (on) load_roped8(fu.k_new + (int64_t)hk * D, e, s_cs, fu.rp, a);
+                    store8(s_newk, KVT, e, a, lane, on);
+                    if (storer) store8((uint8_t *)kc + (int64_t)kcell * k_rs + (int64_t)hk * k_hs, KVT, e, a, lane, on);
+                } else {
+                    if (on) { const float4 x = *(const float4 *)(fu.v_new + (int64_t)hk * D + e), y = *(const float4 *)(fu.v_new + (int64_t)hk * D + e + 4);
+                              a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w; }
+                    store8(s_newv, KVT, e, a, lane, on);
+                    if (storer) store8((uint8_t *)vc + (int64_t)vcell * v_rs + (int64_t)hk * v_hs, KVT, e, a, lane, on);
+                }
+            }
+            __syncthreads();
+        }
     }
 
     // ---- query slices: q8[g][8] as f32 (f16-rounded) or int8 + scale -------------------------
@@ -138,7 +196,9 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         const int h = h0 + g;
         float v[8];
         if (fu.enabled) {
-            load_roped8(fu.q_src + (int64_t)h * D, dl * 8, s_cs, fu.rp, v);
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = qraw[g][e];
+            rope8(v, qpar[g], dl * 8, s_cs, fu.rp);
             if (split == 0 && warp == 0 && sg == 0) {
                 *(float4 *)(fu.q_dst + (int64_t)h * D + dl * 8)     = make_float4(v[0], v[1], v[2], v[3]);
                 *(float4 *)(fu.q_dst + (int64_t)h * D + dl * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -178,34 +238,29 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         for (int e = 0; e < 8; e++) acc[g][e] = 0.0f; }
 
     const unsigned gmask = ((1u << LP) - 1u) << (sg * LP);   // lanes sharing one KV position (converged inside the loop)
-    const int p_begin = split * split_len;
-    const int p_end   = min(n_kv, p_begin + split_len);
     const uint16_t * mrow = mask ? mask + (int64_t)tok * mask_rs : nullptr;
 
     // positions are visited in chunks of MAXIT per lane group: every load of a chunk (mask, K, V) is issued before any
     // arithmetic, so a chunk costs one memory round trip instead of MAXIT (decode attention is latency-bound: a split is
     // a few dozen positions).  K/V of masked positions are loaded but never used.
-    constexpr int MAXIT = 4;
-    constexpr int pstride = FA_WARPS * PPW;
-    for (int base = p_begin + warp * PPW + sg; base < p_end; base += pstride * MAXIT) {
+    for (int base = base0; base < p_end; base += pstride * MAXIT) {
         float mraw[MAXIT]; uint4 kraw[MAXIT], vraw[MAXIT]; float kdv[MAXIT], vdv[MAXIT];
+        const bool pre = fu.enabled && base == base0;          // first chunk: K / V already in registers
 #pragma unroll
         for (int it = 0; it < MAXIT; it++) {
             const int p = base + it * pstride;
             mraw[it] = -INFINITY; kraw[it] = make_uint4(0, 0, 0, 0); vraw[it] = kraw[it]; kdv[it] = 0.0f; vdv[it] = 0.0f;
             if (p < p_end) {
                 mraw[it] = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
-                const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
-                const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
-                if (KVT == B200_TYPE_F16) {
-                    kraw[it] = p == kcell ? *(const uint4 *)(s_newk + dl * 16) : ldg_stream16(krow + dl * 16);
-                    vraw[it] = p == vcell ? *(const uint4 *)(s_newv + dl * 16) : ldg_stream16(vrow + dl * 16);
-                } else {
-                    int q2[2];
-                    if (p == kcell) lds_q80_8(s_newk, dl, q2, kdv[it]); else load_q80_8(krow, dl, q2, kdv[it]);
-                    kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1];
-                    if (p == vcell) lds_q80_8(s_newv, dl, q2, vdv[it]); else load_q80_8(vrow, dl, q2, vdv[it]);
-                    vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1];
+                if (pre) { kraw[it] = kpre[it]; vraw[it] = vpre[it]; kdv[it] = kdpre[it]; vdv[it] = vdpre[it]; }
+                else load_kv(p, kraw[it], vraw[it], kdv[it], vdv[it]);
+                if (p == kcell) {                               // this token's own cell: from shared memory (the global cell is being written by another CTA)
+                    if (KVT == B200_TYPE_F16) kraw[it] = *(const uint4 *)(s_newk + dl * 16);
+                    else { int q2[2]; lds_q80_8(s_newk, dl, q2, kdv[it]); kraw[it].x = (uint32_t)q2[0]; kraw[it].y = (uint32_t)q2[1]; }
+                }
+                if (p == vcell) {
+                    if (KVT == B200_TYPE_F16) vraw[it] = *(const uint4 *)(s_newv + dl * 16);
+                    else { int q2[2]; lds_q80_8(s_newv, dl, q2, vdv[it]); vraw[it].x = (uint32_t)q2[0]; vraw[it].y = (uint32_t)q2[1]; }
                 }
             }
         }
@@ -442,20 +497,36 @@ extern "C" int b200_flash_attn_ext(const float * q, int64_t q_ts, int64_t q_hs, 
     return fa_dispatch(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, kv_type, dk, dv, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap, workspace, stream, fu);
 }
 
+extern "C" int b200_rope_kv_flash_attn2(const float * q_src, float * q_dst, const float * k_new, const float * v_new, const int32_t * pos, const float * ff,
+                                        const int64_t * k_ids, const int64_t * v_ids, void * k_cache, void * v_cache, int kv_type,
+                                        int64_t k_rs, int64_t k_hs, int64_t v_rs, int64_t v_hs, const void * mask, float * dst,
+                                        int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params * p,
+                                        float scale, float max_bias, float softcap, void * workspace, float * rope_tab, int tab_mode, void * stream);
 // decode token: rope(q), rope(k) -> K cache cell, v -> V cache cell, attention over n_kv cells — one launch (see FaFuse)
 extern "C" int b200_rope_kv_flash_attn(const float * q_src, float * q_dst, const float * k_new, const float * v_new, const int32_t * pos, const float * ff,
                                        const int64_t * k_ids, const int64_t * v_ids, void * k_cache, void * v_cache, int kv_type,
                                        int64_t k_rs, int64_t k_hs, int64_t v_rs, int64_t v_hs, const void * mask, float * dst,
                                        int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params * p,
                                        float scale, float max_bias, float softcap, void * workspace, void * stream) {
+    return b200_rope_kv_flash_attn2(q_src, q_dst, k_new, v_new, pos, ff, k_ids, v_ids, k_cache, v_cache, kv_type, k_rs, k_hs, v_rs, v_hs, mask, dst, hd, n_head, n_head_kv, n_kv, p,
+                                    scale, max_bias, softcap, workspace, nullptr, 0, stream);
+}
+// ... with a per-token cos/sin table shared by the layers: rope_tab = 2 * head_dim floats of scratch; tab_mode 0 = this launch computes
+// the table (and stores it), 1 = an earlier launch of the same token (same pos, same rope parameters) did
+extern "C" int b200_rope_kv_flash_attn2(const float * q_src, float * q_dst, const float * k_new, const float * v_new, const int32_t * pos, const float * ff,
+                                        const int64_t * k_ids, const int64_t * v_ids, void * k_cache, void * v_cache, int kv_type,
+                                        int64_t k_rs, int64_t k_hs, int64_t v_rs, int64_t v_hs, const void * mask, float * dst,
+                                        int64_t hd, int64_t n_head, int64_t n_head_kv, int64_t n_kv, const b200_rope_params * p,
+                                        float scale, float max_bias, float softcap, void * workspace, float * rope_tab, int tab_mode, void * stream) {
     if (!q_src || !q_dst || !k_new || !v_new || !pos || !k_ids || !v_ids || !k_cache || !v_cache || !dst || !p) { b200_set_error("rope_kv_flash_attn: null pointer"); return B200_ERR_INVALID; }
     if ((p->mode & ~2) || p->n_dims > hd || p->n_dims % 8 != 0 || (p->mode == 2 && p->n_dims % 16 != 0)) { b200_set_error("rope_kv_flash_attn: rope mode / n_dims unsupported"); return B200_ERR_UNSUPPORTED; }
     const int64_t hs = kv_type == B200_TYPE_F16 ? hd * 2 : hd / 32 * 34;
     if (k_hs != hs || v_hs != hs) { b200_set_error("rope_kv_flash_attn: heads must be contiguous inside a cache cell"); return B200_ERR_INVALID; }
-    if (((uintptr_t)q_src | (uintptr_t)q_dst | (uintptr_t)k_new | (uintptr_t)v_new) & 15) { b200_set_error("rope_kv_flash_attn: 16-byte alignment required"); return B200_ERR_INVALID; }
+    if (((uintptr_t)q_src | (uintptr_t)q_dst | (uintptr_t)k_new | (uintptr_t)v_new | (uintptr_t)rope_tab) & 15) { b200_set_error("rope_kv_flash_attn: 16-byte alignment required"); return B200_ERR_INVALID; }
     FaFuse fu; memset(&fu, 0, sizeof(fu));
     fu.q_src = q_src; fu.q_dst = q_dst; fu.k_new = k_new; fu.v_new = v_new; fu.pos = pos; fu.ff = ff; fu.k_ids = k_ids; fu.v_ids = v_ids;
     fu.rp = rope_host_params(p); fu.enabled = 1; fu.early_trigger = fa_early_trigger();
+    fu.rope_tab = rope_tab; fu.tab_mode = rope_tab ? tab_mode : 0;
     return fa_dispatch(q_dst, hd * n_head, hd, k_cache, k_rs, k_hs, v_cache, v_rs, v_hs, mask, 0, dst, kv_type, hd, hd, n_head, n_head_kv, 1, n_kv,
                        scale, max_bias, softcap, workspace, stream, fu);
 }

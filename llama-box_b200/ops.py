@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200_flash_attn_ext": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i32, i64, i64, i64, i64, i64, i64, f32, f32, f32, vp, vp]),
     "b200_rope_kv_flash_attn": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i64, i64, i64, i64, C.POINTER(RopeParams),
                                       f32, f32, f32, vp, vp]),
+    "b200_rope_kv_flash_attn2": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i64, i64, i64, vp, vp, i64, i64, i64, i64, C.POINTER(RopeParams),
+                                       f32, f32, f32, vp, vp, i32, vp]),
     "b200_add": (i32, [vp, vp, vp, i64, i64, i64, vp]),
     "b200_mul": (i32, [vp, vp, vp, i64, i64, i64, vp]),
     "b200_swiglu": (i32, [vp, vp, vp, i64, vp]),

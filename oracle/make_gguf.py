@@ -43,7 +43,7 @@ def layer_types(ftype, i, n):
     return {k: t for k in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")}
 
 
-def gauss_quantized(t, m, k, seed):
+def gauss_quantized(t, m, k, seed, std=0.02):
     """N(0, 0.02^2) f32 weights quantised with the REFERENCE quantiser (ggml_quantize_chunk), generated and converted in
     row chunks on several threads (each chunk has its own counter-based stream, so the file does not depend on the thread count)"""
     from concurrent.futures import ThreadPoolExecutor
@@ -55,7 +55,7 @@ def gauss_quantized(t, m, k, seed):
     def work(r0):
         r1 = min(m, r0 + rows)
         g = np.random.Generator(np.random.Philox(key=seed, counter=r0))
-        w = g.standard_normal((r1 - r0, k), dtype=np.float32) * np.float32(0.02)
+        w = g.standard_normal((r1 - r0, k), dtype=np.float32) * np.float32(std)
         base.ggml_quantize_chunk(t, ptr(w), ptr(out[r0:r1]), 0, r1 - r0, k, None)
     nthr = max(1, min(32, len(os.sched_getaffinity(0))))
     with ThreadPoolExecutor(nthr) as tp:
@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--weights", default="blocks", choices=["blocks", "gauss"])
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--residual-scale", action="store_true")
     ap.add_argument("--scale-mul", type=float, default=0.25)
     a = ap.parse_args()
     c = dict(CONFIGS[a.config])
@@ -101,17 +102,23 @@ def main():
 
     cache = {}
 
-    def qblocks(t, m, k):
-        key = (t, m, k)
+    def qblocks(t, m, k, std=0.02):
+        key = (t, m, k, std)
         if key not in cache or a.weights == "gauss":
             if a.weights == "gauss":
-                cache[key] = gauss_quantized(t, m, k, int(rng.integers(1 << 31)))
+                cache[key] = gauss_quantized(t, m, k, int(rng.integers(1 << 31)), std)
             else:
                 cache[key] = rand_blocks(rng, t, m, k, a.scale_mul)
         return cache[key]
 
+    # --residual-scale: GPT-2 / LLaMA-style initialisation of the projections that write into the residual stream
+    # (attn_output, ffn_down): std 0.02 / sqrt(2 * n_layer of the FULL model), so that a layer's update is a fraction of the
+    # stream, as in trained models — a 2-layer cut of the 32-layer 8B keeps the 32-layer scaling
+    res_std = 0.02 / np.sqrt(2.0 * CONFIGS[a.config]["n_layer"]) if a.residual_scale else 0.02
+
     def add_q(name, t, m, k):
-        w.add_tensor(name, qblocks(t, m, k), raw_dtype=qt[t])
+        std = res_std if (name.endswith("attn_output.weight") or name.endswith("ffn_down.weight")) else 0.02
+        w.add_tensor(name, qblocks(t, m, k, std), raw_dtype=qt[t])
 
     emb_t = {"Q4_K_M": Q4_K, "Q4_0": Q4_0, "Q8_0": Q8_0}[a.ftype]
     out_t = Q8_0 if a.ftype == "Q8_0" else Q6_K

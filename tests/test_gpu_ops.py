@@ -531,3 +531,54 @@ def test_mul_mat_q_tensor_core_baseline_shape(b200):
     d = (got[:, rows] - want).astype(np.float64)
     nmse = float((d * d).sum() / (want.astype(np.float64) ** 2).sum())
     assert nmse < 1e-10, nmse
+
+
+@pytest.mark.parametrize("kvt", [F16, Q8_0])
+@pytest.mark.parametrize("hd,nh,nhkv", [(128, 32, 8), (64, 32, 4)])
+def test_fused_decode_attention_vs_oracle_at_depth(b200, kvt, hd, nh, nhkv):
+    """the launch every decode token runs (rope q/k + KV store + split-KV attention, b200_rope_kv_flash_attn2) DIRECTLY against the
+    C oracle (rope -> set_rows -> flash_attn_ext) at n_kv = 4096, position 4000; both rope-table modes (layer 0 computes and
+    stores the per-token table, the other layers load it) must give the same bits"""
+    rng = np.random.default_rng(7 + hd + kvt)
+    nkv, pos = 4096, 4000
+    q = rng.standard_normal((1, nh, hd)).astype(np.float32); k = rng.standard_normal((1, nhkv, hd)).astype(np.float32)
+    v = rng.standard_normal((1, nhkv, hd)).astype(np.float32)
+    rb_row = row_bytes(kvt, nhkv * hd); rb_head = row_bytes(kvt, hd)
+    kf = rng.standard_normal((nkv, nhkv * hd)).astype(np.float32); vf = rng.standard_normal((nkv, nhkv * hd)).astype(np.float32)
+    kc = np.zeros((nkv, rb_row), np.uint8); vc = np.zeros((nkv, rb_row), np.uint8)
+    ids_all = np.arange(nkv, dtype=np.int64)
+    oracle().orc_set_rows(ptr(kf), ptr(ids_all), ptr(kc), kvt, nhkv * hd, nkv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids_all), ptr(vc), kvt, nhkv * hd, nkv, rb_row)
+    mask = np.full((64, nkv), -np.inf, np.float32); mask[0, :pos + 1] = 0
+    mask16 = mask.astype(np.float16).view(np.uint16)
+    c = dict(ROPE_CASES[0]); prm = rope_params(b200, c); prm.mode = 0; prm.n_dims = hd
+    scale = 1.0 / np.sqrt(hd)
+    # oracle: rope(q), rope(k) -> cell pos, v -> cell pos, attention over the cache
+    posn = np.array([pos], np.int32)
+    qr = np.zeros_like(q); kr = np.zeros_like(k)
+    oracle().orc_rope(ptr(q), ptr(qr), ptr(posn), None, hd, nh, 1, hd, 0, 8192, c["base"], c["fs"], c["ext"], 1.0, 32.0, 1.0)
+    oracle().orc_rope(ptr(k), ptr(kr), ptr(posn), None, hd, nhkv, 1, hd, 0, 8192, c["base"], c["fs"], c["ext"], 1.0, 32.0, 1.0)
+    kco, vco = kc.copy(), vc.copy()
+    one = np.array([pos], np.int64)
+    oracle().orc_set_rows(ptr(kr.reshape(1, -1)), ptr(one), ptr(kco), kvt, nhkv * hd, 1, rb_row)
+    oracle().orc_set_rows(ptr(v.reshape(1, -1)), ptr(one), ptr(vco), kvt, nhkv * hd, 1, rb_row)
+    want = np.zeros((1, nh, hd), np.float32)
+    oracle().orc_flash_attn_ext(ptr(qr), nh * hd * 4, hd * 4, ptr(kco), rb_row, rb_head, ptr(vco), rb_row, rb_head, ptr(mask16), ptr(want),
+                                kvt, hd, hd, nh, nhkv, 1, nkv, scale, 0.0, 0.0)
+    posd, idsd = dev(posn), dev(one)
+    wsb = max(16, b200.lib.b200_flash_attn_workspace(hd, nh, 1, nkv))
+    tab = torch.zeros(2 * hd, dtype=torch.float32, device="cuda")
+    outs = []
+    for mode in (0, 1, None):                                    # compute + store the table, reuse it, no shared table at all
+        q2 = dev(q); qr2 = torch.zeros_like(q2); kc2, vc2 = dev(kc), dev(vc); ws2 = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+        d2 = torch.full((1, nh, hd), float("nan"), dtype=torch.float32, device="cuda")
+        b200.check(b200.lib.b200_rope_kv_flash_attn2(b200.p(q2), b200.p(qr2), b200.p(dev(k)), b200.p(dev(v)), b200.p(posd), None, b200.p(idsd), b200.p(idsd),
+                                                     b200.p(kc2), b200.p(vc2), kvt, rb_row, rb_head, rb_row, rb_head, b200.p(dev(mask16)), b200.p(d2),
+                                                     hd, nh, nhkv, nkv, C.byref(prm), scale, 0.0, 0.0, b200.p(ws2), b200.p(tab) if mode is not None else None, mode or 0, b200.stream()))
+        torch.cuda.synchronize()
+        assert np.array_equal(kc2.cpu().numpy(), kco) and np.array_equal(vc2.cpu().numpy(), vco)          # cache bytes: bit-exact
+        assert np.abs(qr2.cpu().numpy() - qr).max() <= 2e-6 * np.abs(qr).max()
+        outs.append(d2.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    tol = 2e-5 if kvt == Q8_0 else 2e-3                           # F16 V: the oracle accumulates in fp16 (ops.cpp:8278-8340), we in f32
+    assert np.abs(outs[0] - want).max() <= tol * np.abs(want).max()
