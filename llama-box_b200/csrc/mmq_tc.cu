@@ -25,11 +25,12 @@
 //     running sums in registers.  TMEM is double-buffered (2 x (isum 128 cols + imin 128 cols) = all 512 columns), so the
 //     drain of super-block s overlaps the MMAs of s + 1.
 //
-// Warp roles (448 threads, one persistent CTA per SM):
+// Warp roles (480 threads, one persistent CTA per SM):
 //     warps 0-3 / 4-7  epilogue, columns 0-63 / 64-127 (warp % 4 = TMEM lane quadrant)
 //     warps 8-11       transform: thread t owns weight row t of the tile
-//     warp 12          TMA producer: per-row bulk copies of the packed weight blocks + the B panels
+//     warp 12          TMA producer 1: per-row bulk copies of the packed weight blocks into a 2-4 deep ring, far ahead of the MMAs
 //     warp 13          TMEM allocation + the single MMA-issuing thread
+//     warp 14          TMA producer 2: the activation panels of each stage
 // Shared memory (per CTA): 2 A stages x 32 KB (128 rows x 128 k f16) + 2 B stages x 32 KB + raw weight blocks x 2 + the
 // imin operands + scale rings, ~200 KB.  Data movement: weights are read from HBM once per 128-token tile (L2 serves the
 // other token tiles of the same rows, which run on neighbouring CTAs), activations stream from L2.
@@ -39,7 +40,7 @@
 
 #define TC_TM 128
 #define TC_TN 128
-#define TC_THREADS 448
+#define TC_THREADS 480
 #define TC_STAGE_A 32768
 #define TC_STAGE_B 32768
 #define TC_PANEL 2048             // one K-chunk (8 f16 = 16 bytes) of 128 rows
@@ -154,17 +155,19 @@ struct TcArgs {
 
 // ---- per-type geometry of the raw (packed) weight blocks staged in shared memory ------------------------------------
 template <int T> struct TcType;
-template <> struct TcType<B200_TYPE_Q4_K> { static constexpr int STAGES = 2, RAW = 128 * 144, HAS_MIN = 1, B_BYTES = 32768; };
-template <> struct TcType<B200_TYPE_Q5_K> { static constexpr int STAGES = 2, RAW = 128 * 176, HAS_MIN = 1, B_BYTES = 32768; };
+// RAW_SLOTS: depth of the packed-weight ring.  The raw producer warp runs ahead of everything else (its only dependency is
+// the transform having consumed a slot), so that HBM latency of the weight stream is hidden behind RAW_SLOTS - 1 super-blocks
+template <> struct TcType<B200_TYPE_Q4_K> { static constexpr int STAGES = 2, RAW = 128 * 144, HAS_MIN = 1, B_BYTES = 32768, RAW_SLOTS = 4; };
+template <> struct TcType<B200_TYPE_Q5_K> { static constexpr int STAGES = 2, RAW = 128 * 176, HAS_MIN = 1, B_BYTES = 32768, RAW_SLOTS = 3; };
 // Q6_K rows are repacked [ql 128B x nb][qh 64B x nb][scales 16B x nb][d f16 x nb]; staged with padded row strides
 // (144 / 80 / 16 bytes) so that thread-per-row 16-byte reads are bank-conflict free; d is fetched 8 super-blocks at a time
-template <> struct TcType<B200_TYPE_Q6_K> { static constexpr int STAGES = 4, RAW = 128 * (144 + 80 + 16), HAS_MIN = 0, B_BYTES = 16384; };
+template <> struct TcType<B200_TYPE_Q6_K> { static constexpr int STAGES = 4, RAW = 128 * (144 + 80 + 16), HAS_MIN = 0, B_BYTES = 16384, RAW_SLOTS = 2; };
 
 // shared memory map
 struct TcSmem {
     static constexpr int A = 0, B = A + 2 * TC_STAGE_A, AM = B + 2 * TC_STAGE_B, BM = AM + 2 * 4096, RAWO = BM + 2 * 4096;
-    static constexpr int RAW_MAX = 128 * (144 + 80 + 16);
-    static constexpr int DC = RAWO + 2 * RAW_MAX;            // Q6_K d cache: 2 x 128 rows x 16 B
+    static constexpr int RAW_BYTES = 73728;                  // ring of packed weight blocks: 4 x 18 KB (Q4_K), 3 x 22 KB (Q5_K), 2 x 30 KB (Q6_K)
+    static constexpr int DC = RAWO + RAW_BYTES;              // Q6_K d cache: 2 x 128 rows x 16 B
     static constexpr int RS = DC + 2 * 2048;                 // row scales ring: 4 x 128 x float2
     static constexpr int D8 = RS + 4 * 1024;                 // d_x ring: 4 x 128 f32
     static constexpr int BAR = D8 + 4 * 512;                 // mbarriers
@@ -190,13 +193,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
     using TT = TcType<T>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t * bars = (uint64_t *)(smem + TcSmem::BAR);
-    uint64_t * raw_full = bars, * raw_empty = bars + 2, * b_full = bars + 4, * a_full = bars + 6, * ab_empty = bars + 8, * acc_full = bars + 10, * acc_empty = bars + 12;
-    uint32_t * tmem_slot = (uint32_t *)(bars + 14);
+    uint64_t * raw_full = bars, * raw_empty = bars + 4, * b_full = bars + 8, * a_full = bars + 10, * ab_empty = bars + 12, * acc_full = bars + 14, * acc_empty = bars + 16;
+    uint32_t * tmem_slot = (uint32_t *)(bars + 18);
+    constexpr int RSL = TT::RAW_SLOTS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
+        for (int i = 0; i < 4; i++) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
         for (int i = 0; i < 2; i++) {
-            mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); mbar_init(&b_full[i], 1); mbar_init(&a_full[i], 4);
+            mbar_init(&b_full[i], 1); mbar_init(&a_full[i], 4);
             mbar_init(&ab_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
         }
         mbar_fence_init();
@@ -215,17 +220,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
     const int64_t NT = args.g.nt;
 
     if (warp == 12) {
-        // ===================== TMA producer =====================
-        uint32_t it = 0, sbc = 0, dfc = 0;
+        // ===================== TMA producer 1: packed weight blocks (runs ahead; depends on the transform only) =====================
+        uint32_t sbc = 0, dfc = 0;
         for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
-            const int64_t mt = tile / NT, nt = tile % NT;
+            const int64_t mt = tile / NT;
             const int64_t m0 = mt * TC_TM;
             const int rows = (int)(args.m - m0 < TC_TM ? args.m - m0 : TC_TM);
             for (int sb = 0; sb < nsb; sb++, sbc++) {
-                const int rs = sbc & 1;
-                // ---- packed weight blocks of 128 rows for this super-block
-                mbar_wait(&raw_empty[rs], ((sbc >> 1) & 1) ^ 1);
-                uint8_t * raw = smem + TcSmem::RAWO + rs * TcSmem::RAW_MAX;
+                const int rs = sbc % RSL;
+                mbar_wait(&raw_empty[rs], ((sbc / RSL) & 1) ^ 1);
+                uint8_t * raw = smem + TcSmem::RAWO + rs * TT::RAW;
                 if (T == B200_TYPE_Q6_K) {
                     const bool dfetch = (sb & 7) == 0;                    // d of 8 super-blocks per fetch; slots alternate per FETCH (k % 2048 == 0: every fetch serves 8)
                     const uint32_t dslot = dfc & 1; if (dfetch) dfc++;
@@ -246,7 +250,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                     for (int r = lane; r < rows; r += 32)
                         bulk_g2s(raw + r * BB, args.W + (m0 + r) * args.rb + (int64_t)sb * BB, BB, &raw_full[rs]);
                 }
-                // ---- activation panels, one per stage (+ the bsum panel and d_x of the super-block with the first)
+                __syncwarp();
+            }
+        }
+    } else if (warp == 14) {
+        // ===================== TMA producer 2: activation panels, one per stage (+ the bsum panel and d_x with the first) =====================
+        uint32_t it = 0, sbc = 0;
+        for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+            const int64_t nt = tile % NT;
+            for (int sb = 0; sb < nsb; sb++, sbc++) {
+                const int rs = sbc & 1;
                 for (int s = 0; s < TT::STAGES; s++, it++) {
                     const int st = it & 1;
                     mbar_wait(&ab_empty[st], ((it >> 1) & 1) ^ 1);
@@ -307,9 +320,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
         uint32_t it = 0, sbc = 0, dfc = 0, dslot = 0;
         for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
             for (int sb = 0; sb < nsb; sb++, sbc++) {
-                const int rs = sbc & 1;
-                mbar_wait(&raw_full[rs], (sbc >> 1) & 1);
-                const uint8_t * raw = smem + TcSmem::RAWO + rs * TcSmem::RAW_MAX;
+                const int rs = sbc & 1;                                  // accumulator / imin-operand slot
+                const int rr = sbc % RSL;                                // packed-weight ring slot
+                mbar_wait(&raw_full[rr], (sbc / RSL) & 1);
+                const uint8_t * raw = smem + TcSmem::RAWO + rr * TT::RAW;
                 float2 * rscale = (float2 *)(smem + TcSmem::RS + (sbc & 3) * 1024);
                 if (T == B200_TYPE_Q4_K || T == B200_TYPE_Q5_K) {
                     constexpr int BB = T == B200_TYPE_Q4_K ? 144 : 176;
@@ -415,7 +429,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[rs]);               // packed blocks consumed
+                if (lane == 0) mbar_arrive(&raw_empty[rr]);               // packed blocks consumed
             }
         }
     } else {

@@ -580,5 +580,16 @@ def test_fused_decode_attention_vs_oracle_at_depth(b200, kvt, hd, nh, nhkv):
         assert np.abs(qr2.cpu().numpy() - qr).max() <= 2e-6 * np.abs(qr).max()
         outs.append(d2.cpu().numpy())
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
-    tol = 2e-5 if kvt == Q8_0 else 2e-3                           # F16 V: the oracle accumulates in fp16 (ops.cpp:8278-8340), we in f32
-    assert np.abs(outs[0] - want).max() <= tol * np.abs(want).max()
+    if kvt == Q8_0:
+        assert np.abs(outs[0] - want).max() <= 2e-5 * np.abs(want).max()
+    else:
+        # F16 V: the oracle accumulates V in fp16 (ops.cpp:8278-8340) — over 4000 positions that costs it ~1e-2; judge both against an
+        # f64 evaluation of the same attention on the same f16-rounded Q / K / V
+        K16 = kco.view(np.float16).reshape(nkv, nhkv, hd).astype(np.float64); V16 = vco.view(np.float16).reshape(nkv, nhkv, hd).astype(np.float64)
+        q16 = qr.astype(np.float16).astype(np.float64)
+        truth = np.zeros((1, nh, hd))
+        for h in range(nh):
+            sc = (K16[:pos + 1, h // (nh // nhkv)] @ q16[0, h]) * scale
+            pr = np.exp(sc - sc.max()); truth[0, h] = (pr[:, None] * V16[:pos + 1, h // (nh // nhkv)]).sum(0) / pr.sum()
+        err_gpu = np.abs(outs[0] - truth).max(); err_orc = np.abs(want - truth).max()
+        assert err_gpu <= err_orc and err_gpu <= 2e-5 * np.abs(truth).max(), (err_gpu, err_orc)

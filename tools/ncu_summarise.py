@@ -47,7 +47,14 @@ def raw_rows(rep):
     if len(rows) < 3:
         return [], []
     hdr = rows[0]
-    return hdr, rows[2:]                                   # rows[1] = units
+    global UNITS
+    UNITS = dict(zip(hdr, rows[1]))                        # rows[1] = units
+    return hdr, rows[2:]
+
+
+UNITS = {}
+TO_BASE = {"nsecond": 1e-9, "ns": 1e-9, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3, "ms": 1e-3, "second": 1.0, "s": 1.0,
+           "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
 def num(s):
@@ -68,7 +75,12 @@ def summarise(rep, name):
         for key, metric, scale in METRICS:
             if metric in col:
                 v = num(r[col[metric]])
-                d[key] = None if v is None else round(v * scale, 3)
+                u = TO_BASE.get(UNITS.get(metric, ""), None)
+                if v is not None and u is not None:        # times -> us, bytes -> MB whatever unit ncu chose for this capture
+                    v = v * u * (1e6 if "second" in UNITS[metric] or UNITS[metric] in ("ns", "us", "ms", "s") else 1e-6) / scale * scale
+                    d[key] = round(v, 3)
+                else:
+                    d[key] = None if v is None else round(v * scale, 3)
         out.append(d)
     path = os.path.join(OUT, name + ".tsv")
     keys = ["kernel"] + [k for k, _, _ in METRICS]
