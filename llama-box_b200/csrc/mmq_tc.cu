@@ -25,22 +25,24 @@
 //     running sums in registers.  TMEM is double-buffered (2 x (isum 128 cols + imin 128 cols) = all 512 columns), so the
 //     drain of super-block s overlaps the MMAs of s + 1.
 //
-// Warp roles (480 threads, one persistent CTA per SM):
+// Warp roles (448 threads, one persistent CTA per SM):
 //     warps 0-3 / 4-7  epilogue, columns 0-63 / 64-127 (warp % 4 = TMEM lane quadrant)
-//     warps 8-11       transform: thread t owns weight row t of the tile
-//     warp 12          TMA producer 1: per-row bulk copies of the packed weight blocks into a 2-4 deep ring, far ahead of the MMAs
+//     warps 8-11       transform: thread t owns weight row t of the tile; packed blocks come straight from global memory into
+//                      registers, one super-block ahead
+//     warp 12          TMA producer: the activation panels of each stage (cp.async.bulk, mbarrier complete_tx)
 //     warp 13          TMEM allocation + the single MMA-issuing thread
-//     warp 14          TMA producer 2: the activation panels of each stage
 // Shared memory (per CTA): 2 A stages x 32 KB (128 rows x 128 k f16) + 2 B stages x 32 KB + raw weight blocks x 2 + the
 // imin operands + scale rings, ~200 KB.  Data movement: weights are read from HBM once per 128-token tile (L2 serves the
 // other token tiles of the same rows, which run on neighbouring CTAs), activations stream from L2.
 #include "common.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdio>
+#include <cstdlib>
 
 #define TC_TM 128
 #define TC_TN 128
-#define TC_THREADS 480
+#define TC_THREADS 448
 #define TC_STAGE_A 32768
 #define TC_STAGE_B 32768
 #define TC_PANEL 2048             // one K-chunk (8 f16 = 16 bytes) of 128 rows
@@ -151,7 +153,13 @@ struct TcArgs {
     TcGeom g;
     int32_t nsb, n_mtiles, n_tiles, type;
     uint32_t lbo, sbo;          // descriptor strides (bytes): K-chunk stride / 8-row-group stride
+    unsigned long long * prof;  // bring-up: per-role cycle counters of CTA 0 (B200_MMQ_PROF), normally null
 };
+// wait on an mbarrier, optionally accounting the cycles to a profile counter
+__device__ __forceinline__ void mbar_wait_p(uint64_t * bar, uint32_t parity, unsigned long long * acc) {
+    if (acc) { const long long t0 = clock64(); mbar_wait(bar, parity); *acc += (unsigned long long)(clock64() - t0); }
+    else mbar_wait(bar, parity);
+}
 
 // ---- per-type geometry of the raw (packed) weight blocks staged in shared memory ------------------------------------
 template <int T> struct TcType;
@@ -218,43 +226,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
 
     const int nsb = args.nsb;
     const int64_t NT = args.g.nt;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0;                       // profile: cycles in this role's three kinds of waits
+    const bool prof = args.prof != nullptr && blockIdx.x == 0;
+    unsigned long long * pw0 = prof ? &w0 : nullptr, * pw1 = prof ? &w1 : nullptr, * pw2 = prof ? &w2 : nullptr;
+    const long long t_start = clock64();
 
     if (warp == 12) {
-        // ===================== TMA producer 1: packed weight blocks (runs ahead; depends on the transform only) =====================
-        uint32_t sbc = 0, dfc = 0;
-        for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
-            const int64_t mt = tile / NT;
-            const int64_t m0 = mt * TC_TM;
-            const int rows = (int)(args.m - m0 < TC_TM ? args.m - m0 : TC_TM);
-            for (int sb = 0; sb < nsb; sb++, sbc++) {
-                const int rs = sbc % RSL;
-                mbar_wait(&raw_empty[rs], ((sbc / RSL) & 1) ^ 1);
-                uint8_t * raw = smem + TcSmem::RAWO + rs * TT::RAW;
-                if (T == B200_TYPE_Q6_K) {
-                    const bool dfetch = (sb & 7) == 0;                    // d of 8 super-blocks per fetch; slots alternate per FETCH (k % 2048 == 0: every fetch serves 8)
-                    const uint32_t dslot = dfc & 1; if (dfetch) dfc++;
-                    if (lane == 0) mbar_expect_tx(&raw_full[rs], (uint32_t)rows * (128 + 64 + 16 + (dfetch ? 16 : 0)));
-                    __syncwarp();
-                    const int64_t nb = args.k / 256;
-                    for (int r = lane; r < rows; r += 32) {
-                        const uint8_t * row = args.W + (m0 + r) * args.rb;
-                        bulk_g2s(raw + r * 144, row + (int64_t)sb * 128, 128, &raw_full[rs]);
-                        bulk_g2s(raw + 128 * 144 + r * 80, row + nb * 128 + (int64_t)sb * 64, 64, &raw_full[rs]);
-                        bulk_g2s(raw + 128 * (144 + 80) + r * 16, row + nb * 192 + (int64_t)sb * 16, 16, &raw_full[rs]);
-                        if (dfetch) bulk_g2s(smem + TcSmem::DC + dslot * 2048 + r * 16, row + nb * 208 + (int64_t)sb * 2, 16, &raw_full[rs]);
-                    }
-                } else {
-                    constexpr int BB = T == B200_TYPE_Q4_K ? 144 : 176;
-                    if (lane == 0) mbar_expect_tx(&raw_full[rs], (uint32_t)rows * BB);
-                    __syncwarp();
-                    for (int r = lane; r < rows; r += 32)
-                        bulk_g2s(raw + r * BB, args.W + (m0 + r) * args.rb + (int64_t)sb * BB, BB, &raw_full[rs]);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 14) {
-        // ===================== TMA producer 2: activation panels, one per stage (+ the bsum panel and d_x with the first) =====================
+        // ===================== TMA producer: activation panels, one per stage (+ the bsum panel and d_x with the first) =====================
         uint32_t it = 0, sbc = 0;
         for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
             const int64_t nt = tile % NT;
@@ -262,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                 const int rs = sbc & 1;
                 for (int s = 0; s < TT::STAGES; s++, it++) {
                     const int st = it & 1;
-                    mbar_wait(&ab_empty[st], ((it >> 1) & 1) ^ 1);
+                    mbar_wait_p(&ab_empty[st], ((it >> 1) & 1) ^ 1, pw0);
                     if (lane == 0) {
                         const uint32_t extra = s == 0 ? (512u + (TT::HAS_MIN ? 4096u : 0u)) : 0u;
                         mbar_expect_tx(&b_full[st], (uint32_t)TT::B_BYTES + extra);
@@ -291,13 +269,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                 const uint32_t idesc = (1u << 4) | ((n_eff >> 3) << 17) | ((uint32_t)(TC_TM >> 4) << 24);
                 for (int sb = 0; sb < nsb; sb++, sbc++) {
                     const int rs = sbc & 1;
-                    mbar_wait(&acc_empty[rs], ((sbc >> 1) & 1) ^ 1);       // epilogue has drained this TMEM buffer
+                    mbar_wait_p(&acc_empty[rs], ((sbc >> 1) & 1) ^ 1, pw0);       // epilogue has drained this TMEM buffer
                     tc_fence_after();
                     const uint32_t d_main = tmem + rs * 128, d_min = tmem + 256 + rs * 128;
                     for (int s = 0; s < TT::STAGES; s++, it++) {
                         const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-                        mbar_wait(&b_full[st], ph);
-                        mbar_wait(&a_full[st], ph);
+                        mbar_wait_p(&b_full[st], ph, pw1);
+                        mbar_wait_p(&a_full[st], ph, pw2);
                         tc_fence_after();
                         const uint32_t a0 = smem_u32(smem + TcSmem::A + st * TC_STAGE_A), b0 = smem_u32(smem + TcSmem::B + st * TC_STAGE_B);
 #pragma unroll
@@ -314,30 +292,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
             }
         }
         __syncwarp();
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ===================== transform: packed quants -> f16 sc*q core matrices =====================
+        // Thread t owns weight row t of the tile and reads its packed block of the NEXT super-block straight from global memory
+        // into registers (9-14 16-byte loads, issued one super-block ahead, so HBM / L2 latency hides behind the conversion of
+        // the current one).  (A first version staged the blocks through shared memory with one cp.async.bulk per row: a
+        // warp-wide bulk copy is issued lane by lane through uniform registers, ~65 cycles each — 128 rows cost 8 K cycles per
+        // super-block and starved everything else; profiles/README.md.)
+        constexpr int NW = T == B200_TYPE_Q4_K ? 9 : (T == B200_TYPE_Q5_K ? 11 : 13);
         const int t = tid - 8 * 32;                                      // weight row of the tile
-        uint32_t it = 0, sbc = 0, dfc = 0, dslot = 0;
+        const int64_t nb = args.k / 256;
+        uint32_t it = 0, sbc = 0;
+        uint4 nxt[NW]; uint16_t nxt_d = 0;
+        auto fetch = [&](int tile, int sb) {
+            const int64_t m0 = (int64_t)(tile / NT) * TC_TM;
+            int64_t r = m0 + t; if (r >= args.m) r = args.m - 1;             // rows past the end: any valid row (their results are never stored)
+            const uint8_t * row = args.W + r * args.rb;
+            if (T == B200_TYPE_Q6_K) {
+                const uint4 * ql = (const uint4 *)(row + (int64_t)sb * 128), * qh = (const uint4 *)(row + nb * 128 + (int64_t)sb * 64);
+#pragma unroll
+                for (int i = 0; i < 8; i++) nxt[i] = __ldg(ql + i);
+#pragma unroll
+                for (int i = 0; i < 4; i++) nxt[8 + i] = __ldg(qh + i);
+                nxt[12] = __ldg((const uint4 *)(row + nb * 192 + (int64_t)sb * 16));
+                nxt_d = __ldg((const uint16_t *)(row + nb * 208 + (int64_t)sb * 2));
+            } else {
+                const uint4 * p = (const uint4 *)(row + (int64_t)sb * (T == B200_TYPE_Q4_K ? 144 : 176));
+#pragma unroll
+                for (int i = 0; i < NW; i++) nxt[i] = __ldg(p + i);
+            }
+        };
+        if (blockIdx.x < args.n_tiles) fetch(blockIdx.x, 0);
         for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
             for (int sb = 0; sb < nsb; sb++, sbc++) {
                 const int rs = sbc & 1;                                  // accumulator / imin-operand slot
-                const int rr = sbc % RSL;                                // packed-weight ring slot
-                mbar_wait(&raw_full[rr], (sbc / RSL) & 1);
-                const uint8_t * raw = smem + TcSmem::RAWO + rr * TT::RAW;
+                uint4 cur[NW]; const uint16_t cur_d = nxt_d;
+#pragma unroll
+                for (int i = 0; i < NW; i++) cur[i] = nxt[i];
+                {   // prefetch the next super-block (of this tile, or the first one of this CTA's next tile)
+                    int ntile = tile, nsbi = sb + 1;
+                    if (nsbi == nsb) { nsbi = 0; ntile = tile + gridDim.x; }
+                    if (ntile < args.n_tiles) fetch(ntile, nsbi);
+                }
                 float2 * rscale = (float2 *)(smem + TcSmem::RS + (sbc & 3) * 1024);
                 if (T == B200_TYPE_Q4_K || T == B200_TYPE_Q5_K) {
-                    constexpr int BB = T == B200_TYPE_Q4_K ? 144 : 176;
-                    constexpr int QS = T == B200_TYPE_Q4_K ? 16 : 48;
-                    const uint8_t * blk = raw + t * BB;
-                    const uint4 hdr = *(const uint4 *)blk;
+                    constexpr int QW = T == B200_TYPE_Q4_K ? 1 : 3;       // first 16-byte word of qs
+                    const uint4 hdr = cur[0];
                     uint32_t sc03, sc47, mn03, mn47;
                     k4_unpack(hdr.y, hdr.z, hdr.w, sc03, sc47, mn03, mn47);
-                    uint4 qh0 = make_uint4(0, 0, 0, 0), qh1 = qh0;
-                    if (T == B200_TYPE_Q5_K) { qh0 = *(const uint4 *)(blk + 16); qh1 = *(const uint4 *)(blk + 32); }
-                    const uint32_t qhw[8] = { qh0.x, qh0.y, qh0.z, qh0.w, qh1.x, qh1.y, qh1.z, qh1.w };
+                    uint32_t qhw[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                    if (T == B200_TYPE_Q5_K) { qhw[0] = cur[1].x; qhw[1] = cur[1].y; qhw[2] = cur[1].z; qhw[3] = cur[1].w; qhw[4] = cur[2].x; qhw[5] = cur[2].y; qhw[6] = cur[2].z; qhw[7] = cur[2].w; }
+#pragma unroll
                     for (int s = 0; s < 2; s++, it++) {                   // half super-block = 128 k = one stage
                         const int st = it & 1;
-                        mbar_wait(&ab_empty[st], ((it >> 1) & 1) ^ 1);
+                        mbar_wait_p(&ab_empty[st], ((it >> 1) & 1) ^ 1, pw1);
                         uint8_t * As = smem + TcSmem::A + st * TC_STAGE_A + t * 16;
 #pragma unroll
                         for (int gg = 0; gg < 2; gg++) {
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                             const int sc_lo = (scw >> (16 * (grp & 1))) & 63, sc_hi = (scw >> (16 * (grp & 1) + 8)) & 63;
                             const uint32_t m_lo = h2_of_int(sc_lo), m_hi = h2_of_int(sc_hi);
                             const uint32_t c_lo = h2_of_int(-1024 * sc_lo), c_hi = h2_of_int(-64 * sc_hi);
-                            const uint4 qa = *(const uint4 *)(blk + QS + grp * 32), qb = *(const uint4 *)(blk + QS + grp * 32 + 16);
+                            const uint4 qa = cur[QW + grp * 2], qb = cur[QW + grp * 2 + 1];
                             const uint32_t w[8] = { qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w };
 #pragma unroll
                             for (int i = 0; i < 4; i++) {
@@ -384,22 +392,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                     }
                 } else {
                     // ---- Q6_K: q = ql | qh << 4 (0..63), value sc * (q - 32), scales int8 per 16 elements (ggml-quants.c dequantize_row_q6_K)
-                    const uint8_t * ql = raw + t * 144, * qh = raw + 128 * 144 + t * 80;
-                    const uint4 scv = *(const uint4 *)(raw + 128 * (144 + 80) + t * 16);
-                    const uint32_t scw[4] = { scv.x, scv.y, scv.z, scv.w };
-                    if ((sb & 7) == 0) { dslot = dfc & 1; dfc++; }
-                    const uint16_t dh = *(const uint16_t *)(smem + TcSmem::DC + dslot * 2048 + t * 16 + (sb & 7) * 2);
+                    const uint32_t scw[4] = { cur[12].x, cur[12].y, cur[12].z, cur[12].w };
+#pragma unroll
                     for (int s = 0; s < 4; s++, it++) {                   // quarter super-block = 64 k: chunks 0-7 = even-scale part, 8-15 = odd-scale part
                         const int st = it & 1;
-                        mbar_wait(&ab_empty[st], ((it >> 1) & 1) ^ 1);
+                        mbar_wait_p(&ab_empty[st], ((it >> 1) & 1) ^ 1, pw1);
                         uint8_t * As = smem + TcSmem::A + st * TC_STAGE_A + t * 16;
                         const int hh = s >> 1, u2 = s & 1;
-                        const uint4 qha = *(const uint4 *)(qh + hh * 32), qhb = *(const uint4 *)(qh + hh * 32 + 16);
+                        const uint4 qha = cur[8 + hh * 2], qhb = cur[8 + hh * 2 + 1];
                         const uint32_t qhw[8] = { qha.x, qha.y, qha.z, qha.w, qhb.x, qhb.y, qhb.z, qhb.w };
 #pragma unroll
                         for (int tt = 0; tt < 2; tt++) {
                             const int tg = 2 * u2 + tt;                   // 32-element group of the half: elements 128 hh + 32 tg + l
-                            const uint4 qa = *(const uint4 *)(ql + hh * 64 + (tg & 1) * 32), qb = *(const uint4 *)(ql + hh * 64 + (tg & 1) * 32 + 16);
+                            const uint4 qa = cur[hh * 4 + (tg & 1) * 2], qb = cur[hh * 4 + (tg & 1) * 2 + 1];
                             const uint32_t w[8] = { qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w };
                             const int nsh = 4 * (tg >> 1), hsh = 2 * tg;
 #pragma unroll
@@ -422,14 +427,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
                                 *(uint4 *)(As + (8 + tt * 4 + i) * TC_PANEL) = od;
                             }
                         }
-                        if (s == 0) rscale[t] = make_float2(h2f(dh), 0.0f);
+                        if (s == 0) rscale[t] = make_float2(h2f(cur_d), 0.0f);
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&a_full[st]);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&raw_empty[rr]);               // packed blocks consumed
             }
         }
     } else {
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
             for (int c = 0; c < 64; c++) acc[c] = 0.0f;
             for (int sb = 0; sb < nsb; sb++, sbc++) {
                 const int rs = sbc & 1;
-                mbar_wait(&acc_full[rs], (sbc >> 1) & 1);
+                mbar_wait_p(&acc_full[rs], (sbc >> 1) & 1, pw0);
                 tc_fence_after();
                 const float2 dd = ((const float2 *)(smem + TcSmem::RS + (sbc & 3) * 1024))[r];
                 const float * d8 = (const float *)(smem + TcSmem::D8 + (sbc & 3) * 512) + ch * 64;
@@ -482,6 +485,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mmq_tc_kernel(const __grid_cons
         }
     }
 
+    if (prof && lane == 0) {                                           // [warp][total, wait0, wait1, wait2]
+        unsigned long long * o = args.prof + warp * 4;
+        o[0] = (unsigned long long)(clock64() - t_start); o[1] = w0; o[2] = w1; o[3] = w2;
+    }
     // ---- teardown
     pdl_trigger();
     tc_fence_before();
@@ -516,16 +523,29 @@ int b200_mmq_tc(int type, const void * W, const float * X, int64_t x_col_stride,
     a.W = (const uint8_t *)W; a.ws = (const uint8_t *)workspace; a.dst = dst; a.m = m; a.k = k; a.ncols = ncols; a.ldd = ldd;
     a.rb = (k / 256) * type_block_bytes(type);
     a.g = tc_geom(k, ncols);
-    static const bool swap = getenv("B200_MMQ_DESC_SWAP") != nullptr;       // bring-up switch: exchange the two descriptor strides
-    a.lbo = swap ? 128u : (uint32_t)TC_PANEL; a.sbo = swap ? (uint32_t)TC_PANEL : 128u;
+    a.lbo = (uint32_t)TC_PANEL; a.sbo = 128u;
+    static unsigned long long * prof_buf = nullptr;                        // B200_MMQ_PROF=1: per-role wait cycles of CTA 0, printed after each launch (bring-up only)
+    static const bool want_prof = getenv("B200_MMQ_PROF") != nullptr;
+    if (want_prof && !prof_buf) { cudaMalloc((void **)&prof_buf, 16 * 4 * 8); }
+    a.prof = want_prof ? prof_buf : nullptr;
     a.nsb = (int32_t)(k / 256); a.n_mtiles = (int32_t)((m + TC_TM - 1) / TC_TM); a.n_tiles = (int32_t)(a.n_mtiles * a.g.nt); a.type = type;
     dim3 qgrid((unsigned)a.nsb, (unsigned)(a.g.nt * 16));
     B200_CUDA(b200_launch_pdl(quantize_mmq_kernel, qgrid, dim3(256), 0, st, X, x_col_stride, ncols, k, (uint8_t *)workspace, a.g));
     b200_count_launch();
+    int rc = B200_ERR_UNSUPPORTED;
     switch (type) {
-        case B200_TYPE_Q4_K: return tc_launch<B200_TYPE_Q4_K>(a, st);
-        case B200_TYPE_Q5_K: return tc_launch<B200_TYPE_Q5_K>(a, st);
-        case B200_TYPE_Q6_K: return tc_launch<B200_TYPE_Q6_K>(a, st);
+        case B200_TYPE_Q4_K: rc = tc_launch<B200_TYPE_Q4_K>(a, st); break;
+        case B200_TYPE_Q5_K: rc = tc_launch<B200_TYPE_Q5_K>(a, st); break;
+        case B200_TYPE_Q6_K: rc = tc_launch<B200_TYPE_Q6_K>(a, st); break;
     }
-    return B200_ERR_UNSUPPORTED;
+    if (want_prof && rc == B200_OK) {
+        unsigned long long h[16 * 4];
+        cudaStreamSynchronize(st); cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const char * role[14] = { "epi", "epi", "epi", "epi", "epi", "epi", "epi", "epi", "xform", "xform", "xform", "xform", "b-tma", "mma" };
+        fprintf(stderr, "mmq_tc prof (CTA 0, cycles): type %d m %lld k %lld n %lld tiles %d\n", type, (long long)m, (long long)k, (long long)ncols, a.n_tiles);
+        for (int w = 0; w < 14; w += (w < 8 ? 4 : (w < 12 ? 2 : 1)))
+            fprintf(stderr, "  warp %2d %-8s total %9llu  wait0 %9llu  wait1 %9llu  wait2 %9llu\n", w, role[w], h[w * 4], h[w * 4 + 1], h[w * 4 + 2], h[w * 4 + 3]);
+        fprintf(stderr, "  (epi: wait0 = acc_full | xform: wait1 = ab_empty | mma: wait0 = acc_empty, wait1 = b_full, wait2 = a_full | b-tma: wait0 = ab_empty)\n");
+    }
+    return rc;
 }

@@ -27,7 +27,7 @@ b.check(b.lib.b200_mul_mat_q(T, b.p(Wd), b.p(xd), k, b.p(dst), m, m, k, n, b.p(w
 torch.cuda.synchronize()
 got = dst.cpu().numpy()
 err = np.abs(got - want) / np.abs(want).max()
-print(f"type {sys.argv[1] if len(sys.argv) > 1 else 'q4_K'} m={m} k={k} n={n} swap={'B200_MMQ_DESC_SWAP' in os.environ}: finite {np.isfinite(got).mean():.3f}  max err {np.nanmax(err):.3e}  frac<1e-5 {(err < 1e-5).mean():.4f}")
+print(f"type {sys.argv[1] if len(sys.argv) > 1 else 'q4_K'} m={m} k={k} n={n}: finite {np.isfinite(got).mean():.3f}  max err {np.nanmax(err):.3e}  frac<1e-5 {(err < 1e-5).mean():.4f}")
 print(" got ", got[0, :6], "\n want", want[0, :6])
 if np.nanmax(err) > 1e-4:
     bad = np.argwhere(~(err < 1e-5))
