@@ -460,6 +460,11 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     return B200_OK;
 }
 
+bool b200_fattn_tc_supported(int kv_type, int64_t dk, int64_t dv, int64_t n_tok, int64_t n_kv, float max_bias);
+int  b200_fattn_tc(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs, const void * v, int64_t v_rs, int64_t v_hs,
+                   const void * mask, int64_t mask_rs, float * dst, int kv_type, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv,
+                   float scale, float softcap, void * stream);
+
 static int fa_early_trigger() { static const int v = getenv("B200_FA_EARLY_TRIGGER") ? atoi(getenv("B200_FA_EARLY_TRIGGER")) : 0; return v; }
 static int fa_dispatch(const float * q, int64_t q_ts, int64_t q_hs, const void * k, int64_t k_rs, int64_t k_hs,
                                    const void * v, int64_t v_rs, int64_t v_hs, const void * mask, int64_t mask_rs, float * dst,
@@ -472,6 +477,10 @@ static int fa_dispatch(const float * q, int64_t q_ts, int64_t q_hs, const void *
     if (((uintptr_t)q & 15) || (q_ts & 3) || (q_hs & 3)) { b200_set_error("flash_attn: q must be 16-byte aligned"); return B200_ERR_INVALID; }
     if (kv_type == B200_TYPE_F16 && ((((uintptr_t)k | (uintptr_t)v) & 15) || ((k_rs | k_hs | v_rs | v_hs) & 15))) { b200_set_error("flash_attn: f16 K/V rows must be 16-byte aligned"); return B200_ERR_INVALID; }
     if (n_tok > 65535 || n_tok * n_head * (int64_t)sizeof(unsigned int) > FA_COUNTER_BYTES) { b200_set_error("flash_attn: n_tok * n_head too large for one launch"); return B200_ERR_UNSUPPORTED; }
+    // multi-token batches (prefill, big verify batches): the tensor-core kernel (fattn_tc.cu) — K / V read once per 128 query tokens
+    if (!fu.enabled && b200_fattn_tc_supported(kv_type, dk, dv, n_tok, n_kv, max_bias) && (!mask || ((mask_rs & 7) == 0 && ((uintptr_t)mask & 15) == 0)) &&
+        (kv_type != B200_TYPE_F16 || (((k_rs | k_hs | v_rs | v_hs) & 15) == 0)))
+        return b200_fattn_tc(q, q_ts, q_hs, k, k_rs, k_hs, v, v_rs, v_hs, mask, mask_rs, dst, kv_type, n_head, n_head_kv, n_tok, n_kv, scale, softcap, stream);
     const int64_t gq = n_head / n_head_kv;
     const int G = gq % 4 == 0 ? 4 : (gq % 2 == 0 ? 2 : 1);
     if (!workspace && (n_kv + 31) / 32 > 1) { b200_set_error("flash_attn: workspace required"); return B200_ERR_INVALID; }

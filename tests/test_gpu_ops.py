@@ -593,3 +593,52 @@ def test_fused_decode_attention_vs_oracle_at_depth(b200, kvt, hd, nh, nhkv):
             pr = np.exp(sc - sc.max()); truth[0, h] = (pr[:, None] * V16[:pos + 1, h // (nh // nhkv)]).sum(0) / pr.sum()
         err_gpu = np.abs(outs[0] - truth).max(); err_orc = np.abs(want - truth).max()
         assert err_gpu <= err_orc and err_gpu <= 2e-5 * np.abs(truth).max(), (err_gpu, err_orc)
+
+
+# ------------------------------------------------------------------ a8: multi-token attention on the tensor cores (fattn_tc.cu)
+@pytest.mark.parametrize("kvt", [F16, Q8_0])
+@pytest.mark.parametrize("nh,nhkv,nt,nkv,past", [(8, 2, 128, 256, 100), (4, 4, 200, 768, 512), (32, 8, 512, 1024, 512), (8, 1, 33, 512, 300), (4, 2, 512, 4096, 3584)])
+def test_flash_attn_tensor_core(b200, kvt, nh, nhkv, nt, nkv, past):
+    """prefill-shaped FLASH_ATTN_EXT (>= 16 tokens, head 128): tcgen05 S = Q K^T and O = P V with f16 operands, f32 softmax.
+    Checked against an f64 evaluation of the same attention on the cache's own (f16-rounded / de-quantised) K, V and the f16-rounded
+    Q; f16 P and f16 d*q de-quantisation bound the deviation to ~1e-3 relative (the reference's CUDA path rounds the same way);
+    the CPU oracle (f32 P; fp16 accumulation for F16 V) must agree to its own accuracy.  Causal mask with `past` cached positions,
+    cache padding beyond, ragged token counts, GQA."""
+    dk = 128
+    rng = np.random.default_rng(nh + nt + nkv + kvt)
+    q = rng.standard_normal((nt, nh, dk)).astype(np.float32)
+    kf = rng.standard_normal((nkv, nhkv * dk)).astype(np.float32); vf = rng.standard_normal((nkv, nhkv * dk)).astype(np.float32)
+    rb_row = row_bytes(kvt, nhkv * dk); rb_head = row_bytes(kvt, dk)
+    kc = np.zeros((nkv, rb_row), np.uint8); vc = np.zeros((nkv, rb_row), np.uint8)
+    ids = np.arange(nkv, dtype=np.int64)
+    oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), kvt, nhkv * dk, nkv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), kvt, nhkv * dk, nkv, rb_row)
+    npad = (nt + 63) // 64 * 64
+    mask = np.full((npad, nkv), -np.inf, np.float32)
+    for t in range(nt):
+        mask[t, :min(nkv, past + t + 1)] = 0                      # causal: token t sees the cached positions and the batch up to itself
+    mask16 = mask.astype(np.float16)
+    scale = 1.0 / np.sqrt(dk)
+    want = np.zeros((nt, nh, dk), np.float32)
+    oracle().orc_flash_attn_ext(ptr(q), nh * dk * 4, dk * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(mask16), ptr(want),
+                                kvt, dk, dk, nh, nhkv, nt, nkv, scale, 0.0, 0.0)
+    ws = torch.zeros(max(16, b200.lib.b200_flash_attn_workspace(dk, nh, nt, nkv)), dtype=torch.uint8, device="cuda")
+    dst = torch.full((nt, nh, dk), float("nan"), dtype=torch.float32, device="cuda")
+    b200.check(b200.lib.b200_flash_attn_ext(b200.p(dev(q)), nh * dk, dk, b200.p(dev(kc)), rb_row, rb_head, b200.p(dev(vc)), rb_row, rb_head,
+                                            b200.p(dev(mask16.view(np.uint16))), nkv, b200.p(dst), kvt, dk, dk, nh, nhkv, nt, nkv,
+                                            scale, 0.0, 0.0, b200.p(ws), b200.stream()))
+    got = dst.cpu().numpy()
+    assert np.isfinite(got).all()
+    Kd = orc_dequant(kvt, kc, nkv, nhkv * dk).astype(np.float64).reshape(nkv, nhkv, dk)
+    Vd = orc_dequant(kvt, vc, nkv, nhkv * dk).astype(np.float64).reshape(nkv, nhkv, dk)
+    q16 = q.astype(np.float16).astype(np.float64)
+    truth = np.zeros((nt, nh, dk))
+    for h in range(nh):
+        hk = h // (nh // nhkv)
+        s = (q16[:, h] @ Kd[:, hk].T) * scale + mask[:nt].astype(np.float64)
+        p = np.exp(s - s.max(axis=1, keepdims=True))
+        truth[:, h] = (p @ Vd[:, hk]) / p.sum(axis=1, keepdims=True)
+    err = np.abs(got - truth).max() / np.abs(truth).max()
+    assert err <= 2e-3, err
+    assert nmse(got, truth) < 1e-6
+    assert nmse(got, want) < (1e-5 if kvt == F16 else 1e-6)       # vs the CPU oracle (its F16-V path accumulates in fp16)
