@@ -243,6 +243,7 @@ def product_decode(args, ts, n_past, steps, warmup, prefill_probe=0):
     if path is None or not os.path.exists(PLUGIN):
         return None
     os.environ.setdefault("GGML_B200_HANDOFF_TIMING", "1")
+    home = torch.cuda.current_device()
     d = Drv(path, plugin=PLUGIN, ngl=99, ts=ts, ctx=max(args.ctx, 4096), ubatch=512, threads=8, fa=True, ctk=args.kv, ctv=args.kv)
     try:
         rng = np.random.default_rng(42)
@@ -257,6 +258,7 @@ def product_decode(args, ts, n_past, steps, warmup, prefill_probe=0):
         for _ in range(warmup):
             d.decode([tok]); tok = int(np.argmax(d.logits()))
         d.handoff_stats(reset=True)
+        torch.cuda.set_device(home)                       # the plug-in switches the calling thread's current device as it walks the splits
         ndev = torch.cuda.device_count()
         for i in range(ndev):
             torch.cuda.synchronize(i)
@@ -269,6 +271,7 @@ def product_decode(args, ts, n_past, steps, warmup, prefill_probe=0):
         for i in range(ndev):
             torch.cuda.synchronize(i)
         wall = time.perf_counter() - w0
+        torch.cuda.set_device(home)
         e1.record(); torch.cuda.synchronize()
         dev_ms = e0.elapsed_time(e1)
         hs = d.handoff_stats()
@@ -289,6 +292,7 @@ def product_decode(args, ts, n_past, steps, warmup, prefill_probe=0):
         return out
     finally:
         d.close()
+        torch.cuda.set_device(home)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm, N = 1
@@ -594,8 +598,9 @@ def run_b200_multi(args, G, M, ops, rank, world, local):
                                  "traffic": None, "peak_source": peak_src + " (one device streams at a time)"},
                     "cpu_baseline": None}
     # every rank: barrier + max over ranks of the timed region (ranks other than 0 contribute 0: they only hold their device)
+    torch.cuda.set_device(local)
     dist.barrier()
-    t = torch.tensor([line["ms_per_step"] if (line and line.get("value")) else 0.0], device="cuda")
+    t = torch.tensor([line["ms_per_step"] if (line and line.get("value")) else 0.0], device=torch.device("cuda", local))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     agg = None
     if not args.no_extras:
