@@ -624,8 +624,9 @@ def test_flash_attn_tensor_core(b200, kvt, nh, nhkv, nt, nkv, past):
                                 kvt, dk, dk, nh, nhkv, nt, nkv, scale, 0.0, 0.0)
     ws = torch.zeros(max(16, b200.lib.b200_flash_attn_workspace(dk, nh, nt, nkv)), dtype=torch.uint8, device="cuda")
     dst = torch.full((nt, nh, dk), float("nan"), dtype=torch.float32, device="cuda")
-    b200.check(b200.lib.b200_flash_attn_ext(b200.p(dev(q)), nh * dk, dk, b200.p(dev(kc)), rb_row, rb_head, b200.p(dev(vc)), rb_row, rb_head,
-                                            b200.p(dev(mask16.view(np.uint16))), nkv, b200.p(dst), kvt, dk, dk, nh, nhkv, nt, nkv,
+    qd, kd, vd, md = dev(q), dev(kc), dev(vc), dev(mask16.view(np.uint16))     # named: a temporary's block would be recycled by the next allocation
+    b200.check(b200.lib.b200_flash_attn_ext(b200.p(qd), nh * dk, dk, b200.p(kd), rb_row, rb_head, b200.p(vd), rb_row, rb_head,
+                                            b200.p(md), nkv, b200.p(dst), kvt, dk, dk, nh, nhkv, nt, nkv,
                                             scale, 0.0, 0.0, b200.p(ws), b200.stream()))
     got = dst.cpu().numpy()
     assert np.isfinite(got).all()
@@ -639,6 +640,8 @@ def test_flash_attn_tensor_core(b200, kvt, nh, nhkv, nt, nkv, past):
         p = np.exp(s - s.max(axis=1, keepdims=True))
         truth[:, h] = (p @ Vd[:, hk]) / p.sum(axis=1, keepdims=True)
     err = np.abs(got - truth).max() / np.abs(truth).max()
-    assert err <= 2e-3, err
-    assert nmse(got, truth) < 1e-6
-    assert nmse(got, want) < (1e-5 if kvt == F16 else 1e-6)       # vs the CPU oracle (its F16-V path accumulates in fp16)
+    assert err <= 2e-3, err                                       # observed: 8e-5 .. 5e-4
+    assert nmse(got, truth) < 1e-6, nmse(got, truth)
+    # vs the CPU oracle: its F16-V path accumulates in fp16 (ops.cpp:8278-8340) and is the noisier side at long n_kv
+    assert nmse(got, want) < (1e-3 if kvt == F16 else 1e-6), nmse(got, want)
+    assert nmse(got, truth) <= nmse(want, truth) or kvt == Q8_0
