@@ -614,7 +614,7 @@ def run_b200_multi(args, G, M, ops, rank, world, local):
 
 def weight_bytes_of(M, G, ops, args):
     cfg = M.CONFIGS[args.model]; L = args.layers or cfg["n_layer"]
-    mix, out_t = M.type_mix(args.ftype, L)
+    mix, out_t = M.type_mix(args.ftype, L, cfg["n_ff"], args.model == "qwen2-72b")
     E, H, HK, D, FF, V = cfg["n_embd"], cfg["n_head"], cfg["n_head_kv"], cfg["head_dim"], cfg["n_ff"], cfg["n_vocab"]
     b = V * ops.row_bytes(out_t, E)
     for t in mix:

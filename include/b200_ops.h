@@ -43,6 +43,7 @@ enum b200_type {
     B200_TYPE_F32  = 0,
     B200_TYPE_F16  = 1,
     B200_TYPE_Q4_0 = 2,
+    B200_TYPE_Q5_0 = 6,
     B200_TYPE_Q8_0 = 8,
     B200_TYPE_Q4_K = 12,
     B200_TYPE_Q5_K = 13,
@@ -72,7 +73,13 @@ B200_API int64_t b200_row_bytes(int type, int64_t k);
  * Replaces nothing in ggml-cuda; plays the role ggml-cpu/repack.cpp plays for the CPU backend. */
 B200_API int b200_repack_rows(int type, void *rows, int64_t nrows, int64_t k, void *stream);
 B200_API int b200_unpack_rows(int type, void *rows, int64_t nrows, int64_t k, void *stream);
-B200_API int b200_type_is_repacked(int type);              /* 1 for Q4_0/Q8_0/Q6_K            */
+B200_API int b200_type_is_repacked(int type);              /* 1 for Q4_0/Q5_0/Q8_0/Q6_K       */
+/* Rows of the 32-element block types whose k is not a multiple of 256 (Qwen2-72B's ffn_down: k = 29568, where the reference
+ * quantiser falls back from Q4_K / Q6_K to Q5_0 / Q8_0, src/llama-quant.cpp:442-470) live in a private layout padded with zero
+ * blocks (d = 0) to b200_padded_k(type, k); row stride = b200_row_bytes(type, b200_padded_k).  Out of place (dst != src):
+ * forward = ggml rows -> repacked + padded, inverse = back.  Q5_0 repacked row: [qs 16B x nb][qh 4B x nb][d f16 x nb]. */
+B200_API int64_t b200_padded_k(int type, int64_t k);
+B200_API int b200_repack_rows_padded(int type, const void *src, void *dst, int64_t nrows, int64_t k, int inverse, void *stream);
 
 /* ---- activation quantisation (replaces quantize_row_q8_1_cuda, ggml-cuda/quantize.cu:148-160)
  * We quantise the way the CPU ORACLE does, so integer partial sums are bit-identical:
@@ -88,6 +95,8 @@ B200_API int64_t b200_act_d_offset(int kind, int64_t k);
 B200_API int64_t b200_act_bsum_offset(int kind, int64_t k);
 B200_API int b200_quantize_act(int kind, const float *x, int64_t x_col_stride /* floats */,
                                void *act, int64_t k, int64_t ncols, void *stream);
+/* ... for a padded weight layout: the act buffer covers k elements, of which only the first k_valid exist in x (the rest are 0) */
+B200_API int b200_quantize_act2(int kind, const float *x, int64_t x_col_stride, void *act, int64_t k, int64_t k_valid, int64_t ncols, void *stream);
 
 /* fused RMS_NORM * weight -> act buffer (and optionally the f32 normalised row too);
  * replaces rms_norm_f32<…,do_multiply> + quantize_q8_1 (norm.cu:107-164, quantize.cu:4-48) */
@@ -96,7 +105,7 @@ B200_API int b200_rms_norm_quantize(const float *x, const float *w, float *y_or_
 
 /* ---- MUL_MAT, decode matvec (replaces ggml_cuda_mul_mat_vec_q, mmvq.cu:500-570,139-226) -
  * dst[c][r] = sum_k W[r][k] * x[c][k] (+ bias[r]) (+ residual[c][r]),  ncols <= 8
- *   W        : m rows of `type` (repacked for Q4_0/Q8_0/Q6_K), row stride b200_row_bytes(type,k),
+ *   W        : m rows of `type` (repacked for Q4_0/Q5_0/Q8_0/Q6_K), row stride b200_row_bytes(type,k), k % 256 == 0 (padded layout otherwise),
  *              16-byte aligned, readable up to the next 16-byte boundary past the end
  *   act      : act buffer of kind b200_act_kind_for(type), ncols columns
  *   dst      : f32, column stride dst_col_stride floats
@@ -135,6 +144,7 @@ typedef struct b200_mmv_launch {
     const float  *x;  int64_t x_col_stride;
     const float  *norm_w;
     float        *y_out;            /* optional f32 copy of the (normalised) activation [ncols][k]    */
+    int64_t       k_valid;          /* 0 = k; else: x holds only k_valid elements per column, the weights are padded to k (zero blocks) */
 } b200_mmv_launch;
 B200_API int b200_mul_mat_vec_q_launch(const b200_mmv_launch *launch, void *stream);
 
@@ -153,6 +163,10 @@ B200_API int64_t b200_mul_mat_q_workspace(int type, int64_t m, int64_t k, int64_
 B200_API int b200_mul_mat_q(int type, const void *W, const float *X, int64_t x_col_stride,
                             float *dst, int64_t dst_col_stride, int64_t m, int64_t k, int64_t ncols,
                             void *workspace, void *stream);
+/* ... for a padded weight layout: k = b200_padded_k(type, k_valid); X holds k_valid elements per column */
+B200_API int b200_mul_mat_q2(int type, const void *W, const float *X, int64_t x_col_stride,
+                             float *dst, int64_t dst_col_stride, int64_t m, int64_t k, int64_t k_valid, int64_t ncols,
+                             void *workspace, void *stream);
 
 /* ---- RMS_NORM (+MUL) (replaces ggml_cuda_op_rms_norm[_fused], norm.cu:420-495) ---------- */
 B200_API int b200_rms_norm(const float *x, const float *w_or_null, float *y, int64_t ncols, int64_t nrows,

@@ -36,6 +36,7 @@ inline cudaError_t b200_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block
 // ---- block layouts (ggml/src/ggml-common.h:170-175,219-224,295-344) -----------------------
 // native (ggml) layouts
 struct __align__(2) blk_q4_0 { uint16_t d; uint8_t qs[16]; };                                   // 18
+struct __align__(2) blk_q5_0 { uint16_t d; uint8_t qh[4]; uint8_t qs[16]; };                    // 22
 struct __align__(2) blk_q8_0 { uint16_t d; int8_t  qs[32]; };                                   // 34
 struct __align__(4) blk_q4_K { uint16_t d, dmin; uint8_t sc[12]; uint8_t qs[128]; };            // 144
 struct __align__(4) blk_q5_K { uint16_t d, dmin; uint8_t sc[12]; uint8_t qh[32]; uint8_t qs[128]; }; // 176
@@ -46,7 +47,7 @@ static_assert(sizeof(blk_q4_0) == 18 && sizeof(blk_q8_0) == 34 && sizeof(blk_q4_
 __host__ __device__ inline int64_t type_block_elems(int t) {
     switch (t) {
         case B200_TYPE_F32: case B200_TYPE_F16: return 1;
-        case B200_TYPE_Q4_0: case B200_TYPE_Q8_0: return 32;
+        case B200_TYPE_Q4_0: case B200_TYPE_Q5_0: case B200_TYPE_Q8_0: return 32;
         case B200_TYPE_Q4_K: case B200_TYPE_Q5_K: case B200_TYPE_Q6_K: return 256;
         default: return 0;
     }
@@ -54,11 +55,17 @@ __host__ __device__ inline int64_t type_block_elems(int t) {
 __host__ __device__ inline int64_t type_block_bytes(int t) {
     switch (t) {
         case B200_TYPE_F32: return 4;  case B200_TYPE_F16: return 2;
-        case B200_TYPE_Q4_0: return 18; case B200_TYPE_Q8_0: return 34;
+        case B200_TYPE_Q4_0: return 18; case B200_TYPE_Q5_0: return 22; case B200_TYPE_Q8_0: return 34;
         case B200_TYPE_Q4_K: return 144; case B200_TYPE_Q5_K: return 176; case B200_TYPE_Q6_K: return 210;
         default: return 0;
     }
 }
+
+// 32-element block types may have rows that are not a multiple of 256 elements (Qwen2-72B: n_ff = 29568 — the reference quantiser
+// then falls back from Q4_K / Q6_K to Q5_0 / Q8_0, llama-quant.cpp:442-470).  The kernels work on 256-element units, so such
+// weights are kept in a PRIVATE layout whose rows are padded with zero blocks (d = 0) up to the next multiple of 256.
+__host__ __device__ inline bool type_is_block32(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q5_0 || t == B200_TYPE_Q8_0; }
+__host__ __device__ inline int64_t padded_k(int t, int64_t k) { return type_is_block32(t) ? (k + 255) / 256 * 256 : k; }
 
 // act-buffer geometry (see b200_ops.h)
 __host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }

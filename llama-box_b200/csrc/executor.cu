@@ -16,7 +16,7 @@
 
 namespace {
 
-inline bool is_weight_type(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q4_K || t == B200_TYPE_Q5_K || t == B200_TYPE_Q6_K; }
+inline bool is_weight_type(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q5_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q4_K || t == B200_TYPE_Q5_K || t == B200_TYPE_Q6_K; }
 inline int64_t nrows_of(const b200_tensor & t) { return t.ne[1] * t.ne[2] * t.ne[3]; }
 inline int64_t nelem(const b200_tensor & t) { return t.ne[0] * t.ne[1] * t.ne[2] * t.ne[3]; }
 inline int64_t elem_size(int type) {
@@ -52,7 +52,8 @@ bool mul_mat_ok(const b200_node & n) {
     const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
     if (!is_weight_type(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
     const int64_t k = w.ne[0], m = w.ne[1];
-    if (k <= 0 || k % 256 != 0 || (w.type == B200_TYPE_Q6_K && k % 2048 != 0)) return false;
+    // 32-element block types: any multiple of 32 (rows padded to 256 in the private weight layout, see common.cuh padded_k)
+    if (k <= 0 || (type_is_block32(w.type) ? k % 32 != 0 : k % 256 != 0) || (w.type == B200_TYPE_Q6_K && k % 2048 != 0)) return false;
     if (w.ne[2] != 1 || w.ne[3] != 1 || x.ne[2] != 1 || x.ne[3] != 1) return false;            // no broadcast batches on this path
     if (w.nb[1] != type_block_bytes(w.type) * (k / type_block_elems(w.type))) return false;
     if (x.ne[0] != k || x.nb[0] != 4 || (x.nb[1] & 15) || d.ne[0] != m || d.ne[1] != x.ne[1] || d.nb[0] != 4 || (d.nb[1] & 3)) return false;
@@ -320,9 +321,9 @@ struct Runner {
     uint8_t * act_buf(int kind) const { return ex->ws + ex->off_act[kind]; }
 
     // make sure the act buffer of `kind` holds the quantised form of x (n cols of k)
-    int ensure_act(const b200_tensor & x, int kind) {
-        if (ex->act_id[kind] == x.id && x.id != 0 && ex->act_ptr[kind] == x.data && ex->act_cols[kind] == x.ne[1]) return B200_OK;
-        int s = KL(b200_quantize_act(kind, (const float *)x.data, x.nb[1] / 4, act_buf(kind), x.ne[0], x.ne[1], st));
+    int ensure_act(const b200_tensor & x, int kind, int64_t k_pad) {
+        if (ex->act_id[kind] == x.id && x.id != 0 && ex->act_ptr[kind] == x.data && ex->act_cols[kind] == x.ne[1] && k_pad == x.ne[0]) return B200_OK;
+        int s = KL(b200_quantize_act2(kind, (const float *)x.data, x.nb[1] / 4, act_buf(kind), k_pad, x.ne[0], x.ne[1], st));
         if (s != B200_OK) return s;
         ex->act_id[kind] = x.id; ex->act_ptr[kind] = x.data; ex->act_cols[kind] = x.ne[1];
         return B200_OK;
@@ -427,6 +428,7 @@ struct Runner {
         const b200_node & mq = nodes[i];
         const b200_tensor & x = mq.src[1];
         if (x.ne[1] != 1 || (!dry && !ex->ws)) return false;
+        if (padded_k(mq.src[0].type, mq.src[0].ne[0]) != mq.src[0].ne[0]) return false;      // padded weight rows: the generic path handles k_valid
         struct Proj { int mm = -1, add = -1; const b200_tensor * out = nullptr; const float * bias = nullptr; } P[3];
         int rope[2] = { -1, -1 };
         int cur = i;
@@ -513,18 +515,18 @@ struct Runner {
     int run_mul_mat(int i) {
         const b200_node & n = nodes[i];
         const b200_tensor & w = n.src[0], & x = n.src[1];
-        const int64_t k = w.ne[0], m = w.ne[1], ncols = x.ne[1];
+        const int64_t kv = w.ne[0], k = padded_k(w.type, kv), m = w.ne[1], ncols = x.ne[1];   // kv: elements that exist in x; k: padded weight rows
         if (ncols > 8) {
             { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
             invalidate_act(n.dst);
             ex->act_id[0] = ex->act_id[1] = 0;           // the batched path owns the act buffers
             const int kind = b200_act_kind_for(w.type);
-            return KL(b200_mul_mat_q(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, ncols, act_buf(kind), st));
+            return KL(b200_mul_mat_q2(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, k, kv, ncols, act_buf(kind), st));
         }
         int s = B200_OK;
         if (fuse && ncols == 1 && try_attn_block(i, s)) return s;
         b200_mmv_launch L; memset(&L, 0, sizeof(L));
-        L.k = k; L.ncols = ncols;
+        L.k = k; L.ncols = ncols; L.k_valid = kv;
         if (fuse) {
             // (1) up, gate, GLU (llama-graph.cpp:647-693): MUL_MAT(up,x) MUL_MAT(gate,x) GLU(gate,up)
             const int j = next_compute(i);
@@ -555,7 +557,7 @@ struct Runner {
             for (int j2 = i + 1; j2 < n_limit(i) && ng < MAX_GROUP; j2++) {
                 if (done[j2] || nodes[j2].op != B200_OP_MUL_MAT) continue;
                 const b200_node & o = nodes[j2];
-                if (o.src[1].id != x.id || o.src[1].data != x.data || o.src[1].ne[1] != ncols || o.src[0].ne[0] != k) continue;
+                if (o.src[1].id != x.id || o.src[1].data != x.data || o.src[1].ne[1] != ncols || o.src[0].ne[0] != kv || padded_k(o.src[0].type, kv) != k) continue;
                 if (o.dst.nb[1] != o.src[0].ne[1] * 4 || !can_hoist(i, j2)) continue;
                 if (overlaps(o.dst, x) || (ex->norm.out_id && ex->norm.out_id == x.id && overlaps(o.dst, ex->norm.x))) continue;
                 group[ng++] = j2;
@@ -608,7 +610,7 @@ struct Runner {
         const int kind = b200_act_kind_for(w.type);
         s = mk_flush();
         if (s != B200_OK) return s;
-        s = ensure_act(x, kind);
+        s = ensure_act(x, kind, k);
         if (s != B200_OK) return s;
         invalidate_act(n.dst);
         return KL(b200_mul_mat_vec_q(w.type, w.data, act_buf(kind), (float *)n.dst.data, n.dst.nb[1] / 4, nullptr, nullptr, m, k, ncols, st));
@@ -791,7 +793,7 @@ int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
     for (int i = 0; i < n; i++) {
         const b200_node & nd = nodes[i];
         if (nd.op == B200_OP_MUL_MAT) {
-            const int64_t k = nd.src[0].ne[0], cols = nd.src[1].ne[1];
+            const int64_t k = (nd.src[0].ne[0] + 255) / 256 * 256, cols = nd.src[1].ne[1];
             for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(cols * act_col_bytes(kd, k)); if (b > act[kd]) act[kd] = b; }
             if (cols > 8) {                               // batched path: the tensor-core kernel's pre-tiled activation image
                 const int kd = b200_act_kind_for(nd.src[0].type);

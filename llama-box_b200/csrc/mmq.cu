@@ -20,11 +20,16 @@ extern "C" int64_t b200_mul_mat_q_workspace(int type, int64_t m, int64_t k, int6
 
 extern "C" int b200_mul_mat_q(int type, const void * W, const float * X, int64_t x_col_stride, float * dst, int64_t dst_col_stride,
                               int64_t m, int64_t k, int64_t ncols, void * workspace, void * stream) {
+    return b200_mul_mat_q2(type, W, X, x_col_stride, dst, dst_col_stride, m, k, k, ncols, workspace, stream);
+}
+// k: length of the (padded) weight rows, a multiple of 256; k_valid <= k: elements that exist in X (padded weight layout, see b200_padded_k)
+extern "C" int b200_mul_mat_q2(int type, const void * W, const float * X, int64_t x_col_stride, float * dst, int64_t dst_col_stride,
+                               int64_t m, int64_t k, int64_t k_valid, int64_t ncols, void * workspace, void * stream) {
     const int kind = b200_act_kind_for(type);
     if (kind < 0) { b200_set_error("mul_mat_q: unsupported weight type %d", type); return B200_ERR_UNSUPPORTED; }
     if (!workspace || ((uintptr_t)workspace & 15)) { b200_set_error("mul_mat_q: workspace missing or unaligned"); return B200_ERR_INVALID; }
-    if (b200_mmq_tc_supported(type, m, k, ncols)) return b200_mmq_tc(type, W, X, x_col_stride, dst, dst_col_stride, m, k, ncols, workspace, stream);
-    int s = b200_quantize_act(kind, X, x_col_stride, workspace, k, ncols, stream);
+    if (k_valid == k && b200_mmq_tc_supported(type, m, k, ncols)) return b200_mmq_tc(type, W, X, x_col_stride, dst, dst_col_stride, m, k, ncols, workspace, stream);
+    int s = b200_quantize_act2(kind, X, x_col_stride, workspace, k, k_valid, ncols, stream);
     if (s != B200_OK) return s;
     const int64_t colb = act_col_bytes(kind, k);
     for (int64_t c0 = 0; c0 < ncols; c0 += 8) {

@@ -64,6 +64,7 @@ struct MmvArgs {
     int64_t       x_col_stride;
     float         eps;
     int32_t       _pad2;
+    int64_t       k_valid;      // elements that exist in x per column (<= k; the rest of the padded weight rows are zero blocks)
 };
 
 // ---- activation view in shared memory --------------------------------------------------------
@@ -124,6 +125,30 @@ template <> struct WChunk<B200_TYPE_Q4_0> {
         int s = (dot16m(A, qs, mA) >> (sw * 4)) + (dot16m(B, qs, ~mA) >> (4 - sw * 4));
         s -= 8 * (int)a.bs[i];
         return __fmul_rn(__fmul_rn((float)s, h2f(d)), a.d[i]);          // ggml-cpu/quants.c:146
+    }
+};
+// 5-bit: low / high nibbles as in Q4_0 plus a fifth bit from qh (bit j -> element j, ggml-quants.c dequantize_row_q5_0); value q - 16
+__device__ __forceinline__ uint32_t spread4(uint32_t b) { return (((b & 0xFu) * 0x00204081u) & 0x01010101u) << 4; }   // 4 bits -> bit 4 of 4 bytes
+template <> struct WChunk<B200_TYPE_Q5_0> {
+    uint4 qs; uint32_t qh; uint16_t d;
+    __device__ __forceinline__ void load(const uint8_t * s, int nb, int i) {
+        qs = *(const uint4 *)(s + i * 16); qh = *(const uint32_t *)(s + nb * 16 + i * 4); d = *(const uint16_t *)(s + nb * 20 + i * 2);
+    }
+    __device__ __forceinline__ float dot(const ActView & a, int i) const {
+        const int sw = (i >> 2) & 1;
+        const uint4 A = *(const uint4 *)(a.qs + i * 32 + sw * 16);           // the two 16-element halves, read in lane-dependent order (bank conflicts)
+        const uint4 B = *(const uint4 *)(a.qs + i * 32 + (sw ^ 1) * 16);
+        const uint4 lo = sw ? B : A, hi = sw ? A : B;                        // lo: elements 0..15, hi: 16..31
+        const uint32_t w[4] = { qs.x, qs.y, qs.z, qs.w };
+        const uint32_t al[4] = { lo.x, lo.y, lo.z, lo.w }, ah[4] = { hi.x, hi.y, hi.z, hi.w };
+        int s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            s = dp4a_us((w[j] & 0x0F0F0F0Fu) | spread4(qh >> (4 * j)), (int)al[j], s);
+            s = dp4a_us(((w[j] >> 4) & 0x0F0F0F0Fu) | spread4(qh >> (16 + 4 * j)), (int)ah[j], s);
+        }
+        s -= 16 * (int)a.bs[i];
+        return __fmul_rn(__fmul_rn(h2f(d), a.d[i]), (float)s);              // (d_w * d_x) * sumi, ggml-cpu/quants.c ggml_vec_dot_q5_0_q8_0
     }
 };
 template <> struct WChunk<B200_TYPE_Q8_0> {
@@ -364,6 +389,7 @@ __device__ __forceinline__ void slot_one_type(int t, const uint8_t * s0, const u
         case B200_TYPE_Q5_K: slot_dot<B200_TYPE_Q5_K, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a0, k, 0, lane, acc); break;
         case B200_TYPE_Q6_K: slot_dot<B200_TYPE_Q6_K, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a0, k, 0, lane, acc); break;
         case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a1, k, 1, lane, acc); break;
+        case B200_TYPE_Q5_0: slot_dot<B200_TYPE_Q5_0, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a1, k, 1, lane, acc); break;
         default:             slot_dot<B200_TYPE_Q8_0, NCOLS, NR>(s0, s1, nb, segc, lseg, seg, a1, k, 1, lane, acc); break;
     }
 }
@@ -380,6 +406,7 @@ __device__ __forceinline__ void slot_dispatch(int t0, int t1, const uint8_t * s0
             case B200_TYPE_Q5_K: slot_dot<B200_TYPE_Q5_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc); break;
             case B200_TYPE_Q6_K: slot_dot<B200_TYPE_Q6_K, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a0, k, 0, lane, acc); break;
             case B200_TYPE_Q4_0: slot_dot<B200_TYPE_Q4_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
+            case B200_TYPE_Q5_0: slot_dot<B200_TYPE_Q5_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
             default:             slot_dot<B200_TYPE_Q8_0, NCOLS, NR>(s0, s1, nb0, segc, lseg, seg, a1, k, 1, lane, acc); break;
         }
     } else if (TT == -2) {
@@ -442,6 +469,7 @@ __device__ __forceinline__ RowGroup group_info(const MmvArgs & args, int g, MmvM
 __device__ __forceinline__ uint32_t part_bytes(int type, int nchunks) {
     switch (type) {
         case B200_TYPE_Q4_0: return nchunks * 18;
+        case B200_TYPE_Q5_0: return nchunks * 22;
         case B200_TYPE_Q8_0: return nchunks * 34;
         case B200_TYPE_Q4_K: return nchunks / 8 * 144;
         case B200_TYPE_Q5_K: return nchunks / 8 * 176;
@@ -456,6 +484,11 @@ __device__ __forceinline__ void issue_part(int type, uint8_t * dst, const uint8_
         case B200_TYPE_Q4_0:
             bulk_g2s(dst, row + (int64_t)c0 * 16, n * 16, bar);
             bulk_g2s(dst + n * 16, row + nb * 16 + (int64_t)c0 * 2, n * 2, bar);
+            break;
+        case B200_TYPE_Q5_0:
+            bulk_g2s(dst, row + (int64_t)c0 * 16, n * 16, bar);
+            bulk_g2s(dst + n * 16, row + nb * 16 + (int64_t)c0 * 4, n * 4, bar);
+            bulk_g2s(dst + n * 20, row + nb * 20 + (int64_t)c0 * 2, n * 2, bar);
             break;
         case B200_TYPE_Q8_0:
             bulk_g2s(dst, row + (int64_t)c0 * 32, n * 32, bar);
@@ -536,7 +569,8 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
             if (args.act_source == 2) {
                 double acc2 = 0.0;                                  // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
                 for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
-                    const float4 a = *(const float4 *)(xc + blk * 256 + lane * 8), b = *(const float4 *)(xc + blk * 256 + lane * 8 + 4);
+                    float4 a = make_float4(0, 0, 0, 0), b = a;
+                    if (blk * 256 + lane * 8 < args.k_valid) { a = *(const float4 *)(xc + blk * 256 + lane * 8); b = *(const float4 *)(xc + blk * 256 + lane * 8 + 4); }
                     acc2 += (double)__fmul_rn(a.x, a.x); acc2 += (double)__fmul_rn(a.y, a.y); acc2 += (double)__fmul_rn(a.z, a.z); acc2 += (double)__fmul_rn(a.w, a.w);
                     acc2 += (double)__fmul_rn(b.x, b.x); acc2 += (double)__fmul_rn(b.y, b.y); acc2 += (double)__fmul_rn(b.z, b.z); acc2 += (double)__fmul_rn(b.w, b.w);
                 }
@@ -546,23 +580,25 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
                 __syncthreads();
                 double t = 0.0;
                 for (int i = 0; i < MMV_WARPS; i++) t += red[i];    // every thread: same order, same value — no second barrier
-                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k), args.eps)));
+                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k_valid), args.eps)));
             }
             for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                 const int64_t i = (int64_t)blk * 256 + lane * 8;
-                const float4 a = *(const float4 *)(xc + i), b = *(const float4 *)(xc + i + 4);
+                float4 a = make_float4(0, 0, 0, 0), b = a;
+                const bool have = i < args.k_valid;                 // padded weight layout: x ends at k_valid
+                if (have) { a = *(const float4 *)(xc + i); b = *(const float4 *)(xc + i + 4); }
                 float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
                 if (args.act_source == 2) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) v[j] = __fmul_rn(v[j], scale);
-                    if (args.norm_w) {
+                    if (args.norm_w && have) {
                         const bool pre = blk == warp;
                         const float4 wa = pre ? nwa : *(const float4 *)(args.norm_w + i), wb = pre ? nwb : *(const float4 *)(args.norm_w + i + 4);
                         v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
                         v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
                     }
                 }
-                if (args.y_out && blockIdx.x == 0) {
+                if (args.y_out && blockIdx.x == 0 && have) {
                     float * yo = args.y_out + (int64_t)col * args.k + i;
                     *(float4 *)yo = make_float4(v[0], v[1], v[2], v[3]); *(float4 *)(yo + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 }
@@ -624,7 +660,7 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
 
 // ---- host ------------------------------------------------------------------------------------
 static bool mmv_type_ok(int t) {
-    return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q4_K || t == B200_TYPE_Q5_K || t == B200_TYPE_Q6_K;
+    return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q5_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q4_K || t == B200_TYPE_Q5_K || t == B200_TYPE_Q6_K;
 }
 // k for which every row start and every repacked section is 16-byte aligned
 static bool mmv_k_ok(int t, int64_t k) {
@@ -656,6 +692,7 @@ template <int NCOLS> static int mmv_launch_n(const MmvArgs & a, int mode, size_t
     for (int i = 1; i < a.n_mats; i++) if (a.mat[i].type != tt) tt = -1;
     switch (tt) {
         case B200_TYPE_Q4_0: return mmv_launch_nt<NCOLS, B200_TYPE_Q4_0>(a, mode, smem, grid, st);
+        case B200_TYPE_Q5_0: return mmv_launch_nt<NCOLS, B200_TYPE_Q5_0>(a, mode, smem, grid, st);
         case B200_TYPE_Q8_0: return mmv_launch_nt<NCOLS, B200_TYPE_Q8_0>(a, mode, smem, grid, st);
         case B200_TYPE_Q4_K: return mmv_launch_nt<NCOLS, B200_TYPE_Q4_K>(a, mode, smem, grid, st);
         case B200_TYPE_Q5_K: return mmv_launch_nt<NCOLS, B200_TYPE_Q5_K>(a, mode, smem, grid, st);
@@ -672,6 +709,8 @@ template <int NCOLS> static int mmv_launch_n(const MmvArgs & a, int mode, size_t
 static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
     if (ncols < 1 || ncols > 8) { b200_set_error("mmvq: ncols must be 1..8"); return B200_ERR_INVALID; }
     a.ncols = (int32_t)ncols;
+    if (a.k_valid <= 0 || a.k_valid > a.k) a.k_valid = a.k;
+    if (a.k_valid % 8 != 0) { b200_set_error("mmvq: k_valid must be a multiple of 8"); return B200_ERR_INVALID; }
     if (a.act_source != 0 && (!a.x || ((uintptr_t)a.x & 15) || (a.x_col_stride & 3) || ((uintptr_t)a.norm_w & 15))) { b200_set_error("mmvq: f32 activation source must be 16-byte aligned"); return B200_ERR_INVALID; }
     bool need[2] = { false, false };
     for (int i = 0; i < a.n_mats; i++) {
@@ -818,5 +857,6 @@ extern "C" int b200_mul_mat_vec_q_launch(const b200_mmv_launch * L, void * strea
     a.total_pairs = L->swiglu ? (int32_t)L->mats[0].m : 0;
     a.act[0] = (const uint8_t *)L->act_q8K; a.act[1] = (const uint8_t *)L->act_q80;
     a.act_source = L->act_source; a.x = L->x; a.x_col_stride = L->x_col_stride; a.norm_w = L->norm_w; a.eps = L->eps; a.y_out = L->y_out;
+    a.k_valid = L->k_valid;
     return mmv_launch(a, L->swiglu ? MMV_MODE_SWIGLU : MMV_MODE_PLAIN, L->ncols, (cudaStream_t)stream);
 }

@@ -10,15 +10,18 @@
 #include "actquant.cuh"
 
 __global__ void __launch_bounds__(128) quantize_act_kernel(const float * __restrict__ x, int64_t x_col_stride,
-                                                           void * __restrict__ act, int kind, int64_t k) {
+                                                           void * __restrict__ act, int kind, int64_t k, int64_t k_valid) {
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t blk = (int64_t)blockIdx.x * 4 + warp;
     const int64_t col = blockIdx.y;
     if (blk * 256 >= k) return;
-    const float4 * p = (const float4 *)(x + col * x_col_stride + blk * 256 + lane * 8);
-    const float4 a = p[0], b = p[1];
-    const float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+    float v[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    if (blk * 256 + lane * 8 < k_valid) {                    // elements past k_valid do not exist in x: zero (padded weight layout)
+        const float4 * p = (const float4 *)(x + col * x_col_stride + blk * 256 + lane * 8);
+        const float4 a = p[0], b = p[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
     ActOut o = act_sections(act, kind, k, col);
     if (kind == 0) warp_quant_q8K(v, o, blk, lane); else warp_quant_q80(v, o, blk, lane);
     pdl_trigger();
@@ -27,7 +30,7 @@ __global__ void __launch_bounds__(128) quantize_act_kernel(const float * __restr
 extern "C" int b200_act_kind_for(int t) {
     switch (t) {
         case B200_TYPE_Q4_K: case B200_TYPE_Q5_K: case B200_TYPE_Q6_K: return 0;
-        case B200_TYPE_Q4_0: case B200_TYPE_Q8_0: return 1;
+        case B200_TYPE_Q4_0: case B200_TYPE_Q5_0: case B200_TYPE_Q8_0: return 1;
         default: return B200_ERR_UNSUPPORTED;
     }
 }
@@ -36,10 +39,13 @@ extern "C" int64_t b200_act_d_offset(int kind, int64_t k)    { return act_d_off(
 extern "C" int64_t b200_act_bsum_offset(int kind, int64_t k) { return act_bsum_off(kind, k); }
 
 extern "C" int b200_quantize_act(int kind, const float * x, int64_t x_col_stride, void * act, int64_t k, int64_t ncols, void * stream) {
-    if ((kind != 0 && kind != 1) || k <= 0 || k % 256 != 0 || ncols <= 0) { b200_set_error("quantize_act: k must be a positive multiple of 256"); return B200_ERR_INVALID; }
+    return b200_quantize_act2(kind, x, x_col_stride, act, k, k, ncols, stream);
+}
+extern "C" int b200_quantize_act2(int kind, const float * x, int64_t x_col_stride, void * act, int64_t k, int64_t k_valid, int64_t ncols, void * stream) {
+    if ((kind != 0 && kind != 1) || k <= 0 || k % 256 != 0 || ncols <= 0 || k_valid <= 0 || k_valid > k || k_valid % 8 != 0) { b200_set_error("quantize_act: k must be a positive multiple of 256 (k_valid a multiple of 8)"); return B200_ERR_INVALID; }
     if (((uintptr_t)x | (uintptr_t)act) & 15 || (x_col_stride & 3)) { b200_set_error("quantize_act: pointers must be 16-byte aligned"); return B200_ERR_INVALID; }
     dim3 grid((unsigned)((k / 256 + 3) / 4), (unsigned)ncols);
-    quantize_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, x_col_stride, act, kind, k);
+    quantize_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, x_col_stride, act, kind, k, k_valid);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

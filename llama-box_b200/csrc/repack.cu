@@ -12,6 +12,11 @@ __device__ __forceinline__ int64_t repacked_off(int type, int64_t nb, int64_t of
     if (type == B200_TYPE_Q4_0) {
         const int64_t b = off / 18, o = off % 18;
         return o < 2 ? nb * 16 + b * 2 + o : b * 16 + (o - 2);
+    } else if (type == B200_TYPE_Q5_0) {                     // d[2] qh[4] qs[16] -> [qs][qh][d]
+        const int64_t b = off / 22, o = off % 22;
+        if (o < 2) return nb * 20 + b * 2 + o;
+        if (o < 6) return nb * 16 + b * 4 + (o - 2);
+        return b * 16 + (o - 6);
     } else if (type == B200_TYPE_Q8_0) {
         const int64_t b = off / 34, o = off % 34;
         return o < 2 ? nb * 32 + b * 2 + o : b * 32 + (o - 2);
@@ -37,7 +42,35 @@ __global__ void __launch_bounds__(256) repack_rows_kernel(uint8_t * rows, int ty
     }
 }
 
-extern "C" int b200_type_is_repacked(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q6_K; }
+// out of place, with row padding: native rows of nb blocks (stride rb) <-> repacked rows of nbp >= nb blocks (stride rbp), pad blocks zero
+__global__ void __launch_bounds__(256) repack_pad_kernel(const uint8_t * src, uint8_t * dst, int type, int64_t nb, int64_t rb, int64_t nbp, int64_t rbp, int inverse) {
+    const uint8_t * srow = src + (int64_t)blockIdx.x * (inverse ? rbp : rb);
+    uint8_t * drow = dst + (int64_t)blockIdx.x * (inverse ? rb : rbp);
+    if (!inverse) {
+        for (int64_t u = threadIdx.x; u < rbp / 2; u += blockDim.x) ((uint16_t *)drow)[u] = 0;
+        __syncthreads();
+    }
+    for (int64_t u = threadIdx.x; u < rb / 2; u += blockDim.x) {
+        const int64_t nat = u * 2, rep = repacked_off(type, nbp, nat);
+        if (!inverse) *(uint16_t *)(drow + rep) = *(const uint16_t *)(srow + nat);
+        else          *(uint16_t *)(drow + nat) = *(const uint16_t *)(srow + rep);
+    }
+}
+
+extern "C" int b200_type_is_repacked(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q5_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q6_K; }
+extern "C" int64_t b200_padded_k(int type, int64_t k) { return padded_k(type, k); }
+extern "C" int b200_repack_rows_padded(int type, const void * src, void * dst, int64_t nrows, int64_t k, int inverse, void * stream) {
+    if (!type_is_block32(type)) { b200_set_error("repack_padded: only the 32-element block types have padded rows"); return B200_ERR_UNSUPPORTED; }
+    if (!src || !dst || src == dst || nrows < 0 || k <= 0 || k % 32 != 0 || (((uintptr_t)src | (uintptr_t)dst) & 1)) { b200_set_error("repack_padded: bad arguments"); return B200_ERR_INVALID; }
+    if (nrows == 0) return B200_OK;
+    const int64_t nb = k / 32, nbp = padded_k(type, k) / 32, bb = type_block_bytes(type);
+    for (int64_t r0 = 0; r0 < nrows; r0 += 1 << 30) {
+        const int64_t n = nrows - r0 < (1 << 30) ? nrows - r0 : (1 << 30);
+        repack_pad_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)src + r0 * (inverse ? nbp : nb) * bb, (uint8_t *)dst + r0 * (inverse ? nb : nbp) * bb, type, nb, nb * bb, nbp, nbp * bb, inverse);
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
 
 static int repack_impl(int type, void * rows, int64_t nrows, int64_t k, int inverse, cudaStream_t st) {
     if (!b200_type_is_repacked(type)) return B200_OK;           // Q4_K / Q5_K / F16 / F32 stay native

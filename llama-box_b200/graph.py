@@ -8,7 +8,7 @@ import ctypes as C
 
 from . import ops
 
-F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K, I32, I64 = 0, 1, 2, 8, 12, 13, 14, 26, 27
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K, I32, I64 = 0, 1, 2, 6, 8, 12, 13, 14, 26, 27
 OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY = range(11)
 EXEC_CUDA_GRAPHS, EXEC_FUSION, EXEC_MEGAKERNEL, EXEC_MEGA_MMV = 1, 2, 4, 8
 MAX_SRC = 6

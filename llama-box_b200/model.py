@@ -27,13 +27,16 @@ def use_more_bits(i, n):
     return i < n // 8 or i >= 7 * n // 8 or (i - n // 8) % 3 == 2
 
 
-def type_mix(ftype, n_layer):
-    """per-layer tensor types of a GGUF quantisation mix (llama-quant.cpp:203-227,302-364)"""
+def type_mix(ftype, n_layer, n_ff=0, is_70b=False):
+    """per-layer tensor types of a GGUF quantisation mix (llama-quant.cpp:203-227,302-364), with the reference's fallback for rows that
+    are not a multiple of 256 (llama-quant.cpp:442-470: Q4_K -> Q5_0, Q6_K -> Q8_0 — Qwen2-72B's ffn_down) and the 70B attn_v bump"""
     out = []
     for i in range(n_layer):
         if ftype == "Q4_K_M":
             hi = G.Q6_K if use_more_bits(i, n_layer) else G.Q4_K
-            out.append(dict(wq=G.Q4_K, wk=G.Q4_K, wv=hi, wo=G.Q4_K, gate=G.Q4_K, up=G.Q4_K, down=hi))
+            v = hi if hi == G.Q6_K or not is_70b else G.Q5_K
+            down = hi if n_ff % 256 == 0 else (G.Q8_0 if hi == G.Q6_K else G.Q5_0)
+            out.append(dict(wq=G.Q4_K, wk=G.Q4_K, wv=v, wo=G.Q4_K, gate=G.Q4_K, up=G.Q4_K, down=down))
         elif ftype == "Q4_0":
             out.append({k: G.Q4_0 for k in ("wq", "wk", "wv", "wo", "gate", "up", "down")})
         elif ftype == "Q8_0":
@@ -54,8 +57,8 @@ def rand_blocks_gpu(gen, t, nrows, k):
         if signed:
             v = v * (torch.randint(0, 2, (nb,), device="cuda", generator=gen) * 2 - 1)
         return v.to(torch.float16).view(torch.uint8).reshape(nb, 2)
-    if t in (G.Q4_0, G.Q8_0):
-        raw[:, 0:2] = scales(1e-3, 2e-2 if t == G.Q4_0 else 2e-3, True)
+    if t in (G.Q4_0, G.Q5_0, G.Q8_0):
+        raw[:, 0:2] = scales(1e-3, 2e-3 if t == G.Q8_0 else (1e-2 if t == G.Q5_0 else 2e-2), True)
     elif t in (G.Q4_K, G.Q5_K):
         raw[:, 0:2] = scales(1e-4, 1e-3, False); raw[:, 2:4] = scales(1e-4, 1e-3, False)
     elif t == G.Q6_K:
@@ -69,12 +72,16 @@ class Weights:
     def __init__(self, t, m, k, blocks=None, gen=None):
         self.type, self.m, self.k = t, m, k
         nbytes = m * ops.row_bytes(t, k)
-        self.buf = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
-        if blocks is None:
-            self.buf[:nbytes] = rand_blocks_gpu(gen, t, m, k)
+        kp = ops.lib.b200_padded_k(t, k)
+        native = rand_blocks_gpu(gen, t, m, k) if blocks is None else torch.from_numpy(np.ascontiguousarray(blocks).reshape(-1)).cuda()
+        if kp != k:                                       # rows not a multiple of 256 elements: private padded layout (b200_ops.h)
+            self.buf = torch.zeros(m * ops.row_bytes(t, kp) + 64, dtype=torch.uint8, device="cuda")
+            ops.check(ops.lib.b200_repack_rows_padded(t, ops.p(native), ops.p(self.buf), m, k, 0, ops.stream()))
+            torch.cuda.synchronize()
         else:
-            self.buf[:nbytes] = torch.from_numpy(np.ascontiguousarray(blocks).reshape(-1)).cuda()
-        ops.check(ops.lib.b200_repack_rows(t, ops.p(self.buf), m, k, ops.stream()))
+            self.buf = torch.zeros(nbytes + 64, dtype=torch.uint8, device="cuda")
+            self.buf[:nbytes] = native
+            ops.check(ops.lib.b200_repack_rows(t, ops.p(self.buf), m, k, ops.stream()))
         self.t = G.T(self.buf.data_ptr(), t, [k, m])
         self.nbytes = nbytes
 
@@ -91,7 +98,7 @@ class SyntheticLlama:
         self.layer_ids = list(range(lo, hi))
         gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
         E, H, HK, D, FF, V, L = c["n_embd"], c["n_head"], c["n_head_kv"], c["head_dim"], c["n_ff"], c["n_vocab"], c["n_layer"]
-        mix, out_t = type_mix(ftype, L)
+        mix, out_t = type_mix(ftype, L, FF, c.get("n_embd") == 8192 and L == 80)
         hw = host_weights or {}
 
         def W(name, t, m, k):

@@ -32,7 +32,7 @@ class MmvDesc(C.Structure):
 class MmvLaunch(C.Structure):
     _fields_ = [("mats", MmvDesc * 4), ("residual", vp * 4), ("dst_col_stride", i64 * 4), ("n_mats", C.c_int32), ("swiglu", C.c_int32),
                 ("k", i64), ("ncols", i64), ("act_source", C.c_int32), ("eps", f32), ("act_q8K", vp), ("act_q80", vp),
-                ("x", vp), ("x_col_stride", i64), ("norm_w", vp), ("y_out", vp)]
+                ("x", vp), ("x_col_stride", i64), ("norm_w", vp), ("y_out", vp), ("k_valid", i64)]
 
 
 # name -> (restype, argtypes); must list every symbol include/b200_ops.h declares
@@ -46,6 +46,9 @@ SIGNATURES = {
     "b200_block_bytes": (i64, [i32]),
     "b200_row_bytes": (i64, [i32, i64]),
     "b200_repack_rows": (i32, [i32, vp, i64, i64, vp]),
+    "b200_padded_k": (i64, [i32, i64]),
+    "b200_repack_rows_padded": (i32, [i32, vp, vp, i64, i64, i32, vp]),
+    "b200_quantize_act2": (i32, [i32, vp, i64, vp, i64, i64, i64, vp]),
     "b200_unpack_rows": (i32, [i32, vp, i64, i64, vp]),
     "b200_type_is_repacked": (i32, [i32]),
     "b200_act_kind_for": (i32, [i32]),
@@ -61,6 +64,7 @@ SIGNATURES = {
     "b200_mul_mat_vec_q_swiglu": (i32, [i32, vp, i32, vp, vp, vp, vp, i64, i64, i64, vp]),
     "b200_mul_mat_q_workspace": (i64, [i32, i64, i64, i64]),
     "b200_mul_mat_q": (i32, [i32, vp, vp, i64, vp, i64, i64, i64, i64, vp, vp]),
+    "b200_mul_mat_q2": (i32, [i32, vp, vp, i64, vp, i64, i64, i64, i64, i64, vp, vp]),
     "b200_rms_norm": (i32, [vp, vp, vp, i64, i64, i64, i64, f32, vp]),
     "b200_rope": (i32, [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, C.POINTER(RopeParams), vp]),
     "b200_set_rows": (i32, [vp, i64, vp, vp, i32, i64, i64, i64, vp]),

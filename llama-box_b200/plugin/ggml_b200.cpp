@@ -83,7 +83,11 @@ static int               g_ndev = 0;
 static ggml_backend_reg  g_reg;
 
 static bool is_b200_buffer(ggml_backend_buffer_t b);
-static bool is_repack_type(enum ggml_type t) { return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q6_K; }
+static bool is_repack_type(enum ggml_type t) { return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q5_0 || t == GGML_TYPE_Q8_0 || t == GGML_TYPE_Q6_K; }
+// 32-element block types whose rows are not a multiple of 256 elements (Qwen2-72B ffn_down: 29568, quantised Q5_0 / Q8_0 by the
+// reference's fallback rule, llama-quant.cpp:442-470) are kept in a private layout padded with zero blocks (b200_padded_k)
+static bool is_block32(enum ggml_type t) { return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q5_0 || t == GGML_TYPE_Q8_0; }
+static bool needs_padding(const ggml_tensor * t) { return is_block32(t->type) && t->ne[0] % 256 != 0; }
 
 // ------------------------------------------------------------------------------------------------
 // buffers (ggml_backend_buffer_i, ggml-backend-impl.h:41-66) — all calls synchronous on return,
@@ -99,6 +103,18 @@ static void * buf_get_base(ggml_backend_buffer_t buffer) { return ((b200_buffer_
 
 static enum ggml_status buf_init_tensor(ggml_backend_buffer_t, struct ggml_tensor *) { return GGML_STATUS_SUCCESS; }
 
+// padded private layout <-> ggml rows, through a temporary (rows change their stride, so it cannot be done in place)
+static bool convert_padded(const ggml_tensor * t, int inverse) {
+    const int64_t nrows = ggml_nrows(t), k = t->ne[0];
+    const size_t nat = (size_t)nrows * (size_t)b200_row_bytes((int)t->type, k), pad = (size_t)nrows * (size_t)b200_row_bytes((int)t->type, b200_padded_k((int)t->type, k));
+    void * tmp = nullptr;
+    if (!CUDA_OK(cudaMalloc(&tmp, inverse ? nat : pad))) return false;
+    bool ok = b200_repack_rows_padded((int)t->type, t->data, tmp, nrows, k, inverse, cudaStreamPerThread) == B200_OK;
+    ok = ok && CUDA_OK(cudaMemcpyAsync(t->data, tmp, inverse ? nat : pad, cudaMemcpyDeviceToDevice, cudaStreamPerThread));
+    ok = CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread)) && ok;
+    cudaFree(tmp);
+    return ok;
+}
 // bring a weight tensor back to ggml's layout (before ggml reads or partially writes it)
 static void ensure_native(b200_buffer_ctx * c, const ggml_tensor * t) {
     if (!is_repack_type(t->type)) return;
@@ -106,17 +122,23 @@ static void ensure_native(b200_buffer_ctx * c, const ggml_tensor * t) {
     if (!c->repacked.count(t->data)) return;
     cudaSetDevice(c->device);
     CUDA_OK(cudaDeviceSynchronize());                    // compute streams are non-blocking: order against every reader of the tensor
-    b200_unpack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread);
+    if (needs_padding(t)) convert_padded(t, /* inverse */ 1);
+    else b200_unpack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread);
     CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread));
     c->repacked.erase(t->data);
 }
-static bool repack_k_ok(const ggml_tensor * t) { return t->ne[0] % 256 == 0 && (t->type != GGML_TYPE_Q6_K || t->ne[0] % 2048 == 0) && ggml_is_contiguous(t); }
+static bool repack_k_ok(const ggml_tensor * t) {
+    if (!ggml_is_contiguous(t)) return false;
+    if (is_block32(t->type)) return t->ne[0] % 32 == 0;
+    return t->ne[0] % 256 == 0 && (t->type != GGML_TYPE_Q6_K || t->ne[0] % 2048 == 0);
+}
 // convert a weight tensor to the kernels' layout, exactly once, visible to every stream when this returns
 static bool ensure_repacked(b200_buffer_ctx * c, const ggml_tensor * t) {
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->repacked.count(t->data)) return true;
     cudaSetDevice(c->device);
-    if (b200_repack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread) != B200_OK) return false;
+    if (needs_padding(t)) { if (!convert_padded(t, 0)) return false; }
+    else if (b200_repack_rows((int)t->type, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread) != B200_OK) return false;
     if (!CUDA_OK(cudaStreamSynchronize(cudaStreamPerThread))) return false;
     c->repacked.insert(t->data);
     return true;
@@ -187,7 +209,11 @@ static ggml_backend_buffer_t buft_alloc(ggml_backend_buffer_type_t buft, size_t 
     return ggml_backend_buffer_init(buft, b200_buffer_iface, c, size);
 }
 static size_t buft_alignment(ggml_backend_buffer_type_t) { return 128; }
-static size_t buft_alloc_size(ggml_backend_buffer_type_t, const struct ggml_tensor * t) { return ggml_nbytes(t); }
+static size_t buft_alloc_size(ggml_backend_buffer_type_t, const struct ggml_tensor * t) {
+    // room for the padded private layout of 32-element block weights with k % 256 != 0 (ggml-cuda pads quantised rows too: ggml-cuda.cu:684-698)
+    if (needs_padding(t) && ggml_is_contiguous(t)) return (size_t)ggml_nrows(t) * (size_t)b200_row_bytes((int)t->type, b200_padded_k((int)t->type, t->ne[0]));
+    return ggml_nbytes(t);
+}
 static bool buft_is_host(ggml_backend_buffer_type_t) { return false; }
 
 // ---- pinned host buffer type (used for CPU-side activations and async uploads, llama-context.cpp:231-238)

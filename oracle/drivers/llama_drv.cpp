@@ -64,7 +64,9 @@ void * drv_open(const char * model_path, const char * plugin, int ngl, const cha
                 int fa, const char * ctk, const char * ctv, int no_repack, int embeddings) {
     auto ty = [](const char * s) { return s && !strcmp(s, "q8_0") ? GGML_TYPE_Q8_0 : GGML_TYPE_F16; };
     if (!g_backends_loaded) {
-        llama_log_set([](ggml_log_level lvl, const char * txt, void *) { if (lvl >= GGML_LOG_LEVEL_WARN) fputs(txt, stderr); }, nullptr);
+        // warnings and errors only; LLAMA_DRV_LOG_DEBUG=1 lets everything through (e.g. GGML_SCHED_DEBUG's split assignment)
+        static const bool all = getenv("LLAMA_DRV_LOG_DEBUG") != nullptr;
+        llama_log_set([](ggml_log_level lvl, const char * txt, void *) { if (all || lvl >= GGML_LOG_LEVEL_WARN || lvl == GGML_LOG_LEVEL_CONT) fputs(txt, stderr); }, nullptr);
         ggml_backend_load_all();
         // inside another process (python) the executable's directory holds no backends: also look next to this file's .so
         Dl_info info;

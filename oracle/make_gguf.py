@@ -20,7 +20,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "tests"))
-from refutil import BLOCK_BYTES, BLOCK_ELEMS, Q4_0, Q4_K, Q5_K, Q6_K, Q8_0, rand_blocks, row_bytes  # noqa: E402
+from refutil import BLOCK_BYTES, BLOCK_ELEMS, Q4_0, Q4_K, Q5_0, Q5_K, Q6_K, Q8_0, rand_blocks, row_bytes  # noqa: E402
 
 CONFIGS = {
     "llama3-8b": dict(arch="llama", n_embd=4096, n_head=32, n_head_kv=8, head_dim=128, n_ff=14336, n_vocab=128256, n_layer=32, rope_base=500000.0, eps=1e-5, qkv_bias=False, n_ctx_train=8192),
@@ -35,10 +35,17 @@ def use_more_bits(i, n):
     return i < n // 8 or i >= 7 * n // 8 or (i - n // 8) % 3 == 2
 
 
-def layer_types(ftype, i, n):
+def layer_types(ftype, i, n, n_ff=0, is_70b=False):
+    """per-layer tensor types of a quantisation mix (llama-quant.cpp:185-186,203-227,302-364) including the reference's fallback
+    for rows that are not a multiple of 256 (llama-quant.cpp:442-470: Q4_K -> Q5_0, Q6_K -> Q8_0; Qwen2-72B's ffn_down, n_ff = 29568)
+    and the 70B-class bump of attn_v from Q4_K to Q5_K (llama-quant.cpp:305-310)"""
     if ftype == "Q4_K_M":
         hi = Q6_K if use_more_bits(i, n) else Q4_K
-        return dict(attn_q=Q4_K, attn_k=Q4_K, attn_v=hi, attn_output=Q4_K, ffn_gate=Q4_K, ffn_up=Q4_K, ffn_down=hi)
+        v = hi if hi == Q6_K or not is_70b else Q5_K
+        down = hi
+        if n_ff % 256 != 0:
+            down = Q8_0 if hi == Q6_K else Q5_0
+        return dict(attn_q=Q4_K, attn_k=Q4_K, attn_v=v, attn_output=Q4_K, ffn_gate=Q4_K, ffn_up=Q4_K, ffn_down=down)
     t = Q4_0 if ftype == "Q4_0" else Q8_0
     return {k: t for k in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")}
 
@@ -80,7 +87,7 @@ def main():
         c["n_layer"] = a.layers
     E, H, HK, D, FF, V, L = c["n_embd"], c["n_head"], c["n_head_kv"], c["head_dim"], c["n_ff"], c["n_vocab"], c["n_layer"]
     rng = np.random.default_rng(a.seed)
-    qt = {2: gguf.GGMLQuantizationType.Q4_0, 8: gguf.GGMLQuantizationType.Q8_0, 12: gguf.GGMLQuantizationType.Q4_K,
+    qt = {2: gguf.GGMLQuantizationType.Q4_0, 6: gguf.GGMLQuantizationType.Q5_0, 8: gguf.GGMLQuantizationType.Q8_0, 12: gguf.GGMLQuantizationType.Q4_K,
           13: gguf.GGMLQuantizationType.Q5_K, 14: gguf.GGMLQuantizationType.Q6_K}
 
     w = gguf.GGUFWriter(a.out, c["arch"])
@@ -124,7 +131,7 @@ def main():
     out_t = Q8_0 if a.ftype == "Q8_0" else Q6_K
     add_q("token_embd.weight", emb_t, V, E)
     for i in range(L):
-        ts = layer_types(a.ftype, i, L)
+        ts = layer_types(a.ftype, i, L, FF, a.config == "qwen2-72b")
         w.add_tensor(f"blk.{i}.attn_norm.weight", (1 + 0.05 * rng.standard_normal(E)).astype(np.float32))
         add_q(f"blk.{i}.attn_q.weight", ts["attn_q"], H * D, E)
         add_q(f"blk.{i}.attn_k.weight", ts["attn_k"], HK * D, E)

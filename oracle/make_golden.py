@@ -43,7 +43,7 @@ def main():
     m, k, n = 24, 2048, 3
     w = (rng.standard_normal((m, k)) * 0.05).astype(np.float32)
     X = rng.standard_normal((n, k)).astype(np.float32)
-    names = {2: "q4_0", 8: "q8_0", 12: "q4_K", 13: "q5_K", 14: "q6_K"}
+    names = {2: "q4_0", 6: "q5_0", 8: "q8_0", 12: "q4_K", 13: "q5_K", 14: "q6_K"}
     for t in WEIGHT_TYPES:
         Wq = ref_quantize_weights(t, w)
         deq = np.zeros((m, k), np.float32)

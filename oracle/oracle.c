@@ -21,6 +21,7 @@
 /* ---- block layouts (ggml/src/ggml-common.h:170-175,219-224,295-344); byte-packed ---- */
 #pragma pack(push, 1)
 typedef struct { uint16_t d; uint8_t qs[16]; } blk_q4_0;                                   /* 18  */
+typedef struct { uint16_t d; uint8_t qh[4]; uint8_t qs[16]; } blk_q5_0;                    /* 22  (ggml-common.h:186-191) */
 typedef struct { uint16_t d; int8_t  qs[32]; } blk_q8_0;                                   /* 34  */
 typedef struct { uint16_t d, dmin; uint8_t sc[12]; uint8_t qs[128]; } blk_q4_K;            /* 144 */
 typedef struct { uint16_t d, dmin; uint8_t sc[12]; uint8_t qh[32]; uint8_t qs[128]; } blk_q5_K; /* 176 */
@@ -29,6 +30,7 @@ typedef struct { float d; int8_t qs[256]; int16_t bsums[16]; } blk_q8_K;        
 #pragma pack(pop)
 
 _Static_assert(sizeof(blk_q4_0) == 18,  "q4_0");
+_Static_assert(sizeof(blk_q5_0) == 22,  "q5_0");
 _Static_assert(sizeof(blk_q8_0) == 34,  "q8_0");
 _Static_assert(sizeof(blk_q4_K) == 144, "q4_K");
 _Static_assert(sizeof(blk_q5_K) == 176, "q5_K");
@@ -38,7 +40,7 @@ _Static_assert(sizeof(blk_q8_K) == 292, "q8_K");
 int64_t orc_block_elems(int type) {
     switch (type) {
         case ORC_F32: case ORC_F16: return 1;
-        case ORC_Q4_0: case ORC_Q8_0: return QK;
+        case ORC_Q4_0: case ORC_Q5_0: case ORC_Q8_0: return QK;
         default: return QKK;
     }
 }
@@ -47,6 +49,7 @@ int64_t orc_block_bytes(int type) {
         case ORC_F32:  return 4;
         case ORC_F16:  return 2;
         case ORC_Q4_0: return 18;
+        case ORC_Q5_0: return 22;
         case ORC_Q8_0: return 34;
         case ORC_Q4_K: return 144;
         case ORC_Q5_K: return 176;
@@ -189,6 +192,19 @@ void orc_dequantize_row(int type, const void *vx, float *y, int64_t k) {
         }
         return;
     }
+    if (type == ORC_Q5_0) {                                /* ggml-quants.c dequantize_row_q5_0: fifth bit j / j + 16 of qh */
+        const blk_q5_0 *x = (const blk_q5_0 *)vx;
+        for (int64_t b = 0; b < k/QK; b++) {
+            const float d = orc_fp16_to_fp32(x[b].d);
+            uint32_t qh; memcpy(&qh, x[b].qh, 4);
+            for (int j = 0; j < 16; j++) {
+                const int xh0 = ((qh >> (j + 0)) << 4) & 0x10, xh1 = (qh >> (j + 12)) & 0x10;
+                y[b*QK + j]      = (float)(((x[b].qs[j] & 15) | xh0) - 16) * d;
+                y[b*QK + j + 16] = (float)(((x[b].qs[j] >> 4) | xh1) - 16) * d;
+            }
+        }
+        return;
+    }
     if (type == ORC_Q8_0) {                                /* ggml-quants.c dequantize_row_q8_0 */
         const blk_q8_0 *x = (const blk_q8_0 *)vx;
         for (int64_t b = 0; b < k/QK; b++) {
@@ -229,6 +245,19 @@ static float dot_q4_0(int64_t k, const blk_q4_0 *w, const blk_q8_0 *a) {   /* gg
         for (int j = 0; j < 16; j++)
             s += ((w[b].qs[j] & 15) - 8) * a[b].qs[j] + ((w[b].qs[j] >> 4) - 8) * a[b].qs[j + 16];
         acc += (float)s * orc_fp16_to_fp32(w[b].d) * orc_fp16_to_fp32(a[b].d);
+    }
+    return acc;
+}
+static float dot_q5_0(int64_t k, const blk_q5_0 *w, const blk_q8_0 *a) {   /* ggml-cpu/quants.c ggml_vec_dot_q5_0_q8_0_generic; x86: arch/x86/quants.c:845-925 */
+    float acc = 0.0f;
+    for (int64_t b = 0; b < k/QK; b++) {
+        uint32_t qh; memcpy(&qh, w[b].qh, 4);
+        int s = 0;
+        for (int j = 0; j < 16; j++) {
+            const int xh0 = ((qh >> (j + 0)) << 4) & 0x10, xh1 = (qh >> (j + 12)) & 0x10;
+            s += (((w[b].qs[j] & 15) | xh0) - 16) * a[b].qs[j] + (((w[b].qs[j] >> 4) | xh1) - 16) * a[b].qs[j + 16];
+        }
+        acc += (orc_fp16_to_fp32(w[b].d) * orc_fp16_to_fp32(a[b].d)) * (float)s;
     }
     return acc;
 }
@@ -279,6 +308,7 @@ static float dot_kquant(int type, int64_t k, const void *vw, const blk_q8_K *a) 
 float orc_vec_dot(int type, int64_t k, const void *w, const void *a) {
     switch (type) {
         case ORC_Q4_0: return dot_q4_0(k, (const blk_q4_0 *)w, (const blk_q8_0 *)a);
+        case ORC_Q5_0: return dot_q5_0(k, (const blk_q5_0 *)w, (const blk_q8_0 *)a);
         case ORC_Q8_0: return dot_q8_0(k, (const blk_q8_0 *)w, (const blk_q8_0 *)a);
         case ORC_Q4_K: case ORC_Q5_K: case ORC_Q6_K: return dot_kquant(type, k, w, (const blk_q8_K *)a);
         default: return NAN;
@@ -288,7 +318,7 @@ float orc_vec_dot(int type, int64_t k, const void *w, const void *a) {
 /* ggml-cpu/ggml-cpu.c:1202-1394: quantise each src1 row to the weight's vec_dot_type, then one
  * vec_dot per (row of W, row of X). */
 void orc_mul_mat(int type, const void *W, const float *X, float *dst, int64_t m, int64_t n, int64_t k) {
-    const int kq = (type == ORC_Q4_0 || type == ORC_Q8_0);
+    const int kq = (type == ORC_Q4_0 || type == ORC_Q5_0 || type == ORC_Q8_0);
     const int64_t abytes = kq ? k/QK*34 : k/QKK*292;
     const int64_t wbytes = orc_row_bytes(type, k);
     uint8_t *aq = (uint8_t *)malloc((size_t)abytes);

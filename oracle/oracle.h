@@ -26,6 +26,7 @@ enum orc_type {
     ORC_F32  = 0,
     ORC_F16  = 1,
     ORC_Q4_0 = 2,
+    ORC_Q5_0 = 6,
     ORC_Q8_0 = 8,
     ORC_Q4_K = 12,
     ORC_Q5_K = 13,

@@ -17,13 +17,13 @@ REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 # enum ggml_type values (ggml/include/ggml.h:377-418)
-F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K, Q8_K = 0, 1, 2, 8, 12, 13, 14, 15
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K, Q8_K = 0, 1, 2, 6, 8, 12, 13, 14, 15
 I32, I64 = 26, 27
-TYPE_NAME = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K"}
-BLOCK_ELEMS = {F32: 1, F16: 1, Q4_0: 32, Q8_0: 32, Q4_K: 256, Q5_K: 256, Q6_K: 256, Q8_K: 256, I32: 1, I64: 1}
-BLOCK_BYTES = {F32: 4, F16: 2, Q4_0: 18, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q8_K: 292, I32: 4, I64: 8}
-WEIGHT_TYPES = [Q4_0, Q8_0, Q4_K, Q5_K, Q6_K]
-ACT_TYPE = {Q4_0: Q8_0, Q8_0: Q8_0, Q4_K: Q8_K, Q5_K: Q8_K, Q6_K: Q8_K}
+TYPE_NAME = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q5_0: "q5_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K"}
+BLOCK_ELEMS = {F32: 1, F16: 1, Q4_0: 32, Q5_0: 32, Q8_0: 32, Q4_K: 256, Q5_K: 256, Q6_K: 256, Q8_K: 256, I32: 1, I64: 1}
+BLOCK_BYTES = {F32: 4, F16: 2, Q4_0: 18, Q5_0: 22, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q8_K: 292, I32: 4, I64: 8}
+WEIGHT_TYPES = [Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K]
+ACT_TYPE = {Q4_0: Q8_0, Q5_0: Q8_0, Q8_0: Q8_0, Q4_K: Q8_K, Q5_K: Q8_K, Q6_K: Q8_K}
 
 
 def row_bytes(t, k):
@@ -138,12 +138,12 @@ def ref():
         vp, i64 = C.c_void_p, C.c_int64
         base.ggml_quantize_chunk.restype = C.c_size_t
         base.ggml_quantize_chunk.argtypes = [C.c_int, vp, vp, i64, i64, i64, vp]
-        for nm in ("q4_0", "q8_0", "q4_K", "q5_K", "q6_K"):
+        for nm in ("q4_0", "q5_0", "q8_0", "q4_K", "q5_K", "q6_K"):
             getattr(base, "dequantize_row_" + nm).argtypes = [vp, vp, i64]
         cpu.quantize_row_q8_0.argtypes = [vp, vp, i64]
         cpu.quantize_row_q8_K.argtypes = [vp, vp, i64]
         cpu.ggml_cpu_fp32_to_fp16.argtypes = [vp, vp, i64]
-        for nm in ("q4_0_q8_0", "q8_0_q8_0", "q4_K_q8_K", "q5_K_q8_K", "q6_K_q8_K"):
+        for nm in ("q4_0_q8_0", "q5_0_q8_0", "q8_0_q8_0", "q4_K_q8_K", "q5_K_q8_K", "q6_K_q8_K"):
             getattr(cpu, "ggml_vec_dot_" + nm).argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_int]
         cpu.ggml_cpu_init()
         _ref = (base, cpu)
@@ -205,7 +205,7 @@ def rand_blocks(rng, t, nrows, k, scale_mul=1.0):
     rand_f16_scale_l = lambda rng, n, lo=1e-3, hi=2e-2, signed=False: _rs(rng, n, lo * scale_mul, hi * scale_mul, signed)  # noqa: E731
     nb = nrows * (k // BLOCK_ELEMS[t])
     raw = rng.integers(0, 256, size=(nb, BLOCK_BYTES[t]), dtype=np.uint8)
-    if t in (Q4_0, Q8_0):
+    if t in (Q4_0, Q5_0, Q8_0):
         raw[:, 0:2] = rand_f16_scale_l(rng, nb, signed=True).view(np.uint8).reshape(nb, 2)
     elif t in (Q4_K, Q5_K):
         raw[:, 0:2] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)

@@ -645,3 +645,39 @@ def test_flash_attn_tensor_core(b200, kvt, nh, nhkv, nt, nkv, past):
     # vs the CPU oracle: its F16-V path accumulates in fp16 (ops.cpp:8278-8340) and is the noisier side at long n_kv
     assert nmse(got, want) < (1e-3 if kvt == F16 else 1e-6), nmse(got, want)
     assert nmse(got, truth) <= nmse(want, truth) or kvt == Q8_0
+
+
+# ------------------------------------------------------------------ rows that are not a multiple of 256 elements (Qwen2-72B ffn_down)
+@pytest.mark.parametrize("t", [Q5_0, Q8_0, Q4_0])
+@pytest.mark.parametrize("m,k,n", [(48, 29568, 1), (16, 29568, 4), (8, 96, 2), (40, 29568, 19)])
+def test_mul_mat_padded_rows(b200, t, m, k, n):
+    """k % 256 != 0 for the 32-element block types: the reference quantiser falls back to Q5_0 / Q8_0 for Qwen2-72B's ffn_down
+    (n_ff = 29568, llama-quant.cpp:442-470).  Weights go through b200_repack_rows_padded (zero blocks up to the next multiple of
+    256), the activation prologue zero-fills past k_valid; decode matvec (fused in-kernel quantisation) and the batched path;
+    the inverse conversion restores the ggml bytes exactly."""
+    rng = np.random.default_rng(t * 100 + m + n)
+    W = rand_blocks(rng, t, m, k)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    want = orc_mul_mat(t, W, x, m, n, k)
+    kp = b200.lib.b200_padded_k(t, k)
+    assert kp % 256 == 0 and kp >= k
+    src = dev(np.concatenate([W.reshape(-1), np.zeros(64, np.uint8)]))
+    Wd = torch.zeros(m * row_bytes(t, kp) + 64, dtype=torch.uint8, device="cuda")
+    b200.check(b200.lib.b200_repack_rows_padded(t, b200.p(src), b200.p(Wd), m, k, 0, b200.stream()))
+    back = torch.zeros_like(src)
+    b200.check(b200.lib.b200_repack_rows_padded(t, b200.p(Wd), b200.p(back), m, k, 1, b200.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(back[:W.size], src[:W.size])
+    xd = dev(x)
+    dst = torch.full((n, m), float("nan"), dtype=torch.float32, device="cuda")
+    if n <= 8:
+        L = b200.MmvLaunch()
+        L.n_mats = 1; L.k = kp; L.k_valid = k; L.ncols = n; L.act_source = 1; L.x = xd.data_ptr(); L.x_col_stride = k
+        L.mats[0].W = Wd.data_ptr(); L.mats[0].dst = dst.data_ptr(); L.mats[0].m = m; L.mats[0].type = t
+        b200.check(b200.lib.b200_mul_mat_vec_q_launch(C.byref(L), b200.stream()))
+    else:
+        ws = torch.zeros(b200.lib.b200_mul_mat_q_workspace(t, m, kp, n), dtype=torch.uint8, device="cuda")
+        b200.check(b200.lib.b200_mul_mat_q2(t, b200.p(Wd), b200.p(xd), k, b200.p(dst), m, m, kp, k, n, b200.p(ws), b200.stream()))
+    got = dst.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()

@@ -102,11 +102,13 @@ def cpu_builds(tmp_path, tmp_path_factory, gguf, **kw):
     return [drv(gguf, str(tmp_path / ("cpu_" + w)), False, ref_dir=variant_ref_dir(tmp_path_factory, w), **kw) for w in ("haswell", "sandybridge")]
 
 
-def drv(gguf, out_prefix, plugin, kv="f16", prompt_len=24, gen=N_STEPS, verify=1, ngl=99, ts=None, embeddings=False, ctx=1024, ref_dir=None):
+def drv(gguf, out_prefix, plugin, kv="f16", prompt_len=24, gen=N_STEPS, verify=1, ngl=99, ts=None, embeddings=False, ctx=1024, ref_dir=None, extra_env=None):
     logits = out_prefix + ".logits"
     env = ENV
     if ref_dir:
         env = dict(ENV, LD_LIBRARY_PATH=ref_dir)
+    if extra_env:
+        env = dict(env, **extra_env)
     cmd = [os.path.join(ref_dir or REF_DIR, "llama_drv"), "--model", gguf, "--ctx", str(ctx), "--prompt-len", str(prompt_len), "--gen", str(gen), "--logits-out", logits, "--fa",
            "--ctk", kv, "--ctv", kv, "--verify-batch", str(verify)]
     if plugin:
@@ -204,6 +206,24 @@ def test_as_close_to_ggml_cpu_as_its_own_other_build(tmp_path, tmp_path_factory,
     others = cpu_builds(tmp_path, tmp_path_factory, gguf, kv=kv, verify=verify, prompt_len=prompt, gen=gen)
     gpu = drv(gguf, str(tmp_path / "gpu"), True, kv=kv, verify=verify, prompt_len=prompt, gen=gen)
     assert_within_reference_self_consistency(gpu, cpu, others, f"{config} {ftype} kv={kv} verify={verify} prompt={prompt}")
+
+
+def test_qwen2_72b_shapes_stay_on_the_device(tmp_path, tmp_path_factory):
+    """BASELINE config 4: Qwen2-72B shapes (n_embd 8192, n_ff 29568, QKV bias, NEOX rope, 152064-row output) with the tensor types the
+    reference quantiser REALLY produces for Q4_K_M: ffn_down rows are not a multiple of 256, so it falls back to Q5_0 / Q8_0
+    (llama-quant.cpp:442-470), attn_v is Q5_K / Q6_K.  Every MUL_MAT must be accepted by the backend (no CPU split after the
+    embedding), and the run must be as close to ggml-cpu as ggml-cpu's own builds are to each other."""
+    gguf = model_file(tmp_path_factory, "qwen2-72b", "Q4_K_M", 2)
+    cpu = drv(gguf, str(tmp_path / "cpu"), False, gen=9)
+    others = cpu_builds(tmp_path, tmp_path_factory, gguf, gen=9)
+    env_dbg = dict(GGML_SCHED_DEBUG="1", LLAMA_DRV_LOG_DEBUG="1")
+    gpu = drv(gguf, str(tmp_path / "gpu"), True, gen=9, extra_env=env_dbg)
+    splits = [ln for ln in gpu["stderr"].splitlines() if ln.startswith("## SPLIT")]
+    cpu_splits = [ln for ln in splits if "CPU" in ln]
+    # one CPU split per graph at most: the token-embedding GET_ROWS (llama-model.cpp:1960-1962 keeps the input layer on the CPU)
+    n_graphs = max(1, sum(1 for ln in splits if ln.startswith("## SPLIT #0")))
+    assert len(cpu_splits) <= n_graphs, cpu_splits[:6]
+    assert_within_reference_self_consistency(gpu, cpu, others, "qwen2-72b shapes, Q4_K_M fallback mix")
 
 
 @pytest.mark.parametrize("ngl", [0, 1, 2])
