@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from refutil import (F16, F32, Q4_0, Q4_K, Q5_K, Q6_K, Q8_0, Q8_K, ACT_TYPE, WEIGHT_TYPES, nmse, oracle, orc_dequant,
+from refutil import (F16, F32, Q4_0, Q5_0, Q4_K, Q5_K, Q6_K, Q8_0, Q8_K, ACT_TYPE, WEIGHT_TYPES, nmse, oracle, orc_dequant,
                      orc_mul_mat, orc_quantize_act, ptr, rand_blocks, row_bytes)
 
 pytestmark = pytest.mark.gpu
