@@ -642,9 +642,10 @@ def test_flash_attn_tensor_core(b200, kvt, nh, nhkv, nt, nkv, past):
     err = np.abs(got - truth).max() / np.abs(truth).max()
     assert err <= 2e-3, err                                       # observed: 8e-5 .. 5e-4
     assert nmse(got, truth) < 1e-6, nmse(got, truth)
-    # vs the CPU oracle: its F16-V path accumulates in fp16 (ops.cpp:8278-8340) and is the noisier side at long n_kv
-    assert nmse(got, want) < (1e-3 if kvt == F16 else 1e-6), nmse(got, want)
-    assert nmse(got, truth) <= nmse(want, truth) or kvt == Q8_0
+    # vs the CPU oracle, which is the noisier side in both modes: its F16-V path accumulates in fp16 (ops.cpp:8278-8340) and
+    # its Q8_0-K path quantises the query row to int8 first (ops.cpp:8210-8222) where the tensor-core kernel keeps f16 queries
+    assert nmse(got, want) < (1e-3 if kvt == F16 else 1e-4), nmse(got, want)
+    assert nmse(got, truth) <= nmse(want, truth)
 
 
 # ------------------------------------------------------------------ rows that are not a multiple of 256 elements (Qwen2-72B ffn_down)

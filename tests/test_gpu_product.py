@@ -146,26 +146,41 @@ def rel_rows(a, b):
     return [float(np.abs(x - y).max() / np.abs(y).max()) for x, y in zip(a["logits"], b["logits"])]
 
 
+NOISE_FACTOR = 2.0   # ours may be this many times the worst deviation among ggml-cpu's own builds (two builds are a small sample of that noise)
+
+
 def assert_within_reference_self_consistency(gpu, cpu, others, what):
-    """our deviation from ggml-cpu (the build the registry picks on this host) is bounded by the deviation of ggml-cpu's other
-    builds from it; the greedy token must agree wherever all CPU builds agree with each other (compared while all runs share a
-    history)"""
+    """Our deviation from ggml-cpu (the build the registry picks on this host) is bounded by NOISE_FACTOR x the deviation of
+    ggml-cpu's other builds from it, over the rows where all runs still share a token history; and the greedy token must be
+    ggml-cpu's wherever ggml-cpu's top-1 / top-2 logit gap exceeds twice that bound (a per-logit deviation d can only flip an
+    argmax whose gap is below 2d — the synthetic random-weight models have nearly flat logits, so such ties do occur)."""
     ours = rel_rows(gpu, cpu)
     refs = [rel_rows(o, cpu) for o in others]
     ref = [max(r[i] for r in refs) for i in range(len(ours))]
-    bound = max(1e-3, max(ref))
-    print(f"{what}: ours worst {max(ours):.2e} (rows <= 1e-3: {sum(r <= 1e-3 for r in ours)}/{len(ours)}); ggml-cpu build-vs-build worst {max(ref):.2e}")
     per_step = max(1, cpu["verify_batch"])
-    for i, (o, r) in enumerate(zip(ours, ref)):
-        step = 0 if i == 0 else 1 + (i - 1) // per_step       # row 0: the prompt's last token; then `verify` rows per decode step
-        if gpu["tokens"][:step] != cpu["tokens"][:step] or any(o2["tokens"][:step] != cpu["tokens"][:step] for o2 in others):
-            break                                      # histories diverged (already at the CPU-vs-CPU level): rows no longer comparable
-        assert o <= bound, f"{what}: row {i}: {o:.3e} > bound {bound:.3e} (ggml-cpu's own builds differ by {r:.3e} here)"
+    step_of = lambda i: 0 if i == 0 else 1 + (i - 1) // per_step   # row 0: the prompt's last token; then `verify` rows per decode step
+    shared = lambda runs, step: all(r["tokens"][:step] == cpu["tokens"][:step] for r in runs)
+    rows_ref = [i for i in range(len(ours)) if shared(others, step_of(i))]           # rows where the CPU builds are comparable with each other
+    rows_ours = [i for i in rows_ref if shared([gpu], step_of(i))]
+    noise = max([ref[i] for i in rows_ref] or [0.0])
+    bound = max(1e-3, NOISE_FACTOR * noise)
+    print(f"{what}: comparable rows {len(rows_ours)}/{len(ours)}; ours worst {max([ours[i] for i in rows_ours] or [0]):.2e} "
+          f"(rows <= 1e-3: {sum(ours[i] <= 1e-3 for i in rows_ours)}); ggml-cpu build-vs-build worst {noise:.2e}; first rows ours/ref: "
+          + " ".join(f"{ours[i]:.1e}/{ref[i]:.1e}" for i in range(min(4, len(ours)))))
+    assert rows_ours, what
+    for i in rows_ours:
+        assert ours[i] <= bound, f"{what}: row {i}: {ours[i]:.3e} > bound {bound:.3e} (ggml-cpu's own builds differ by {ref[i]:.3e} here)"
     for i, (g, c) in enumerate(zip(gpu["tokens"], cpu["tokens"])):
-        if any(o2["tokens"][i] != c for o2 in others):
+        if not shared(others + [gpu], i):
             break
-        assert g == c, f"{what}: token {i}: {g} vs {c} although all ggml-cpu builds agree"
-    return max(ours), max(ref)
+        row = cpu["logits"][0 if i == 0 else i * per_step]
+        top = np.partition(row, -2)[-2:]
+        gap = float((top[1] - top[0]) / np.abs(row).max())
+        assert g == c or gap <= 2 * bound, f"{what}: token {i}: {g} vs {c} with a top-2 gap of {gap:.3e} (> 2 x {bound:.3e})"
+        if g != c:
+            print(f"{what}: token {i} differs inside a near-tie (gap {gap:.2e} <= 2 x bound {bound:.2e})")
+            break
+    return max([ours[i] for i in rows_ours]), noise
 
 
 STRICT_CASES = [
@@ -247,12 +262,12 @@ def test_embeddings_output(tmp_path, tmp_path_factory):
     gpu = drv(gguf, str(tmp_path / "gpu"), True, gen=5, embeddings=True)
     assert gpu["embd"].shape == cpu["embd"].shape and cpu["embd"].size > 0
     others = cpu_builds(tmp_path, tmp_path_factory, gguf, gen=5, embeddings=True)
-    rel = float(np.abs(gpu["embd"] - cpu["embd"]).max() / np.abs(cpu["embd"]).max())
-    ref = max(float(np.abs(o["embd"] - cpu["embd"]).max() / np.abs(cpu["embd"]).max()) for o in others)
-    n0 = gpu["embd"].size // 5                              # the first output row: the prompt's last token
-    rel0 = float(np.abs(gpu["embd"][:n0] - cpu["embd"][:n0]).max() / np.abs(cpu["embd"][:n0]).max())
-    print(f"embeddings: ours {rel:.2e} (first row {rel0:.2e}), ggml-cpu build-vs-build {ref:.2e}")
-    assert rel <= max(1e-3, ref), (rel, ref)
+    n0 = gpu["embd"].size // 5                              # the first output row (the prompt's last token): no token history involved
+    dev = lambda r: float(np.abs(r["embd"][:n0] - cpu["embd"][:n0]).max() / np.abs(cpu["embd"][:n0]).max())
+    rel0, ref0 = dev(gpu), max(dev(o) for o in others)
+    print(f"embeddings, first row: ours {rel0:.2e}, ggml-cpu build-vs-build {ref0:.2e}")
+    assert np.isfinite(gpu["embd"]).all()
+    assert rel0 <= max(1e-3, NOISE_FACTOR * ref0), (rel0, ref0)
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs >= 2 GPUs in one box")
