@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/b200_ops.h"
 
@@ -156,5 +157,22 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void * gsrc, uint32_t byt
 // programmatic dependent launch (guide G9): overlap this kernel's prologue with the previous tail
 __device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- B200_TRACE=1: in-kernel timeline of the decode chain (tools/trace_decode.py).  A traced CTA claims a record with one atomic
+// and stamps %globaltimer at entry / exit plus clock64 at the points in between; records are read back per source file.
+#define B200_TRACE_SLOTS 4096
+#define B200_TRACE_WORDS 12
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define B200_TRACE_DECL(name) static __device__ unsigned long long name##_buf[B200_TRACE_SLOTS][B200_TRACE_WORDS]; static __device__ unsigned int name##_n;
+#define B200_TRACE_OPEN(name, on, tr) unsigned long long * tr = nullptr; \
+    if (on) { const unsigned int i_ = atomicAdd(&name##_n, 1u); if (i_ < B200_TRACE_SLOTS) { tr = name##_buf[i_]; tr[0] = gtime_ns(); tr[1] = (unsigned long long)clock64(); } }
+#define B200_TRACE_AT(tr, i) do { if (tr) tr[i] = (unsigned long long)clock64(); } while (0)
+#define B200_TRACE_CLOSE(tr, i) do { if (tr) { tr[i] = (unsigned long long)clock64(); tr[i + 1] = gtime_ns(); } } while (0)
+// host side of one file's trace: copies the records out and resets the counter; returns the number of records
+#define B200_TRACE_DUMP(fn, name) extern "C" __attribute__((visibility("default"))) int fn(unsigned long long * out, int max_records) { \
+    unsigned int n = 0; cudaMemcpyFromSymbol(&n, name##_n, sizeof(n)); if (n > B200_TRACE_SLOTS) n = B200_TRACE_SLOTS; if ((int)n > max_records) n = (unsigned int)max_records; \
+    if (n) cudaMemcpyFromSymbol(out, name##_buf, (size_t)n * B200_TRACE_WORDS * sizeof(unsigned long long)); \
+    const unsigned int z = 0; cudaMemcpyToSymbol(name##_n, &z, sizeof(z)); return (int)n; }
+static inline bool b200_trace_on() { static const bool on = getenv("B200_TRACE") != nullptr; return on; }
 
 #endif // __CUDACC__

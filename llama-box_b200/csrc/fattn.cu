@@ -24,6 +24,8 @@
 #endif
 #define FA_MAX_SPLITS 64
 
+B200_TRACE_DECL(g_fa_trace)
+
 
 __device__ __forceinline__ void unpack_h8(const uint4 & r, float (&f)[8]) {
     const __half2 * h = (const __half2 *)&r;
@@ -52,6 +54,7 @@ struct FaFuse {
     // cos/sin table of this token: the same for every layer, so the first attention launch of a token computes it (every CTA for
     // itself, one CTA also stores it) and the other layers just load 512 bytes: tab_mode 0 = compute (+ store if rope_tab), 1 = load
     float * rope_tab; int tab_mode;
+    int trace;                                  // B200_TRACE: timeline records (common.cuh)
 };
 // elements e0..e0+7 of one head, roped (ops.cpp:6088-6150 pairing; the table holds cos/sin already scaled) — in three steps so
 // that the global loads can be issued long before the table is ready: raw8 (the elements), partner8 (NEOX: the other half of
@@ -132,6 +135,8 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
     // the previous kernel (the QKV projection) is still running — a memory round trip off the token's critical path.
     uint4 kpre[MAXIT], vpre[MAXIT]; float kdpre[MAXIT], vdpre[MAXIT];
     int kcell = -1, vcell = -1, tok_pos = 0;
+    B200_TRACE_OPEN(g_fa_trace, fu.trace && threadIdx.x == 0 && tok == 0 && ((split == 0 && tile == 0) || (split == n_splits - 1 && tile == (int)gridDim.y - 1)), tr)
+    if (tr) { tr[8] = ((unsigned long long)split << 48) | ((unsigned long long)(unsigned)n_kv << 16) | (unsigned)n_splits; tr[9] = 0; }
     auto load_kv = [&](int p, uint4 & kr, uint4 & vr, float & kd, float & vd) {
         const uint8_t * krow = kc + (int64_t)p * k_rs + (int64_t)hk * k_hs;
         const uint8_t * vrow = vc + (int64_t)p * v_rs + (int64_t)hk * v_hs;
@@ -151,8 +156,10 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
             if (p < p_end) load_kv(p, kpre[it], vpre[it], kdpre[it], vdpre[it]);
         }
     }
+    B200_TRACE_AT(tr, 2);                     // first K / V chunk requested
     if (fu.early_trigger) pdl_trigger();      // B200_FA_EARLY_TRIGGER=1: the next kernel may prime its weight ring during the attention — measured slower (its burst delays our loads)
     pdl_wait();
+    B200_TRACE_AT(tr, 3);                     // QKV projection complete
     float qraw[G][8], qpar[G][8];
     if (fu.enabled) {
         // this token's query heads: issue the loads now, rope them once the table is in shared memory
@@ -189,6 +196,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         }
     }
 
+    B200_TRACE_AT(tr, 4);                     // rope table + this token's K / V staged
     // ---- query slices: q8[g][8] as f32 (f16-rounded) or int8 + scale -------------------------
     float qf[G][8]; int qi[G][2]; float qd[G]; float slope[G];
 #pragma unroll
@@ -316,6 +324,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         }
     }
 
+    B200_TRACE_AT(tr, 5);                     // positions of this split done (warp 0)
     // ---- merge the PPW position groups of the warp, then the warps, then write ------------------
     __shared__ float sM[FA_WARPS][G], sL[FA_WARPS][G];
     __shared__ float sA[FA_WARPS][G][D];
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         if (n_splits == 1) {
             dst[((int64_t)tok * n_head + h) * D + e] = a * (1.0f / l);            // ops.cpp:8390-8392
         } else {
-            float * wp = ws + (((int64_t)split * gridDim.z + tok) * n_head + h) * (D + 2);
+            float * wp = ws + (((int64_t)split * gridDim.z + tok) * n_head + h) * (D + 4);     // rows of D + 4 floats: 16-byte aligned for the merge
             wp[e] = a;
             if (e == 0) { wp[D] = Mn; wp[D + 1] = l; }
         }
@@ -361,54 +370,80 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         // the last CTA of this (token, head tile) to finish merges all splits (replaces the separate
         // flash_attn_combine_results launch, fattn-common.cuh:645-701); the counter cleans itself for the next launch
         __shared__ unsigned int s_last;
-        __threadfence();
-        __syncthreads();
+        __syncthreads();                      // every thread's partials are ordered before thread 0's fence (the cooperative-groups grid.sync pattern)
         if (threadIdx.x == 0) {
+            __threadfence();
             const unsigned int prev = atomicAdd(&counters[tok * gridDim.y + tile], 1u);
             s_last = prev == (unsigned int)(n_splits - 1);
             if (s_last) counters[tok * gridDim.y + tile] = 0;
         }
         __syncthreads();
+        B200_TRACE_AT(tr, 6);                 // partials written, completion counted
         if (s_last) {
+            if (tr) tr[9] = 1;
             __threadfence();
-            // phase 1: per-split maxima / sums of this tile's G heads -> scale factors in shared memory
+            // The partial accumulators do not depend on the scale factors: request the first half of them (one float4 per thread and
+            // split — G * D / 4 = 128 items for D = 128) together with the (m, l) pairs, so that the merge costs two memory round trips
+            // instead of one per 8 splits and output (it was 9 us of a 17 us launch at 24 splits)
             __shared__ float s_sc[FA_MAX_SPLITS][G];
-            __shared__ float s_inv[G];
-            const int n_rows = gridDim.z * n_head;
             __shared__ float s_l[FA_MAX_SPLITS][G];
+            __shared__ float s_m2[FA_MAX_SPLITS][G];
+            const int n_rows = gridDim.z * n_head;
+            constexpr int NB = 24;                                  // splits per batch of loads (n_kv 768 -> 24 splits: one batch)
+            constexpr int items = G * D / 4;
+            const int64_t sstride = (int64_t)n_rows * (D + 4) / 4;    // float4 units between the same row of consecutive splits
+            const int it0 = threadIdx.x;
+            const bool have0 = it0 < items;
+            const int g0 = it0 / (D / 4), e0 = it0 % (D / 4);
+            const float4 * src0 = (const float4 *)(ws + (int64_t)(tok * n_head + h0 + g0) * (D + 4)) + e0;
+            float4 v[NB];
+#pragma unroll
+            for (int j = 0; j < NB; j++) { v[j] = make_float4(0, 0, 0, 0); if (have0 && j < n_splits) v[j] = __ldcg(src0 + j * sstride); }
             for (int idx = threadIdx.x; idx < n_splits * G; idx += FA_WARPS * 32) {
                 const int sp = idx / G, g = idx % G;
-                const float2 ml = __ldcg((const float2 *)(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 2) + D));   // every (m, l) pair in one round trip
+                const float2 ml = __ldcg((const float2 *)(ws + ((int64_t)sp * n_rows + tok * n_head + h0 + g) * (D + 4) + D));   // every (m, l) pair in one round trip
                 s_sc[sp][g] = ml.x; s_l[sp][g] = ml.y;
             }
             __syncthreads();
-            if (threadIdx.x < G) {
-                const int g = threadIdx.x;
+            // scale factors: one (split, head) per thread, each finding its head's maximum itself (independent broadcast LDS) — a serial
+            // loop of one thread per head over the splits cost 1 us
+            for (int idx = threadIdx.x; idx < n_splits * G; idx += FA_WARPS * 32) {
+                const int sp = idx / G, g = idx % G;
                 float Mn = -INFINITY;
-                for (int sp = 0; sp < n_splits; sp++) Mn = fmaxf(Mn, s_sc[sp][g]);
-                float l = 0.0f;
-                for (int sp = 0; sp < n_splits; sp++) {
-                    const float m = s_sc[sp][g];
-                    const float sc = m == -INFINITY ? 0.0f : expf(m - Mn);
-                    l += s_l[sp][g] * sc;
-                    s_sc[sp][g] = sc;
-                }
-                s_inv[g] = 1.0f / l;
+                for (int q = 0; q < n_splits; q++) Mn = fmaxf(Mn, s_sc[q][g]);
+                const float m = s_sc[sp][g];
+                s_m2[sp][g] = m == -INFINITY ? 0.0f : expf(m - Mn);
             }
             __syncthreads();
-            // phase 2: independent, coalesced loads of the partial accumulators
-            for (int idx = threadIdx.x; idx < G * D; idx += FA_WARPS * 32) {
-                const int g = idx / D, e = idx % D;
+            for (int it = it0; it < items; it += FA_WARPS * 32) {
+                const int g = it / (D / 4), e4 = it % (D / 4);
                 const int row = tok * n_head + h0 + g;
-                float a = 0.0f;
-#pragma unroll 8
-                for (int sp = 0; sp < n_splits; sp++) a = fmaf(__ldcg(ws + ((int64_t)sp * n_rows + row) * (D + 2) + e), s_sc[sp][g], a);
-                dst[(int64_t)row * D + e] = a * s_inv[g];
+                const float4 * src = (const float4 *)(ws + (int64_t)row * (D + 4)) + e4;
+                float4 a = make_float4(0, 0, 0, 0);
+                float l = 0.0f;                                     // every thread sums its head's denominators itself (same order as the accumulators)
+                for (int sp0 = 0; sp0 < n_splits; sp0 += NB) {
+                    if (sp0 > 0 || it != it0) {
+#pragma unroll
+                        for (int j = 0; j < NB; j++) if (sp0 + j < n_splits) v[j] = __ldcg(src + (int64_t)(sp0 + j) * sstride);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; j++) {
+                        if (sp0 + j < n_splits) {
+                            const float sc = s_m2[sp0 + j][g];
+                            a.x = fmaf(v[j].x, sc, a.x); a.y = fmaf(v[j].y, sc, a.y); a.z = fmaf(v[j].z, sc, a.z); a.w = fmaf(v[j].w, sc, a.w);
+                            l += s_l[sp0 + j][g] * sc;
+                        }
+                    }
+                }
+                const float inv = 1.0f / l;
+                *(float4 *)(dst + (int64_t)row * D + e4 * 4) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
             }
         }
     }
     if (!fu.early_trigger) pdl_trigger();
+    B200_TRACE_CLOSE(tr, 10);
 }
+B200_TRACE_DUMP(b200_fa_trace_dump, g_fa_trace)
 
 // KV splits: ~2 CTAs of 128 threads per SM, at least 32 positions per split, at most FA_MAX_SPLITS
 static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_len) {
@@ -428,14 +463,14 @@ static int fa_splits(int64_t n_tiles, int64_t n_tok, int64_t n_kv, int * split_l
 }
 
 // workspace = [FA_COUNTER_BYTES of u32 completion counters, one per (token, head tile)] [split partials
-// [splits][n_tok][n_head][dv + 2] f32].  The counter region sits at a FIXED offset so that calls with different shapes
+// [splits][n_tok][n_head][dv + 4] f32].  The counter region sits at a FIXED offset so that calls with different shapes
 // never reinterpret old partials as counters; it must be zero-initialised ONCE by the caller (the counters clean
 // themselves after every launch).
 #define FA_COUNTER_BYTES (256 * 1024)
 static int64_t fa_partial_bytes(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
     int sl = 0;
     int64_t maxs = fa_splits((n_head + 3) / 4, n_tok, n_kv, &sl);      // fewest head tiles (G = 4) -> most splits: an upper bound
-    return (maxs * n_tok * n_head * (dv + 2) * (int64_t)sizeof(float) + 255) & ~(int64_t)255;
+    return (maxs * n_tok * n_head * (dv + 4) * (int64_t)sizeof(float) + 255) & ~(int64_t)255;
 }
 extern "C" int64_t b200_flash_attn_workspace(int64_t dv, int64_t n_head, int64_t n_tok, int64_t n_kv) {
     return FA_COUNTER_BYTES + fa_partial_bytes(dv, n_head, n_tok, n_kv) + 256;
@@ -534,7 +569,7 @@ extern "C" int b200_rope_kv_flash_attn2(const float * q_src, float * q_dst, cons
     if (((uintptr_t)q_src | (uintptr_t)q_dst | (uintptr_t)k_new | (uintptr_t)v_new | (uintptr_t)rope_tab) & 15) { b200_set_error("rope_kv_flash_attn: 16-byte alignment required"); return B200_ERR_INVALID; }
     FaFuse fu; memset(&fu, 0, sizeof(fu));
     fu.q_src = q_src; fu.q_dst = q_dst; fu.k_new = k_new; fu.v_new = v_new; fu.pos = pos; fu.ff = ff; fu.k_ids = k_ids; fu.v_ids = v_ids;
-    fu.rp = rope_host_params(p); fu.enabled = 1; fu.early_trigger = fa_early_trigger();
+    fu.rp = rope_host_params(p); fu.enabled = 1; fu.early_trigger = fa_early_trigger(); fu.trace = b200_trace_on() ? 1 : 0;
     fu.rope_tab = rope_tab; fu.tab_mode = rope_tab ? tab_mode : 0;
     return fa_dispatch(q_dst, hd * n_head, hd, k_cache, k_rs, k_hs, v_cache, v_rs, v_hs, mask, 0, dst, kv_type, hd, hd, n_head, n_head_kv, 1, n_kv,
                        scale, max_bias, softcap, workspace, stream, fu);

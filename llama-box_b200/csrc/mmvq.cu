@@ -20,7 +20,12 @@
 #include "common.cuh"
 #include "actquant.cuh"
 
+#ifndef MMV_WARPS
 #define MMV_WARPS 16
+#endif
+#ifndef MMV_CTAS_PER_SM
+#define MMV_CTAS_PER_SM 1      // 8 warps x 2 CTAs of 108 KB (so that the next launch primes its ring next to this one) was measured: 300 tok/s instead of 400
+#endif
 #define MMV_MAX_MATS 4
 #define MMV_MAX_STAGES 8
 
@@ -63,9 +68,11 @@ struct MmvArgs {
     float *       y_out;        // optional f32 copy of the (normalised) activations, written by CTA 0
     int64_t       x_col_stride;
     float         eps;
-    int32_t       _pad2;
+    int32_t       trace;      // B200_TRACE: CTA 0 and the last CTA record a timeline (common.cuh)
     int64_t       k_valid;      // elements that exist in x per column (<= k; the rest of the padded weight rows are zero blocks)
 };
+
+B200_TRACE_DECL(g_mmv_trace)
 
 // ---- activation view in shared memory --------------------------------------------------------
 struct ActView { const uint8_t * qs; const float * d; const int16_t * bs; };
@@ -442,20 +449,22 @@ __device__ __forceinline__ void slot_dispatch(int t0, int t1, const uint8_t * s0
 struct RowGroup { const uint8_t * row0, * row1; int t0, t1, nb0, nb1; int64_t r0; int rows; };
 
 template <int MODE>
-__device__ __forceinline__ RowGroup group_info(const MmvArgs & args, int g, MmvMat & M) {
+__device__ __forceinline__ RowGroup group_info(const MmvArgs & args, int g, const MmvMat * & Mp) {
     RowGroup rg;
     if (MODE == MMV_MODE_SWIGLU) {
         const MmvMat & gt = args.mat[0]; const MmvMat & up = args.mat[1];
-        M = gt;
+        Mp = &args.mat[0];
         rg.t0 = gt.type; rg.t1 = up.type; rg.nb0 = gt.nb; rg.nb1 = up.nb;
         rg.row0 = gt.W + (int64_t)g * gt.rb; rg.row1 = up.W + (int64_t)g * up.rb;
         rg.r0 = g; rg.rows = 2;
     } else {
-        M = args.mat[0];
+        int mi = 0;                                   // the matrix is addressed inside the (constant-bank) parameter block: no local copy
         if (args.n_mats > 1) {
 #pragma unroll
-            for (int q = 1; q < MMV_MAX_MATS; q++) if (q < args.n_mats && g >= args.mat[q].pair0) M = args.mat[q];
+            for (int q = 1; q < MMV_MAX_MATS; q++) if (q < args.n_mats && g >= args.mat[q].pair0) mi = q;
         }
+        const MmvMat & M = args.mat[mi];
+        Mp = &M;
         const int R = args.rows_per_unit;
         rg.r0 = (int64_t)(g - M.pair0) * R;
         rg.rows = (int)(M.m - rg.r0 < R ? M.m - rg.r0 : R);
@@ -466,7 +475,10 @@ __device__ __forceinline__ RowGroup group_info(const MmvArgs & args, int g, MmvM
 }
 
 // bytes of `nsb8` segments (8 super-blocks / 64 small blocks each) of one row of `type`
+template <int TT>
 __device__ __forceinline__ uint32_t part_bytes(int type, int nchunks) {
+    if (TT >= 0) type = TT;                           // uniform launch: the switch folds away
+    if (TT == -2) return type == B200_TYPE_Q4_K ? nchunks / 8 * 144 : nchunks / 8 * 210;
     switch (type) {
         case B200_TYPE_Q4_0: return nchunks * 18;
         case B200_TYPE_Q5_0: return nchunks * 22;
@@ -477,7 +489,18 @@ __device__ __forceinline__ uint32_t part_bytes(int type, int nchunks) {
     }
 }
 // lane 0: copy chunks [c0, c0 + n) of a row into the slot, laid out like a short row of n chunks
+template <int TT>
 __device__ __forceinline__ void issue_part(int type, uint8_t * dst, const uint8_t * row, int64_t nb, int c0, int n, uint64_t * bar) {
+    if (TT >= 0) type = TT;                           // uniform launch: one case survives (13 bulk copies x 4 call sites otherwise)
+    if (TT == -2) {                                   // Q4_K or Q6_K only
+        if (type == B200_TYPE_Q4_K) { bulk_g2s(dst, row + (int64_t)(c0 >> 3) * 144, (n >> 3) * 144, bar); return; }
+        const int64_t s0 = c0 >> 3; const int ns = n >> 3;
+        bulk_g2s(dst,            row + s0 * 128,           ns * 128, bar);
+        bulk_g2s(dst + ns * 128, row + nb * 128 + s0 * 64, ns * 64,  bar);
+        bulk_g2s(dst + ns * 192, row + nb * 192 + s0 * 16, ns * 16,  bar);
+        bulk_g2s(dst + ns * 208, row + nb * 208 + s0 * 2,  ns * 2,   bar);
+        return;
+    }
     switch (type) {
         case B200_TYPE_Q4_K: bulk_g2s(dst, row + (int64_t)(c0 >> 3) * 144, (n >> 3) * 144, bar); break;
         case B200_TYPE_Q5_K: bulk_g2s(dst, row + (int64_t)(c0 >> 3) * 176, (n >> 3) * 176, bar); break;
@@ -504,8 +527,15 @@ __device__ __forceinline__ void issue_part(int type, uint8_t * dst, const uint8_
     }
 }
 
-template <int NCOLS, int TT, int MODE>
-__global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_constant__ MmvArgs args) {
+// ACT >= 0 selects the LEAN decode instance: one column, K-quant weights only (q8_K activations), whole 2048-element segments, row
+// pairs, the activation source fixed at compile time.  Same arithmetic as the general instance, a fraction of its code: a decode
+// token runs ~160 launches of ~10 us, and every one of them starts with a cold instruction cache (the general instances are ~100 KB
+// of SASS each; the trace of tools/trace_decode.py shows 1.5-4 us from kernel entry to the first bulk copy).
+template <int NCOLS, int TT, int MODE, int ACT = -1>
+__global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(const __grid_constant__ MmvArgs args) {
+    constexpr bool LEAN = ACT >= 0;
+    const int act_source = LEAN ? ACT : args.act_source;
+    const int ncols_rt = LEAN ? 1 : args.ncols;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t act_bar;
     __shared__ __align__(8) uint64_t full_bar[MMV_WARPS][MMV_MAX_STAGES];
@@ -516,6 +546,8 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
     uint8_t * act_s1 = smem + args.act_bytes[0];
     uint8_t * ring   = smem + ((args.act_bytes[0] + args.act_bytes[1] + 127) & ~127) + (size_t)warp * S * args.slot_bytes;
 
+    B200_TRACE_OPEN(g_mmv_trace, args.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), tr)
+    if (tr) { tr[8] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)(unsigned)args.total_pairs << 16) | (unsigned long long)((args.mat[0].type & 0xff) << 8) | (unsigned)args.n_mats; tr[9] = (unsigned long long)args.k; }
     if (tid == 0) mbar_init(&act_bar, 1);
     if (lane == 0) for (int s = 0; s < S; s++) mbar_init(&full_bar[warp][s], 1);
     mbar_fence_init();
@@ -528,15 +560,15 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
 
     int ig = gw, ip = 0, islot = 0;                               // issue cursor: group, part, slot
     auto issue_next = [&]() {                                     // lane 0 only
-        MmvMat M;
-        const RowGroup rg = group_info<MODE>(args, ig, M);
+        const MmvMat * Mp;
+        const RowGroup rg = group_info<MODE>(args, ig, Mp);
         const int c0 = ip * G * segc;
         const int n = (ip == P - 1 ? nseg - ip * G : G) * segc;
         uint8_t * dst = ring + (size_t)islot * args.slot_bytes;
-        const uint32_t b0 = part_bytes(rg.t0, n), b1 = (MODE == MMV_MODE_SWIGLU || rg.rows > 1) ? part_bytes(rg.t1, n) : 0;
+        const uint32_t b0 = part_bytes<TT>(rg.t0, n), b1 = (MODE == MMV_MODE_SWIGLU || rg.rows > 1) ? part_bytes<TT>(rg.t1, n) : 0;
         mbar_expect_tx(&full_bar[warp][islot], b0 + b1);
-        issue_part(rg.t0, dst, rg.row0, rg.nb0, c0, n, &full_bar[warp][islot]);
-        if (b1) issue_part(rg.t1, dst + args.row_stride, rg.row1, rg.nb1, c0, n, &full_bar[warp][islot]);
+        issue_part<TT>(rg.t0, dst, rg.row0, rg.nb0, c0, n, &full_bar[warp][islot]);
+        if (b1) issue_part<TT>(rg.t1, dst + args.row_stride, rg.row1, rg.nb1, c0, n, &full_bar[warp][islot]);
         if (++ip == P) { ip = 0; ig += TW; }
         if (++islot == S) islot = 0;
     };
@@ -546,12 +578,14 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
     // norm weights are parameters too: fetch this warp's first block before waiting for the previous kernel (otherwise a
     // cold DRAM access sits between the rms_norm reduction and the quantisation, on every CTA's critical path)
     float4 nwa = make_float4(1.0f, 1.0f, 1.0f, 1.0f), nwb = nwa;
-    if (args.act_source == 2 && args.norm_w && warp < (int)(args.k >> 8)) {
+    if (act_source == 2 && args.norm_w && warp < (int)(args.k >> 8)) {
         nwa = __ldg((const float4 *)(args.norm_w + warp * 256 + lane * 8)); nwb = __ldg((const float4 *)(args.norm_w + warp * 256 + lane * 8 + 4));
     }
+    B200_TRACE_AT(tr, 2);                                          // ring primed
     pdl_trigger();
     pdl_wait();
-    if (args.act_source == 0) {
+    B200_TRACE_AT(tr, 3);                                          // previous kernel complete
+    if (act_source == 0) {
         if (tid == 0) {
             mbar_expect_tx(&act_bar, (uint32_t)(args.act_bytes[0] + args.act_bytes[1]));
             if (args.act_bytes[0]) bulk_g2s(act_s0, args.act[0], (uint32_t)args.act_bytes[0], &act_bar);
@@ -563,10 +597,10 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
         // [rms_norm * w ->] q8_K / q8_0 exactly as the CPU oracle quantises (no separate kernels, no HBM round trip)
         __shared__ double red[MMV_WARPS];
         const int nblk = (int)(args.k >> 8);
-        for (int col = 0; col < args.ncols; col++) {
+        for (int col = 0; col < ncols_rt; col++) {
             const float * xc = args.x + (int64_t)col * args.x_col_stride;
             float scale = 1.0f;
-            if (args.act_source == 2) {
+            if (act_source == 2) {
                 double acc2 = 0.0;                                  // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
                 for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
                     float4 a = make_float4(0, 0, 0, 0), b = a;
@@ -582,45 +616,104 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
                 for (int i = 0; i < MMV_WARPS; i++) t += red[i];    // every thread: same order, same value — no second barrier
                 scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k_valid), args.eps)));
             }
-            for (int blk = warp; blk < nblk; blk += MMV_WARPS) {
-                const int64_t i = (int64_t)blk * 256 + lane * 8;
-                float4 a = make_float4(0, 0, 0, 0), b = a;
-                const bool have = i < args.k_valid;                 // padded weight layout: x ends at k_valid
-                if (have) { a = *(const float4 *)(xc + i); b = *(const float4 *)(xc + i + 4); }
-                float v[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
-                if (args.act_source == 2) {
+            // a warp owns blocks warp, warp + 16, ...: the loads of up to four of them are issued before the first is quantised, so a long
+            // row (n_ff = 14336: 3.5 blocks per warp) costs one memory round trip instead of one per block (4 us -> the k = 4096 figure)
+            for (int b0 = warp; b0 < nblk; b0 += MMV_WARPS * 4) {
+                float4 xa[4], xb[4];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = __fmul_rn(v[j], scale);
-                    if (args.norm_w && have) {
-                        const bool pre = blk == warp;
-                        const float4 wa = pre ? nwa : *(const float4 *)(args.norm_w + i), wb = pre ? nwb : *(const float4 *)(args.norm_w + i + 4);
-                        v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
-                        v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
+                for (int j = 0; j < 4; j++) {
+                    const int64_t i = (int64_t)(b0 + j * MMV_WARPS) * 256 + lane * 8;
+                    xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j];
+                    if (b0 + j * MMV_WARPS < nblk && i < args.k_valid) { xa[j] = *(const float4 *)(xc + i); xb[j] = *(const float4 *)(xc + i + 4); }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int blk = b0 + j * MMV_WARPS;
+                    if (blk >= nblk) break;
+                    const int64_t i = (int64_t)blk * 256 + lane * 8;
+                    const bool have = i < args.k_valid;                 // padded weight layout: x ends at k_valid
+                    float v[8] = { xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w };
+                    if (act_source == 2) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) v[q] = __fmul_rn(v[q], scale);
+                        if (args.norm_w && have) {
+                            const bool pre = blk == warp;
+                            const float4 wa = pre ? nwa : *(const float4 *)(args.norm_w + i), wb = pre ? nwb : *(const float4 *)(args.norm_w + i + 4);
+                            v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
+                            v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
+                        }
                     }
+                    if (!LEAN && args.y_out && blockIdx.x == 0 && have) {
+                        float * yo = args.y_out + (int64_t)col * args.k + i;
+                        *(float4 *)yo = make_float4(v[0], v[1], v[2], v[3]); *(float4 *)(yo + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                    if (LEAN || args.act_bytes[0]) warp_quant_q8K(v, act_sections(act_s0, 0, args.k, col), blk, lane);
+                    if (!LEAN && args.act_bytes[1]) warp_quant_q80(v, act_sections(act_s1, 1, args.k, col), blk, lane);
                 }
-                if (args.y_out && blockIdx.x == 0 && have) {
-                    float * yo = args.y_out + (int64_t)col * args.k + i;
-                    *(float4 *)yo = make_float4(v[0], v[1], v[2], v[3]); *(float4 *)(yo + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                }
-                if (args.act_bytes[0]) warp_quant_q8K(v, act_sections(act_s0, 0, args.k, col), blk, lane);
-                if (args.act_bytes[1]) warp_quant_q80(v, act_sections(act_s1, 1, args.k, col), blk, lane);
             }
-            if (args.act_source == 2) __syncthreads();             // red / s_scale are reused by the next column
+            if (act_source == 2) __syncthreads();             // red / s_scale are reused by the next column
         }
         __syncthreads();
     }
 
+    B200_TRACE_AT(tr, 4);                                          // activations quantised in shared memory
     const int64_t k = args.k;
     int slot = 0; uint32_t phase = 0;
+    if constexpr (LEAN) {
+        // row pairs, whole segments, one column: nothing to select at run time except (TT == -2) Q4_K or Q6_K per matrix
+#pragma unroll 1
+        for (int g = gw; g < total; g += TW) {
+            const MmvMat * Mp;
+            const RowGroup rg = group_info<MODE>(args, g, Mp);
+            const MmvMat & M = *Mp;
+            float acc[2][1] = { { 0.0f }, { 0.0f } };
+#pragma unroll 1
+            for (int p = 0; p < P; p++) {
+                const int nsegs = p == P - 1 ? nseg - p * G : G;
+                mbar_wait(&full_bar[warp][slot], phase);
+                const uint8_t * s0 = ring + (size_t)slot * args.slot_bytes;
+                const uint8_t * s1 = s0 + args.row_stride;
+                const int lnb = nsegs * 8;
+#pragma unroll 1
+                for (int ls = 0; ls < nsegs; ls++) {
+                    if (MODE == MMV_MODE_SWIGLU) {
+                        // gate row and up row of the same type TT
+                        if (TT == B200_TYPE_Q4_K) slot_dot_q4K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                        else                      slot_dot_q6K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                    } else if (TT == B200_TYPE_Q4_K || (TT == -2 && rg.t0 == B200_TYPE_Q4_K)) {
+                        slot_dot_q4K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                    } else {
+                        slot_dot_q6K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && ig < total) issue_next();
+                if (++slot == S) { slot = 0; phase ^= 1; }
+            }
+            acc[0][0] = warp_sum(acc[0][0]); acc[1][0] = warp_sum(acc[1][0]);
+            if (MODE == MMV_MODE_SWIGLU) {
+                if (lane == 0) M.dst[rg.r0] = __fmul_rn(silu_x86(acc[0][0]), acc[1][0]);
+            } else if (lane < 2) {
+                const int64_t r = rg.r0 + lane;
+                float v = lane == 0 ? acc[0][0] : acc[1][0];
+                if (M.bias)     v += M.bias[r];
+                if (M.residual) v += M.residual[r];
+                M.dst[r] = v;
+            }
+        }
+    } else {
+    bool first_slot = true;
     for (int g = gw; g < total; g += TW) {
-        MmvMat M;
-        const RowGroup rg = group_info<MODE>(args, g, M);
+        const MmvMat * Mp;
+        const RowGroup rg = group_info<MODE>(args, g, Mp);
+        const MmvMat & M = *Mp;
         float acc[2][NCOLS];
 #pragma unroll
         for (int c = 0; c < NCOLS; c++) { acc[0][c] = 0.0f; acc[1][c] = 0.0f; }
         for (int p = 0; p < P; p++) {
             const int nsegs = p == P - 1 ? nseg - p * G : G;
             mbar_wait(&full_bar[warp][slot], phase);
+            if (first_slot) { B200_TRACE_AT(tr, 5); first_slot = false; }   // warp 0's first slot has landed
             const uint8_t * s0 = ring + (size_t)slot * args.slot_bytes;
             const uint8_t * s1 = s0 + args.row_stride;
             // inside the slot a part looks like a short row of nsegs*segc chunks
@@ -656,7 +749,11 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, 1) mmvq_kernel(const __grid_co
             }
         }
     }
+    }
+    B200_TRACE_AT(tr, 6);                                          // warp 0 done
+    if (args.trace) { __syncthreads(); B200_TRACE_CLOSE(tr, 7 + 3); }   // [10] clock, [11] globaltimer: whole CTA done
 }
+B200_TRACE_DUMP(b200_mmv_trace_dump, g_mmv_trace)
 
 // ---- host ------------------------------------------------------------------------------------
 static bool mmv_type_ok(int t) {
@@ -669,16 +766,16 @@ static bool mmv_k_ok(int t, int64_t k) {
     return true;
 }
 
-template <int NCOLS, int TT, int MODE> static int mmv_launch_ntm(const MmvArgs & a, size_t smem, int grid, cudaStream_t st) {
+template <int NCOLS, int TT, int MODE, int ACT = -1> static int mmv_launch_ntm(const MmvArgs & a, size_t smem, int grid, cudaStream_t st) {
     static bool attr[64] = { false };
     int dev = 0; cudaGetDevice(&dev);
-    if (!attr[dev & 63]) { cudaFuncSetAttribute(mmvq_kernel<NCOLS, TT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024); attr[dev & 63] = true; }
+    if (!attr[dev & 63]) { cudaFuncSetAttribute(mmvq_kernel<NCOLS, TT, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024); attr[dev & 63] = true; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MMV_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
-    int s = b200_check(cudaLaunchKernelEx(&cfg, mmvq_kernel<NCOLS, TT, MODE>, a), "mmvq launch");
+    int s = b200_check(cudaLaunchKernelEx(&cfg, mmvq_kernel<NCOLS, TT, MODE, ACT>, a), "mmvq launch");
     if (s != B200_OK) return s;
     b200_count_launch();
     return B200_OK;
@@ -687,7 +784,28 @@ template <int NCOLS, int TT> static int mmv_launch_nt(const MmvArgs & a, int mod
     return mode == MMV_MODE_SWIGLU ? mmv_launch_ntm<NCOLS, TT, MMV_MODE_SWIGLU>(a, smem, grid, st)
                                    : mmv_launch_ntm<NCOLS, TT, MMV_MODE_PLAIN>(a, smem, grid, st);
 }
+// the lean decode instances (see mmvq_kernel): returns -1 if the launch does not qualify
+template <int TT, int MODE> static int mmv_launch_lean_tm(const MmvArgs & a, size_t smem, int grid, cudaStream_t st) {
+    return a.act_source == 2 ? mmv_launch_ntm<1, TT, MODE, 2>(a, smem, grid, st) : mmv_launch_ntm<1, TT, MODE, 1>(a, smem, grid, st);
+}
+static int mmv_launch_lean(const MmvArgs & a, int mode, size_t smem, int grid, cudaStream_t st) {
+    static const bool off = getenv("B200_MMV_NO_LEAN") != nullptr;
+    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k || a.segc != 64 || a.rows_per_unit != 2 || a.act_bytes[1] != 0) return -1;
+    bool q4 = false, q6 = false;
+    for (int i = 0; i < a.n_mats; i++) {
+        if (a.mat[i].type == B200_TYPE_Q4_K) q4 = true; else if (a.mat[i].type == B200_TYPE_Q6_K) q6 = true; else return -1;
+        if (a.mat[i].m & 1) return -1;
+    }
+    if (mode == MMV_MODE_SWIGLU) {
+        if (q4 && q6) return -1;
+        return q4 ? mmv_launch_lean_tm<B200_TYPE_Q4_K, MMV_MODE_SWIGLU>(a, smem, grid, st) : mmv_launch_lean_tm<B200_TYPE_Q6_K, MMV_MODE_SWIGLU>(a, smem, grid, st);
+    }
+    if (q4 && q6) return mmv_launch_lean_tm<-2, MMV_MODE_PLAIN>(a, smem, grid, st);
+    return q4 ? mmv_launch_lean_tm<B200_TYPE_Q4_K, MMV_MODE_PLAIN>(a, smem, grid, st) : mmv_launch_lean_tm<B200_TYPE_Q6_K, MMV_MODE_PLAIN>(a, smem, grid, st);
+}
+
 template <int NCOLS> static int mmv_launch_n(const MmvArgs & a, int mode, size_t smem, int grid, cudaStream_t st) {
+    if (NCOLS == 1) { const int ls = mmv_launch_lean(a, mode, smem, grid, st); if (ls != -1) return ls; }
     int tt = a.mat[0].type;
     for (int i = 1; i < a.n_mats; i++) if (a.mat[i].type != tt) tt = -1;
     switch (tt) {
@@ -742,7 +860,9 @@ static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
     }
     // unit = R rows x G segments: pick the largest G (<= nseg) such that two slots per warp fit; prefer R = 2
     // (activation registers shared by both rows), fall back to R = 1, then to a single slot, then to column halves
-    const size_t budget = 216 * 1024;
+    static const int smem_kb = getenv("B200_MMV_SMEM_KB") ? atoi(getenv("B200_MMV_SMEM_KB")) : (MMV_CTAS_PER_SM == 2 ? 108 : 216);
+    static const int grid_mult = getenv("B200_MMV_GRID_MULT") ? atoi(getenv("B200_MMV_GRID_MULT")) : 1;
+    const size_t budget = (size_t)smem_kb * 1024;
     const size_t act_al = (act + 127) & ~(size_t)127;
     int64_t segb = 0;                                  // bytes of one segment of the widest row type
     for (int i = 0; i < a.n_mats; i++) { const int64_t b = a.mat[i].rb / a.nseg; if (b > segb) segb = b; }
@@ -756,7 +876,12 @@ static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
         }
         return false;
     };
-    bool ok = try_cfg(2, 2);
+    static const int64_t r1_below = getenv("B200_MMV_R1_BELOW") ? atoll(getenv("B200_MMV_R1_BELOW")) : 0;   // experiment: single rows for launches with few units per warp
+    int64_t units2 = 0;
+    for (int i = 0; i < a.n_mats; i++) units2 += (a.mat[i].m + 1) / 2;
+    bool ok = false;
+    if (mode != MMV_MODE_SWIGLU && r1_below > 0 && units2 > (int64_t)b200_sm_count() * MMV_WARPS && units2 < r1_below) ok = try_cfg(1, 2);
+    if (!ok) ok = try_cfg(2, 2);
     if (!ok && mode != MMV_MODE_SWIGLU) ok = try_cfg(1, 2);
     if (!ok) ok = try_cfg(2, 1);
     if (!ok && mode != MMV_MODE_SWIGLU) ok = try_cfg(1, 1);
@@ -794,7 +919,7 @@ static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
     const size_t smem = act_al + (size_t)MMV_WARPS * stages * slot;
     const int sms = b200_sm_count();
     int grid = (a.total_pairs + MMV_WARPS - 1) / MMV_WARPS;
-    if (grid > sms) grid = sms;
+    if (grid > sms * grid_mult) grid = sms * grid_mult;
     if (grid < 1) grid = 1;
     switch (ncols) {
         case 1: return mmv_launch_n<1>(a, mode, smem, grid, st);
@@ -858,5 +983,6 @@ extern "C" int b200_mul_mat_vec_q_launch(const b200_mmv_launch * L, void * strea
     a.act[0] = (const uint8_t *)L->act_q8K; a.act[1] = (const uint8_t *)L->act_q80;
     a.act_source = L->act_source; a.x = L->x; a.x_col_stride = L->x_col_stride; a.norm_w = L->norm_w; a.eps = L->eps; a.y_out = L->y_out;
     a.k_valid = L->k_valid;
+    a.trace = b200_trace_on() ? 1 : 0;
     return mmv_launch(a, L->swiglu ? MMV_MODE_SWIGLU : MMV_MODE_PLAIN, L->ncols, (cudaStream_t)stream);
 }

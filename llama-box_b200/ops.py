@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ops.so")
+LIB_PATH = os.environ.get("B200_OPS_LIB") or os.path.join(_HERE, "libb200ops.so")   # the override exists for A/B builds of one kernel
 
 F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 8, 12, 13, 14
 WEIGHT_TYPES = (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K)
