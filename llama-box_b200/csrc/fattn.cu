@@ -106,7 +106,10 @@ __device__ __forceinline__ void lds_q80_8(const uint8_t * row, int dl, int (&q)[
     q[1] = (int)((uint32_t)p[2] | ((uint32_t)p[3] << 16));
 }
 
-template <int D, int KVT, int G>
+// LEAN = 1: the decode instance of layers 1..n-1 — fused rope / KV store with the cos/sin table loaded (tab_mode 1), a mask, no ALiBi,
+// no soft-cap: the switches below become constants and powf / tanhf / the table computation (sincosf, YaRN) leave the kernel.  These
+// launches last ~10 us and start with a cold instruction cache, so the size of the code they step through is their critical path.
+template <int D, int KVT, int G, int LEAN = 0>
 __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         const float * __restrict__ q, int64_t q_ts, int64_t q_hs,
         const uint8_t * __restrict__ kc, int64_t k_rs, int64_t k_hs,
@@ -114,12 +117,14 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         const uint16_t * __restrict__ mask, int64_t mask_rs,
         float * __restrict__ dst, float * __restrict__ ws, unsigned int * __restrict__ counters,
         int n_head, int n_head_kv, int n_kv, int split_len, int n_splits,
-        float scale, float max_bias, float softcap, float m0, float m1, int nh_log2, const FaFuse fu) {
+        float scale, float max_bias_rt, float softcap_rt, float m0, float m1, int nh_log2, const FaFuse fu) {
+    const float max_bias = LEAN ? 0.0f : max_bias_rt, softcap = LEAN ? 0.0f : softcap_rt;
+    const bool fused = LEAN ? true : (bool)fu.enabled;
     constexpr int LP  = D / 8;          // lanes per position
     constexpr int PPW = 32 / LP;        // positions per warp step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sg = lane / LP, dl = lane % LP;
-    const int split = blockIdx.x, tile = blockIdx.y, tok = blockIdx.z;
+    const int split = blockIdx.x, tile = blockIdx.y, tok = LEAN ? 0 : (int)blockIdx.z;
     const int gq = n_head / n_head_kv;                  // query heads per kv head
     const int h0 = tile * G;                            // first query head of this tile
     const int hk = h0 / gq;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
             load_q80_8(vrow, dl, q2, vd); vr = make_uint4((uint32_t)q2[0], (uint32_t)q2[1], 0, 0);
         }
     };
-    if (fu.enabled) {
+    if (fused) {
         kcell = (int)fu.k_ids[0]; vcell = (int)fu.v_ids[0]; tok_pos = fu.pos[0];
 #pragma unroll
         for (int it = 0; it < MAXIT; it++) {
@@ -161,18 +166,18 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
     pdl_wait();
     B200_TRACE_AT(tr, 3);                     // QKV projection complete
     float qraw[G][8], qpar[G][8];
-    if (fu.enabled) {
+    if (fused) {
         // this token's query heads: issue the loads now, rope them once the table is in shared memory
 #pragma unroll
         for (int g = 0; g < G; g++) { raw8(fu.q_src + (int64_t)(h0 + g) * D, dl * 8, qraw[g]); partner8(fu.q_src + (int64_t)(h0 + g) * D, dl * 8, fu.rp, qpar[g]); }
         // rope table: computed by the first layer's launch (kept for the others), loaded by the rest
-        if (fu.tab_mode == 1) {
+        if (LEAN || fu.tab_mode == 1) {
             if (threadIdx.x < D / 4) *(float4 *)(s_cs + threadIdx.x * 4) = __ldcg((const float4 *)(fu.rope_tab) + threadIdx.x);
         } else {
             rope_table(s_cs, tok_pos, fu.ff, fu.rp, threadIdx.x, FA_WARPS * 32);
         }
         __syncthreads();
-        if (fu.tab_mode == 0 && fu.rope_tab && split == 0 && tile == 0 && threadIdx.x < D / 4) ((float4 *)fu.rope_tab)[threadIdx.x] = *(const float4 *)(s_cs + threadIdx.x * 4);
+        if (!LEAN && fu.tab_mode == 0 && fu.rope_tab && split == 0 && tile == 0 && threadIdx.x < D / 4) ((float4 *)fu.rope_tab)[threadIdx.x] = *(const float4 *)(s_cs + threadIdx.x * 4);
         // this token's K (roped) / V for kv head hk in cache format: only the CTA whose split holds the cell reads it from shared
         // memory, and one CTA per kv head writes the cell — every other CTA skips the staging (and its barrier) altogether
         const bool storer = split == 0 && (h0 % gq) == 0;
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
     for (int g = 0; g < G; g++) {
         const int h = h0 + g;
         float v[8];
-        if (fu.enabled) {
+        if (fused) {
 #pragma unroll
             for (int e = 0; e < 8; e++) v[e] = qraw[g][e];
             rope8(v, qpar[g], dl * 8, s_cs, fu.rp);
@@ -246,20 +251,20 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         for (int e = 0; e < 8; e++) acc[g][e] = 0.0f; }
 
     const unsigned gmask = ((1u << LP) - 1u) << (sg * LP);   // lanes sharing one KV position (converged inside the loop)
-    const uint16_t * mrow = mask ? mask + (int64_t)tok * mask_rs : nullptr;
+    const uint16_t * mrow = (LEAN || mask) ? mask + (int64_t)tok * mask_rs : nullptr;
 
     // positions are visited in chunks of MAXIT per lane group: every load of a chunk (mask, K, V) is issued before any
     // arithmetic, so a chunk costs one memory round trip instead of MAXIT (decode attention is latency-bound: a split is
     // a few dozen positions).  K/V of masked positions are loaded but never used.
     for (int base = base0; base < p_end; base += pstride * MAXIT) {
         float mraw[MAXIT]; uint4 kraw[MAXIT], vraw[MAXIT]; float kdv[MAXIT], vdv[MAXIT];
-        const bool pre = fu.enabled && base == base0;          // first chunk: K / V already in registers
+        const bool pre = fused && base == base0;          // first chunk: K / V already in registers
 #pragma unroll
         for (int it = 0; it < MAXIT; it++) {
             const int p = base + it * pstride;
             mraw[it] = -INFINITY; kraw[it] = make_uint4(0, 0, 0, 0); vraw[it] = kraw[it]; kdv[it] = 0.0f; vdv[it] = 0.0f;
             if (p < p_end) {
-                mraw[it] = mrow ? h2f(__ldg(mrow + p)) : 0.0f;
+                mraw[it] = (LEAN || mrow) ? h2f(__ldg(mrow + p)) : 0.0f;
                 if (pre) { kraw[it] = kpre[it]; vraw[it] = vpre[it]; kdv[it] = kdpre[it]; vdv[it] = vdpre[it]; }
                 else load_kv(p, kraw[it], vraw[it], kdv[it], vdv[it]);
                 if (p == kcell) {                               // this token's own cell: from shared memory (the global cell is being written by another CTA)
@@ -272,17 +277,16 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
                 }
             }
         }
-#pragma unroll
-        for (int it = 0; it < MAXIT; it++) {
-            if (mraw[it] == -INFINITY && max_bias <= 0.0f) continue;       // masked, or beyond the split (uniform inside the LP-lane group)
-            if (base + it * pstride >= p_end) continue;
+        // one position per lane group and step.  The decode instance keeps this loop ROLLED (the K / V registers rotate through
+        // slot 0): unrolled it is 20 KB of straight-line code that every launch fetches cold, rolled it is 5 KB fetched once
+        auto step = [&](const float mr, const uint4 & kr, const uint4 & vr, const float kd, const float vd) {
             float kf[8], vf[8];
             if (KVT == B200_TYPE_F16) {
-                unpack_h8(kraw[it], kf);
-                unpack_h8(vraw[it], vf);
+                unpack_h8(kr, kf);
+                unpack_h8(vr, vf);
             } else {
 #pragma unroll
-                for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)(((e < 4 ? vraw[it].x : vraw[it].y) >> (8 * (e & 3))) & 0xff), vdv[it]);
+                for (int e = 0; e < 8; e++) vf[e] = __fmul_rn((float)(int8_t)(((e < 4 ? vr.x : vr.y) >> (8 * (e & 3))) & 0xff), vd);
             }
             float s[G];
 #pragma unroll
@@ -295,11 +299,11 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
                     for (int o = LP / 2; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
                     s[g] = a;
                 } else {
-                    int is = dp4a_s((int)kraw[it].x, qi[g][0], 0);
-                    is = dp4a_s((int)kraw[it].y, qi[g][1], is);
+                    int is = dp4a_s((int)kr.x, qi[g][0], 0);
+                    is = dp4a_s((int)kr.y, qi[g][1], is);
                     is += __shfl_xor_sync(gmask, is, 1, LP);          // whole 32-element block
                     is += __shfl_xor_sync(gmask, is, 2, LP);
-                    float a = __fmul_rn((float)is, __fmul_rn(kdv[it], qd[g]));   // ggml-cpu/quants.c:305-333
+                    float a = __fmul_rn((float)is, __fmul_rn(kd, qd[g]));   // ggml-cpu/quants.c:305-333
                     a = (dl & 3) == 0 ? a : 0.0f;
 #pragma unroll
                     for (int o = LP / 2; o >= 4; o >>= 1) a += __shfl_xor_sync(gmask, a, o, LP);
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
             for (int g = 0; g < G; g++) {
                 float sv = s[g] * scale;
                 if (softcap != 0.0f) sv = softcap * tanhf(sv);
-                sv += slope[g] * mraw[it];
+                sv += slope[g] * mr;
                 if (sv == -INFINITY) continue;
                 float ms = 1.0f, vs = 1.0f;
                 if (sv > M[g]) { ms = expf(M[g] - sv); M[g] = sv;
@@ -320,6 +324,23 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
 #pragma unroll
                 for (int e = 0; e < 8; e++) acc[g][e] = fmaf(vf[e], vs, acc[g][e]);
                 L[g] = L[g] * ms + vs;
+            }
+        };
+        if constexpr (LEAN) {
+#pragma unroll 1
+            for (int it = 0; it < MAXIT; it++) {
+                const float mr = mraw[0]; const uint4 kr = kraw[0], vr = vraw[0]; const float kd = kdv[0], vd = vdv[0];
+#pragma unroll
+                for (int j = 0; j + 1 < MAXIT; j++) { mraw[j] = mraw[j + 1]; kraw[j] = kraw[j + 1]; vraw[j] = vraw[j + 1]; kdv[j] = kdv[j + 1]; vdv[j] = vdv[j + 1]; }
+                if (mr == -INFINITY || base + it * pstride >= p_end) continue;      // masked, or beyond the split (uniform inside the LP-lane group)
+                step(mr, kr, vr, kd, vd);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < MAXIT; it++) {
+                if (mraw[it] == -INFINITY && max_bias <= 0.0f) continue;       // masked, or beyond the split (uniform inside the LP-lane group)
+                if (base + it * pstride >= p_end) continue;
+                step(mraw[it], kraw[it], vraw[it], kdv[it], vdv[it]);
             }
         }
     }
@@ -372,7 +393,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         __shared__ unsigned int s_last;
         __syncthreads();                      // every thread's partials are ordered before thread 0's fence (the cooperative-groups grid.sync pattern)
         if (threadIdx.x == 0) {
-            __threadfence();
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");       // (__threadfence() is the sequentially-consistent MEMBAR.SC)
             const unsigned int prev = atomicAdd(&counters[tok * gridDim.y + tile], 1u);
             s_last = prev == (unsigned int)(n_splits - 1);
             if (s_last) counters[tok * gridDim.y + tile] = 0;
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
         B200_TRACE_AT(tr, 6);                 // partials written, completion counted
         if (s_last) {
             if (tr) tr[9] = 1;
-            __threadfence();
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
             // The partial accumulators do not depend on the scale factors: request the first half of them (one float4 per thread and
             // split — G * D / 4 = 128 items for D = 128) together with the (m, l) pairs, so that the merge costs two memory round trips
             // instead of one per 8 splits and output (it was 9 us of a 17 us launch at 24 splits)
@@ -389,7 +410,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
             __shared__ float s_l[FA_MAX_SPLITS][G];
             __shared__ float s_m2[FA_MAX_SPLITS][G];
             const int n_rows = gridDim.z * n_head;
-            constexpr int NB = 24;                                  // splits per batch of loads (n_kv 768 -> 24 splits: one batch)
+            constexpr int NB = 12;                                  // splits per batch of loads; the batch loop stays rolled (code size)
             constexpr int items = G * D / 4;
             const int64_t sstride = (int64_t)n_rows * (D + 4) / 4;    // float4 units between the same row of consecutive splits
             const int it0 = threadIdx.x;
@@ -421,6 +442,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, FA_MIN_CTAS) fattn_vec_kernel(
                 const float4 * src = (const float4 *)(ws + (int64_t)row * (D + 4)) + e4;
                 float4 a = make_float4(0, 0, 0, 0);
                 float l = 0.0f;                                     // every thread sums its head's denominators itself (same order as the accumulators)
+#pragma unroll 1
                 for (int sp0 = 0; sp0 < n_splits; sp0 += NB) {
                     if (sp0 > 0 || it != it0) {
 #pragma unroll
@@ -489,6 +511,11 @@ static int fa_launch(const float * q, int64_t q_ts, int64_t q_hs, const void * k
     dim3 grid((unsigned)n_splits, (unsigned)n_tiles, (unsigned)n_tok);
     unsigned int * counters = (unsigned int *)ws;
     if (ws) ws = (float *)((uint8_t *)ws + FA_COUNTER_BYTES);
+    static const bool no_lean = getenv("B200_FA_NO_LEAN") != nullptr;
+    if (!no_lean && fu.enabled && fu.tab_mode == 1 && fu.rope_tab && mask && max_bias == 0.0f && softcap == 0.0f && n_tok == 1) {
+        B200_CUDA(b200_launch_pdl(fattn_vec_kernel<D, KVT, G, 1>, grid, dim3(FA_WARPS * 32), 0, st, q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
+            (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2, fu));
+    } else
     B200_CUDA(b200_launch_pdl(fattn_vec_kernel<D, KVT, G>, grid, dim3(FA_WARPS * 32), 0, st, q, q_ts, q_hs, (const uint8_t *)k, k_rs, k_hs, (const uint8_t *)v, v_rs, v_hs,
         (const uint16_t *)mask, mask_rs, dst, ws, counters, (int)n_head, (int)n_head_kv, (int)n_kv, split_len, n_splits, scale, max_bias, softcap, m0, m1, nh_log2, fu));
     b200_count_launch();
