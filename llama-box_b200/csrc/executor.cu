@@ -204,9 +204,10 @@ struct Runner {
     int mk_flush_rope_only() { return rope_pend.valid ? mk_flush() : B200_OK; }
     // a decode matvec launch as a phase of the persistent kernel (Q4_K / Q6_K, one column, in-kernel activation)
     bool mk_try_mmv(const b200_mmv_launch & L) {
-        // (the persistent kernel's lane-per-super-block loops stream long matrices faster than the per-op kernel: 5.2 vs 4.1 TB/s
-        //  on the 525 MB output matrix — so a lone big matvec always goes there, as a one-phase program)
-        const bool big = L.n_mats == 1 && !L.swiglu && (int64_t)L.mats[0].m * L.k >= ((int64_t)192 << 20) && !ex->env_no_mega && fuse;
+        // (round 1 sent the lone 525 MB output matrix here: 5.2 vs 4.1 TB/s.  With the lean matvec instances the per-op kernel is the
+        //  faster one — 534 vs 521 tok/s — so this is opt-in now: GGML_B200_LMHEAD_MEGAKERNEL=1)
+        static const bool big_on = getenv("GGML_B200_LMHEAD_MEGAKERNEL") != nullptr;
+        const bool big = big_on && L.n_mats == 1 && !L.swiglu && (int64_t)L.mats[0].m * L.k >= ((int64_t)192 << 20) && !ex->env_no_mega && fuse;
         if (!((mega && mega_mmv) || big) || L.ncols != 1 || (L.act_source != 1 && L.act_source != 2) || L.y_out || !mk_phase_ok_k(L.k, L.act_source) || L.n_mats < 1 || L.n_mats > MK_MAX_MATS) return false;
         for (int q = 0; q < L.n_mats; q++) {
             const b200_mmv_desc & d = L.mats[q];

@@ -534,6 +534,7 @@ __device__ __forceinline__ void issue_part(int type, uint8_t * dst, const uint8_
 template <int NCOLS, int TT, int MODE, int ACT = -1>
 __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(const __grid_constant__ MmvArgs args) {
     constexpr bool LEAN = ACT >= 0;
+    constexpr bool B32 = TT == B200_TYPE_Q4_0 || TT == B200_TYPE_Q5_0 || TT == B200_TYPE_Q8_0;   // lean instances of the 32-element block types: q8_0 activations
     const int act_source = LEAN ? ACT : args.act_source;
     const int ncols_rt = LEAN ? 1 : args.ncols;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -647,8 +648,8 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
                         float * yo = args.y_out + (int64_t)col * args.k + i;
                         *(float4 *)yo = make_float4(v[0], v[1], v[2], v[3]); *(float4 *)(yo + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     }
-                    if (LEAN || args.act_bytes[0]) warp_quant_q8K(v, act_sections(act_s0, 0, args.k, col), blk, lane);
-                    if (!LEAN && args.act_bytes[1]) warp_quant_q80(v, act_sections(act_s1, 1, args.k, col), blk, lane);
+                    if (LEAN ? !B32 : (bool)args.act_bytes[0]) warp_quant_q8K(v, act_sections(act_s0, 0, args.k, col), blk, lane);
+                    if (LEAN ? B32 : (bool)args.act_bytes[1]) warp_quant_q80(v, act_sections(act_s1, 1, args.k, col), blk, lane);
                 }
             }
             if (act_source == 2) __syncthreads();             // red / s_scale are reused by the next column
@@ -676,7 +677,9 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
                 const int lnb = nsegs * 8;
 #pragma unroll 1
                 for (int ls = 0; ls < nsegs; ls++) {
-                    if (MODE == MMV_MODE_SWIGLU) {
+                    if constexpr (B32) {
+                        slot_dot<TT, 1, 2>(s0, s1, nsegs * segc, segc, ls, p * G + ls, act_s1, k, 1, lane, acc);
+                    } else if (MODE == MMV_MODE_SWIGLU) {
                         // gate row and up row of the same type TT
                         if (TT == B200_TYPE_Q4_K) slot_dot_q4K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
                         else                      slot_dot_q6K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
@@ -790,13 +793,24 @@ template <int TT, int MODE> static int mmv_launch_lean_tm(const MmvArgs & a, siz
 }
 static int mmv_launch_lean(const MmvArgs & a, int mode, size_t smem, int grid, cudaStream_t st) {
     static const bool off = getenv("B200_MMV_NO_LEAN") != nullptr;
-    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k || a.segc != 64 || a.rows_per_unit != 2 || a.act_bytes[1] != 0) return -1;
-    bool q4 = false, q6 = false;
+    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k || a.rows_per_unit != 2) return -1;
+    const int t0 = a.mat[0].type;
+    bool q4 = false, q6 = false, uniform = true;
     for (int i = 0; i < a.n_mats; i++) {
-        if (a.mat[i].type == B200_TYPE_Q4_K) q4 = true; else if (a.mat[i].type == B200_TYPE_Q6_K) q6 = true; else return -1;
+        if (a.mat[i].type != t0) uniform = false;
+        if (a.mat[i].type == B200_TYPE_Q4_K) q4 = true; else if (a.mat[i].type == B200_TYPE_Q6_K) q6 = true;
         if (a.mat[i].m & 1) return -1;
     }
-    if (mode == MMV_MODE_SWIGLU) {
+    const bool swiglu = mode == MMV_MODE_SWIGLU;
+    if (uniform && (t0 == B200_TYPE_Q4_0 || t0 == B200_TYPE_Q5_0 || t0 == B200_TYPE_Q8_0)) {       // q8_0 activations only
+        if (a.act_bytes[0] != 0) return -1;
+#define LEAN32(T) (swiglu ? mmv_launch_lean_tm<T, MMV_MODE_SWIGLU>(a, smem, grid, st) : mmv_launch_lean_tm<T, MMV_MODE_PLAIN>(a, smem, grid, st))
+        return t0 == B200_TYPE_Q4_0 ? LEAN32(B200_TYPE_Q4_0) : t0 == B200_TYPE_Q5_0 ? LEAN32(B200_TYPE_Q5_0) : LEAN32(B200_TYPE_Q8_0);
+#undef LEAN32
+    }
+    if (!(q4 || q6) || (int)q4 + (int)q6 == 0 || a.act_bytes[1] != 0 || a.segc != 64) return -1;
+    for (int i = 0; i < a.n_mats; i++) if (a.mat[i].type != B200_TYPE_Q4_K && a.mat[i].type != B200_TYPE_Q6_K) return -1;
+    if (swiglu) {
         if (q4 && q6) return -1;
         return q4 ? mmv_launch_lean_tm<B200_TYPE_Q4_K, MMV_MODE_SWIGLU>(a, smem, grid, st) : mmv_launch_lean_tm<B200_TYPE_Q6_K, MMV_MODE_SWIGLU>(a, smem, grid, st);
     }
