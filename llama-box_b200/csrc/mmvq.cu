@@ -531,7 +531,7 @@ __device__ __forceinline__ void issue_part(int type, uint8_t * dst, const uint8_
 // pairs, the activation source fixed at compile time.  Same arithmetic as the general instance, a fraction of its code: a decode
 // token runs ~160 launches of ~10 us, and every one of them starts with a cold instruction cache (the general instances are ~100 KB
 // of SASS each; the trace of tools/trace_decode.py shows 1.5-4 us from kernel entry to the first bulk copy).
-template <int NCOLS, int TT, int MODE, int ACT = -1>
+template <int NCOLS, int TT, int MODE, int ACT = -1, int NR = 2>
 __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(const __grid_constant__ MmvArgs args) {
     constexpr bool LEAN = ACT >= 0;
     constexpr bool B32 = TT == B200_TYPE_Q4_0 || TT == B200_TYPE_Q5_0 || TT == B200_TYPE_Q8_0;   // lean instances of the 32-element block types: q8_0 activations
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
     const int64_t k = args.k;
     int slot = 0; uint32_t phase = 0;
     if constexpr (LEAN) {
-        // row pairs, whole segments, one column: nothing to select at run time except (TT == -2) Q4_K or Q6_K per matrix
+        // row pairs (NR = 1: single rows, for launches whose pair count divides badly over the warps), whole segments, one column: nothing to select at run time except (TT == -2) Q4_K or Q6_K per matrix
 #pragma unroll 1
         for (int g = gw; g < total; g += TW) {
             const MmvMat * Mp;
@@ -678,15 +678,15 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
 #pragma unroll 1
                 for (int ls = 0; ls < nsegs; ls++) {
                     if constexpr (B32) {
-                        slot_dot<TT, 1, 2>(s0, s1, nsegs * segc, segc, ls, p * G + ls, act_s1, k, 1, lane, acc);
+                        slot_dot<TT, 1, NR>(s0, s1, nsegs * segc, segc, ls, p * G + ls, act_s1, k, 1, lane, acc);
                     } else if (MODE == MMV_MODE_SWIGLU) {
                         // gate row and up row of the same type TT
-                        if (TT == B200_TYPE_Q4_K) slot_dot_q4K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
-                        else                      slot_dot_q6K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                        if (TT == B200_TYPE_Q4_K) slot_dot_q4K_fast<1, NR>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                        else                      slot_dot_q6K_fast<1, NR>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
                     } else if (TT == B200_TYPE_Q4_K || (TT == -2 && rg.t0 == B200_TYPE_Q4_K)) {
-                        slot_dot_q4K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                        slot_dot_q4K_fast<1, NR>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
                     } else {
-                        slot_dot_q6K_fast<1, 2>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
+                        slot_dot_q6K_fast<1, NR>(s0, s1, lnb, ls, p * G + ls, act_s0, k, lane, acc);
                     }
                 }
                 __syncwarp();
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
             acc[0][0] = warp_sum(acc[0][0]); acc[1][0] = warp_sum(acc[1][0]);
             if (MODE == MMV_MODE_SWIGLU) {
                 if (lane == 0) M.dst[rg.r0] = __fmul_rn(silu_x86(acc[0][0]), acc[1][0]);
-            } else if (lane < 2) {
+            } else if (lane < NR) {
                 const int64_t r = rg.r0 + lane;
                 float v = lane == 0 ? acc[0][0] : acc[1][0];
                 if (M.bias)     v += M.bias[r];
@@ -769,16 +769,16 @@ static bool mmv_k_ok(int t, int64_t k) {
     return true;
 }
 
-template <int NCOLS, int TT, int MODE, int ACT = -1> static int mmv_launch_ntm(const MmvArgs & a, size_t smem, int grid, cudaStream_t st) {
+template <int NCOLS, int TT, int MODE, int ACT = -1, int NR = 2> static int mmv_launch_ntm(const MmvArgs & a, size_t smem, int grid, cudaStream_t st) {
     static bool attr[64] = { false };
     int dev = 0; cudaGetDevice(&dev);
-    if (!attr[dev & 63]) { cudaFuncSetAttribute(mmvq_kernel<NCOLS, TT, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024); attr[dev & 63] = true; }
+    if (!attr[dev & 63]) { cudaFuncSetAttribute(mmvq_kernel<NCOLS, TT, MODE, ACT, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024); attr[dev & 63] = true; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(MMV_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
-    int s = b200_check(cudaLaunchKernelEx(&cfg, mmvq_kernel<NCOLS, TT, MODE, ACT>, a), "mmvq launch");
+    int s = b200_check(cudaLaunchKernelEx(&cfg, mmvq_kernel<NCOLS, TT, MODE, ACT, NR>, a), "mmvq launch");
     if (s != B200_OK) return s;
     b200_count_launch();
     return B200_OK;
@@ -793,7 +793,15 @@ template <int TT, int MODE> static int mmv_launch_lean_tm(const MmvArgs & a, siz
 }
 static int mmv_launch_lean(const MmvArgs & a, int mode, size_t smem, int grid, cudaStream_t st) {
     static const bool off = getenv("B200_MMV_NO_LEAN") != nullptr;
-    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k || a.rows_per_unit != 2) return -1;
+    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k) return -1;
+    if (a.rows_per_unit == 1) {                     // single rows: Q4_K (+ Q6_K) launches without SwiGLU only (the QKV projection)
+        bool q6 = false;
+        for (int i = 0; i < a.n_mats; i++) { if (a.mat[i].type == B200_TYPE_Q6_K) q6 = true; else if (a.mat[i].type != B200_TYPE_Q4_K) return -1; }
+        if (mode == MMV_MODE_SWIGLU || a.act_bytes[1] != 0 || a.segc != 64) return -1;
+        if (q6) return a.act_source == 2 ? mmv_launch_ntm<1, -2, MMV_MODE_PLAIN, 2, 1>(a, smem, grid, st) : mmv_launch_ntm<1, -2, MMV_MODE_PLAIN, 1, 1>(a, smem, grid, st);
+        return a.act_source == 2 ? mmv_launch_ntm<1, B200_TYPE_Q4_K, MMV_MODE_PLAIN, 2, 1>(a, smem, grid, st) : mmv_launch_ntm<1, B200_TYPE_Q4_K, MMV_MODE_PLAIN, 1, 1>(a, smem, grid, st);
+    }
+    if (a.rows_per_unit != 2) return -1;
     const int t0 = a.mat[0].type;
     bool q4 = false, q6 = false, uniform = true;
     for (int i = 0; i < a.n_mats; i++) {
@@ -890,11 +898,15 @@ static int mmv_launch(MmvArgs & a, int mode, int64_t ncols, cudaStream_t st) {
         }
         return false;
     };
-    static const int64_t r1_below = getenv("B200_MMV_R1_BELOW") ? atoll(getenv("B200_MMV_R1_BELOW")) : 0;   // experiment: single rows for launches with few units per warp
-    int64_t units2 = 0;
-    for (int i = 0; i < a.n_mats; i++) units2 += (a.mat[i].m + 1) / 2;
+    // single rows when row PAIRS divide badly over the warps: QKV of Llama-3-8B is 3072 pairs on 2368 warps — 704 warps get two pairs
+    // (4 rows) while 6144 single rows give at most 3 per warp; a single row costs ~15 % more than half a pair (no activation reuse)
+    static const int r1_mode = getenv("B200_MMV_R1") ? atoi(getenv("B200_MMV_R1")) : 0;      // 0 = never, 1 = by the estimate below
+    int64_t units2 = 0, rows1 = 0;
+    for (int i = 0; i < a.n_mats; i++) { units2 += (a.mat[i].m + 1) / 2; rows1 += a.mat[i].m; }
+    const int64_t Wn = (int64_t)b200_sm_count() * MMV_WARPS;
+    const double t2 = 2.0 * (double)((units2 + Wn - 1) / Wn), t1 = 1.15 * (double)((rows1 + Wn - 1) / Wn);
     bool ok = false;
-    if (mode != MMV_MODE_SWIGLU && r1_below > 0 && units2 > (int64_t)b200_sm_count() * MMV_WARPS && units2 < r1_below) ok = try_cfg(1, 2);
+    if (mode != MMV_MODE_SWIGLU && r1_mode == 1 && ncols == 1 && t1 < t2) ok = try_cfg(1, 2);
     if (!ok) ok = try_cfg(2, 2);
     if (!ok && mode != MMV_MODE_SWIGLU) ok = try_cfg(1, 2);
     if (!ok) ok = try_cfg(2, 1);
