@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
     uint8_t * act_s1 = smem + args.act_bytes[0];
     uint8_t * ring   = smem + ((args.act_bytes[0] + args.act_bytes[1] + 127) & ~127) + (size_t)warp * S * args.slot_bytes;
 
-    B200_TRACE_OPEN(g_mmv_trace, args.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), tr)
+    B200_TRACE_OPEN(g_mmv_trace, (args.trace & 1) && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1), tr)
     if (tr) { tr[8] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)(unsigned)args.total_pairs << 16) | (unsigned long long)((args.mat[0].type & 0xff) << 8) | (unsigned)args.n_mats; tr[9] = (unsigned long long)args.k; }
     if (tid == 0) mbar_init(&act_bar, 1);
     if (lane == 0) for (int s = 0; s < S; s++) mbar_init(&full_bar[warp][s], 1);
@@ -575,7 +575,9 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
     };
 
     // prime the ring: weights do not depend on the previous kernel (PDL overlap)
-    if (lane == 0) for (int s = 0; s < S && ig < total; s++) issue_next();
+    // (lean instances: only the first slot now — the rest of the ring is issued behind this CTA's activation loads, see below)
+    const int pre_slots = (LEAN && !(args.trace & 2)) ? 1 : S;       // (bit 1 of args.trace: B200_MMV_PRIME_ALL=1, the old order, for A/B runs)
+    if (lane == 0) for (int s = 0; s < pre_slots && ig < total; s++) issue_next();
     // norm weights are parameters too: fetch this warp's first block before waiting for the previous kernel (otherwise a
     // cold DRAM access sits between the rms_norm reduction and the quantisation, on every CTA's critical path)
     float4 nwa = make_float4(1.0f, 1.0f, 1.0f, 1.0f), nwb = nwa;
@@ -586,6 +588,60 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
     pdl_trigger();
     pdl_wait();
     B200_TRACE_AT(tr, 3);                                          // previous kernel complete
+    if constexpr (LEAN) {
+        // one column, k <= 16384: a warp owns at most four 256-element blocks and keeps them in registers for both passes.  The loads go
+        // out FIRST, the remaining ring slots behind them: a CTA that starts late (most do: its SM was busy with the previous kernel)
+        // otherwise queues 128 KB of weight requests in front of the 16 KB everything else waits for (act rebuild 3.5-4.8 us vs 2.5)
+        __shared__ double red[MMV_WARPS];
+        const int nblk = (int)(args.k >> 8);
+        const float * xc = args.x;
+        float4 xa[4], xb[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int blk = warp + j * MMV_WARPS;
+            xa[j] = make_float4(0, 0, 0, 0); xb[j] = xa[j];
+            if (blk < nblk) { xa[j] = *(const float4 *)(xc + blk * 256 + lane * 8); xb[j] = *(const float4 *)(xc + blk * 256 + lane * 8 + 4); }
+        }
+        if (lane == 0) for (int s = pre_slots; s < S && ig < total; s++) issue_next();
+        float scale = 1.0f;
+        if (ACT == 2) {
+            double acc2 = 0.0;                                      // ggml-cpu/ops.cpp:4164-4170: f32 squares summed in double
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (warp + j * MMV_WARPS < nblk) {
+                    const float4 a = xa[j], b = xb[j];
+                    acc2 += (double)__fmul_rn(a.x, a.x); acc2 += (double)__fmul_rn(a.y, a.y); acc2 += (double)__fmul_rn(a.z, a.z); acc2 += (double)__fmul_rn(a.w, a.w);
+                    acc2 += (double)__fmul_rn(b.x, b.x); acc2 += (double)__fmul_rn(b.y, b.y); acc2 += (double)__fmul_rn(b.z, b.z); acc2 += (double)__fmul_rn(b.w, b.w);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+            if (lane == 0) red[warp] = acc2;
+            __syncthreads();
+            double t = 0.0;
+            for (int i = 0; i < MMV_WARPS; i++) t += red[i];
+            scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)(t / (double)args.k), args.eps)));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int blk = warp + j * MMV_WARPS;
+            if (blk >= nblk) break;
+            const int64_t i = (int64_t)blk * 256 + lane * 8;
+            float v[8] = { xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w };
+            if (ACT == 2) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) v[q] = __fmul_rn(v[q], scale);
+                if (args.norm_w) {
+                    const float4 wa = j == 0 ? nwa : *(const float4 *)(args.norm_w + i), wb = j == 0 ? nwb : *(const float4 *)(args.norm_w + i + 4);
+                    v[0] = __fmul_rn(v[0], wa.x); v[1] = __fmul_rn(v[1], wa.y); v[2] = __fmul_rn(v[2], wa.z); v[3] = __fmul_rn(v[3], wa.w);
+                    v[4] = __fmul_rn(v[4], wb.x); v[5] = __fmul_rn(v[5], wb.y); v[6] = __fmul_rn(v[6], wb.z); v[7] = __fmul_rn(v[7], wb.w);
+                }
+            }
+            if (B32) warp_quant_q80(v, act_sections(act_s1, 1, args.k, 0), blk, lane);
+            else     warp_quant_q8K(v, act_sections(act_s0, 0, args.k, 0), blk, lane);
+        }
+        __syncthreads();
+    } else
     if (act_source == 0) {
         if (tid == 0) {
             mbar_expect_tx(&act_bar, (uint32_t)(args.act_bytes[0] + args.act_bytes[1]));
@@ -754,7 +810,7 @@ __global__ void __launch_bounds__(MMV_WARPS * 32, MMV_CTAS_PER_SM) mmvq_kernel(c
     }
     }
     B200_TRACE_AT(tr, 6);                                          // warp 0 done
-    if (args.trace) { __syncthreads(); B200_TRACE_CLOSE(tr, 7 + 3); }   // [10] clock, [11] globaltimer: whole CTA done
+    if (args.trace & 1) { __syncthreads(); B200_TRACE_CLOSE(tr, 7 + 3); }   // [10] clock, [11] globaltimer: whole CTA done
 }
 B200_TRACE_DUMP(b200_mmv_trace_dump, g_mmv_trace)
 
@@ -793,7 +849,7 @@ template <int TT, int MODE> static int mmv_launch_lean_tm(const MmvArgs & a, siz
 }
 static int mmv_launch_lean(const MmvArgs & a, int mode, size_t smem, int grid, cudaStream_t st) {
     static const bool off = getenv("B200_MMV_NO_LEAN") != nullptr;
-    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k) return -1;
+    if (off || a.ncols != 1 || (a.act_source != 1 && a.act_source != 2) || a.y_out || a.k_valid != a.k || a.k > 16384) return -1;
     if (a.rows_per_unit == 1) {                     // single rows: Q4_K (+ Q6_K) launches without SwiGLU only (the QKV projection)
         bool q6 = false;
         for (int i = 0; i < a.n_mats; i++) { if (a.mat[i].type == B200_TYPE_Q6_K) q6 = true; else if (a.mat[i].type != B200_TYPE_Q4_K) return -1; }
@@ -1009,6 +1065,7 @@ extern "C" int b200_mul_mat_vec_q_launch(const b200_mmv_launch * L, void * strea
     a.act[0] = (const uint8_t *)L->act_q8K; a.act[1] = (const uint8_t *)L->act_q80;
     a.act_source = L->act_source; a.x = L->x; a.x_col_stride = L->x_col_stride; a.norm_w = L->norm_w; a.eps = L->eps; a.y_out = L->y_out;
     a.k_valid = L->k_valid;
-    a.trace = b200_trace_on() ? 1 : 0;
+    static const int prime_all = getenv("B200_MMV_PRIME_ALL") ? 2 : 0;
+    a.trace = (b200_trace_on() ? 1 : 0) | prime_all;
     return mmv_launch(a, L->swiglu ? MMV_MODE_SWIGLU : MMV_MODE_PLAIN, L->ncols, (cudaStream_t)stream);
 }
