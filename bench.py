@@ -559,7 +559,11 @@ def run_b200_multi(args, G, M, ops, rank, world, local):
     import torch.distributed as dist
     hbm_peak, peak_src = peaks()
     line = None
+    # The other ranks must WAIT ON THE CPU while rank 0 drives every device through libllama: an NCCL barrier is a kernel spinning on
+    # their GPU, and the product path's layers on that GPU would time-slice against it (measured: 80 tok/s instead of ~500).
+    cpu_group = dist.new_group(backend="gloo")
     dist.barrier()
+    torch.cuda.synchronize()
     if rank == 0:
         sampler = ClockSampler(0); sampler.start()
         one = product_decode(args, ",".join(["1"] + ["0"] * (world - 1)), args.n_past, args.steps, min(args.warmup, 8))    # all layers on device 0, same process
@@ -599,7 +603,7 @@ def run_b200_multi(args, G, M, ops, rank, world, local):
                     "cpu_baseline": None}
     # every rank: barrier + max over ranks of the timed region (ranks other than 0 contribute 0: they only hold their device)
     torch.cuda.set_device(local)
-    dist.barrier()
+    dist.barrier(group=cpu_group)
     t = torch.tensor([line["ms_per_step"] if (line and line.get("value")) else 0.0], device=torch.device("cuda", local))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     agg = None
