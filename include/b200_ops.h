@@ -56,6 +56,12 @@ B200_API int         b200_device_count(void);              /* 0 when no CUDA dev
 B200_API int         b200_device_sm_count(int device);
 B200_API const char *b200_last_error(void);                /* thread-local, never NULL         */
 B200_API int64_t     b200_kernel_launches(void);           /* kernels launched by this library */
+/* B200_TRACE=1 (read once per process): CTA 0 and the last CTA of every decode matvec / fused attention launch record a timeline —
+ * 12 x u64 per record: [0] %globaltimer at entry, [1..6] clock64 stamps, [8] launch info, [10] clock64 at exit, [11] %globaltimer at
+ * exit (layout: csrc/common.cuh, reader: tools/trace_decode.py).  The dump copies up to max_records records out, resets the counter
+ * and returns the number copied.  Debugging aid; not part of the compute interface. */
+B200_API int         b200_mmv_trace_dump(unsigned long long * out, int max_records);
+B200_API int         b200_fa_trace_dump(unsigned long long * out, int max_records);
 
 /* block geometry of a weight / cache type: elements and bytes per block, bytes per row of k */
 B200_API int64_t b200_block_elems(int type);
