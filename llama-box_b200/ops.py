@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200_device_sm_count": (i32, [i32]),
     "b200_last_error": (C.c_char_p, []),
     "b200_kernel_launches": (i64, []),
+    "b200_mmv_trace_dump": (i32, [vp, i32]),
+    "b200_fa_trace_dump": (i32, [vp, i32]),
     "b200_block_elems": (i64, [i32]),
     "b200_block_bytes": (i64, [i32]),
     "b200_row_bytes": (i64, [i32, i64]),
