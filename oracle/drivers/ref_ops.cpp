@@ -107,6 +107,9 @@ int main(int argc, char ** argv) {
     ggml_tensor * out = nullptr;
     if (op == "mul_mat") {
         out = ggml_mul_mat(ctx, need("w"), need("x"));
+    } else if (op == "mul_mat_id") {
+        // as [k, m, n_expert], b [k, n_b1, n_tok] f32, ids i32 [n_used, n_tok] (llama-graph.cpp build_moe_ffn)
+        out = ggml_mul_mat_id(ctx, need("w"), need("x"), need("ids"));
     } else if (op == "rms_norm") {
         out = ggml_rms_norm(ctx, need("x"), (float)P("eps", 1e-5));
         if (opt("w")) out = ggml_mul(ctx, out, opt("w"));

@@ -40,7 +40,7 @@ _Static_assert(sizeof(blk_q8_K) == 292, "q8_K");
 int64_t orc_block_elems(int type) {
     switch (type) {
         case ORC_F32: case ORC_F16: return 1;
-        case ORC_Q4_0: case ORC_Q5_0: case ORC_Q8_0: return QK;
+        case ORC_Q4_0: case ORC_Q5_0: case ORC_Q8_0: case ORC_Q4_1: case ORC_Q5_1: case ORC_Q8_1: case ORC_IQ4_NL: case ORC_MXFP4: return QK;
         default: return QKK;
     }
 }
@@ -55,6 +55,9 @@ int64_t orc_block_bytes(int type) {
         case ORC_Q5_K: return 176;
         case ORC_Q6_K: return 210;
         case ORC_Q8_K: return 292;
+        case ORC_Q4_1: return 20;  case ORC_Q5_1: return 24;  case ORC_Q8_1: return 36;   /* ggml-common.h:176-237 */
+        case ORC_Q2_K: return 84;  case ORC_Q3_K: return 110;                               /* ggml-common.h:262-286 */
+        case ORC_IQ4_NL: return 18; case ORC_IQ4_XS: return 136; case ORC_MXFP4: return 17; /* ggml-common.h:190-194,414-428 */
         default: return 0;
     }
 }
@@ -179,6 +182,7 @@ static void q6K_ints(const blk_q6_K *w, int *q) {          /* ggml-quants.c dequ
 }
 
 void orc_dequantize_row(int type, const void *vx, float *y, int64_t k) {
+    if (orc_dequantize_row_ext(type, vx, y, k)) return;            /* oracle_ext.c */
     if (type == ORC_F32) { memcpy(y, vx, (size_t)k*4); return; }
     if (type == ORC_F16) { for (int64_t i = 0; i < k; i++) y[i] = orc_fp16_to_fp32(((const uint16_t *)vx)[i]); return; }
     if (type == ORC_Q4_0) {                                /* ggml-quants.c dequantize_row_q4_0 */
@@ -311,19 +315,19 @@ float orc_vec_dot(int type, int64_t k, const void *w, const void *a) {
         case ORC_Q5_0: return dot_q5_0(k, (const blk_q5_0 *)w, (const blk_q8_0 *)a);
         case ORC_Q8_0: return dot_q8_0(k, (const blk_q8_0 *)w, (const blk_q8_0 *)a);
         case ORC_Q4_K: case ORC_Q5_K: case ORC_Q6_K: return dot_kquant(type, k, w, (const blk_q8_K *)a);
-        default: return NAN;
+        default: return orc_vec_dot_ext(type, k, w, a);            /* oracle_ext.c; NAN for unknown types */
     }
 }
 
 /* ggml-cpu/ggml-cpu.c:1202-1394: quantise each src1 row to the weight's vec_dot_type, then one
  * vec_dot per (row of W, row of X). */
 void orc_mul_mat(int type, const void *W, const float *X, float *dst, int64_t m, int64_t n, int64_t k) {
-    const int kq = (type == ORC_Q4_0 || type == ORC_Q5_0 || type == ORC_Q8_0);
-    const int64_t abytes = kq ? k/QK*34 : k/QKK*292;
+    const int at = orc_act_type(type);                             /* vec_dot_type: q8_0, q8_1 or q8_K */
+    const int64_t abytes = orc_row_bytes(at, k);
     const int64_t wbytes = orc_row_bytes(type, k);
     uint8_t *aq = (uint8_t *)malloc((size_t)abytes);
     for (int64_t j = 0; j < n; j++) {
-        if (kq) orc_quantize_row_q8_0(X + j*k, aq, k); else orc_quantize_row_q8_K(X + j*k, aq, k);
+        if (at == ORC_Q8_0) orc_quantize_row_q8_0(X + j*k, aq, k); else if (at == ORC_Q8_1) orc_quantize_row_q8_1(X + j*k, aq, k); else orc_quantize_row_q8_K(X + j*k, aq, k);
         for (int64_t i = 0; i < m; i++)
             dst[j*m + i] = orc_vec_dot(type, k, (const uint8_t *)W + i*wbytes, aq);
     }

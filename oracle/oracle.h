@@ -26,12 +26,20 @@ enum orc_type {
     ORC_F32  = 0,
     ORC_F16  = 1,
     ORC_Q4_0 = 2,
+    ORC_Q4_1 = 3,
     ORC_Q5_0 = 6,
+    ORC_Q5_1 = 7,
     ORC_Q8_0 = 8,
+    ORC_Q8_1 = 9,
+    ORC_Q2_K = 10,
+    ORC_Q3_K = 11,
     ORC_Q4_K = 12,
     ORC_Q5_K = 13,
     ORC_Q6_K = 14,
     ORC_Q8_K = 15,
+    ORC_IQ4_NL = 20,
+    ORC_IQ4_XS = 23,
+    ORC_MXFP4 = 39,
 };
 
 /* block geometry (ggml/src/ggml-common.h:170-175,219-224,295-344) */
@@ -87,6 +95,20 @@ void orc_flash_attn_ext(const void *q, int64_t q_nb1, int64_t q_nb2,
                         const uint16_t *mask, float *dst,
                         int kv_type, int64_t dk, int64_t dv, int64_t n_head, int64_t n_head_kv,
                         int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap);
+
+/* ---- oracle_ext.c: the formats / ops of SURVEY.md §8 rows f2-f4 (orc_dequantize_row / orc_vec_dot / orc_mul_mat route to them) ----
+ * Q4_1, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS, MXFP4 (ggml-common.h:176-300,414-428) */
+int   orc_is_ext_type(int type);
+int   orc_act_type(int weight_type);                       /* vec_dot_type: ORC_Q8_0 / ORC_Q8_1 / ORC_Q8_K (ggml-cpu/ggml-cpu.c:209-303) */
+void  orc_quantize_row_q8_1(const float *x, void *y, int64_t k);   /* ggml-cpu/arch/x86/quants.c:388-492 */
+int   orc_dequantize_row_ext(int type, const void *x, float *y, int64_t k);
+float orc_vec_dot_ext(int type, int64_t k, const void *w, const void *a);
+/* MUL_MAT_ID (ggml-cpu/ggml-cpu.c:1400-1620): dst[t][s] = as[ids[t][s]] * b[t][s % n_b1];  as [n_expert][m] rows, b [n_tok][n_b1][k],
+ * ids i32 [n_tok][ids_stride], dst [n_tok][n_used][m] */
+void  orc_mul_mat_id(int type, const void *as, const float *b, const int32_t *ids, float *dst,
+                     int64_t m, int64_t k, int64_t n_expert, int64_t n_used, int64_t n_tok, int64_t n_b1, int64_t ids_stride);
+/* GET_ROWS on a quantised table (ggml-cpu/ops.cpp get_rows_q) */
+void  orc_get_rows_q(int type, const void *src, const int32_t *ids, float *dst, int64_t ncols, int64_t n_ids);
 
 /* glue (ggml-cpu/vec.h:691, ops.cpp swiglu / binary-ops.cpp / get_rows / cpy) */
 void orc_swiglu(const float *gate, const float *up, float *y, int64_t n);

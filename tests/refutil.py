@@ -18,12 +18,18 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 # enum ggml_type values (ggml/include/ggml.h:377-418)
 F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K, Q8_K = 0, 1, 2, 6, 8, 12, 13, 14, 15
+Q4_1, Q5_1, Q8_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS, MXFP4 = 3, 7, 9, 10, 11, 20, 23, 39      # the wide kernels' formats
 I32, I64 = 26, 27
-TYPE_NAME = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q5_0: "q5_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K"}
-BLOCK_ELEMS = {F32: 1, F16: 1, Q4_0: 32, Q5_0: 32, Q8_0: 32, Q4_K: 256, Q5_K: 256, Q6_K: 256, Q8_K: 256, I32: 1, I64: 1}
-BLOCK_BYTES = {F32: 4, F16: 2, Q4_0: 18, Q5_0: 22, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q8_K: 292, I32: 4, I64: 8}
+TYPE_NAME = {F32: "f32", F16: "f16", Q4_0: "q4_0", Q5_0: "q5_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K", Q8_K: "q8_K",
+             Q4_1: "q4_1", Q5_1: "q5_1", Q8_1: "q8_1", Q2_K: "q2_K", Q3_K: "q3_K", IQ4_NL: "iq4_nl", IQ4_XS: "iq4_xs", MXFP4: "mxfp4"}
+BLOCK_ELEMS = {F32: 1, F16: 1, Q4_0: 32, Q5_0: 32, Q8_0: 32, Q4_K: 256, Q5_K: 256, Q6_K: 256, Q8_K: 256, I32: 1, I64: 1,
+               Q4_1: 32, Q5_1: 32, Q8_1: 32, Q2_K: 256, Q3_K: 256, IQ4_NL: 32, IQ4_XS: 256, MXFP4: 32}
+BLOCK_BYTES = {F32: 4, F16: 2, Q4_0: 18, Q5_0: 22, Q8_0: 34, Q4_K: 144, Q5_K: 176, Q6_K: 210, Q8_K: 292, I32: 4, I64: 8,
+               Q4_1: 20, Q5_1: 24, Q8_1: 36, Q2_K: 84, Q3_K: 110, IQ4_NL: 18, IQ4_XS: 136, MXFP4: 17}
 WEIGHT_TYPES = [Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K]
-ACT_TYPE = {Q4_0: Q8_0, Q5_0: Q8_0, Q8_0: Q8_0, Q4_K: Q8_K, Q5_K: Q8_K, Q6_K: Q8_K}
+EXT_TYPES = [Q4_1, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS, MXFP4]
+ACT_TYPE = {Q4_0: Q8_0, Q5_0: Q8_0, Q8_0: Q8_0, Q4_K: Q8_K, Q5_K: Q8_K, Q6_K: Q8_K,
+            Q4_1: Q8_1, Q5_1: Q8_1, Q2_K: Q8_K, Q3_K: Q8_K, IQ4_NL: Q8_0, IQ4_XS: Q8_K, MXFP4: Q8_0}
 
 
 def row_bytes(t, k):
@@ -86,6 +92,9 @@ def oracle():
         L.orc_mul.argtypes = [vp, vp, vp, i64, i64, i64]
         L.orc_get_rows_f32.argtypes = [vp, vp, vp, i64, i64]
         L.orc_cpy_f32_f16.argtypes = [vp, vp, i64]
+        L.orc_quantize_row_q8_1.argtypes = [vp, vp, i64]
+        L.orc_mul_mat_id.argtypes = [i32, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64]
+        L.orc_get_rows_q.argtypes = [i32, vp, vp, vp, i64, i64]
         _oracle = L
     return _oracle
 
@@ -100,7 +109,7 @@ def orc_quantize_act(wtype, x):
     n, k = x.shape
     at = ACT_TYPE[wtype]
     out = np.zeros((n, row_bytes(at, k)), dtype=np.uint8)
-    fn = oracle().orc_quantize_row_q8_0 if at == Q8_0 else oracle().orc_quantize_row_q8_K
+    fn = {Q8_0: oracle().orc_quantize_row_q8_0, Q8_1: oracle().orc_quantize_row_q8_1, Q8_K: oracle().orc_quantize_row_q8_K}[at]
     for i in range(n):
         fn(ptr(x[i]), ptr(out[i]), k)
     return out
@@ -138,12 +147,14 @@ def ref():
         vp, i64 = C.c_void_p, C.c_int64
         base.ggml_quantize_chunk.restype = C.c_size_t
         base.ggml_quantize_chunk.argtypes = [C.c_int, vp, vp, i64, i64, i64, vp]
-        for nm in ("q4_0", "q5_0", "q8_0", "q4_K", "q5_K", "q6_K"):
+        for nm in ("q4_0", "q5_0", "q8_0", "q4_K", "q5_K", "q6_K", "q4_1", "q5_1", "q2_K", "q3_K", "iq4_nl", "iq4_xs", "mxfp4"):
             getattr(base, "dequantize_row_" + nm).argtypes = [vp, vp, i64]
         cpu.quantize_row_q8_0.argtypes = [vp, vp, i64]
+        cpu.quantize_row_q8_1.argtypes = [vp, vp, i64]
         cpu.quantize_row_q8_K.argtypes = [vp, vp, i64]
         cpu.ggml_cpu_fp32_to_fp16.argtypes = [vp, vp, i64]
-        for nm in ("q4_0_q8_0", "q5_0_q8_0", "q8_0_q8_0", "q4_K_q8_K", "q5_K_q8_K", "q6_K_q8_K"):
+        for nm in ("q4_0_q8_0", "q5_0_q8_0", "q8_0_q8_0", "q4_K_q8_K", "q5_K_q8_K", "q6_K_q8_K",
+                   "q4_1_q8_1", "q5_1_q8_1", "q2_K_q8_K", "q3_K_q8_K", "iq4_nl_q8_0", "iq4_xs_q8_K", "mxfp4_q8_0"):
             getattr(cpu, "ggml_vec_dot_" + nm).argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_int]
         cpu.ggml_cpu_init()
         _ref = (base, cpu)
@@ -212,7 +223,39 @@ def rand_blocks(rng, t, nrows, k, scale_mul=1.0):
         raw[:, 2:4] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
     elif t == Q6_K:
         raw[:, 208:210] = rand_f16_scale_l(rng, nb, 1e-5, 2e-4, signed=True).view(np.uint8).reshape(nb, 2)
+    elif t in (Q4_1, Q5_1):                                  # {d, m, ...}
+        raw[:, 0:2] = rand_f16_scale_l(rng, nb).view(np.uint8).reshape(nb, 2)
+        raw[:, 2:4] = rand_f16_scale_l(rng, nb, 1e-3, 1e-1, signed=True).view(np.uint8).reshape(nb, 2)
+    elif t == IQ4_NL:
+        raw[:, 0:2] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3, signed=True).view(np.uint8).reshape(nb, 2)
+    elif t == IQ4_XS:
+        raw[:, 0:2] = rand_f16_scale_l(rng, nb, 1e-5, 2e-4, signed=True).view(np.uint8).reshape(nb, 2)
+    elif t == MXFP4:                                         # E8M0 exponent byte: 2^-17 .. 2^-7 (halved)
+        raw[:, 0] = rng.integers(112, 122, size=nb, dtype=np.uint8)
+    elif t == Q2_K:                                          # {scales[16], qs[64], d, dmin}
+        raw[:, 80:82] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
+        raw[:, 82:84] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3).view(np.uint8).reshape(nb, 2)
+    elif t == Q3_K:                                          # {hmask[32], qs[64], scales[12], d}
+        raw[:, 108:110] = rand_f16_scale_l(rng, nb, 1e-4, 2e-3, signed=True).view(np.uint8).reshape(nb, 2)
     return raw.reshape(nrows, -1)
+
+
+def repack_rows_np(t, W, k):
+    """numpy model of b200_repack_rows (llama-box_b200/csrc/repack.cu): ggml rows -> the library's row layout."""
+    W = np.ascontiguousarray(W).reshape(-1, row_bytes(t, k))
+    nb = k // BLOCK_ELEMS[t]
+    blk = W.reshape(W.shape[0], nb, BLOCK_BYTES[t])
+    if t == Q4_0:
+        parts = [blk[:, :, 2:18], blk[:, :, 0:2]]
+    elif t == Q5_0:
+        parts = [blk[:, :, 6:22], blk[:, :, 2:6], blk[:, :, 0:2]]
+    elif t == Q8_0:
+        parts = [blk[:, :, 2:34], blk[:, :, 0:2]]
+    elif t == Q6_K:
+        parts = [blk[:, :, 0:128], blk[:, :, 128:192], blk[:, :, 192:208], blk[:, :, 208:210]]
+    else:
+        return W.copy()
+    return np.concatenate([p.reshape(W.shape[0], -1) for p in parts], axis=1)
 
 
 def cos_data(n, off=0.0):

@@ -62,3 +62,81 @@ def test_reference_parity_harness_runs():
     r = subprocess.run([os.path.join(REF_DIR, "test-backend-ops"), "support", "-o", "MUL_MAT"], capture_output=True, text=True,
                        env=dict(os.environ, LD_LIBRARY_PATH=REF_DIR))
     assert r.returncode == 0 and "CPU" in (r.stdout + r.stderr)
+
+
+# ---- the wide kernels' formats, MUL_MAT_ID, GET_ROWS on quantised tables (oracle/oracle_ext.c) ----------
+from refutil import EXT_TYPES, ACT_TYPE, I32, Q8_1, TYPE_NAME, orc_dequant  # noqa: E402
+
+
+def test_q8_1_quantiser_bit_exact():
+    _, cpu = ref()
+    for k in (32, 4096, 29568):
+        rng = np.random.default_rng(k)
+        x = (rng.standard_normal(k) * rng.uniform(0.01, 50)).astype(np.float32)
+        x[:32] = 0
+        a = np.zeros(row_bytes(Q8_1, k), np.uint8); b = a.copy()
+        oracle().orc_quantize_row_q8_1(ptr(x), ptr(a), k); cpu.quantize_row_q8_1(ptr(x), ptr(b), k)
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("t", EXT_TYPES)
+def test_ext_dequant_bit_exact_and_vec_dot(t):
+    base, cpu = ref()
+    rng = np.random.default_rng(100 + t)
+    m, k = 8, 2048
+    for W in (ref_quantize_weights(t, (rng.standard_normal((m, k)) * 0.05).astype(np.float32)), rand_blocks(rng, t, m, k)):
+        deq = np.zeros((m, k), np.float32)
+        for i in range(m):
+            getattr(base, "dequantize_row_" + TYPE_NAME[t])(ptr(W[i]), ptr(deq[i]), k)
+        assert np.array_equal(orc_dequant(t, W, m, k), deq)
+        x = rng.standard_normal((1, k)).astype(np.float32)
+        aq = orc_quantize_act(t, x)
+        fn = getattr(cpu, f"ggml_vec_dot_{TYPE_NAME[t]}_{TYPE_NAME[ACT_TYPE[t]]}")
+        for i in range(m):
+            want = np.zeros(1, np.float32)
+            fn(k, ptr(want), 0, ptr(W[i]), 0, ptr(aq[0]), 0, 1)
+            got = oracle().orc_vec_dot(t, k, ptr(W[i]), ptr(aq[0]))
+            assert abs(got - want[0]) <= 3e-6 * max(abs(want[0]), np.abs(deq[i]).max() * 30)
+
+
+@pytest.mark.parametrize("t", EXT_TYPES)
+def test_ext_mul_mat_through_cpu_backend(t):
+    rng = np.random.default_rng(200 + t)
+    m, k, n = 32, 4096, 2
+    for W in (ref_quantize_weights(t, (rng.standard_normal((m, k)) * 0.02).astype(np.float32)), rand_blocks(rng, t, m, k)):
+        X = rng.standard_normal((n, k)).astype(np.float32)
+        _, _, out = run_ref_op("mul_mat", [("w", t, [k, m], W), ("x", F32, [k, n], X)])
+        want = np.frombuffer(out, np.float32).reshape(n, m)
+        got = orc_mul_mat(t, W, X, m, n, k)
+        assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("t", [2, 12, 14, 3, 11, 23])
+@pytest.mark.parametrize("n_b1", [1, 0])
+def test_mul_mat_id_through_cpu_backend(t, n_b1):
+    """MUL_MAT_ID as build_moe_ffn emits it (llama-graph.cpp): shared activation (up / gate) and one activation per used expert (down)"""
+    rng = np.random.default_rng(300 + t)
+    m, k, n_expert, n_used, n_tok = 24, 512, 6, 3, 4
+    n_b1 = n_b1 or n_used
+    W = ref_quantize_weights(t, (rng.standard_normal((n_expert * m, k)) * 0.05).astype(np.float32))
+    b = rng.standard_normal((n_tok, n_b1, k)).astype(np.float32)
+    ids = np.stack([rng.permutation(n_expert)[:n_used] for _ in range(n_tok)]).astype(np.int32)
+    _, ne, out = run_ref_op("mul_mat_id", [("w", t, [k, m, n_expert], W), ("x", F32, [k, n_b1, n_tok], b), ("ids", I32, [n_used, n_tok], ids)])
+    assert list(ne[:3]) == [m, n_used, n_tok]
+    want = np.frombuffer(out, np.float32).reshape(n_tok, n_used, m)
+    got = np.zeros_like(want)
+    oracle().orc_mul_mat_id(t, ptr(W), ptr(b), ptr(ids), ptr(got), m, k, n_expert, n_used, n_tok, n_b1, n_used)
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("t", WEIGHT_TYPES + EXT_TYPES)
+def test_get_rows_quantised_through_cpu_backend(t):
+    rng = np.random.default_rng(400 + t)
+    nrows, k = 40, 1024
+    W = ref_quantize_weights(t, (rng.standard_normal((nrows, k)) * 0.05).astype(np.float32))
+    ids = np.array([3, 39, 0, 3, 17], np.int32)
+    _, _, out = run_ref_op("get_rows", [("src", t, [k, nrows], W), ("ids", I32, [ids.size], ids)])
+    want = np.frombuffer(out, np.float32).reshape(ids.size, k)
+    got = np.zeros_like(want)
+    oracle().orc_get_rows_q(t, ptr(W), ptr(ids), ptr(got), k, ids.size)
+    assert np.array_equal(got, want)
