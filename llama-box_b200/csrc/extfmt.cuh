@@ -19,7 +19,7 @@
 #if defined(__CUDACC__)
 #  define XF_HD __host__ __device__ __forceinline__
 #else
-#  define XF_HD static inline
+#  define XF_HD inline
 #endif
 
 // enum ggml_type values (ggml/include/ggml.h:377-418)
