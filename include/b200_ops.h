@@ -48,6 +48,14 @@ enum b200_type {
     B200_TYPE_Q4_K = 12,
     B200_TYPE_Q5_K = 13,
     B200_TYPE_Q6_K = 14,
+    /* formats only the wide kernels (b200_mul_mat_vec_wide / b200_mul_mat_id / b200_get_rows_q) read, in ggml's own block layout */
+    B200_TYPE_Q4_1   = 3,
+    B200_TYPE_Q5_1   = 7,
+    B200_TYPE_Q2_K   = 10,
+    B200_TYPE_Q3_K   = 11,
+    B200_TYPE_IQ4_NL = 20,
+    B200_TYPE_IQ4_XS = 23,
+    B200_TYPE_MXFP4  = 39,
 };
 
 /* ---- library / device ------------------------------------------------------------------ */
@@ -159,6 +167,36 @@ B200_API int b200_mul_mat_vec_q_launch(const b200_mmv_launch *launch, void *stre
 B200_API int b200_mul_mat_vec_q_swiglu(int type_gate, const void *Wg, int type_up, const void *Wu,
                                        const void *act_q8K, const void *act_q80, float *dst,
                                        int64_t m, int64_t k, int64_t ncols, void *stream);
+
+/* ---- the wide kernels: more weight formats, MUL_MAT_ID, GET_ROWS on quantised tables ------------------
+ * One format-generic matvec (csrc/mmvq_ext.cu, per-format arithmetic in csrc/extfmt.cuh) for what the tuned kernels above do not carry.
+ * Weight layouts: Q4_1 / Q5_1 / Q2_K / Q3_K / IQ4_NL / IQ4_XS / MXFP4 in ggml's block layout (ggml-common.h:176-300,414-428), any
+ * k that is a multiple of the block size; Q4_0 / Q5_0 / Q8_0 / Q4_K / Q5_K / Q6_K as everywhere in this library ("repacked" for the
+ * first three and Q6_K), k % 256 == 0 (Q6_K: k % 512 == 0).  Activations are f32: every CTA quantises the column it needs in its
+ * prologue the way the CPU oracle does (q8_0 / q8_1 / q8_K by the weight's vec_dot_type, ggml-cpu/ggml-cpu.c:209-303), so integer
+ * sums match the oracle's and no activation buffer exists in HBM.  Replaces the remaining vec_dot_*_q8_1 of ggml-cuda/vecdotq.cuh
+ * behind mul_mat_vec_q (mmvq.cu:139-226). */
+B200_API int     b200_wide_type_supported(int type);                 /* 1 for the 13 formats above                      */
+B200_API int     b200_wide_shape_supported(int type, int64_t k);     /* 1 if rows of k elements of `type` can be read   */
+B200_API int64_t b200_wide_row_bytes(int type, int64_t k);
+/* dst[c][r] = sum_k W[r][k] x[c][k] (+ bias[r]) (+ residual[c][r]); x f32 [ncols][k] with column stride x_col_stride floats (16-byte
+ * aligned columns); any ncols (one pass over the weights per column: decode / verify batches) */
+B200_API int b200_mul_mat_vec_wide(int type, const void *W, const float *x, int64_t x_col_stride, float *dst, int64_t dst_col_stride,
+                                   const float *bias, const float *residual, int64_t m, int64_t k, int64_t ncols, void *stream);
+/* MUL_MAT_ID — mixture-of-experts routing (replaces ggml_cuda_mul_mat_id, ggml-cuda.cu:2064-2205; contract ggml.c:3064-3106):
+ *   dst[t][s][:] = as[ids[t][s]] * b[t][s % n_b1]     t < n_tok, s < n_used
+ *   as  : n_expert matrices of m rows (layout as above), expert e at as + e * expert_stride_bytes
+ *   b   : f32, column (t, j) at b + t * b_tok_stride + j * b_slot_stride (floats), n_b1 = 1 (up / gate: shared) or n_used (down)
+ *   ids : i32 on the DEVICE, (t, s) at ids[t * ids_tok_stride + s]; read by the kernel — no device->host synchronisation
+ *         (the reference copies ids to the host and synchronises per op: ggml-cuda.cu:2115-2125).  Out-of-range ids write nothing.
+ *   dst : f32, row block (t, s) at dst + t * dst_tok_stride + s * dst_slot_stride (floats) */
+B200_API int b200_mul_mat_id(int type, const void *as, int64_t expert_stride_bytes, const float *b, int64_t b_tok_stride, int64_t b_slot_stride, int64_t n_b1,
+                             const int32_t *ids, int64_t ids_tok_stride, float *dst, int64_t dst_tok_stride, int64_t dst_slot_stride,
+                             int64_t m, int64_t k, int64_t n_expert, int64_t n_used, int64_t n_tok, void *stream);
+/* GET_ROWS on a quantised table: dst row i = de-quantised row ids[i] of src (replaces k_get_rows, ggml-cuda/getrows.cu:5-67; values
+ * bit-identical to ggml's dequantize_row_*: products rounded separately).  The token-embedding lookup on the device. */
+B200_API int b200_get_rows_q(int type, const void *src, int64_t src_row_stride_bytes, int64_t nrows, const int32_t *ids, float *dst,
+                             int64_t dst_row_stride /* floats */, int64_t ncols, int64_t n_ids, void *stream);
 
 /* ---- MUL_MAT, batched / prefill (replaces ggml_cuda_mul_mat_q, mmq.cu:71-143) -----------
  * dst[c][r] for any ncols; X is f32 [ncols][k].  Internally: activation quantisation as above,

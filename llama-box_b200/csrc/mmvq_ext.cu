@@ -1,0 +1,241 @@
+// mmvq_ext.cu — the "wide" kernels: one simple, format-generic matvec that carries
+//   * MUL_MAT for the formats the tuned decode kernels (mmvq.cu) do not have — Q4_1, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS, MXFP4
+//     (replaces the rest of ggml-cuda/vecdotq.cuh:75-175,656-1171 behind mul_mat_vec_q, ggml-cuda/mmvq.cu:139-226),
+//   * MUL_MAT_ID (mixture-of-experts routing, replaces ggml_cuda_mul_mat_id, ggml-cuda/ggml-cuda.cu:2064-2205 and the ids path of
+//     mmvq.cu:163-166) for those formats AND for Q4_0 / Q5_0 / Q8_0 / Q4_K / Q5_K / Q6_K in the library's weight layout: the expert
+//     ids are read ON THE DEVICE by the CTA that needs them — no device->host synchronisation per op (the reference copies ids to
+//     the host and synchronises the stream, ggml-cuda.cu:2115-2125),
+//   * GET_ROWS on quantised tables (replaces k_get_rows, ggml-cuda/getrows.cu:5-67): the token-embedding lookup on the device.
+//
+// Design (HBM-bound byte/integer work; correctness first, this is the widening stage — the five formats of the BASELINE
+// configs keep their tuned kernels):
+//   grid = (row groups, problems); a problem is ONE activation column against one weight matrix: column c of a MUL_MAT, or
+//   (token, expert slot) of a MUL_MAT_ID.  The CTA quantises its column in the prologue straight into shared memory the way the CPU
+//   oracle does (q8_K / q8_0 / q8_1: same warp-level quantisers as mmvq.cu's prologue, actquant.cuh) — no activation buffer in HBM —
+//   then each of its 8 warps walks whole weight rows, lanes striding over 32-element sub-blocks (extfmt.cuh: dp4a integer sums, the
+//   oracle's scale arithmetic), warp-reduces and writes dst (+ bias, + residual).  Weights are read once per column; the few
+//   columns of a decode / verify batch re-read them from L2.
+//   The per-format arithmetic lives in extfmt.cuh and is ALSO compiled for the host and checked against the reference on the CPU
+//   (tests/test_extfmt_hostsim.py).
+#include "common.cuh"
+
+#include "actquant.cuh"
+#include "extfmt.cuh"
+
+namespace {
+
+struct ExtArgs {
+    const uint8_t * W; int64_t row_bytes, nb_layout, expert_stride;          // weights; expert_stride (bytes) only with ids
+    const int32_t * ids; int64_t ids_tok_stride; int32_t n_used, n_expert;   // MUL_MAT_ID routing (ids == nullptr: plain MUL_MAT)
+    const float * x; int64_t x_col_stride, x_slot_stride, n_b1;              // activations (floats); slot stride / n_b1 only with ids
+    float * dst; int64_t dst_col_stride, dst_slot_stride;
+    const float * bias; const float * residual; int64_t res_col_stride;
+    int64_t m, k, prob0;                                                     // prob0: first problem of this launch (grid.y chunking)
+};
+
+constexpr int EXT_WARPS = 8;
+
+__host__ __device__ inline int64_t ext_kp(int64_t k) { return (k + 255) & ~(int64_t)255; }
+// shared-memory column: [qs kp][d][s (family 1)][bs]
+__host__ __device__ inline int64_t ext_off_d(int64_t kp) { return kp; }
+__host__ __device__ inline int64_t ext_off_s(int fam, int64_t kp) { return ext_off_d(kp) + (fam ? kp / 32 * 4 : align16(kp / 256 * 4)); }
+__host__ __device__ inline int64_t ext_off_bs(int fam, int64_t kp) { return ext_off_s(fam, kp) + (fam ? kp / 32 * 4 : 0); }
+__host__ __device__ inline int64_t ext_smem_bytes(int fam, int64_t kp) { return ext_off_bs(fam, kp) + (fam ? kp / 32 * 2 : kp / 16 * 2); }
+
+// 256 elements (8 per lane) as 8 blocks of q8_0 / q8_1 in the x86 CPU backend's arithmetic (ggml-cpu/arch/x86/quants.c:290-492): the same
+// int8 values for both; d = f16(max/127); s = f16((max/127) * sum) (q8_1); bs = sum (the -8 / -16 offsets of Q4_0 / Q5_0 use it)
+__device__ __forceinline__ void warp_quant_q8_01(const float (&v)[8], int8_t * qs, float * ad, float * as, int16_t * bs, int64_t blk256, int lane) {
+    float am = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) am = fmaxf(am, fabsf(v[j]));
+    am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+    am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+    const float d  = __fdiv_rn(am, 127.0f);
+    const float id = am != 0.0f ? __fdiv_rn(127.0f, am) : 0.0f;
+    int q[8]; int s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { q[j] = __float2int_rn(__fmul_rn(v[j], id)); s += q[j]; }
+    uint2 pk;
+    pk.x = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((q[3] & 0xff) << 24);
+    pk.y = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((q[7] & 0xff) << 24);
+    *(uint2 *)(qs + blk256 * 256 + lane * 8) = pk;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((lane & 3) == 0) {
+        const int64_t b = blk256 * 8 + (lane >> 2);
+        ad[b] = __half2float(__float2half_rn(d));
+        as[b] = __half2float(__float2half_rn(__fmul_rn(d, (float)s)));
+        bs[b] = (int16_t)s;
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(EXT_WARPS * 32) ext_mmv_kernel(const ExtArgs a) {
+    extern __shared__ __align__(16) uint8_t ext_smem[];
+    constexpr int FAM = (T == XF_Q2_K || T == XF_Q3_K || T == XF_Q4_K || T == XF_Q5_K || T == XF_Q6_K || T == XF_IQ4_XS) ? 0 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t k = a.k, kp = ext_kp(k);
+    int8_t  * qs = (int8_t *)ext_smem;
+    float   * ad = (float *)(ext_smem + ext_off_d(kp));
+    float   * as = (float *)(ext_smem + ext_off_s(FAM, kp));
+    int16_t * bs = (int16_t *)(ext_smem + ext_off_bs(FAM, kp));
+
+    pdl_wait();                                                    // activations and expert ids come from earlier kernels
+
+    const int64_t p = a.prob0 + blockIdx.y;
+    const uint8_t * W = a.W; const float * x; float * dst; const float * resid = nullptr;
+    if (a.ids) {
+        const int64_t tok = p / a.n_used, slot = p % a.n_used;
+        const int e = a.ids[tok * a.ids_tok_stride + slot];
+        if (e < 0 || e >= a.n_expert) return;                      // uniform over the CTA (the reference asserts the range: ggml-cpu.c:1496)
+        W  += (int64_t)e * a.expert_stride;
+        x   = a.x + tok * a.x_col_stride + (slot % a.n_b1) * a.x_slot_stride;
+        dst = a.dst + tok * a.dst_col_stride + slot * a.dst_slot_stride;
+    } else {
+        x   = a.x + p * a.x_col_stride;
+        dst = a.dst + p * a.dst_col_stride;
+        if (a.residual) resid = a.residual + p * a.res_col_stride;
+    }
+
+    // ---- prologue: this column, quantised like the oracle, into shared memory (elements past k: zero)
+    for (int64_t c = warp; c < kp / 256; c += EXT_WARPS) {
+        float v[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        const int64_t e0 = c * 256 + lane * 8;
+        if (e0 < k) {                                              // k % 32 == 0: a lane's 8 elements are all inside or all outside
+            const float4 * px = (const float4 *)(x + e0);
+            const float4 f0 = px[0], f1 = px[1];
+            v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+        }
+        if (FAM == 0) { ActOut o; o.qs = qs; o.d = ad; o.bs = bs; warp_quant_q8K(v, o, c, lane); }
+        else          warp_quant_q8_01(v, qs, ad, as, bs, c, lane);
+    }
+    __syncthreads();
+
+    XfAct A; A.qs = qs; A.d = ad; A.s = as; A.bs = bs;
+    const int64_t nsub = k / 32;
+    for (int64_t row = (int64_t)blockIdx.x * EXT_WARPS + warp; row < a.m; row += (int64_t)gridDim.x * EXT_WARPS) {
+        const uint8_t * wr = W + row * a.row_bytes;
+        float acc = 0.0f;
+        for (int64_t u = lane; u < nsub; u += 32) acc += xf_sub_dot<T>(wr, a.nb_layout, u, A);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float r = acc;
+            if (a.bias)  r += a.bias[row];
+            if (resid)   r += resid[row];
+            dst[row] = r;
+        }
+    }
+}
+
+// one thread per 32-element sub-block of a gathered row
+template <int T>
+__global__ void __launch_bounds__(128) ext_get_rows_kernel(const uint8_t * __restrict__ src, int64_t row_stride, int64_t nb_layout, int64_t nrows,
+                                                           const int32_t * __restrict__ ids, float * __restrict__ dst, int64_t dst_row_stride, int64_t ncols, int64_t id0) {
+    pdl_wait();
+    const int64_t u = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (u >= ncols / 32) return;
+    const int64_t r = id0 + blockIdx.y;
+    const int64_t id = ids[r];
+    float y[32];
+    if (id >= 0 && id < nrows) xf_sub_dequant<T>(src + id * row_stride, nb_layout, u, y);
+    else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) y[i] = 0.0f;
+    }
+    float4 * o = (float4 *)(dst + r * dst_row_stride + 32 * u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+}
+
+// k / alignment rules of a weight row in the layout these kernels read
+bool ext_shape_ok(int type, int64_t k) {
+    if (xf_act_family(type) < 0 || k <= 0) return false;
+    if (xf_is_ext_only(type)) return k % xf_block_elems(type) == 0;             // ggml layout, rows at least 2-byte aligned for every k
+    if (type == XF_Q6_K) return k % 512 == 0;                                   // library layout: 4-byte aligned rows and sections
+    return k % 256 == 0;                                                        // library layout of the other tuned formats
+}
+
+template <int T> int ext_launch_t(const ExtArgs & a0, int64_t n_prob, cudaStream_t st) {
+    const int fam = xf_act_family(T);
+    const int64_t smem = ext_smem_bytes(fam, ext_kp(a0.k));
+    if (smem > 200 * 1024) { b200_set_error("wide matvec: k = %lld does not fit shared memory", (long long)a0.k); return B200_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) {
+        static bool attr[64];
+        int dev = 0; cudaGetDevice(&dev);
+        if (!attr[dev & 63]) { B200_CUDA(cudaFuncSetAttribute(ext_mmv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[dev & 63] = true; }
+    }
+    int64_t gx = (a0.m + 31) / 32;                                              // >= 4 rows per warp before a CTA's prologue is amortised
+    const int64_t cap = (int64_t)b200_sm_count() * 4;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    for (int64_t p0 = 0; p0 < n_prob; p0 += 32768) {
+        ExtArgs a = a0; a.prob0 = p0;
+        const int64_t ny = n_prob - p0 < 32768 ? n_prob - p0 : 32768;
+        ext_mmv_kernel<T><<<dim3((unsigned)gx, (unsigned)ny), EXT_WARPS * 32, (size_t)smem, st>>>(a);
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
+int ext_launch(int type, const ExtArgs & a, int64_t n_prob, cudaStream_t st) {
+    int s = B200_ERR_UNSUPPORTED;
+    XF_DISPATCH(type, s = ext_launch_t<T>(a, n_prob, st));
+    return s;
+}
+
+template <int T> void ext_get_rows_launch_t(dim3 grid, cudaStream_t st, const uint8_t * src, int64_t row_stride, int64_t nb, int64_t nrows, const int32_t * ids,
+                                            float * dst, int64_t dst_row_stride, int64_t ncols, int64_t id0) {
+    ext_get_rows_kernel<T><<<grid, 128, 0, st>>>(src, row_stride, nb, nrows, ids, dst, dst_row_stride, ncols, id0);
+}
+
+bool al16(const void * p) { return ((uintptr_t)p & 15) == 0; }
+
+} // namespace
+
+extern "C" int b200_wide_type_supported(int type) { return xf_act_family(type) >= 0 ? 1 : 0; }
+extern "C" int b200_wide_shape_supported(int type, int64_t k) { return ext_shape_ok(type, k) ? 1 : 0; }
+extern "C" int64_t b200_wide_row_bytes(int type, int64_t k) { const int be = xf_block_elems(type); return be ? k / be * xf_block_bytes(type) : 0; }
+
+extern "C" int b200_mul_mat_vec_wide(int type, const void * W, const float * x, int64_t x_col_stride, float * dst, int64_t dst_col_stride,
+                                     const float * bias, const float * residual, int64_t m, int64_t k, int64_t ncols, void * stream) {
+    if (b200_device_count() <= 0) { b200_set_error("no CUDA device"); return B200_ERR_CUDA; }
+    if (!ext_shape_ok(type, k)) { b200_set_error("wide matvec: type %d with k = %lld is not supported", type, (long long)k); return B200_ERR_UNSUPPORTED; }
+    if (!W || !x || !dst || m <= 0 || ncols <= 0 || !al16(W) || !al16(x) || (x_col_stride & 3) || ((uintptr_t)dst & 3)) { b200_set_error("wide matvec: bad arguments (W, x 16-byte aligned; x column stride a multiple of 4 floats)"); return B200_ERR_INVALID; }
+    ExtArgs a = {};
+    a.W = (const uint8_t *)W; a.row_bytes = b200_wide_row_bytes(type, k); a.nb_layout = k / xf_block_elems(type);
+    a.x = x; a.x_col_stride = x_col_stride; a.dst = dst; a.dst_col_stride = dst_col_stride ? dst_col_stride : m;
+    a.bias = bias; a.residual = residual; a.res_col_stride = a.dst_col_stride; a.m = m; a.k = k; a.n_b1 = 1; a.n_used = 1;
+    return ext_launch(type, a, ncols, (cudaStream_t)stream);
+}
+
+extern "C" int b200_mul_mat_id(int type, const void * as, int64_t expert_stride_bytes, const float * b, int64_t b_tok_stride, int64_t b_slot_stride, int64_t n_b1,
+                               const int32_t * ids, int64_t ids_tok_stride, float * dst, int64_t dst_tok_stride, int64_t dst_slot_stride,
+                               int64_t m, int64_t k, int64_t n_expert, int64_t n_used, int64_t n_tok, void * stream) {
+    if (b200_device_count() <= 0) { b200_set_error("no CUDA device"); return B200_ERR_CUDA; }
+    if (!ext_shape_ok(type, k)) { b200_set_error("mul_mat_id: type %d with k = %lld is not supported", type, (long long)k); return B200_ERR_UNSUPPORTED; }
+    if (!as || !b || !ids || !dst || m <= 0 || n_expert <= 0 || n_used <= 0 || n_tok <= 0 || n_b1 <= 0 || n_expert > INT32_MAX || n_used > INT32_MAX ||
+        !al16(as) || !al16(b) || (b_tok_stride & 3) || (b_slot_stride & 3) || (expert_stride_bytes & 15) || ((uintptr_t)dst & 3)) {
+        b200_set_error("mul_mat_id: bad arguments (as, b 16-byte aligned; b strides multiples of 4 floats; expert stride a multiple of 16 bytes)"); return B200_ERR_INVALID;
+    }
+    ExtArgs a = {};
+    a.W = (const uint8_t *)as; a.row_bytes = b200_wide_row_bytes(type, k); a.nb_layout = k / xf_block_elems(type); a.expert_stride = expert_stride_bytes;
+    a.ids = ids; a.ids_tok_stride = ids_tok_stride; a.n_used = (int32_t)n_used; a.n_expert = (int32_t)n_expert;
+    a.x = b; a.x_col_stride = b_tok_stride; a.x_slot_stride = b_slot_stride; a.n_b1 = n_b1;
+    a.dst = dst; a.dst_col_stride = dst_tok_stride; a.dst_slot_stride = dst_slot_stride; a.m = m; a.k = k;
+    return ext_launch(type, a, n_tok * n_used, (cudaStream_t)stream);
+}
+
+extern "C" int b200_get_rows_q(int type, const void * src, int64_t src_row_stride, int64_t nrows, const int32_t * ids, float * dst, int64_t dst_row_stride,
+                               int64_t ncols, int64_t n_ids, void * stream) {
+    if (b200_device_count() <= 0) { b200_set_error("no CUDA device"); return B200_ERR_CUDA; }
+    if (!ext_shape_ok(type, ncols)) { b200_set_error("get_rows: type %d with %lld columns is not supported", type, (long long)ncols); return B200_ERR_UNSUPPORTED; }
+    if (!src || !ids || !dst || nrows <= 0 || n_ids <= 0 || !al16(src) || !al16(dst) || (dst_row_stride & 3) || (src_row_stride & 1)) { b200_set_error("get_rows: bad arguments"); return B200_ERR_INVALID; }
+    const int64_t nb = ncols / xf_block_elems(type);
+    const unsigned gx = (unsigned)((ncols / 32 + 127) / 128);
+    for (int64_t i0 = 0; i0 < n_ids; i0 += 32768) {
+        const unsigned ny = (unsigned)(n_ids - i0 < 32768 ? n_ids - i0 : 32768);
+        const dim3 grid(gx, ny);
+        XF_DISPATCH(type, ext_get_rows_launch_t<T>(grid, (cudaStream_t)stream, (const uint8_t *)src, src_row_stride, nb, nrows, ids, dst, dst_row_stride, ncols, i0));
+        B200_LAUNCH_CHECK();
+    }
+    return B200_OK;
+}

@@ -83,6 +83,12 @@ SIGNATURES = {
     "b200_get_rows_f32": (i32, [vp, i64, vp, vp, i64, i64, vp]),
     "b200_cpy_f32_f16": (i32, [vp, vp, i64, vp]),
     "b200_argmax_f32": (i32, [vp, vp, i64, i64, vp]),
+    "b200_wide_type_supported": (i32, [i32]),
+    "b200_wide_shape_supported": (i32, [i32, i64]),
+    "b200_wide_row_bytes": (i64, [i32, i64]),
+    "b200_mul_mat_vec_wide": (i32, [i32, vp, vp, i64, vp, i64, vp, vp, i64, i64, i64, vp]),
+    "b200_mul_mat_id": (i32, [i32, vp, i64, vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
+    "b200_get_rows_q": (i32, [i32, vp, i64, i64, vp, vp, i64, i64, i64, vp]),
 }
 for _n, (_r, _a) in SIGNATURES.items():
     _f = getattr(lib, _n)

@@ -76,7 +76,7 @@ def test_sub_block_dot_and_dequant(sim, t, k):
         assert np.array_equal(y, deq_want[i]), (t, i)
 
 
-@pytest.mark.parametrize("t", [2, 6, 8, 3, 7, 20, 39])
+@pytest.mark.parametrize("t", [3, 7, 20, 39])
 def test_rows_that_are_not_a_multiple_of_256(sim, t):
     """32-element block formats: any k % 32 == 0 (the wide kernels do not need 256-element units)"""
     rng = np.random.default_rng(t)
