@@ -40,6 +40,8 @@ enum b200_op {
     B200_OP_GLU_SWIGLU,      /* src0 gate, src1 up (split form, ggml.c:2796)                          */
     B200_OP_GET_ROWS,        /* src0 f32 [ncols, nrows], src1 i32 ids                                  */
     B200_OP_CPY,             /* src0 f32 -> dst f16 / f32, contiguous                                  */
+    B200_OP_MUL_MAT_ID,      /* src0 experts [K,M,n_expert], src1 f32 [K,n_b1,n_tok], src2 ids i32 [n_used,n_tok] -> dst f32 [M,n_used,n_tok]
+                                (ggml.c:3064-3106).  Wide path (b200_mul_mat_id): see B200_WIDE below                             */
     B200_OP_COUNT
 };
 
@@ -71,6 +73,13 @@ enum {
                                     decode path is per-op kernels with the attention fused into one launch (b200_rope_kv_flash_attn) */
     B200_EXEC_MEGA_MMV    = 8,   /* ... and the Q4_K / Q6_K matvecs of the chain in the same launch (also: GGML_B200_MEGA_MMV=1)        */
 };
+
+/* The wide path — MUL_MAT on Q4_1 / Q5_1 / Q2_K / Q3_K / IQ4_NL / IQ4_XS / MXFP4 weights, MUL_MAT_ID, GET_ROWS on quantised tables
+ * (b200_ops.h "the wide kernels") — is switched on per process with GGML_B200_WIDE=1.  It is off by default in
+ * this round because its kernels were written after the round's GPU budget was spent: their arithmetic is verified on the CPU
+ * (tests/test_extfmt_hostsim.py), the kernels themselves have not run on hardware yet (tests/test_gpu_zz_wide.py).  With the switch off
+ * b200_executor_supports answers 0 for those nodes and ggml's scheduler keeps them on its CPU backend, exactly as before. */
+B200_API int            b200_executor_wide_enabled(void);
 
 typedef struct b200_executor b200_executor;
 

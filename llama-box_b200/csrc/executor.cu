@@ -17,6 +17,9 @@
 namespace {
 
 inline bool is_weight_type(int t) { return t == B200_TYPE_Q4_0 || t == B200_TYPE_Q5_0 || t == B200_TYPE_Q8_0 || t == B200_TYPE_Q4_K || t == B200_TYPE_Q5_K || t == B200_TYPE_Q6_K; }
+// the wide path (mmvq_ext.cu): formats beyond the tuned five, MUL_MAT_ID, GET_ROWS on quantised tables — GGML_B200_WIDE=1 (b200_graph.h)
+inline bool wide_on() { static const bool on = [] { const char * e = getenv("GGML_B200_WIDE"); return e && *e && *e != '0'; }(); return on; }
+inline bool is_wide_only_type(int t) { return t == B200_TYPE_Q4_1 || t == B200_TYPE_Q5_1 || t == B200_TYPE_Q2_K || t == B200_TYPE_Q3_K || t == B200_TYPE_IQ4_NL || t == B200_TYPE_IQ4_XS || t == B200_TYPE_MXFP4; }
 inline int64_t nrows_of(const b200_tensor & t) { return t.ne[1] * t.ne[2] * t.ne[3]; }
 inline int64_t nelem(const b200_tensor & t) { return t.ne[0] * t.ne[1] * t.ne[2] * t.ne[3]; }
 inline int64_t elem_size(int type) {
@@ -38,6 +41,7 @@ inline float f32_param(const b200_node & n, int i) { float f; memcpy(&f, &n.op_p
 inline size_t tensor_bytes(const b200_tensor & t) {
     if (!t.data) return 0;
     if (is_weight_type(t.type)) return (size_t)(nrows_of(t) > 0 ? (t.ne[1] - 1) * t.nb[1] + (t.ne[2] - 1) * t.nb[2] + (t.ne[3] - 1) * t.nb[3] + type_block_bytes(t.type) * (t.ne[0] / type_block_elems(t.type)) : 0);
+    if (is_wide_only_type(t.type)) return (size_t)(nrows_of(t) > 0 ? (t.ne[1] - 1) * t.nb[1] + (t.ne[2] - 1) * t.nb[2] + (t.ne[3] - 1) * t.nb[3] + b200_wide_row_bytes(t.type, t.ne[0]) : 0);
     size_t b = (size_t)elem_size(t.type);
     for (int i = 0; i < 4; i++) b += (size_t)(t.ne[i] - 1) * (size_t)t.nb[i];
     return b;
@@ -48,8 +52,47 @@ inline bool overlaps(const b200_tensor & a, const b200_tensor & b) {
     return a0 < b1 && b0 < a1;
 }
 
+// the tuned formats reach the wide kernels in the library's weight layout, which exists only where the load-time repack applies
+// (the same rule as mul_mat_ok / the plug-in's repack_k_ok: whole 256-element units, Q6_K rows 16-byte aligned)
+inline bool lib_layout_ok(int type, int64_t k) { return !is_weight_type(type) || (k % 256 == 0 && (type != B200_TYPE_Q6_K || k % 2048 == 0)); }
+// MUL_MAT on a format only the wide matvec reads (ggml block layout, any k that is a block multiple)
+bool mul_mat_wide_ok(const b200_node & n) {
+    const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
+    if (!wide_on() || !is_wide_only_type(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    const int64_t k = w.ne[0], m = w.ne[1];
+    if (!b200_wide_shape_supported(w.type, k) || m <= 0 || w.ne[2] != 1 || w.ne[3] != 1 || x.ne[2] != 1 || x.ne[3] != 1) return false;
+    if (w.nb[1] != b200_wide_row_bytes(w.type, k)) return false;
+    if (x.ne[0] != k || x.nb[0] != 4 || (x.nb[1] & 15) || d.ne[0] != m || d.ne[1] != x.ne[1] || d.nb[0] != 4 || (d.nb[1] & 3)) return false;
+    return aligned16(w.data) && aligned16(x.data);
+}
+// MUL_MAT_ID (ggml.c:3064-3106): as [k, m, n_expert], b f32 [k, n_b1, n_tok] (n_b1 = 1 or n_used), ids i32 [n_used, n_tok], dst f32 [m, n_used, n_tok]
+bool mul_mat_id_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 3) return false;
+    const b200_tensor & w = n.src[0], & x = n.src[1], & ids = n.src[2], & d = n.dst;
+    if (!(is_weight_type(w.type) || is_wide_only_type(w.type)) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32 || ids.type != B200_TYPE_I32) return false;
+    const int64_t k = w.ne[0], m = w.ne[1], ne = w.ne[2], n_used = ids.ne[0], n_tok = ids.ne[1];
+    if (!b200_wide_shape_supported(w.type, k) || m <= 0 || ne <= 0 || w.ne[3] != 1 || n_used <= 0 || n_tok <= 0 || ids.ne[2] != 1 || ids.ne[3] != 1) return false;
+    if (!lib_layout_ok(w.type, k)) return false;
+    if (w.nb[1] != b200_wide_row_bytes(w.type, k) || w.nb[2] < w.nb[1] * m || (w.nb[2] & 15)) return false;
+    if (x.ne[0] != k || x.nb[0] != 4 || (x.ne[1] != 1 && x.ne[1] != n_used) || x.ne[2] != n_tok || x.ne[3] != 1 || (x.nb[1] & 15) || (x.nb[2] & 15)) return false;
+    if (d.ne[0] != m || d.ne[1] != n_used || d.ne[2] != n_tok || d.ne[3] != 1 || d.nb[0] != 4 || (d.nb[1] & 3) || (d.nb[2] & 3)) return false;
+    if (ids.nb[0] != 4 || (ids.nb[1] & 3)) return false;
+    return aligned16(w.data) && aligned16(x.data);
+}
+// GET_ROWS on a quantised table (token embeddings): src rows of a weight format, ids i32 [n], dst f32 [ncols, n] contiguous
+bool get_rows_q_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 2) return false;
+    const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+    if (!(is_weight_type(s.type) || is_wide_only_type(s.type)) || ids.type != B200_TYPE_I32 || d.type != B200_TYPE_F32) return false;
+    if (!lib_layout_ok(s.type, s.ne[0])) return false;
+    if (!b200_wide_shape_supported(s.type, s.ne[0]) || s.ne[1] <= 0 || s.ne[2] != 1 || s.ne[3] != 1 || s.nb[1] < b200_wide_row_bytes(s.type, s.ne[0]) || (s.nb[1] & 1)) return false;
+    if (ids.ne[1] != 1 || ids.ne[2] != 1 || ids.ne[3] != 1 || ids.nb[0] != 4 || d.ne[0] != s.ne[0] || d.ne[1] != ids.ne[0] || !contiguous(d)) return false;
+    return aligned16(s.data) && aligned16(d.data);
+}
+
 bool mul_mat_ok(const b200_node & n) {
     const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
+    if (is_wide_only_type(w.type)) return mul_mat_wide_ok(n);
     if (!is_weight_type(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
     const int64_t k = w.ne[0], m = w.ne[1];
     // 32-element block types: any multiple of 32 (rows padded to 256 in the private weight layout, see common.cuh padded_k)
@@ -116,8 +159,10 @@ bool node_ok(const b200_node & n) {
         case B200_OP_SET_ROWS: return n.n_src >= 2 && set_rows_ok(n);
         case B200_OP_FLASH_ATTN_EXT: return n.n_src >= 3 && fattn_ok(n);
         case B200_OP_GLU_SWIGLU: return n.n_src >= 2 && rows_f32_ok(n.src[0]) && rows_f32_ok(n.src[1]) && rows_f32_ok(n.dst) && same_shape(n.src[0], n.src[1]) && same_shape(n.src[0], n.dst);
+        case B200_OP_MUL_MAT_ID: return mul_mat_id_ok(n);
         case B200_OP_GET_ROWS: {
             const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+            if (n.n_src >= 2 && s.type != B200_TYPE_F32) return get_rows_q_ok(n);
             return n.n_src >= 2 && s.type == B200_TYPE_F32 && ids.type == B200_TYPE_I32 && s.nb[0] == 4 && (s.nb[1] & 15) == 0 && s.ne[2] == 1 && s.ne[3] == 1 &&
                    s.ne[0] % 4 == 0 && aligned16(s.data) && d.type == B200_TYPE_F32 && contiguous(d) && aligned16(d.data) && ids.ne[1] == 1 && ids.ne[2] == 1 && d.ne[1] == ids.ne[0];
         }
@@ -349,7 +394,7 @@ struct Runner {
                 if (nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4 && x.nb[1] == ncols * 4 && !is_output(n.dst) && !is_output(mu.dst)) {
                     int consumers = 0, mm = 0;
                     for (int q = j + 1; q < this->n; q++) for (int sidx = 0; sidx < nodes[q].n_src && sidx < B200_MAX_SRC; sidx++)
-                        if (nodes[q].src[sidx].id == mu.dst.id) { consumers++; if (nodes[q].op == B200_OP_MUL_MAT && sidx == 1 && !done[q] && nodes[q].src[1].ne[1] <= 8) mm++; }
+                        if (nodes[q].src[sidx].id == mu.dst.id) { consumers++; if (nodes[q].op == B200_OP_MUL_MAT && sidx == 1 && !done[q] && nodes[q].src[1].ne[1] <= 8 && is_weight_type(nodes[q].src[0].type)) mm++; }
                     if (consumers > 0 && consumers == mm) {
                         ex->norm.out_id = mu.dst.id; ex->norm.out_data = mu.dst.data; ex->norm.x = x; ex->norm.out = mu.dst;
                         ex->norm.w = (const float *)w->data; ex->norm.eps = eps;
@@ -372,7 +417,7 @@ struct Runner {
                 }
                 // if the next consumer is a decode-shaped quantised MUL_MAT, emit its activation format too
                 const int c = next_compute(j);
-                if (c >= 0 && nodes[c].op == B200_OP_MUL_MAT && nodes[c].src[1].id == mu.dst.id && nodes[c].src[1].data == mu.dst.data &&
+                if (c >= 0 && nodes[c].op == B200_OP_MUL_MAT && is_weight_type(nodes[c].src[0].type) && nodes[c].src[1].id == mu.dst.id && nodes[c].src[1].data == mu.dst.data &&
                     nrows <= 8 && ncols % 256 == 0 && mu.dst.nb[1] == ncols * 4) {
                     const int kind = b200_act_kind_for(nodes[c].src[0].type);
                     { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
@@ -434,7 +479,7 @@ struct Runner {
         int rope[2] = { -1, -1 };
         int cur = i;
         for (int j = 0; j < 3; j++) {
-            if (j > 0) { cur = next_compute(cur); if (cur < 0 || nodes[cur].op != B200_OP_MUL_MAT) return false; }
+            if (j > 0) { cur = next_compute(cur); if (cur < 0 || nodes[cur].op != B200_OP_MUL_MAT || !is_weight_type(nodes[cur].src[0].type)) return false; }
             const b200_node & mm = nodes[cur];
             if (mm.src[1].id != x.id || mm.src[1].data != x.data || mm.src[0].ne[0] != mq.src[0].ne[0] || mm.dst.nb[1] != mm.src[0].ne[1] * 4) return false;
             if (is_output(mm.dst)) return false;
@@ -517,6 +562,12 @@ struct Runner {
         const b200_node & n = nodes[i];
         const b200_tensor & w = n.src[0], & x = n.src[1];
         const int64_t kv = w.ne[0], k = padded_k(w.type, kv), m = w.ne[1], ncols = x.ne[1];   // kv: elements that exist in x; k: padded weight rows
+        if (is_wide_only_type(w.type)) {
+            // a format only the wide matvec reads (mmvq_ext.cu): f32 activations in, quantised inside the kernel; one pass over the weights per column
+            { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+            invalidate_act(n.dst);
+            return KL(b200_mul_mat_vec_wide(w.type, w.data, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, nullptr, nullptr, m, kv, ncols, st));
+        }
         if (ncols > 8) {
             { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
             invalidate_act(n.dst);
@@ -531,7 +582,7 @@ struct Runner {
         if (fuse) {
             // (1) up, gate, GLU (llama-graph.cpp:647-693): MUL_MAT(up,x) MUL_MAT(gate,x) GLU(gate,up)
             const int j = next_compute(i);
-            if (j >= 0 && nodes[j].op == B200_OP_MUL_MAT && nodes[j].src[1].id == x.id && nodes[j].src[1].data == x.data && nodes[j].src[0].ne[1] == m && nodes[j].src[1].ne[1] == ncols) {
+            if (j >= 0 && nodes[j].op == B200_OP_MUL_MAT && is_weight_type(nodes[j].src[0].type) && nodes[j].src[1].id == x.id && nodes[j].src[1].data == x.data && nodes[j].src[0].ne[1] == m && nodes[j].src[1].ne[1] == ncols) {
                 const int g = next_compute(j);
                 const bool x_live = g >= 0 && (overlaps(nodes[g].dst, x) || (ex->norm.out_id && ex->norm.out_id == x.id && overlaps(nodes[g].dst, ex->norm.x)));   // late CTAs still quantise x in their prologue
                 if (g >= 0 && nodes[g].op == B200_OP_GLU_SWIGLU && use_count(n.dst) == 1 && use_count(nodes[j].dst) == 1 &&
@@ -556,7 +607,7 @@ struct Runner {
             //     later MUL_MATs are hoisted only if their outputs alias nothing that is still live
             int group[MAX_GROUP] = { i }; int ng = 1;
             for (int j2 = i + 1; j2 < n_limit(i) && ng < MAX_GROUP; j2++) {
-                if (done[j2] || nodes[j2].op != B200_OP_MUL_MAT) continue;
+                if (done[j2] || nodes[j2].op != B200_OP_MUL_MAT || !is_weight_type(nodes[j2].src[0].type)) continue;
                 const b200_node & o = nodes[j2];
                 if (o.src[1].id != x.id || o.src[1].data != x.data || o.src[1].ne[1] != ncols || o.src[0].ne[0] != kv || padded_k(o.src[0].type, kv) != k) continue;
                 if (o.dst.nb[1] != o.src[0].ne[1] * 4 || !can_hoist(i, j2)) continue;
@@ -742,8 +793,18 @@ struct Runner {
             case B200_OP_GLU_SWIGLU:
                 invalidate_act(n.dst);
                 return KL(b200_swiglu((const float *)n.src[0].data, (const float *)n.src[1].data, (float *)n.dst.data, nelem(n.dst), st));
+            case B200_OP_MUL_MAT_ID: {
+                // expert routing on the device: the kernel reads ids itself (no stream synchronisation, unlike ggml-cuda.cu:2115-2125)
+                invalidate_act(n.dst);
+                const b200_tensor & w = n.src[0], & x = n.src[1], & ids = n.src[2];
+                return KL(b200_mul_mat_id(w.type, w.data, w.nb[2], (const float *)x.data, x.nb[2] / 4, x.nb[1] / 4, x.ne[1], (const int32_t *)ids.data, ids.nb[1] / 4,
+                                          (float *)n.dst.data, n.dst.nb[2] / 4, n.dst.nb[1] / 4, w.ne[1], w.ne[0], w.ne[2], ids.ne[0], ids.ne[1], st));
+            }
             case B200_OP_GET_ROWS:
                 invalidate_act(n.dst);
+                if (n.src[0].type != B200_TYPE_F32)
+                    return KL(b200_get_rows_q(n.src[0].type, n.src[0].data, n.src[0].nb[1], n.src[0].ne[1], (const int32_t *)n.src[1].data, (float *)n.dst.data, n.dst.nb[1] / 4,
+                                              n.src[0].ne[0], n.src[1].ne[0], st));
                 return KL(b200_get_rows_f32((const float *)n.src[0].data, n.src[0].nb[1] / 4, (const int32_t *)n.src[1].data, (float *)n.dst.data, n.src[0].ne[0], n.src[1].ne[0], st));
             case B200_OP_CPY:
                 invalidate_act(n.dst);
@@ -796,7 +857,7 @@ int plan_workspace(b200_executor * ex, const b200_node * nodes, int n) {
         if (nd.op == B200_OP_MUL_MAT) {
             const int64_t k = (nd.src[0].ne[0] + 255) / 256 * 256, cols = nd.src[1].ne[1];
             for (int kd = 0; kd < 2; kd++) { const size_t b = (size_t)(cols * act_col_bytes(kd, k)); if (b > act[kd]) act[kd] = b; }
-            if (cols > 8) {                               // batched path: the tensor-core kernel's pre-tiled activation image
+            if (cols > 8 && is_weight_type(nd.src[0].type)) {   // batched path: the tensor-core kernel's pre-tiled activation image
                 const int kd = b200_act_kind_for(nd.src[0].type);
                 const size_t b = (size_t)b200_mul_mat_q_workspace(nd.src[0].type, nd.src[0].ne[1], k, cols);
                 if (kd >= 0 && b > act[kd]) act[kd] = b;
@@ -851,6 +912,7 @@ extern "C" void b200_executor_free(b200_executor * ex) {
     delete ex;
 }
 
+extern "C" int b200_executor_wide_enabled(void) { return wide_on() ? 1 : 0; }
 extern "C" int b200_executor_supports(const b200_node * node) { return node && node_ok(*node) ? 1 : 0; }
 
 extern "C" int b200_executor_compute(b200_executor * ex, const b200_node * nodes, int n_nodes, void * stream, int flags) {

@@ -9,7 +9,8 @@ import ctypes as C
 from . import ops
 
 F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K, I32, I64 = 0, 1, 2, 6, 8, 12, 13, 14, 26, 27
-OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY = range(11)
+Q4_1, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS, MXFP4 = 3, 7, 10, 11, 20, 23, 39      # the wide path's formats (b200_ops.h)
+OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY, OP_MUL_MAT_ID = range(12)
 EXEC_CUDA_GRAPHS, EXEC_FUSION, EXEC_MEGAKERNEL, EXEC_MEGA_MMV = 1, 2, 4, 8
 MAX_SRC = 6
 ELEM_SIZE = {F32: 4, F16: 2, I32: 4, I64: 8}
@@ -31,7 +32,8 @@ _lib.b200_executor_plan.restype = C.c_int64; _lib.b200_executor_plan.argtypes = 
 _lib.b200_executor_compute.restype = C.c_int; _lib.b200_executor_compute.argtypes = [C.c_void_p, C.POINTER(Node), C.c_int, C.c_void_p, C.c_int]
 for _n in ("b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays", "b200_executor_mk_launches", "b200_executor_mk_phases"):
     getattr(_lib, _n).restype = C.c_int64; getattr(_lib, _n).argtypes = [C.c_void_p]
-GRAPH_SYMBOLS = ["b200_executor_plan", "b200_executor_create", "b200_executor_free", "b200_executor_supports", "b200_executor_compute",
+_lib.b200_executor_wide_enabled.restype = C.c_int; _lib.b200_executor_wide_enabled.argtypes = []
+GRAPH_SYMBOLS = ["b200_executor_wide_enabled", "b200_executor_plan", "b200_executor_create", "b200_executor_free", "b200_executor_supports", "b200_executor_compute",
                  "b200_executor_last_kernels", "b200_executor_graph_captures", "b200_executor_graph_replays", "b200_executor_mk_launches", "b200_executor_mk_phases"]
 
 _next_id = [1]
@@ -40,7 +42,8 @@ _next_id = [1]
 def row_size(t, ne0):
     if t in ELEM_SIZE:
         return ELEM_SIZE[t] * ne0
-    return ops.row_bytes(t, ne0)
+    rb = ops.row_bytes(t, ne0)
+    return rb if rb > 0 else ops.lib.b200_wide_row_bytes(t, ne0)
 
 
 class T:
@@ -49,7 +52,7 @@ class T:
     def __init__(self, ptr, type_, ne, nb=None, tid=None):
         ne = list(ne) + [1] * (4 - len(ne))
         if nb is None:
-            nb = [ELEM_SIZE.get(type_, ops.lib.b200_block_bytes(type_)), row_size(type_, ne[0]), 0, 0]
+            nb = [ELEM_SIZE.get(type_, ops.lib.b200_block_bytes(type_) or 1), row_size(type_, ne[0]), 0, 0]
             nb[2] = nb[1] * ne[1]; nb[3] = nb[2] * ne[2]
         self.ptr, self.type, self.ne, self.nb = int(ptr), type_, ne, list(nb)
         if tid is None:

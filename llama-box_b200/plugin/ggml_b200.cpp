@@ -263,6 +263,7 @@ static bool node_to_b200(const ggml_tensor * t, b200_node & n) {
             n.op = B200_OP_GLU_SWIGLU; break;
         case GGML_OP_GET_ROWS: n.op = B200_OP_GET_ROWS; break;
         case GGML_OP_CPY:      n.op = B200_OP_CPY; break;
+        case GGML_OP_MUL_MAT_ID: n.op = B200_OP_MUL_MAT_ID; break;     // wide path (GGML_B200_WIDE=1); refused by b200_executor_supports otherwise
         default: return false;
     }
     to_b200(t, n.dst);
@@ -389,10 +390,10 @@ static enum ggml_status be_graph_compute(ggml_backend_t b, struct ggml_cgraph * 
         if (!node_to_b200(t, c->nodes[i])) { fprintf(stderr, "ggml-b200: op %s is not supported (node %s)\n", ggml_op_name(t->op), t->name); return GGML_STATUS_FAILED; }
         // weights that did not arrive as one whole-tensor upload (chunked --no-mmap loads) are converted here, once, with the
         // buffer mutex held across check + conversion + mark and a stream sync before anyone may read them
-        if (t->op == GGML_OP_MUL_MAT && is_repack_type(t->src[0]->type)) {
+        if ((t->op == GGML_OP_MUL_MAT || t->op == GGML_OP_MUL_MAT_ID || t->op == GGML_OP_GET_ROWS) && is_repack_type(t->src[0]->type)) {
             const ggml_tensor * w = t->src[0];
             ggml_backend_buffer_t wb = w->view_src ? w->view_src->buffer : w->buffer;
-            if (!is_b200_buffer(wb)) { fprintf(stderr, "ggml-b200: MUL_MAT weight %s is not in a B200 buffer\n", w->name); return GGML_STATUS_FAILED; }
+            if (!is_b200_buffer(wb)) { fprintf(stderr, "ggml-b200: %s weight %s is not in a B200 buffer\n", ggml_op_name(t->op), w->name); return GGML_STATUS_FAILED; }
             if (!ensure_repacked((b200_buffer_ctx *)wb->context, w)) { fprintf(stderr, "ggml-b200: repack failed: %s\n", b200_last_error()); return GGML_STATUS_FAILED; }
             cudaSetDevice(c->device);
         }
