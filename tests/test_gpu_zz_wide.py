@@ -1,0 +1,84 @@
+"""GPU: the wide path — MUL_MAT on Q4_1 / Q5_1 / Q2_K / Q3_K / IQ4_NL / IQ4_XS / MXFP4, MUL_MAT_ID (expert routing read on the device) and
+GET_ROWS on quantised tables (llama-box_b200/csrc/mmvq_ext.cu) — against the C oracle, through the C-ABI
+(b200_mul_mat_vec_wide / b200_mul_mat_id / b200_get_rows_q), through the graph executor, and through the plug-in with the reference's own
+test-backend-ops harness.
+
+STATUS: these kernels were written after round 2's GPU budget had been spent.  Their per-format arithmetic (extfmt.cuh) is the same code
+tests/test_extfmt_hostsim.py checks on the CPU against the reference, but the kernels themselves have NOT run on hardware yet, which is why
+  * the path is off by default (GGML_B200_WIDE=1 switches it on),
+  * every case runs in a child process (a faulting kernel must not poison the CUDA context of the rest of the GPU suite), and
+  * the cases are marked xfail(strict=False): XPASS = verified on this box; XFAIL = a defect to fix next round, not a regression of the
+    verified path.  The file sorts last on purpose."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from refutil import REF_DIR, ROOT, have_ref
+
+UNVERIFIED = "wide path: written after the round's GPU budget was spent, first hardware run is this one (see module docstring)"
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason=UNVERIFIED)]
+CHILD = os.path.join(ROOT, "tests", "wide_gpu_child.py")
+CORE = [2, 6, 8, 12, 13, 14]
+EXT = [3, 7, 10, 11, 20, 23, 39]
+
+
+def child(*args, wide=False, timeout=600):
+    env = dict(os.environ)
+    env.pop("GGML_B200_WIDE", None)
+    if wide:
+        env["GGML_B200_WIDE"] = "1"
+    r = subprocess.run([sys.executable, CHILD] + [str(a) for a in args], capture_output=True, text=True, env=env, timeout=timeout)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    return json.loads(line[7:])
+
+
+@pytest.mark.parametrize("t", [2, 6, 8, 14])
+def test_numpy_model_of_the_library_layout_matches_the_repack_kernel(t):
+    assert child("repack_model", t, 2048)["equal"]
+
+
+@pytest.mark.parametrize("t", EXT + CORE)
+def test_wide_kernels_vs_oracle(t):
+    """one format: b200_mul_mat_vec_wide (4 shapes x {random bit patterns, reference-quantised weights}, with and without bias + residual; rows that
+    are not a multiple of 256 for the 32-element formats), b200_mul_mat_id (shared / per-expert activations, 1 and 5 tokens), b200_get_rows_q"""
+    o = child("type_suite", t, timeout=1200)
+    bad = {}
+    for name, r in o.items():
+        if "error" in r:
+            bad[name] = r
+        elif name.startswith("mul_mat_id"):
+            if r["err"] > 2e-5:
+                bad[name] = r
+        elif name.startswith("mul_mat"):
+            if r["plain"] > 2e-5 or r["bias_residual"] > 2e-5:
+                bad[name] = r
+        elif not r["bit_exact"]:
+            bad[name] = r
+    assert len(o) >= 13 and not bad, bad
+
+
+@pytest.mark.parametrize("wtype", [3, 11, 23])
+@pytest.mark.parametrize("n_tok", [1, 4])
+def test_executor_moe_block_vs_oracle(wtype, n_tok):
+    o = child("executor", wtype, n_tok, wide=True)
+    assert all(o["supports"]), o
+    assert max(o["errs"]) <= 5e-5, o                         # chained ops: each re-quantises its input like the oracle does
+    assert o["captures"] >= 1 and o["replays"] >= 1, o
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")
+@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("MUL_MAT", 60), ("GET_ROWS", 4)])
+def test_reference_backend_ops_harness_with_the_wide_path(op, min_ok):
+    """the reference's own parity harness (tests/test-backend-ops.cpp) against the plug-in with GGML_B200_WIDE=1"""
+    plugin = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=REF_DIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), GGML_BACKEND_PATH=plugin, GGML_B200_WIDE="1")
+    r = subprocess.run([os.path.join(REF_DIR, "test-backend-ops"), "test", "-b", "B2000", "-o", op], capture_output=True, text=True, env=env, timeout=1800)
+    plain = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout + r.stderr)
+    ok = len(re.findall(r"\): OK", plain)); fail = len(re.findall(r"FAIL", plain))
+    assert fail == 0 and r.returncode == 0, plain[-4000:]
+    assert ok >= min_ok, (ok, plain[-2000:])

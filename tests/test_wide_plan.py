@@ -15,7 +15,7 @@ sys.path.insert(0, %r)
 from conftest import load_pkg
 load_pkg()
 G = importlib.import_module("llama_box_b200.graph")
-E, FF, NE, NU, NT, VOC = 4096, 1024, 8, 2, %d, 32000
+E, FF, NE, NU, NT, VOC = 4096, 2048, 8, 2, %d, 32000
 base = [0x10000000]
 def buf(n):
     p = base[0]; base[0] += (n + 0xfffff) & ~0xfffff; return p
