@@ -97,6 +97,36 @@ def main():
     g = (rng.standard_normal((2, 512)) * 3).astype(np.float32); u = rng.standard_normal((2, 512)).astype(np.float32)
     _, _, out = run_ref_op("swiglu", [("gate", F32, [512, 2], g), ("up", F32, [512, 2], u)])
     write_bundle(os.path.join(GOLDEN_DIR, "swiglu.bin"), [("gate", F32, [512, 2], g), ("up", F32, [512, 2], u), ("dst", F32, [512, 2], out)])
+    # ---- the wide path's formats: reference quantiser output, de-quantised values, MUL_MAT through the CPU backend
+    from refutil import EXT_TYPES, Q4_K, Q8_1
+    rng = np.random.default_rng(4321)                # its own stream: the fixtures above stay byte-identical
+    m2, k2, n2 = 8, 1024, 2
+    w2 = (rng.standard_normal((m2, k2)) * 0.05).astype(np.float32); X2 = rng.standard_normal((n2, k2)).astype(np.float32)
+    for t in EXT_TYPES:
+        Wq = ref_quantize_weights(t, w2)
+        deq = np.zeros((m2, k2), np.float32)
+        for i in range(m2):
+            getattr(base, "dequantize_row_" + TYPE_NAME[t])(ptr(Wq[i]), ptr(deq[i]), k2)
+        _, _, out = run_ref_op("mul_mat", [("w", t, [k2, m2], Wq), ("x", F32, [k2, n2], X2)])
+        write_bundle(os.path.join(GOLDEN_DIR, f"ext_mul_mat_{TYPE_NAME[t]}.bin"),
+                     [("w", t, [k2, m2], Wq), ("x", F32, [k2, n2], X2), ("deq", F32, [k2, m2], deq), ("dst", F32, [m2, n2], out)])
+    q81 = np.zeros((3, row_bytes(Q8_1, k)), np.uint8)
+    for i in range(3):
+        cpu.quantize_row_q8_1(ptr(x[i]), ptr(q81[i]), k)
+    # ---- MUL_MAT_ID (f2) as build_moe_ffn emits it: shared activation and one activation per used expert; GET_ROWS on a quantised table (f4)
+    me, ke, n_expert, n_used, n_tok = 16, 512, 5, 2, 3
+    We = ref_quantize_weights(Q4_K, (rng.standard_normal((n_expert * me, ke)) * 0.05).astype(np.float32))
+    ids = np.stack([rng.permutation(n_expert)[:n_used] for _ in range(n_tok)]).astype(np.int32)
+    T = [("w", Q4_K, [ke, me, n_expert], We), ("ids", I32, [n_used, n_tok], ids), ("q8_1", Q8_1, [k, 3], q81), ("x81", F32, [k, 3], x)]
+    for tag, n_b1 in (("shared", 1), ("per_expert", n_used)):
+        b = rng.standard_normal((n_tok, n_b1, ke)).astype(np.float32)
+        _, _, out = run_ref_op("mul_mat_id", [("w", Q4_K, [ke, me, n_expert], We), ("x", F32, [ke, n_b1, n_tok], b), ("ids", I32, [n_used, n_tok], ids)])
+        T += [("b_" + tag, F32, [ke, n_b1, n_tok], b), ("dst_" + tag, F32, [me, n_used, n_tok], out)]
+    gid = np.array([7, 0, 79, 7], np.int32)
+    _, _, out = run_ref_op("get_rows", [("src", Q4_K, [ke, n_expert * me], We), ("ids", I32, [gid.size], gid)])
+    T += [("gr_ids", I32, [gid.size], gid), ("gr_dst", F32, [ke, gid.size], out)]
+    write_bundle(os.path.join(GOLDEN_DIR, "ext_moe_get_rows.bin"), T)
+
     print("golden fixtures:", sorted(os.listdir(GOLDEN_DIR)))
 
 

@@ -90,3 +90,37 @@ def test_swiglu():
     a, b, want = f32(g["gate"]), f32(g["up"]), f32(g["dst"])
     y = np.zeros_like(a); oracle().orc_swiglu(ptr(a), ptr(b), ptr(y), a.size)
     assert np.abs(y - want).max() <= 1e-6 * np.abs(want).max()   # the reference uses a vectorised expf (ggml_v_expf)
+
+
+# ---- the wide path: oracle_ext.c against fixtures the unmodified reference produced (oracle/make_golden.py) ----------
+from refutil import EXT_TYPES, Q4_K, Q8_1  # noqa: E402
+
+
+@pytest.mark.parametrize("t", EXT_TYPES)
+def test_ext_dequant_and_mul_mat(t):
+    g = load(f"ext_mul_mat_{TYPE_NAME[t]}.bin")
+    _, ne, _ = g["w"]; k, m = ne[0], ne[1]
+    W = raw2d(g["w"], m); X = f32(g["x"]); n = X.shape[0]
+    assert np.array_equal(orc_dequant(t, W, m, k), f32(g["deq"]))
+    want = f32(g["dst"]); got = orc_mul_mat(t, W, X, m, n, k)
+    assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+
+
+def test_q8_1_mul_mat_id_get_rows():
+    g = load("ext_moe_get_rows.bin")
+    x = f32(g["x81"]); k = x.shape[1]
+    for i in range(x.shape[0]):
+        a = np.zeros(row_bytes(Q8_1, k), np.uint8); oracle().orc_quantize_row_q8_1(ptr(x[i]), ptr(a), k)
+        assert np.array_equal(a, raw2d(g["q8_1"], 3)[i])
+    _, ne, W = g["w"]; ke, me, n_expert = ne[0], ne[1], ne[2]
+    ids = g["ids"][2].view(np.int32); n_used, n_tok = g["ids"][1][0], g["ids"][1][1]
+    for tag in ("shared", "per_expert"):
+        b = g["b_" + tag][2].view(np.float32); n_b1 = g["b_" + tag][1][1]
+        want = g["dst_" + tag][2].view(np.float32)
+        got = np.zeros_like(want)
+        oracle().orc_mul_mat_id(Q4_K, ptr(W), ptr(b), ptr(ids), ptr(got), me, ke, n_expert, n_used, n_tok, n_b1, n_used)
+        assert np.abs(got - want).max() <= 3e-6 * np.abs(want).max()
+    gid = g["gr_ids"][2].view(np.int32); want = g["gr_dst"][2].view(np.float32)
+    got = np.zeros_like(want)
+    oracle().orc_get_rows_q(Q4_K, ptr(W), ptr(gid), ptr(got), ke, gid.size)
+    assert np.array_equal(got, want)
