@@ -110,14 +110,15 @@ def main():
         _, _, out = run_ref_op("mul_mat", [("w", t, [k2, m2], Wq), ("x", F32, [k2, n2], X2)])
         write_bundle(os.path.join(GOLDEN_DIR, f"ext_mul_mat_{TYPE_NAME[t]}.bin"),
                      [("w", t, [k2, m2], Wq), ("x", F32, [k2, n2], X2), ("deq", F32, [k2, m2], deq), ("dst", F32, [m2, n2], out)])
-    q81 = np.zeros((3, row_bytes(Q8_1, k)), np.uint8)
+    kx = x.shape[1]                                   # the activation rows of quantize_act.bin
+    q81 = np.zeros((3, row_bytes(Q8_1, kx)), np.uint8)
     for i in range(3):
-        cpu.quantize_row_q8_1(ptr(x[i]), ptr(q81[i]), k)
+        cpu.quantize_row_q8_1(ptr(x[i]), ptr(q81[i]), kx)
     # ---- MUL_MAT_ID (f2) as build_moe_ffn emits it: shared activation and one activation per used expert; GET_ROWS on a quantised table (f4)
     me, ke, n_expert, n_used, n_tok = 16, 512, 5, 2, 3
     We = ref_quantize_weights(Q4_K, (rng.standard_normal((n_expert * me, ke)) * 0.05).astype(np.float32))
     ids = np.stack([rng.permutation(n_expert)[:n_used] for _ in range(n_tok)]).astype(np.int32)
-    T = [("w", Q4_K, [ke, me, n_expert], We), ("ids", I32, [n_used, n_tok], ids), ("q8_1", Q8_1, [k, 3], q81), ("x81", F32, [k, 3], x)]
+    T = [("w", Q4_K, [ke, me, n_expert], We), ("ids", I32, [n_used, n_tok], ids), ("q8_1", Q8_1, [kx, 3], q81), ("x81", F32, [kx, 3], x)]
     for tag, n_b1 in (("shared", 1), ("per_expert", n_used)):
         b = rng.standard_normal((n_tok, n_b1, ke)).astype(np.float32)
         _, _, out = run_ref_op("mul_mat_id", [("w", Q4_K, [ke, me, n_expert], We), ("x", F32, [ke, n_b1, n_tok], b), ("ids", I32, [n_used, n_tok], ids)])
