@@ -74,7 +74,7 @@ bool mul_mat_id_ok(const b200_node & n) {
     if (!b200_wide_shape_supported(w.type, k) || m <= 0 || ne <= 0 || w.ne[3] != 1 || n_used <= 0 || n_tok <= 0 || ids.ne[2] != 1 || ids.ne[3] != 1) return false;
     if (!lib_layout_ok(w.type, k)) return false;
     if (w.nb[1] != b200_wide_row_bytes(w.type, k) || w.nb[2] < w.nb[1] * m || (w.nb[2] & 15)) return false;
-    if (x.ne[0] != k || x.nb[0] != 4 || (x.ne[1] != 1 && x.ne[1] != n_used) || x.ne[2] != n_tok || x.ne[3] != 1 || (x.nb[1] & 15) || (x.nb[2] & 15)) return false;
+    if (x.ne[0] != k || x.nb[0] != 4 || x.ne[1] <= 0 || n_used % x.ne[1] != 0 || x.ne[2] != n_tok || x.ne[3] != 1 || (x.nb[1] & 15) || (x.nb[2] & 15)) return false;
     if (d.ne[0] != m || d.ne[1] != n_used || d.ne[2] != n_tok || d.ne[3] != 1 || d.nb[0] != 4 || (d.nb[1] & 3) || (d.nb[2] & 3)) return false;
     if (ids.nb[0] != 4 || (ids.nb[1] & 3)) return false;
     return aligned16(w.data) && aligned16(x.data);

@@ -402,6 +402,7 @@ void orc_set_rows(const float *src, const int64_t *ids, void *dst, int dst_type,
         uint8_t *drow = (uint8_t *)dst + ids[r]*stride;
         if (dst_type == ORC_F16)       orc_cpy_f32_f16(src + r*ncols, (uint16_t *)drow, ncols);
         else if (dst_type == ORC_Q8_0) orc_quantize_row_q8_0(src + r*ncols, drow, ncols);
+        else if (dst_type == ORC_Q4_0) orc_quantize_row_q4_0(src + r*ncols, drow, ncols);   /* oracle_ext.c */
         else if (dst_type == ORC_F32)  memcpy(drow, src + r*ncols, (size_t)ncols*4);
     }
 }
@@ -449,7 +450,7 @@ void orc_flash_attn_ext(const void *q, int64_t q_nb1, int64_t q_nb2,
                     a += orc_fp16_to_fp32(((const uint16_t *)krow)[i]) * orc_fp16_to_fp32(((const uint16_t *)qq)[i]);
                 s = a;
             } else {
-                s = dot_q8_0(dk, (const blk_q8_0 *)krow, (const blk_q8_0 *)qq);
+                s = orc_vec_dot(kv_type, dk, krow, qq);        /* Q8_0 / Q4_0 K against the q8_0 form of the Q row */
             }
             s *= scale;
             if (softcap != 0.0f) s = softcap * tanhf(s);

@@ -80,13 +80,13 @@ void orc_rope(const float *x, float *y, const int32_t *pos, const float *freq_fa
               float ext_factor, float attn_factor, float beta_fast, float beta_slow);
 
 /* SET_ROWS (ggml-cpu/ops.cpp:5359-5415): dst row ids[i] <- from_float(src row i);
- * dst_type F16 or Q8_0; dst_row_stride in bytes */
+ * dst_type F32, F16, Q8_0 or Q4_0; dst_row_stride in bytes */
 void orc_set_rows(const float *src, const int64_t *ids, void *dst, int dst_type,
                   int64_t ncols, int64_t nrows, int64_t dst_row_stride);
 
 /* FLASH_ATTN_EXT (ggml-cpu/ops.cpp:8169-8405), one sequence:
  *   q   [n_head][n_tok][dk] f32 given with byte strides (q_nb1 between tokens, q_nb2 between heads)
- *   k,v [n_head_kv][n_kv] rows of kv_type (F16 or Q8_0) with byte strides (nb1 row, nb2 head)
+ *   k,v [n_head_kv][n_kv] rows of kv_type (F16, Q8_0 or Q4_0) with byte strides (nb1 row, nb2 head)
  *   mask f16 [n_tok_pad][n_kv] (row stride n_kv halves) or NULL
  *   dst [n_tok][n_head][dv] f32 contiguous (the op's permuted output, ggml.c:4814-4858) */
 void orc_flash_attn_ext(const void *q, int64_t q_nb1, int64_t q_nb2,
@@ -101,6 +101,8 @@ void orc_flash_attn_ext(const void *q, int64_t q_nb1, int64_t q_nb2,
 int   orc_is_ext_type(int type);
 int   orc_act_type(int weight_type);                       /* vec_dot_type: ORC_Q8_0 / ORC_Q8_1 / ORC_Q8_K (ggml-cpu/ggml-cpu.c:209-303) */
 void  orc_quantize_row_q8_1(const float *x, void *y, int64_t k);   /* ggml-cpu/arch/x86/quants.c:388-492 */
+/* Q4_0 as ggml's from_float writes it (KV cache type q4_0): ggml-quants.c quantize_row_q4_0_ref (ggml-cpu/quants.c:25-27 calls it) */
+void  orc_quantize_row_q4_0(const float *x, void *y, int64_t k);
 int   orc_dequantize_row_ext(int type, const void *x, float *y, int64_t k);
 float orc_vec_dot_ext(int type, int64_t k, const void *w, const void *a);
 /* MUL_MAT_ID (ggml-cpu/ggml-cpu.c:1400-1620): dst[t][s] = as[ids[t][s]] * b[t][s % n_b1];  as [n_expert][m] rows, b [n_tok][n_b1][k],

@@ -63,6 +63,26 @@ void orc_quantize_row_q8_1(const float *x, void *vy, int64_t k) {
     }
 }
 
+/* Q4_0 from f32 (ggml-quants.c quantize_row_q4_0_ref): the element of largest magnitude (first one on ties) maps to -8; values are
+ * truncated after adding 8.5, clamped to 15 */
+void orc_quantize_row_q4_0(const float *x, void *vy, int64_t k) {
+    uint8_t *y = (uint8_t *)vy;
+    for (int64_t b = 0; b < k / 32; b++, y += 18) {
+        float amax = 0.0f, mx = 0.0f;
+        for (int j = 0; j < 32; j++) { const float v = x[b*32 + j]; if (amax < fabsf(v)) { amax = fabsf(v); mx = v; } }
+        const float d = mx / -8.0f, id = d != 0.0f ? 1.0f / d : 0.0f;
+        const uint16_t dh = orc_fp32_to_fp16(d);
+        memcpy(y, &dh, 2);
+        for (int j = 0; j < 16; j++) {
+            const float x0 = x[b*32 + j] * id, x1 = x[b*32 + 16 + j] * id;
+            int q0 = (int)(int8_t)(x0 + 8.5f), q1 = (int)(int8_t)(x1 + 8.5f);
+            if (q0 > 15) q0 = 15;
+            if (q1 > 15) q1 = 15;
+            y[2 + j] = (uint8_t)(q0 | (q1 << 4));
+        }
+    }
+}
+
 /* Q3_K: the 16 six-bit scales of a super-block, unpacked (ggml-quants.c:1143-1148) */
 static void q3K_scales(const uint8_t *sc12, int8_t *out16) {
     uint32_t aux[4]; memcpy(aux, sc12, 12);

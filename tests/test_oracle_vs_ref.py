@@ -140,3 +140,30 @@ def test_get_rows_quantised_through_cpu_backend(t):
     got = np.zeros_like(want)
     oracle().orc_get_rows_q(t, ptr(W), ptr(ids), ptr(got), k, ids.size)
     assert np.array_equal(got, want)
+
+
+def test_q4_0_kv_cache_set_rows_and_flash_attn_through_cpu_backend():
+    """KV cache type q4_0 (llama-box -ctk q4_0 -ctv q4_0): SET_ROWS bytes identical, FLASH_ATTN_EXT within the Q8_0 tolerance"""
+    from refutil import Q4_0
+    rng = np.random.default_rng(40)
+    dk, nh, nhkv, nt, nkv = 128, 8, 2, 2, 512
+    kf = rng.standard_normal((nkv, nhkv * dk)).astype(np.float32); vf = rng.standard_normal((nkv, nhkv * dk)).astype(np.float32)
+    kf[3, :32] = 0; kf[5, 7] = -kf[5, :32].max() if False else kf[5, 7]
+    rb_row, rb_head = row_bytes(Q4_0, nhkv * dk), row_bytes(Q4_0, dk)
+    z = np.zeros((nkv, rb_row), np.uint8); ids = np.arange(nkv, dtype=np.int64)
+    _, _, kc_ref = run_ref_op("set_rows", [("cache", Q4_0, [nhkv * dk, nkv], z), ("src", F32, [nhkv * dk, nkv], kf), ("ids", I64, [nkv], ids)])
+    _, _, vc_ref = run_ref_op("set_rows", [("cache", Q4_0, [nhkv * dk, nkv], z), ("src", F32, [nhkv * dk, nkv], vf), ("ids", I64, [nkv], ids)])
+    kc = z.copy(); vc = z.copy()
+    oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), Q4_0, nhkv * dk, nkv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), Q4_0, nhkv * dk, nkv, rb_row)
+    assert np.array_equal(kc.reshape(-1), np.frombuffer(kc_ref, np.uint8)) and np.array_equal(vc.reshape(-1), np.frombuffer(vc_ref, np.uint8))
+    q = rng.standard_normal((nt, nh, dk)).astype(np.float32)
+    mask = np.full((64, nkv), -np.inf, np.float32); mask[0, :333] = 0; mask[1, :334] = 0
+    m16 = mask.astype(np.float16)
+    _, _, out = run_ref_op("flash_attn", [("q", F32, [dk, nh, nt], q), ("k", Q4_0, [nhkv * dk, nkv], kc), ("v", Q4_0, [nhkv * dk, nkv], vc), ("mask", F16, [nkv, 64], m16)],
+                           dict(dk=dk, dv=dk, n_head_kv=nhkv, n_kv=nkv, scale=float(1 / np.sqrt(dk))))
+    want = np.frombuffer(out, np.float32).reshape(nt, nh, dk)
+    y = np.zeros_like(want)
+    oracle().orc_flash_attn_ext(ptr(q), nh * dk * 4, dk * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), ptr(y),
+                                Q4_0, dk, dk, nh, nhkv, nt, nkv, float(1 / np.sqrt(dk)), 0.0, 0.0)
+    assert np.abs(y - want).max() <= 2e-6 * np.abs(want).max()
