@@ -198,6 +198,16 @@ B200_API int b200_mul_mat_id(int type, const void *as, int64_t expert_stride_byt
 B200_API int b200_get_rows_q(int type, const void *src, int64_t src_row_stride_bytes, int64_t nrows, const int32_t *ids, float *dst,
                              int64_t dst_row_stride /* floats */, int64_t ncols, int64_t n_ids, void *stream);
 
+/* KV cache type q4_0 (`-ctk q4_0 -ctv q4_0`): the cache keeps ggml's native 18-byte blocks.  SET_ROWS writes what ggml's from_float writes
+ * (ggml-quants.c quantize_row_q4_0_ref; replaces k_set_rows_quant<block_q4_0>, ggml-cuda/set-rows.cu:13-52); FLASH_ATTN_EXT follows the CPU
+ * oracle (q8_0 query x Q4_0 K in integers, f32 online softmax, V expanded to f32; replaces the q4_0-q4_0 flash_attn_vec_ext instances,
+ * ggml-cuda/fattn.cu:184).  Arguments as b200_set_rows / b200_flash_attn_ext; head size 64 or 128; no workspace. */
+B200_API int b200_set_rows_q4_0(const float *src, int64_t src_row_stride /* floats */, const int64_t *ids, void *dst, int64_t dst_row_stride /* bytes */,
+                                int64_t ncols, int64_t nrows, void *stream);
+B200_API int b200_flash_attn_q4_0(const float *q, int64_t q_tok_stride, int64_t q_head_stride, const void *k, int64_t k_row_stride, int64_t k_head_stride,
+                                  const void *v, int64_t v_row_stride, int64_t v_head_stride, const void *mask, int64_t mask_row_stride, float *dst,
+                                  int64_t d, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap, void *stream);
+
 /* ---- MUL_MAT, batched / prefill (replaces ggml_cuda_mul_mat_q, mmq.cu:71-143) -----------
  * dst[c][r] for any ncols; X is f32 [ncols][k].  Internally: activation quantisation as above,
  * then tiles on the tensor cores (tcgen05, TMEM accumulators) when ncols >= B200_MMQ_MIN_COLS,

@@ -122,19 +122,22 @@ bool rope_ok(const b200_node & n) {
 bool set_rows_ok(const b200_node & n) {
     const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
     if (s.type != B200_TYPE_F32 || ids.type != B200_TYPE_I64 || s.nb[0] != 4 || (s.nb[1] & 15) || !aligned16(s.data)) return false;
-    if (d.type != B200_TYPE_F32 && d.type != B200_TYPE_F16 && d.type != B200_TYPE_Q8_0) return false;
+    const bool q4 = d.type == B200_TYPE_Q4_0 && wide_on();          // KV cache type q4_0: wide path (fattn_ext.cu)
+    if (d.type != B200_TYPE_F32 && d.type != B200_TYPE_F16 && d.type != B200_TYPE_Q8_0 && !q4) return false;
+    if (q4 && (s.ne[1] > 65535 || (((uintptr_t)d.data | (uintptr_t)d.nb[1] | (uintptr_t)d.nb[2] | (uintptr_t)d.nb[3]) & 1))) return false;
     // batches (ggml.c:3661-3686): dst [ne0, rows, ne2, ne3], src [ne0, n, ne2, ne3], ids [n, ne11, ne12] broadcast over dims 2/3
     if (s.ne[2] != d.ne[2] || s.ne[3] != d.ne[3] || s.ne[0] != d.ne[0] || s.ne[0] % 32 != 0 || ids.ne[0] != s.ne[1] || ids.ne[3] != 1) return false;
     if (ids.ne[1] <= 0 || ids.ne[2] <= 0 || s.ne[2] % ids.ne[1] != 0 || s.ne[3] % ids.ne[2] != 0) return false;
     if ((s.nb[2] | s.nb[3]) & 15) return false;
-    if (d.type != B200_TYPE_Q8_0 && (((uintptr_t)d.data | (uintptr_t)d.nb[1] | (uintptr_t)d.nb[2] | (uintptr_t)d.nb[3]) & 15)) return false;
+    if (d.type != B200_TYPE_Q8_0 && !q4 && (((uintptr_t)d.data | (uintptr_t)d.nb[1] | (uintptr_t)d.nb[2] | (uintptr_t)d.nb[3]) & 15)) return false;
     return true;
 }
 bool fattn_ok(const b200_node & n) {
     const b200_tensor & q = n.src[0], & k = n.src[1], & v = n.src[2], & d = n.dst;
     if (n.n_src > 4 && n.src[4].data) return false;                                  // attention sinks: not on this path
     if (q.type != B200_TYPE_F32 || d.type != B200_TYPE_F32 || k.type != v.type) return false;
-    if (k.type != B200_TYPE_F16 && k.type != B200_TYPE_Q8_0) return false;
+    if (k.type != B200_TYPE_F16 && k.type != B200_TYPE_Q8_0 && !(k.type == B200_TYPE_Q4_0 && wide_on())) return false;
+    if (k.type == B200_TYPE_Q4_0 && ((((uintptr_t)k.data | (uintptr_t)v.data) & 1) || ((k.nb[1] | k.nb[2] | v.nb[1] | v.nb[2]) & 1))) return false;
     const int64_t dk = q.ne[0], dv = v.ne[0];
     if (dk != dv || (dk != 64 && dk != 128) || k.ne[0] != dk) return false;
     if (q.ne[3] != 1 || k.ne[3] != 1 || v.ne[3] != 1 || k.ne[1] != v.ne[1] || k.ne[2] != v.ne[2] || k.ne[2] <= 0 || q.ne[2] % k.ne[2] != 0) return false;
@@ -771,6 +774,13 @@ struct Runner {
                 const b200_tensor & s = n.src[0], & ids = n.src[1];
                 for (int64_t i3 = 0; i3 < s.ne[3]; i3++) for (int64_t i2 = 0; i2 < s.ne[2]; i2++) {
                     const int64_t i11 = i2 % ids.ne[1], i12 = i3 % ids.ne[2];
+                    if (n.dst.type == B200_TYPE_Q4_0) {
+                        const int r4 = KL(b200_set_rows_q4_0((const float *)((const char *)s.data + i2 * s.nb[2] + i3 * s.nb[3]), s.nb[1] / 4,
+                                                            (const int64_t *)((const char *)ids.data + i11 * ids.nb[1] + i12 * ids.nb[2]),
+                                                            (char *)n.dst.data + i2 * n.dst.nb[2] + i3 * n.dst.nb[3], n.dst.nb[1], s.ne[0], s.ne[1], st));
+                        if (r4 != B200_OK) return r4;
+                        continue;
+                    }
                     const int r = KL(b200_set_rows((const float *)((const char *)s.data + i2 * s.nb[2] + i3 * s.nb[3]), s.nb[1] / 4,
                                                 (const int64_t *)((const char *)ids.data + i11 * ids.nb[1] + i12 * ids.nb[2]),
                                                 (char *)n.dst.data + i2 * n.dst.nb[2] + i3 * n.dst.nb[3], n.dst.type, n.dst.nb[1], s.ne[0], s.ne[1], st));
@@ -786,6 +796,9 @@ struct Runner {
                 if (mk_try_attn(n)) return B200_OK;
                 if (attn_matches(n)) return launch_fused_attn(n);
                 { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+                if (k.type == B200_TYPE_Q4_0)
+                    return KL(b200_flash_attn_q4_0((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
+                                                   (float *)n.dst.data, q.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1], f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), st));
                 return KL(b200_flash_attn_ext((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
                                            (float *)n.dst.data, k.type, q.ne[0], v.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1],
                                            f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), ex->ws + ex->off_fa, st));

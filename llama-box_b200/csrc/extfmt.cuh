@@ -425,6 +425,61 @@ template <> XF_HD void xf_sub_dequant<XF_IQ4_XS>(const uint8_t * row, int64_t, i
     for (int jj = 0; jj < 16; jj++) { y[jj] = xf_mul(dl, (float)xf_kv_iq4nl(b[8 + 16 * s + jj] & 0xF)); y[jj + 16] = xf_mul(dl, (float)xf_kv_iq4nl(b[8 + 16 * s + jj] >> 4)); }
 }
 
+// =========================================================================================================================
+// Q4_0 in ggml's NATIVE block layout {d f16, qs[16]} — the KV cache type q4_0 (caches keep ggml's layout so that llama.cpp's state
+// save / restore and defragmentation see what they expect).
+// =========================================================================================================================
+// f32 -> one block, as ggml's from_float writes it (ggml-quants.c quantize_row_q4_0_ref): the element of largest magnitude (first on
+// ties) maps to -8; (int8_t)(x*id + 8.5f) truncated, clamped to 15.  blk 2-byte aligned.
+XF_HD void xf_q4_0_quantize_block(const float * x, uint8_t * blk) {
+    float amax = 0.0f, mx = 0.0f;
+    for (int j = 0; j < 32; j++) { const float v = x[j]; const float av = v < 0.0f ? -v : v; if (amax < av) { amax = av; mx = v; } }
+    const float d = mx / -8.0f;
+    const float id = d != 0.0f ? 1.0f / d : 0.0f;
+    // f32 -> f16 round-to-nearest-even, bit-level (== ggml's GGML_FP32_TO_FP16 / F16C)
+    uint32_t fb; memcpy(&fb, &d, 4);
+    const uint32_t sign = (fb >> 16) & 0x8000u; fb &= 0x7fffffffu;
+    uint32_t hb;
+    if (fb >= 0x7f800000u) hb = fb > 0x7f800000u ? 0x7e00u : 0x7c00u;
+    else if (fb >= 0x477ff000u) hb = 0x7c00u;                                  // rounds to infinity
+    else if (fb >= 0x38800000u) {                                              // normal half
+        const uint32_t mant = fb & 0x7fffffu, e = (fb >> 23) - 112;
+        hb = (e << 10) | (mant >> 13);
+        const uint32_t rem = mant & 0x1fffu;
+        if (rem > 0x1000u || (rem == 0x1000u && (hb & 1))) hb++;
+    } else if (fb >= 0x33000000u) {                                            // subnormal half
+        const uint32_t mant = (fb & 0x7fffffu) | 0x800000u; const int shift = 126 - (int)(fb >> 23);   // 14..24
+        hb = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (hb & 1))) hb++;
+    } else hb = 0;
+    hb |= sign;
+    blk[0] = (uint8_t)(hb & 0xff); blk[1] = (uint8_t)(hb >> 8);
+    for (int j = 0; j < 16; j++) {
+        int q0 = (int)(int8_t)xf_add(xf_mul(x[j], id), 8.5f), q1 = (int)(int8_t)xf_add(xf_mul(x[16 + j], id), 8.5f);
+        if (q0 > 15) q0 = 15;
+        if (q1 > 15) q1 = 15;
+        blk[2 + j] = (uint8_t)(q0 | (q1 << 4));
+    }
+}
+// (sum (nib - 8) * q8) * d_k * d_q for one native block against 32 int8 of the q8_0 form of the query (ggml-cpu/quants.c:115-149)
+XF_HD float xf_q4_0n_dot(const uint8_t * blk, const int8_t * q8, float ad, int bs) {
+    const uint32_t * a = (const uint32_t *)q8;
+    int sumi = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t w = xf_ld16x2(blk + 2 + 4 * i);
+        sumi = xf_dp4a(w & 0x0F0F0F0Fu, a[i], sumi);
+        sumi = xf_dp4a((w >> 4) & 0x0F0F0F0Fu, a[i + 4], sumi);
+    }
+    sumi -= 8 * bs;
+    return (float)sumi * (xf_h2f((uint16_t)xf_ld16(blk)) * ad);
+}
+// element e (0..31) of a native block as f32 (ggml-quants.c dequantize_row_q4_0)
+XF_HD float xf_q4_0n_value(const uint8_t * blk, int e) {
+    const int nib = e < 16 ? (blk[2 + e] & 0xF) : (blk[2 + e - 16] >> 4);
+    return xf_mul((float)(nib - 8), xf_h2f((uint16_t)xf_ld16(blk)));
+}
+
 // run F<T>(args...) for a runtime type id; false when the type is not one of ours
 #define XF_DISPATCH(t, CALL) \
     switch (t) { \

@@ -18,6 +18,14 @@ int sim_row_dequant(int type, const uint8_t * row, int64_t k, int64_t nb_layout,
     XF_DISPATCH(type, { for (int64_t u = 0; u < k / 32; u++) xf_sub_dequant<T>(row, nb_layout, u, y + 32 * u); ok = 1; });
     return ok;
 }
+// KV cache type q4_0 (ggml's native blocks): quantise a row, dot one row of K blocks with the q8_0 form of a query, de-quantise
+void sim_q4_0_quantize_row(const float * x, uint8_t * y, int64_t k) { for (int64_t b = 0; b < k / 32; b++) xf_q4_0_quantize_block(x + 32 * b, y + 18 * b); }
+float sim_q4_0n_row_dot(const uint8_t * row, int64_t k, const int8_t * qs, const float * d, const int16_t * bs) {
+    float acc = 0.0f;
+    for (int64_t b = 0; b < k / 32; b++) acc += xf_q4_0n_dot(row + 18 * b, qs + 32 * b, d[b], bs[b]);
+    return acc;
+}
+void sim_q4_0n_row_dequant(const uint8_t * row, int64_t k, float * y) { for (int64_t e = 0; e < k; e++) y[e] = xf_q4_0n_value(row + 18 * (e / 32), (int)(e % 32)); }
 float sim_h2f(uint16_t h) { return xf_h2f(h); }
 int sim_block_bytes(int t) { return xf_block_bytes(t); }
 int sim_act_family(int t) { return xf_act_family(t); }

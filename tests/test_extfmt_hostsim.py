@@ -25,6 +25,9 @@ def sim():
     L.sim_row_dot.argtypes = [C.c_int, vp, i64, i64, vp, vp, vp, vp, vp]
     L.sim_row_dequant.argtypes = [C.c_int, vp, i64, i64, vp]
     L.sim_h2f.restype = C.c_float; L.sim_h2f.argtypes = [C.c_uint16]
+    L.sim_q4_0_quantize_row.argtypes = [vp, vp, i64]
+    L.sim_q4_0n_row_dot.restype = C.c_float; L.sim_q4_0n_row_dot.argtypes = [vp, i64, vp, vp, vp]
+    L.sim_q4_0n_row_dequant.argtypes = [vp, i64, vp]
     return L
 
 
@@ -88,3 +91,24 @@ def test_rows_that_are_not_a_multiple_of_256(sim, t):
         got = np.zeros(1, np.float32)
         sim.sim_row_dot(t, ptr(Wl[i]), k, k // 32, ptr(qs), ptr(d), ptr(s), ptr(bs), ptr(got))
         assert abs(got[0] - want[i]) <= 2e-5 * np.abs(want).max()
+
+
+def test_q4_0_kv_cache_block_functions(sim):
+    """KV cache type q4_0: the quantiser SET_ROWS runs (bytes identical to ggml's from_float, incl. f16 rounding of d over 12 decades, ties, zero
+    blocks), the K-row dot against the q8_0 form of a query and the V de-quantisation of the wide attention kernel"""
+    from refutil import Q4_0
+    rng = np.random.default_rng(5)
+    k = 32 * 4096
+    x = (rng.standard_normal(k) * 10.0 ** rng.uniform(-7, 5, k // 32).repeat(32)).astype(np.float32)
+    x[:32] = 0; x[32:64] = 1.0; x[64:96] = -1.0; x[96] = 3.0; x[97] = -3.0; x[128:160] = 1e-9
+    want = np.zeros(row_bytes(Q4_0, k), np.uint8); got = want.copy()
+    oracle().orc_quantize_row_q4_0(ptr(x), ptr(want), k); sim.sim_q4_0_quantize_row(ptr(x), ptr(got), k)
+    assert np.array_equal(got, want)
+    kk = 128
+    K = rand_blocks(rng, Q4_0, 16, kk); q = rng.standard_normal((1, kk)).astype(np.float32)
+    qs, d, s, bs = split_act(Q4_0, orc_quantize_act(Q4_0, q)[0], kk)
+    wantd = orc_mul_mat(Q4_0, K, q, 16, 1, kk)[0]; deq = orc_dequant(Q4_0, K, 16, kk)
+    for i in range(16):
+        assert abs(sim.sim_q4_0n_row_dot(ptr(K[i]), kk, ptr(qs), ptr(d), ptr(bs)) - wantd[i]) <= 2e-6 * np.abs(wantd).max()
+        y = np.zeros(kk, np.float32); sim.sim_q4_0n_row_dequant(ptr(K[i]), kk, ptr(y))
+        assert np.array_equal(y, deq[i])

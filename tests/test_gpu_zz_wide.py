@@ -1,5 +1,5 @@
 """GPU: the wide path — MUL_MAT on Q4_1 / Q5_1 / Q2_K / Q3_K / IQ4_NL / IQ4_XS / MXFP4, MUL_MAT_ID (expert routing read on the device) and
-GET_ROWS on quantised tables (llama-box_b200/csrc/mmvq_ext.cu) — against the C oracle, through the C-ABI
+GET_ROWS on quantised tables, and the KV cache type q4_0 (llama-box_b200/csrc/mmvq_ext.cu, fattn_ext.cu) — against the C oracle, through the C-ABI
 (b200_mul_mat_vec_wide / b200_mul_mat_id / b200_get_rows_q), through the graph executor, and through the plug-in with the reference's own
 test-backend-ops harness.
 
@@ -62,6 +62,14 @@ def test_wide_kernels_vs_oracle(t):
     assert len(o) >= 13 and not bad, bad
 
 
+@pytest.mark.parametrize("shape", [(128, 32, 8, 1, 768), (128, 8, 2, 5, 4096), (64, 32, 4, 1, 1024), (64, 8, 8, 33, 256)])
+def test_q4_0_kv_cache_set_rows_and_flash_attn_vs_oracle(shape):
+    """KV cache type q4_0 (`-ctk q4_0 -ctv q4_0`): b200_set_rows_q4_0 bytes == ggml's from_float; b200_flash_attn_q4_0 within the Q8_0-cache tolerance"""
+    o = child("kv_q4_0", *shape)
+    assert o["set_rows_equal"], o
+    assert o["attn_err"] <= 2e-5, o
+
+
 @pytest.mark.parametrize("wtype", [3, 11, 23])
 @pytest.mark.parametrize("n_tok", [1, 4])
 def test_executor_moe_block_vs_oracle(wtype, n_tok):
@@ -72,7 +80,7 @@ def test_executor_moe_block_vs_oracle(wtype, n_tok):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")
-@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("MUL_MAT", 60), ("GET_ROWS", 4)])
+@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("MUL_MAT", 60), ("GET_ROWS", 4), ("SET_ROWS", 7), ("FLASH_ATTN_EXT", 24)])
 def test_reference_backend_ops_harness_with_the_wide_path(op, min_ok):
     """the reference's own parity harness (tests/test-backend-ops.cpp) against the plug-in with GGML_B200_WIDE=1"""
     plugin = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")

@@ -152,6 +152,45 @@ def do_executor(wtype, n_tok):
     return {"supports": sup, "errs": errs, "captures": int(ex.captures), "replays": int(ex.replays)}
 
 
+def do_kv_q4_0(d, n_head, n_head_kv, n_tok, n_kv):
+    """KV cache type q4_0: SET_ROWS bytes vs the oracle's from_float, then FLASH_ATTN_EXT over the cache vs the oracle (causal-style mask, GQA)"""
+    from refutil import Q4_0
+    rng = np.random.default_rng(d + n_kv + n_tok)
+    rb_row, rb_head = row_bytes(Q4_0, n_head_kv * d), row_bytes(Q4_0, d)
+    kf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32); vf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32)
+    kf[1, :32] = 0
+    ids = rng.permutation(n_kv).astype(np.int64)
+    kc = np.zeros((n_kv, rb_row), np.uint8); vc = kc.copy()
+    oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), Q4_0, n_head_kv * d, n_kv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), Q4_0, n_head_kv * d, n_kv, rb_row)
+    kfd, vfd, idd = dev(kf), dev(vf), torch.from_numpy(ids).cuda()
+    kcd = torch.zeros(n_kv * rb_row + 64, dtype=torch.uint8, device="cuda"); vcd = torch.zeros_like(kcd)
+    for lo in range(0, n_kv, 4096):                         # a few calls like a sequence of ubatches
+        n = min(4096, n_kv - lo)
+        ops.check(L.b200_set_rows_q4_0(C.c_void_p(kfd.data_ptr() + lo * n_head_kv * d * 4), n_head_kv * d, C.c_void_p(idd.data_ptr() + lo * 8), ops.p(kcd), rb_row, n_head_kv * d, n, ops.stream()))
+        ops.check(L.b200_set_rows_q4_0(C.c_void_p(vfd.data_ptr() + lo * n_head_kv * d * 4), n_head_kv * d, C.c_void_p(idd.data_ptr() + lo * 8), ops.p(vcd), rb_row, n_head_kv * d, n, ops.stream()))
+    torch.cuda.synchronize()
+    out = {"set_rows_equal": bool(np.array_equal(kcd.cpu().numpy()[:kc.size], kc.reshape(-1)) and np.array_equal(vcd.cpu().numpy()[:vc.size], vc.reshape(-1)))}
+    q = rng.standard_normal((n_tok, n_head, d)).astype(np.float32)
+    npad = (n_tok + 63) // 64 * 64
+    mask = np.full((npad, n_kv), -np.inf, np.float32)
+    for t in range(n_tok):
+        mask[t, :max(1, n_kv - n_tok + t + 1 - 7)] = 0
+    m16 = mask.astype(np.float16)
+    scale = float(1 / np.sqrt(d))
+    want = np.zeros((n_tok, n_head, d), np.float32)
+    oracle().orc_flash_attn_ext(ptr(q), n_head * d * 4, d * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), ptr(want),
+                                Q4_0, d, d, n_head, n_head_kv, n_tok, n_kv, scale, 0.0, 0.0)
+    qd = dev(q); md = torch.from_numpy(m16.view(np.int16)).cuda()
+    dst = torch.zeros((n_tok, n_head, d), dtype=torch.float32, device="cuda")
+    kc2 = dev(np.concatenate([kc.reshape(-1), np.zeros(64, np.uint8)])); vc2 = dev(np.concatenate([vc.reshape(-1), np.zeros(64, np.uint8)]))
+    ops.check(L.b200_flash_attn_q4_0(ops.p(qd), n_head * d, d, ops.p(kc2), rb_row, rb_head, ops.p(vc2), rb_row, rb_head, ops.p(md), n_kv, ops.p(dst),
+                                     d, n_head, n_head_kv, n_tok, n_kv, scale, 0.0, 0.0, ops.stream()))
+    torch.cuda.synchronize()
+    out["attn_err"] = rel(dst.cpu().numpy(), want)
+    return out
+
+
 def do_type_suite(t):
     """every C-ABI case of one format in ONE process (a fresh interpreter + torch import per case would dominate the run time)"""
     out = {}
@@ -178,7 +217,7 @@ def do_type_suite(t):
 def main():
     what = sys.argv[1]; a = [int(v) if v.lstrip("-").isdigit() else v for v in sys.argv[2:]]
     torch.cuda.set_device(0)
-    fn = {"type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
+    fn = {"kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
     print("RESULT " + json.dumps(fn(*a)))
 
 
