@@ -20,15 +20,22 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "tests"))
-from refutil import BLOCK_BYTES, BLOCK_ELEMS, Q4_0, Q4_K, Q5_0, Q5_K, Q6_K, Q8_0, rand_blocks, row_bytes  # noqa: E402
+from refutil import (BLOCK_BYTES, BLOCK_ELEMS, IQ4_NL, IQ4_XS, Q2_K, Q3_K, Q4_0, Q4_1, Q4_K, Q5_0, Q5_1, Q5_K, Q6_K, Q8_0, rand_blocks,  # noqa: E402
+                     row_bytes)
 
 CONFIGS = {
     "llama3-8b": dict(arch="llama", n_embd=4096, n_head=32, n_head_kv=8, head_dim=128, n_ff=14336, n_vocab=128256, n_layer=32, rope_base=500000.0, eps=1e-5, qkv_bias=False, n_ctx_train=8192),
     "tinyllama-1.1b": dict(arch="llama", n_embd=2048, n_head=32, n_head_kv=4, head_dim=64, n_ff=5632, n_vocab=32000, n_layer=22, rope_base=10000.0, eps=1e-5, qkv_bias=False, n_ctx_train=2048),
     "qwen2-72b": dict(arch="qwen2", n_embd=8192, n_head=64, n_head_kv=8, head_dim=128, n_ff=29568, n_vocab=152064, n_layer=80, rope_base=1000000.0, eps=1e-6, qkv_bias=True, n_ctx_train=32768),
     "test-small": dict(arch="llama", n_embd=2048, n_head=16, n_head_kv=4, head_dim=128, n_ff=4096, n_vocab=4096, n_layer=2, rope_base=500000.0, eps=1e-5, qkv_bias=False, n_ctx_train=8192),
+    # Mixtral-style mixture of experts on the llama architecture (llama-model.cpp load_tensors LLM_ARCH_LLAMA with n_expert > 0:
+    # ffn_gate_inp f32 + ffn_{gate,down,up}_exps; graph: llm_build_llama -> build_moe_ffn): exercises MUL_MAT_ID
+    "test-moe": dict(arch="llama", n_embd=2048, n_head=16, n_head_kv=4, head_dim=128, n_ff=2048, n_vocab=4096, n_layer=2, rope_base=500000.0, eps=1e-5, qkv_bias=False, n_ctx_train=8192,
+                     n_expert=8, n_expert_used=2),
 }
-FTYPE_ID = {"Q4_0": 2, "Q8_0": 7, "Q4_K_M": 15}
+# llama_ftype values (include/llama.h); the single-type ones below put every matrix in that format (the wide path's formats)
+FTYPE_ID = {"Q4_0": 2, "Q8_0": 7, "Q4_K_M": 15, "Q4_1": 3, "Q5_1": 9, "Q2_K": 10, "Q3_K_M": 12, "IQ4_NL": 25, "IQ4_XS": 30}
+SINGLE_TYPE = {"Q4_0": Q4_0, "Q8_0": Q8_0, "Q4_1": Q4_1, "Q5_1": Q5_1, "Q2_K": Q2_K, "Q3_K_M": Q3_K, "IQ4_NL": IQ4_NL, "IQ4_XS": IQ4_XS}
 
 
 def use_more_bits(i, n):
@@ -46,7 +53,7 @@ def layer_types(ftype, i, n, n_ff=0, is_70b=False):
         if n_ff % 256 != 0:
             down = Q8_0 if hi == Q6_K else Q5_0
         return dict(attn_q=Q4_K, attn_k=Q4_K, attn_v=v, attn_output=Q4_K, ffn_gate=Q4_K, ffn_up=Q4_K, ffn_down=down)
-    t = Q4_0 if ftype == "Q4_0" else Q8_0
+    t = SINGLE_TYPE[ftype]
     return {k: t for k in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")}
 
 
@@ -88,13 +95,17 @@ def main():
     E, H, HK, D, FF, V, L = c["n_embd"], c["n_head"], c["n_head_kv"], c["head_dim"], c["n_ff"], c["n_vocab"], c["n_layer"]
     rng = np.random.default_rng(a.seed)
     qt = {2: gguf.GGMLQuantizationType.Q4_0, 6: gguf.GGMLQuantizationType.Q5_0, 8: gguf.GGMLQuantizationType.Q8_0, 12: gguf.GGMLQuantizationType.Q4_K,
-          13: gguf.GGMLQuantizationType.Q5_K, 14: gguf.GGMLQuantizationType.Q6_K}
+          13: gguf.GGMLQuantizationType.Q5_K, 14: gguf.GGMLQuantizationType.Q6_K, 3: gguf.GGMLQuantizationType.Q4_1, 7: gguf.GGMLQuantizationType.Q5_1,
+          10: gguf.GGMLQuantizationType.Q2_K, 11: gguf.GGMLQuantizationType.Q3_K, 20: gguf.GGMLQuantizationType.IQ4_NL, 23: gguf.GGMLQuantizationType.IQ4_XS}
+    NE, NU = c.get("n_expert", 0), c.get("n_expert_used", 0)
 
     w = gguf.GGUFWriter(a.out, c["arch"])
     w.add_name(f"synthetic-{a.config}-{a.ftype}")
     w.add_context_length(c["n_ctx_train"]); w.add_embedding_length(E); w.add_block_count(L); w.add_feed_forward_length(FF)
     w.add_head_count(H); w.add_head_count_kv(HK); w.add_rope_dimension_count(D); w.add_rope_freq_base(c["rope_base"])
     w.add_layer_norm_rms_eps(c["eps"]); w.add_vocab_size(V); w.add_file_type(FTYPE_ID[a.ftype])
+    if NE:
+        w.add_expert_count(NE); w.add_expert_used_count(NU)
     # synthetic SPM vocabulary: <unk>, <s>, </s>, 256 byte tokens, then plain pieces
     toks, scores, types = [], [], []
     for i in range(V):
@@ -127,7 +138,12 @@ def main():
         std = res_std if (name.endswith("attn_output.weight") or name.endswith("ffn_down.weight")) else 0.02
         w.add_tensor(name, qblocks(t, m, k, std), raw_dtype=qt[t])
 
-    emb_t = {"Q4_K_M": Q4_K, "Q4_0": Q4_0, "Q8_0": Q8_0}[a.ftype]
+    def add_q3(name, t, ne, m, k):
+        # expert stack [k, m, n_expert] (llama-model.cpp: ffn_*_exps)
+        data = np.stack([qblocks(t, m, k, res_std if "down" in name else 0.02) if a.weights == "gauss" else rand_blocks(rng, t, m, k, a.scale_mul) for _ in range(ne)])
+        w.add_tensor(name, data, raw_dtype=qt[t])
+
+    emb_t = Q4_K if a.ftype == "Q4_K_M" else SINGLE_TYPE[a.ftype]
     out_t = Q8_0 if a.ftype == "Q8_0" else Q6_K
     add_q("token_embd.weight", emb_t, V, E)
     for i in range(L):
@@ -142,6 +158,12 @@ def main():
             w.add_tensor(f"blk.{i}.attn_v.bias", (0.1 * rng.standard_normal(HK * D)).astype(np.float32))
         add_q(f"blk.{i}.attn_output.weight", ts["attn_output"], E, H * D)
         w.add_tensor(f"blk.{i}.ffn_norm.weight", (1 + 0.05 * rng.standard_normal(E)).astype(np.float32))
+        if NE:
+            w.add_tensor(f"blk.{i}.ffn_gate_inp.weight", (0.5 * rng.standard_normal((NE, E))).astype(np.float32))
+            add_q3(f"blk.{i}.ffn_gate_exps.weight", ts["ffn_gate"], NE, FF, E)
+            add_q3(f"blk.{i}.ffn_down_exps.weight", ts["ffn_down"], NE, E, FF)
+            add_q3(f"blk.{i}.ffn_up_exps.weight", ts["ffn_up"], NE, FF, E)
+            continue
         add_q(f"blk.{i}.ffn_gate.weight", ts["ffn_gate"], FF, E)
         add_q(f"blk.{i}.ffn_up.weight", ts["ffn_up"], FF, E)
         add_q(f"blk.{i}.ffn_down.weight", ts["ffn_down"], E, FF)

@@ -90,3 +90,36 @@ def test_reference_backend_ops_harness_with_the_wide_path(op, min_ok):
     ok = len(re.findall(r"\): OK", plain)); fail = len(re.findall(r"FAIL", plain))
     assert fail == 0 and r.returncode == 0, plain[-4000:]
     assert ok >= min_ok, (ok, plain[-2000:])
+
+
+# ---- the product boundary: the unmodified libllama over the plug-in with GGML_B200_WIDE=1, against ggml-cpu on the same file and prompt ----------
+@pytest.fixture(scope="module")
+def product():
+    import test_gpu_product as P
+    yield P
+    for path in list(P._models.values()):
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")
+@pytest.mark.parametrize("config,ftype,kv,must_be_on_device", [
+    ("test-moe", "Q4_K_M", "f16", "MUL_MAT_ID"),            # Mixtral-style experts: build_moe_ffn -> 3 x MUL_MAT_ID per layer
+    ("test-small", "Q4_1", "f16", "MUL_MAT"), ("test-small", "Q5_1", "f16", "MUL_MAT"), ("test-small", "Q2_K", "f16", "MUL_MAT"),
+    ("test-small", "Q3_K_M", "f16", "MUL_MAT"), ("test-small", "IQ4_NL", "f16", "MUL_MAT"), ("test-small", "IQ4_XS", "f16", "MUL_MAT"),
+    ("test-small", "Q4_K_M", "q4_0", "FLASH_ATTN"),         # -ctk q4_0 -ctv q4_0
+])
+def test_libllama_over_the_wide_path(tmp_path, tmp_path_factory, product, config, ftype, kv, must_be_on_device):
+    """llama_decode (prefill of 24 tokens, then greedy decode) on files whose matrices are in the wide path's formats / a mixture-of-experts
+    FFN / a q4_0 KV cache.  The scheduler must place the named op on the B200 backend (GGML_SCHED_DEBUG=2 assignment dump — otherwise the test
+    would pass through ggml's CPU fallback), and the run must be as close to ggml-cpu as ggml-cpu's own other builds are."""
+    P = product
+    gguf = P.model_file(tmp_path_factory, config, ftype, 2)
+    cpu = P.drv(gguf, str(tmp_path / "cpu"), False, kv=kv, gen=9)
+    others = P.cpu_builds(tmp_path, tmp_path_factory, gguf, kv=kv, gen=9)
+    gpu = P.drv(gguf, str(tmp_path / "gpu"), True, kv=kv, gen=9, extra_env=dict(GGML_B200_WIDE="1", GGML_SCHED_DEBUG="2", LLAMA_DRV_LOG_DEBUG="1"))
+    placed = re.findall(r"node #\s*\d+ \(\s*" + must_be_on_device + r"\w*\):.*?\[\s*(\w+)", gpu["stderr"])
+    assert placed and all(b.startswith("B200") for b in placed), (len(placed), sorted(set(placed)))
+    P.assert_within_reference_self_consistency(gpu, cpu, others, f"wide path: {config} {ftype} kv={kv}")
