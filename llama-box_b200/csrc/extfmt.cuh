@@ -68,10 +68,17 @@ XF_HD float xf_h2f(uint16_t h) {
 // E8M0 -> float, halved (ggml-impl.h:451-470 ggml_e8m0_to_fp32_half)
 XF_HD float xf_e8m0_half(uint8_t x) { return xf_bits2f(x < 2 ? (0x00200000u << x) : ((uint32_t)(x - 1) << 23)); }
 
+// host builds of the test harness (tests/hostsim, -DXF_CHECK_ALIGN) count loads a GPU would trap on; x86 tolerates them silently
+#if !defined(__CUDA_ARCH__) && defined(XF_CHECK_ALIGN)
+extern "C" long xf_misaligned;
+#  define XF_AL(p, n) do { if ((uintptr_t)(p) & ((n) - 1)) __atomic_add_fetch(&xf_misaligned, 1, __ATOMIC_RELAXED); } while (0)
+#else
+#  define XF_AL(p, n) do { } while (0)
+#endif
 XF_HD uint32_t xf_ld8x4(const uint8_t * p)  { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
-XF_HD uint32_t xf_ld16(const uint8_t * p)   { return *(const uint16_t *)p; }                            // p 2-byte aligned
+XF_HD uint32_t xf_ld16(const uint8_t * p)   { XF_AL(p, 2); return *(const uint16_t *)p; }               // p 2-byte aligned
 XF_HD uint32_t xf_ld16x2(const uint8_t * p) { return xf_ld16(p) | (xf_ld16(p + 2) << 16); }             // p 2-byte aligned
-XF_HD uint32_t xf_ld32(const uint8_t * p)   { return *(const uint32_t *)p; }                            // p 4-byte aligned
+XF_HD uint32_t xf_ld32(const uint8_t * p)   { XF_AL(p, 4); return *(const uint32_t *)p; }               // p 4-byte aligned
 
 // 4 x (s8 * s8) + c.  Weight bytes below 128 may be passed as they are (u8 == s8 there).
 XF_HD int xf_dp4a(uint32_t a, uint32_t b, int c) {

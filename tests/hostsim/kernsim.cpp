@@ -1,0 +1,71 @@
+// kernsim.cpp — TEST INFRASTRUCTURE.  Runs the SOURCE of the wide path's CUDA kernels on the CPU under tests/hostsim/simt.h and exposes
+// one C entry point per kernel with the argument lists of the product's C-ABI (b200_mul_mat_vec_wide / b200_mul_mat_id / b200_get_rows_q /
+// b200_set_rows_q4_0 / b200_flash_attn_q4_0), host pointers instead of device pointers.  The launch geometry mirrors mmvq_ext.cu /
+// fattn_ext.cu (grid = (row groups, problems), 256 / 128 threads) with a small row-group count.
+#define XF_CHECK_ALIGN 1
+#include "simt.h"
+
+#include "../../llama-box_b200/csrc/mmvq_ext_kernels.cuh"
+#include "../../llama-box_b200/csrc/fattn_ext_kernels.cuh"
+
+void b200_set_error(const char *, ...) {}
+extern "C" { long xf_misaligned = 0; long sim_misaligned(void) { return xf_misaligned; } }
+
+namespace {
+template <int T> void run_mmv(const ExtArgs & a, int64_t n_prob, int gx) {
+    const int fam = xf_act_family(T);
+    simt::launch(dim3((unsigned)gx, (unsigned)n_prob), dim3(EXT_WARPS * 32), (size_t)ext_smem_bytes(fam, ext_kp(a.k)), [a] { ext_mmv_kernel<T>(a); });
+}
+template <int T> void run_get_rows(const uint8_t * src, int64_t rs, int64_t nb, int64_t nrows, const int32_t * ids, float * dst, int64_t drs, int64_t ncols, int64_t n_ids) {
+    simt::launch(dim3((unsigned)((ncols / 32 + 127) / 128), (unsigned)n_ids), dim3(128), 0, [=] { ext_get_rows_kernel<T>(src, rs, nb, nrows, ids, dst, drs, ncols, 0); });
+}
+int64_t wide_row_bytes(int type, int64_t k) { return k / xf_block_elems(type) * xf_block_bytes(type); }
+}
+
+extern "C" {
+int sim_mul_mat_vec_wide(int type, const void * W, const float * x, int64_t x_col_stride, float * dst, int64_t dst_col_stride, const float * bias, const float * residual,
+                         int64_t m, int64_t k, int64_t ncols, int gx) {
+    ExtArgs a = {};
+    a.W = (const uint8_t *)W; a.row_bytes = wide_row_bytes(type, k); a.nb_layout = k / xf_block_elems(type);
+    a.x = x; a.x_col_stride = x_col_stride; a.dst = dst; a.dst_col_stride = dst_col_stride ? dst_col_stride : m;
+    a.bias = bias; a.residual = residual; a.res_col_stride = a.dst_col_stride; a.m = m; a.k = k; a.n_b1 = 1; a.n_used = 1;
+    int ok = 0;
+    XF_DISPATCH(type, { run_mmv<T>(a, ncols, gx); ok = 1; });
+    return ok;
+}
+int sim_mul_mat_id(int type, const void * as, int64_t expert_stride_bytes, const float * b, int64_t b_tok_stride, int64_t b_slot_stride, int64_t n_b1,
+                   const int32_t * ids, int64_t ids_tok_stride, float * dst, int64_t dst_tok_stride, int64_t dst_slot_stride,
+                   int64_t m, int64_t k, int64_t n_expert, int64_t n_used, int64_t n_tok, int gx) {
+    ExtArgs a = {};
+    a.W = (const uint8_t *)as; a.row_bytes = wide_row_bytes(type, k); a.nb_layout = k / xf_block_elems(type); a.expert_stride = expert_stride_bytes;
+    a.ids = ids; a.ids_tok_stride = ids_tok_stride; a.n_used = (int32_t)n_used; a.n_expert = (int32_t)n_expert;
+    a.x = b; a.x_col_stride = b_tok_stride; a.x_slot_stride = b_slot_stride; a.n_b1 = n_b1;
+    a.dst = dst; a.dst_col_stride = dst_tok_stride; a.dst_slot_stride = dst_slot_stride; a.m = m; a.k = k;
+    int ok = 0;
+    XF_DISPATCH(type, { run_mmv<T>(a, n_tok * n_used, gx); ok = 1; });
+    return ok;
+}
+int sim_get_rows_q(int type, const void * src, int64_t src_row_stride, int64_t nrows, const int32_t * ids, float * dst, int64_t dst_row_stride, int64_t ncols, int64_t n_ids) {
+    int ok = 0;
+    XF_DISPATCH(type, { run_get_rows<T>((const uint8_t *)src, src_row_stride, ncols / xf_block_elems(type), nrows, ids, dst, dst_row_stride, ncols, n_ids); ok = 1; });
+    return ok;
+}
+void sim_set_rows_q4_0(const float * src, int64_t src_row_stride, const int64_t * ids, void * dst, int64_t dst_row_stride, int64_t ncols, int64_t nrows) {
+    const int64_t nblk = ncols / 32;
+    simt::launch(dim3((unsigned)((nblk + 127) / 128), (unsigned)nrows), dim3(128), 0, [=] { set_rows_q4_0_kernel(src, src_row_stride, ids, (uint8_t *)dst, dst_row_stride, nblk); });
+}
+void sim_flash_attn_q4_0(const float * q, int64_t q_tok_stride, int64_t q_head_stride, const void * k, int64_t k_row_stride, int64_t k_head_stride,
+                         const void * v, int64_t v_row_stride, int64_t v_head_stride, const void * mask, int64_t mask_row_stride, float * dst,
+                         int64_t d, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap) {
+    FaWideArgs a = {};
+    a.q = q; a.q_ts = q_tok_stride; a.q_hs = q_head_stride; a.k = (const uint8_t *)k; a.k_rs = k_row_stride; a.k_hs = k_head_stride;
+    a.v = (const uint8_t *)v; a.v_rs = v_row_stride; a.v_hs = v_head_stride; a.mask = (const uint16_t *)mask; a.mask_rs = mask_row_stride;
+    a.dst = dst; a.n_head = n_head; a.n_head_kv = n_head_kv; a.n_kv = n_kv;
+    a.scale = logit_softcap != 0.0f ? scale / logit_softcap : scale; a.max_bias = max_bias; a.softcap = logit_softcap;
+    a.nh_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    a.m0 = powf(2.0f, -max_bias / (float)a.nh_log2); a.m1 = powf(2.0f, -(max_bias / 2.0f) / (float)a.nh_log2);
+    const dim3 grid((unsigned)n_head, (unsigned)n_tok);
+    if (d == 128) simt::launch(grid, dim3(128), 0, [a] { fattn_q4_0_kernel<128>(a); });
+    else          simt::launch(grid, dim3(128), 0, [a] { fattn_q4_0_kernel<64>(a); });
+}
+}

@@ -1,0 +1,141 @@
+"""CPU: the SOURCE of the wide path's CUDA kernels (llama-box_b200/csrc/mmvq_ext_kernels.cuh, fattn_ext_kernels.cuh, with the warp quantisers
+of actquant.cuh / actquant_ext.cuh) executed under a small SIMT emulation (tests/hostsim/simt.h: one OS thread per CUDA thread, barriers for
+__syncthreads and warp shuffles) and compared with the C oracle.  This exercises what tests/test_extfmt_hostsim.py cannot: the shared-memory
+layout, the in-kernel activation quantisers, row / sub-block loop bounds and tails, warp reductions, MUL_MAT_ID indexing, the softmax merge of the
+q4_0 attention kernel.  What remains for the GPU: real memory-model / alignment behaviour and launch plumbing (tests/test_gpu_zz_wide.py)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from refutil import (BLOCK_ELEMS, EXT_TYPES, Q4_0, Q6_K, ROOT, WEIGHT_TYPES, oracle, orc_mul_mat, ptr, rand_blocks, repack_rows_np, row_bytes)
+
+SIM_DIR = os.path.join(ROOT, "tests", "hostsim")
+CSRC = os.path.join(ROOT, "llama-box_b200", "csrc")
+CUDA_INC = "/usr/local/cuda/include"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")), reason="CUDA headers not installed")
+
+
+@pytest.fixture(scope="module")
+def K():
+    so = os.path.join(SIM_DIR, "libkernsim.so")
+    deps = [os.path.join(SIM_DIR, f) for f in ("kernsim.cpp", "simt.h")] + [os.path.join(CSRC, f) for f in
+            ("mmvq_ext_kernels.cuh", "fattn_ext_kernels.cuh", "extfmt.cuh", "actquant.cuh", "actquant_ext.cuh", "common.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + CUDA_INC, "-x", "c++",
+                               os.path.join(SIM_DIR, "kernsim.cpp"), "-o", so])
+    L = C.CDLL(so)
+    vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+    L.sim_mul_mat_vec_wide.argtypes = [i32, vp, vp, i64, vp, i64, vp, vp, i64, i64, i64, i32]
+    L.sim_mul_mat_id.argtypes = [i32, vp, i64, vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, i64, i64, i32]
+    L.sim_get_rows_q.argtypes = [i32, vp, i64, i64, vp, vp, i64, i64, i64]
+    L.sim_set_rows_q4_0.argtypes = [vp, i64, vp, vp, i64, i64, i64]
+    L.sim_misaligned.restype = C.c_long
+    L.sim_flash_attn_q4_0.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32]
+    return L
+
+
+@pytest.fixture(autouse=True)
+def no_misaligned_loads(K):
+    """weight loads the kernels issue as 2- / 4-byte accesses must be naturally aligned (a GPU traps on them; x86 would not)"""
+    before = K.sim_misaligned()
+    yield
+    assert K.sim_misaligned() == before
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("t", WEIGHT_TYPES + EXT_TYPES)
+def test_wide_matvec_kernel(K, t):
+    rng = np.random.default_rng(t)
+    m, k, n = 20, 512, 2                                         # 20 rows over 2 row groups of 8 warps: a second, partial pass of the row loop
+    W = rand_blocks(rng, t, m, k); X = (rng.standard_normal((n, k)) * 3).astype(np.float32)
+    X[1, 256:288] = 0                                            # an all-zero activation block
+    bias = rng.standard_normal(m).astype(np.float32); res = rng.standard_normal((n, m)).astype(np.float32)
+    want = orc_mul_mat(t, W, X, m, n, k)
+    Wl = repack_rows_np(t, W, k)
+    dst = np.full((n, m), 7.0, np.float32)
+    assert K.sim_mul_mat_vec_wide(t, ptr(Wl), ptr(X), k, ptr(dst), m, None, None, m, k, n, 2) == 1
+    assert rel(dst, want) <= 2e-5
+    assert K.sim_mul_mat_vec_wide(t, ptr(Wl), ptr(X), k, ptr(dst), m, ptr(bias), ptr(res), m, k, n, 2) == 1
+    assert rel(dst, want + bias[None, :] + res) <= 2e-5
+
+
+@pytest.mark.parametrize("t", [3, 7, 20, 39])
+def test_wide_matvec_kernel_rows_not_a_multiple_of_256(K, t):
+    rng = np.random.default_rng(t)
+    m, k = 9, 29568 // 4                                         # 7392 = 231 blocks: the last 256-chunk of the prologue is partial
+    W = rand_blocks(rng, t, m, k); X = rng.standard_normal((1, k)).astype(np.float32)
+    want = orc_mul_mat(t, W, X, m, 1, k)
+    dst = np.zeros((1, m), np.float32)
+    K.sim_mul_mat_vec_wide(t, ptr(W), ptr(X), k, ptr(dst), m, None, None, m, k, 1, 1)
+    assert rel(dst, want) <= 2e-5
+
+
+@pytest.mark.parametrize("t", [2, 8, 12, 14, 3, 11, 23])
+@pytest.mark.parametrize("shared", [True, False])
+def test_mul_mat_id_kernel(K, t, shared):
+    rng = np.random.default_rng(10 * t + shared)
+    m, k, n_expert, n_used, n_tok = 12, 512, 4, 2, 3
+    n_b1 = 1 if shared else n_used
+    W = rand_blocks(rng, t, n_expert * m, k)
+    b = rng.standard_normal((n_tok, n_b1, k)).astype(np.float32)
+    ids_stride = n_expert                                        # ids as llama's top-k VIEW of the argsort result: row stride = n_expert
+    ids = np.full((n_tok, ids_stride), -5, np.int32)
+    for tk in range(n_tok):
+        ids[tk, :n_used] = rng.permutation(n_expert)[:n_used]
+    ids[2, 1] = n_expert + 3                                     # out of range: that output block must stay untouched
+    want = np.full((n_tok, n_used, m), 7.0, np.float32)
+    oracle().orc_mul_mat_id(t, ptr(W), ptr(b), ptr(ids), ptr(want), m, k, n_expert, n_used, n_tok, n_b1, ids_stride)
+    Wl = repack_rows_np(t, W, k)
+    dst = np.full((n_tok, n_used, m), 7.0, np.float32)
+    assert K.sim_mul_mat_id(t, ptr(Wl), m * row_bytes(t, k), ptr(b), n_b1 * k, k, n_b1, ptr(ids), ids_stride, ptr(dst), n_used * m, m, m, k, n_expert, n_used, n_tok, 1) == 1
+    assert np.all(dst[2, 1] == 7.0)
+    assert rel(dst, want) <= 2e-5
+
+
+@pytest.mark.parametrize("t,ncols", [(t, 512) for t in WEIGHT_TYPES + EXT_TYPES] + [(12, 8192), (3, 8192 + 32)])
+def test_get_rows_kernel_bit_exact(K, t, ncols):
+    rng = np.random.default_rng(t + ncols)
+    if BLOCK_ELEMS[t] == 256:
+        ncols = ncols // 256 * 256
+    nrows = 9
+    W = rand_blocks(rng, t, nrows, ncols)
+    ids = np.array([8, 0, 3, 8, 100, -1], np.int32)              # the last two are out of range: zeros
+    want = np.zeros((ids.size, ncols), np.float32)
+    oracle().orc_get_rows_q(t, ptr(W), ptr(ids[:4]), ptr(want), ncols, 4)
+    dst = np.full((ids.size, ncols), 7.0, np.float32)
+    assert K.sim_get_rows_q(t, ptr(repack_rows_np(t, W, ncols)), row_bytes(t, ncols), nrows, ptr(ids), ptr(dst), ncols, ncols, ids.size) == 1
+    assert np.array_equal(dst, want)
+
+
+@pytest.mark.parametrize("d,n_head,n_head_kv,n_tok,n_kv,max_bias,softcap", [(128, 4, 2, 2, 80, 0.0, 0.0), (64, 4, 4, 1, 37, 8.0, 0.0), (128, 2, 1, 1, 5, 0.0, 30.0)])
+def test_q4_0_kv_cache_kernels(K, d, n_head, n_head_kv, n_tok, n_kv, max_bias, softcap):
+    rng = np.random.default_rng(d + n_kv)
+    rb_row, rb_head = row_bytes(Q4_0, n_head_kv * d), row_bytes(Q4_0, d)
+    kf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32); vf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32)
+    kf[1, :32] = 0
+    ids = rng.permutation(n_kv).astype(np.int64)
+    kc = np.zeros((n_kv, rb_row), np.uint8); vc = kc.copy(); kc2 = kc.copy(); vc2 = kc.copy()
+    oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), Q4_0, n_head_kv * d, n_kv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), Q4_0, n_head_kv * d, n_kv, rb_row)
+    K.sim_set_rows_q4_0(ptr(kf), n_head_kv * d, ptr(ids), ptr(kc2), rb_row, n_head_kv * d, n_kv)
+    K.sim_set_rows_q4_0(ptr(vf), n_head_kv * d, ptr(ids), ptr(vc2), rb_row, n_head_kv * d, n_kv)
+    assert np.array_equal(kc2, kc) and np.array_equal(vc2, vc)
+    q = rng.standard_normal((n_tok, n_head, d)).astype(np.float32)
+    mask = np.full((64, n_kv), -np.inf, np.float32)
+    for t in range(n_tok):
+        mask[t, :max(1, n_kv - n_tok + t + 1 - 3)] = rng.uniform(-1, 0, max(1, n_kv - n_tok + t + 1 - 3)) if max_bias > 0 else 0
+    m16 = mask.astype(np.float16)
+    scale = float(1 / np.sqrt(d))
+    want = np.zeros((n_tok, n_head, d), np.float32)
+    oracle().orc_flash_attn_ext(ptr(q), n_head * d * 4, d * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), ptr(want),
+                                Q4_0, d, d, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap)
+    dst = np.zeros_like(want)
+    K.sim_flash_attn_q4_0(ptr(q), n_head * d, d, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), n_kv, ptr(dst),
+                          d, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap)
+    assert rel(dst, want) <= 2e-5
