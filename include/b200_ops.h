@@ -198,6 +198,24 @@ B200_API int b200_mul_mat_id(int type, const void *as, int64_t expert_stride_byt
 B200_API int b200_get_rows_q(int type, const void *src, int64_t src_row_stride_bytes, int64_t nrows, const int32_t *ids, float *dst,
                              int64_t dst_row_stride /* floats */, int64_t ncols, int64_t n_ids, void *stream);
 
+/* Mixture-of-experts router glue (llama.cpp/src/llama-graph.cpp build_moe_ffn; csrc/glue_ext.cu): with these a Mixtral-style FFN stays on the
+ * device from its RMS_NORM to the residual ADD.  Numerics are the CPU oracle's (ggml-cpu/ops.cpp): double-precision sums, the reference's
+ * exchange sort (tie order is part of TOP_K's contract).  Strides in elements unless stated.
+ *   b200_binary_strided : dst = a op b with ggml's broadcasting (op 0 add, 1 mul, 2 div); ne / nb as in ggml (nb in BYTES); replaces the strided and
+ *                         broadcast cases of k_bin_bcast (binbcast.cu:26-93): the expert-weight MUL ([E,n_used,n_tok] * [1,n_used,n_tok]), the DIV of the
+ *                         weight normalisation and the ADDs over expert slices (views with a row stride of n_used * E)
+ *   b200_soft_max_rows  : SOFT_MAX without mask (softmax.cu:47-165)       b200_argsort_rows : ARGSORT (argsort.cu)     b200_sum_rows : sumrows.cu
+ *   b200_get_rows_f32_batched : dst[:, i, b] = src[:, ids[i, b], b] (getrows.cu, batched)      b200_mul_mat_f32 : the f32 router matmul (ffn_gate_inp) */
+B200_API int b200_binary_strided(int op, const float *a, const int64_t *a_nb, const float *b, const int64_t *b_ne, const int64_t *b_nb,
+                                 float *dst, const int64_t *ne, const int64_t *d_nb, void *stream);
+B200_API int b200_soft_max_rows(const float *x, int64_t x_row_stride, float *y, int64_t y_row_stride, int64_t ncols, int64_t nrows, float scale, void *stream);
+B200_API int b200_argsort_rows(const float *x, int64_t x_row_stride, int32_t *idx, int64_t idx_row_stride, int64_t ncols, int64_t nrows, int descending, void *stream);
+B200_API int b200_sum_rows(const float *x, int64_t x_row_stride, float *y, int64_t ncols, int64_t nrows, void *stream);
+B200_API int b200_get_rows_f32_batched(const float *src, int64_t src_row_stride, int64_t src_batch_stride, int64_t n_src_rows, const int32_t *ids, int64_t ids_batch_stride,
+                                       float *dst, int64_t dst_row_stride, int64_t dst_batch_stride, int64_t ncols, int64_t n_ids, int64_t n_batch, void *stream);
+B200_API int b200_mul_mat_f32(const float *W, int64_t w_row_stride, const float *x, int64_t x_col_stride, float *dst, int64_t dst_col_stride,
+                              int64_t m, int64_t k, int64_t ncols, void *stream);
+
 /* KV cache type q4_0 (`-ctk q4_0 -ctv q4_0`): the cache keeps ggml's native 18-byte blocks.  SET_ROWS writes what ggml's from_float writes
  * (ggml-quants.c quantize_row_q4_0_ref; replaces k_set_rows_quant<block_q4_0>, ggml-cuda/set-rows.cu:13-52); FLASH_ATTN_EXT follows the CPU
  * oracle (q8_0 query x Q4_0 K in integers, f32 online softmax, V expanded to f32; replaces the q4_0-q4_0 flash_attn_vec_ext instances,

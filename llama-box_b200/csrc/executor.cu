@@ -85,14 +85,64 @@ bool get_rows_q_ok(const b200_node & n) {
     const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
     if (!(is_weight_type(s.type) || is_wide_only_type(s.type)) || ids.type != B200_TYPE_I32 || d.type != B200_TYPE_F32) return false;
     if (!lib_layout_ok(s.type, s.ne[0])) return false;
+    if (is_weight_type(s.type) && s.nb[1] != b200_wide_row_bytes(s.type, s.ne[0])) return false;     // the load-time repack works on whole, dense tensors
     if (!b200_wide_shape_supported(s.type, s.ne[0]) || s.ne[1] <= 0 || s.ne[2] != 1 || s.ne[3] != 1 || s.nb[1] < b200_wide_row_bytes(s.type, s.ne[0]) || (s.nb[1] & 1)) return false;
     if (ids.ne[1] != 1 || ids.ne[2] != 1 || ids.ne[3] != 1 || ids.nb[0] != 4 || d.ne[0] != s.ne[0] || d.ne[1] != ids.ne[0] || !contiguous(d)) return false;
     return aligned16(s.data) && aligned16(d.data);
 }
 
+// ---- mixture-of-experts router glue (wide path): small f32 ops of build_moe_ffn (llama-graph.cpp:820-1010)
+inline bool f32_strided(const b200_tensor & t) { return t.type == B200_TYPE_F32 && t.data && !((uintptr_t)t.data & 3) && !((t.nb[0] | t.nb[1] | t.nb[2] | t.nb[3]) & 3) && t.ne[0] > 0 && t.ne[1] > 0 && t.ne[2] > 0 && t.ne[3] > 0; }
+// ADD / MUL / DIV with ggml's broadcasting over any strides (the expert-weight MUL, the weight-normalising DIV, the ADDs over expert slices)
+bool bin_strided_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 2) return false;
+    const b200_tensor & a = n.src[0], & b = n.src[1], & d = n.dst;
+    if (!f32_strided(a) || !f32_strided(b) || !f32_strided(d) || !same_shape(a, d)) return false;
+    for (int i = 0; i < 4; i++) if (d.ne[i] % b.ne[i] != 0) return false;
+    return true;
+}
+// the f32 router matrix (ffn_gate_inp [n_embd, n_expert]) times the activations
+bool mul_mat_f32_ok(const b200_node & n) {
+    const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
+    if (!wide_on() || w.type != B200_TYPE_F32 || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    if (w.ne[2] != 1 || w.ne[3] != 1 || x.ne[2] != 1 || x.ne[3] != 1 || w.ne[1] <= 0 || w.ne[1] > 1024 || w.ne[0] <= 0) return false;     // router-sized only
+    if (w.nb[0] != 4 || (w.nb[1] & 3) || x.ne[0] != w.ne[0] || x.nb[0] != 4 || (x.nb[1] & 3) || d.ne[0] != w.ne[1] || d.ne[1] != x.ne[1] || d.nb[0] != 4 || (d.nb[1] & 3)) return false;
+    return w.data && x.data && !(((uintptr_t)w.data | (uintptr_t)x.data | (uintptr_t)d.data) & 3);
+}
+bool rows2d_f32(const b200_tensor & t) { return t.type == B200_TYPE_F32 && t.nb[0] == 4 && contiguous(t) && !((uintptr_t)t.data & 3); }
+bool soft_max_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 1 || (n.n_src > 1 && n.src[1].id) || (n.n_src > 2 && n.src[2].id)) return false;        // mask / sinks: attention without -fa, not this path
+    return rows2d_f32(n.src[0]) && rows2d_f32(n.dst) && same_shape(n.src[0], n.dst) && f32_param(n, 1) == 0.0f && n.src[0].ne[0] <= 65536;
+}
+bool argsort_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 1) return false;
+    const b200_tensor & s = n.src[0], & d = n.dst;
+    return rows2d_f32(s) && d.type == B200_TYPE_I32 && contiguous(d) && same_shape(s, d) && s.ne[0] <= 4096 && (n.op_params[0] == 0 || n.op_params[0] == 1) && !((uintptr_t)d.data & 3);
+}
+bool sum_rows_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 1) return false;
+    const b200_tensor & s = n.src[0], & d = n.dst;
+    return rows2d_f32(s) && rows2d_f32(d) && d.ne[0] == 1 && d.ne[1] == s.ne[1] && d.ne[2] == s.ne[2] && d.ne[3] == s.ne[3];
+}
+// GET_ROWS f32, one id list, 16-byte rows (the output-row gather of the last layer)
+bool get_rows_f32_ok(const b200_node & n) {
+    const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+    return n.n_src >= 2 && s.type == B200_TYPE_F32 && ids.type == B200_TYPE_I32 && s.nb[0] == 4 && (s.nb[1] & 15) == 0 && s.ne[2] == 1 && s.ne[3] == 1 &&
+           s.ne[0] % 4 == 0 && aligned16(s.data) && d.type == B200_TYPE_F32 && contiguous(d) && aligned16(d.data) && ids.ne[1] == 1 && ids.ne[2] == 1 && d.ne[1] == ids.ne[0];
+}
+// GET_ROWS f32 with one id list per batch (ggml.c:3620-3650): src [c, r, b], ids [n, b], dst [c, n, b]
+bool get_rows_f32_batched_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 2) return false;
+    const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+    if (s.type != B200_TYPE_F32 || ids.type != B200_TYPE_I32 || d.type != B200_TYPE_F32 || !f32_strided(s) || s.nb[0] != 4 || s.ne[3] != 1 || ids.ne[2] != 1 || ids.ne[3] != 1) return false;
+    if (ids.nb[0] != 4 || (ids.nb[1] & 3) || ids.ne[1] != s.ne[2] || !contiguous(d) || d.ne[0] != s.ne[0] || d.ne[1] != ids.ne[0] || d.ne[2] != s.ne[2] || d.ne[3] != 1) return false;
+    return ids.data && !(((uintptr_t)ids.data | (uintptr_t)d.data) & 3);
+}
+
 bool mul_mat_ok(const b200_node & n) {
     const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
     if (is_wide_only_type(w.type)) return mul_mat_wide_ok(n);
+    if (w.type == B200_TYPE_F32) return mul_mat_f32_ok(n);
     if (!is_weight_type(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
     const int64_t k = w.ne[0], m = w.ne[1];
     // 32-element block types: any multiple of 32 (rows padded to 256 in the private weight layout, see common.cuh padded_k)
@@ -157,7 +207,11 @@ bool node_ok(const b200_node & n) {
         case B200_OP_NONE:     return true;
         case B200_OP_MUL_MAT:  return n.n_src >= 2 && mul_mat_ok(n);
         case B200_OP_RMS_NORM: return n.n_src >= 1 && rows_f32_ok(n.src[0]) && rows_f32_ok(n.dst) && same_shape(n.src[0], n.dst) && n.src[0].ne[0] * 4 <= 200 * 1024;
-        case B200_OP_MUL: case B200_OP_ADD: return n.n_src >= 2 && bin_ok(n);
+        case B200_OP_MUL: case B200_OP_ADD: return n.n_src >= 2 && (bin_ok(n) || bin_strided_ok(n));
+        case B200_OP_DIV:      return bin_strided_ok(n);
+        case B200_OP_SOFT_MAX: return soft_max_ok(n);
+        case B200_OP_ARGSORT:  return argsort_ok(n);
+        case B200_OP_SUM_ROWS: return sum_rows_ok(n);
         case B200_OP_ROPE:     return n.n_src >= 2 && rope_ok(n);
         case B200_OP_SET_ROWS: return n.n_src >= 2 && set_rows_ok(n);
         case B200_OP_FLASH_ATTN_EXT: return n.n_src >= 3 && fattn_ok(n);
@@ -166,8 +220,7 @@ bool node_ok(const b200_node & n) {
         case B200_OP_GET_ROWS: {
             const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
             if (n.n_src >= 2 && s.type != B200_TYPE_F32) return get_rows_q_ok(n);
-            return n.n_src >= 2 && s.type == B200_TYPE_F32 && ids.type == B200_TYPE_I32 && s.nb[0] == 4 && (s.nb[1] & 15) == 0 && s.ne[2] == 1 && s.ne[3] == 1 &&
-                   s.ne[0] % 4 == 0 && aligned16(s.data) && d.type == B200_TYPE_F32 && contiguous(d) && aligned16(d.data) && ids.ne[1] == 1 && ids.ne[2] == 1 && d.ne[1] == ids.ne[0];
+            return n.n_src >= 2 && (get_rows_f32_ok(n) || get_rows_f32_batched_ok(n));
         }
         case B200_OP_CPY: {
             const b200_tensor & s = n.src[0], & d = n.dst;
@@ -565,6 +618,12 @@ struct Runner {
         const b200_node & n = nodes[i];
         const b200_tensor & w = n.src[0], & x = n.src[1];
         const int64_t kv = w.ne[0], k = padded_k(w.type, kv), m = w.ne[1], ncols = x.ne[1];   // kv: elements that exist in x; k: padded weight rows
+        if (w.type == B200_TYPE_F32) {
+            // the f32 router matrix of a mixture-of-experts layer (ffn_gate_inp): router-sized, one warp per output
+            { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+            invalidate_act(n.dst);
+            return KL(b200_mul_mat_f32((const float *)w.data, w.nb[1] / 4, (const float *)x.data, x.nb[1] / 4, (float *)n.dst.data, n.dst.nb[1] / 4, m, kv, ncols, st));
+        }
         if (is_wide_only_type(w.type)) {
             // a format only the wide matvec reads (mmvq_ext.cu): f32 activations in, quantised inside the kernel; one pass over the weights per column
             { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
@@ -750,9 +809,12 @@ struct Runner {
             case B200_OP_NONE: return B200_OK;
             case B200_OP_RMS_NORM: return run_rms_norm(i);
             case B200_OP_MUL_MAT:  return run_mul_mat(i);
-            case B200_OP_MUL: case B200_OP_ADD: {
+            case B200_OP_MUL: case B200_OP_ADD: case B200_OP_DIV: {
                 invalidate_act(n.dst);
                 const b200_tensor & a = n.src[0], & b = n.src[1];
+                if (n.op == B200_OP_DIV || !bin_ok(n))        // broadcast over other dims / strided views (MoE router glue): the general kernel
+                    return KL(b200_binary_strided(n.op == B200_OP_ADD ? 0 : (n.op == B200_OP_MUL ? 1 : 2), (const float *)a.data, a.nb, (const float *)b.data, b.ne, b.nb,
+                                                  (float *)n.dst.data, n.dst.ne, n.dst.nb, st));
                 const int64_t rows = nrows_of(a), brows = same_shape(a, b) ? rows : b.ne[1];
                 return KL(n.op == B200_OP_ADD ? b200_add((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st)
                                               : b200_mul((const float *)a.data, (const float *)b.data, (float *)n.dst.data, a.ne[0], rows, brows, st));
@@ -806,6 +868,14 @@ struct Runner {
             case B200_OP_GLU_SWIGLU:
                 invalidate_act(n.dst);
                 return KL(b200_swiglu((const float *)n.src[0].data, (const float *)n.src[1].data, (float *)n.dst.data, nelem(n.dst), st));
+            case B200_OP_SOFT_MAX:
+                invalidate_act(n.dst);
+                return KL(b200_soft_max_rows((const float *)n.src[0].data, n.src[0].ne[0], (float *)n.dst.data, n.dst.ne[0], n.src[0].ne[0], nrows_of(n.src[0]), f32_param(n, 0), st));
+            case B200_OP_ARGSORT:
+                return KL(b200_argsort_rows((const float *)n.src[0].data, n.src[0].ne[0], (int32_t *)n.dst.data, n.dst.ne[0], n.src[0].ne[0], nrows_of(n.src[0]), n.op_params[0] == 1, st));
+            case B200_OP_SUM_ROWS:
+                invalidate_act(n.dst);
+                return KL(b200_sum_rows((const float *)n.src[0].data, n.src[0].ne[0], (float *)n.dst.data, n.src[0].ne[0], nrows_of(n.src[0]), st));
             case B200_OP_MUL_MAT_ID: {
                 // expert routing on the device: the kernel reads ids itself (no stream synchronisation, unlike ggml-cuda.cu:2115-2125)
                 invalidate_act(n.dst);
@@ -815,6 +885,9 @@ struct Runner {
             }
             case B200_OP_GET_ROWS:
                 invalidate_act(n.dst);
+                if (n.src[0].type == B200_TYPE_F32 && !get_rows_f32_ok(n))
+                    return KL(b200_get_rows_f32_batched((const float *)n.src[0].data, n.src[0].nb[1] / 4, n.src[0].nb[2] / 4, n.src[0].ne[1], (const int32_t *)n.src[1].data, n.src[1].nb[1] / 4,
+                                                        (float *)n.dst.data, n.dst.nb[1] / 4, n.dst.nb[2] / 4, n.src[0].ne[0], n.src[1].ne[0], n.src[0].ne[2], st));
                 if (n.src[0].type != B200_TYPE_F32)
                     return KL(b200_get_rows_q(n.src[0].type, n.src[0].data, n.src[0].nb[1], n.src[0].ne[1], (const int32_t *)n.src[1].data, (float *)n.dst.data, n.dst.nb[1] / 4,
                                               n.src[0].ne[0], n.src[1].ne[0], st));

@@ -89,6 +89,12 @@ SIGNATURES = {
     "b200_mul_mat_vec_wide": (i32, [i32, vp, vp, i64, vp, i64, vp, vp, i64, i64, i64, vp]),
     "b200_mul_mat_id": (i32, [i32, vp, i64, vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, i64, i64, vp]),
     "b200_get_rows_q": (i32, [i32, vp, i64, i64, vp, vp, i64, i64, i64, vp]),
+    "b200_binary_strided": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b200_soft_max_rows": (i32, [vp, i64, vp, i64, i64, i64, f32, vp]),
+    "b200_argsort_rows": (i32, [vp, i64, vp, i64, i64, i64, i32, vp]),
+    "b200_sum_rows": (i32, [vp, i64, vp, i64, i64, vp]),
+    "b200_get_rows_f32_batched": (i32, [vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, vp]),
+    "b200_mul_mat_f32": (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]),
     "b200_set_rows_q4_0": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),
     "b200_flash_attn_q4_0": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32, vp]),
 }

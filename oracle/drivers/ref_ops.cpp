@@ -110,6 +110,14 @@ int main(int argc, char ** argv) {
     } else if (op == "mul_mat_id") {
         // as [k, m, n_expert], b [k, n_b1, n_tok] f32, ids i32 [n_used, n_tok] (llama-graph.cpp build_moe_ffn)
         out = ggml_mul_mat_id(ctx, need("w"), need("x"), need("ids"));
+    } else if (op == "soft_max") {
+        out = ggml_soft_max_ext(ctx, need("x"), nullptr, (float)P("scale", 1), 0.0f);
+    } else if (op == "argsort") {
+        out = ggml_argsort(ctx, need("x"), P("desc", 1) != 0 ? GGML_SORT_ORDER_DESC : GGML_SORT_ORDER_ASC);
+    } else if (op == "sum_rows") {
+        out = ggml_sum_rows(ctx, need("x"));
+    } else if (op == "div") {
+        out = ggml_div(ctx, need("a"), need("b"));
     } else if (op == "rms_norm") {
         out = ggml_rms_norm(ctx, need("x"), (float)P("eps", 1e-5));
         if (opt("w")) out = ggml_mul(ctx, out, opt("w"));

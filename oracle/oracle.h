@@ -112,6 +112,13 @@ void  orc_mul_mat_id(int type, const void *as, const float *b, const int32_t *id
 /* GET_ROWS on a quantised table (ggml-cpu/ops.cpp get_rows_q) */
 void  orc_get_rows_q(int type, const void *src, const int32_t *ids, float *dst, int64_t ncols, int64_t n_ids);
 
+/* mixture-of-experts router glue (llama-graph.cpp build_moe_ffn): SOFT_MAX without mask (ggml-cpu/ops.cpp:5685-5800), ARGSORT with the reference's
+ * tie order (ops.cpp:8110-8147), SUM_ROWS (double accumulation).  The broadcasting ADD / MUL / DIV and the batched GET_ROWS of that graph are
+ * exact f32 element operations; tests state them with numpy. */
+void orc_soft_max_rows(const float *x, float *y, int64_t ncols, int64_t nrows, float scale);
+void orc_argsort_rows(const float *x, int32_t *idx, int64_t ncols, int64_t nrows, int descending);
+void orc_sum_rows(const float *x, float *y, int64_t ncols, int64_t nrows);
+
 /* glue (ggml-cpu/vec.h:691, ops.cpp swiglu / binary-ops.cpp / get_rows / cpy) */
 void orc_swiglu(const float *gate, const float *up, float *y, int64_t n);
 void orc_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows);

@@ -287,3 +287,33 @@ void orc_get_rows_q(int type, const void *src, const int32_t *ids, float *dst, i
     const int64_t rb = orc_row_bytes(type, ncols);
     for (int64_t i = 0; i < n_ids; i++) orc_dequantize_row(type, (const uint8_t *)src + (int64_t)ids[i] * rb, dst + i * ncols, ncols);
 }
+
+/* ---- mixture-of-experts router glue (llama.cpp/src/llama-graph.cpp build_moe_ffn) ---- */
+
+/* SOFT_MAX of rows without mask (ggml-cpu/ops.cpp:5685-5800; vec.cpp ggml_vec_soft_max_f32): w = x*scale, exp(w - max) summed in double,
+ * scaled by (float)(1/sum).  The reference evaluates exp with expf or with its vectorised polynomial depending on build and row length;
+ * both are within 2 ulp of this expf. */
+void orc_soft_max_rows(const float *x, float *y, int64_t ncols, int64_t nrows, float scale) {
+    for (int64_t r = 0; r < nrows; r++) {
+        const float *xr = x + r*ncols; float *yr = y + r*ncols;
+        float mx = -INFINITY;
+        for (int64_t i = 0; i < ncols; i++) { const float w = xr[i] * scale; if (w > mx) mx = w; }
+        double sum = 0.0;
+        for (int64_t i = 0; i < ncols; i++) { const float v = expf(xr[i] * scale - mx); yr[i] = v; sum += (double)v; }
+        const float inv = (float)(1.0 / sum);
+        for (int64_t i = 0; i < ncols; i++) yr[i] *= inv;
+    }
+}
+/* ARGSORT (ggml-cpu/ops.cpp:8110-8147): the reference's exchange sort, whose result for equal keys is part of the contract (TOP_K) */
+void orc_argsort_rows(const float *x, int32_t *idx, int64_t ncols, int64_t nrows, int descending) {
+    for (int64_t r = 0; r < nrows; r++) {
+        const float *xr = x + r*ncols; int32_t *d = idx + r*ncols;
+        for (int64_t j = 0; j < ncols; j++) d[j] = (int32_t)j;
+        for (int64_t j = 0; j < ncols; j++) for (int64_t k = j + 1; k < ncols; k++)
+            if (descending ? xr[d[j]] < xr[d[k]] : xr[d[j]] > xr[d[k]]) { const int32_t t = d[j]; d[j] = d[k]; d[k] = t; }
+    }
+}
+/* SUM_ROWS (ggml-cpu/ops.cpp sum_rows_f32 -> ggml_vec_sum_f32): sequential double sum, stored as float */
+void orc_sum_rows(const float *x, float *y, int64_t ncols, int64_t nrows) {
+    for (int64_t r = 0; r < nrows; r++) { double s = 0.0; for (int64_t i = 0; i < ncols; i++) s += (double)x[r*ncols + i]; y[r] = (float)s; }
+}

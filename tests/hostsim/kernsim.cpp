@@ -7,6 +7,7 @@
 
 #include "../../llama-box_b200/csrc/mmvq_ext_kernels.cuh"
 #include "../../llama-box_b200/csrc/fattn_ext_kernels.cuh"
+#include "../../llama-box_b200/csrc/glue_ext_kernels.cuh"
 
 void b200_set_error(const char *, ...) {}
 extern "C" { long xf_misaligned = 0; long sim_misaligned(void) { return xf_misaligned; } }
@@ -67,5 +68,29 @@ void sim_flash_attn_q4_0(const float * q, int64_t q_tok_stride, int64_t q_head_s
     const dim3 grid((unsigned)n_head, (unsigned)n_tok);
     if (d == 128) simt::launch(grid, dim3(128), 0, [a] { fattn_q4_0_kernel<128>(a); });
     else          simt::launch(grid, dim3(128), 0, [a] { fattn_q4_0_kernel<64>(a); });
+}
+
+// ---- mixture-of-experts router glue (glue_ext_kernels.cuh); geometry as in glue_ext.cu with a small grid
+void sim_binary_strided(int op, const float * a, const int64_t * a_nb, const float * b, const int64_t * b_ne, const int64_t * b_nb, float * dst, const int64_t * ne, const int64_t * d_nb) {
+    BinArgs A; A.a = a; A.b = b; A.d = dst;
+    for (int i = 0; i < 4; i++) { A.ne[i] = ne[i]; A.a_nb[i] = a_nb[i]; A.b_ne[i] = b_ne[i]; A.b_nb[i] = b_nb[i]; A.d_nb[i] = d_nb[i]; }
+    if (op == 0) simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<0>(A); });
+    else if (op == 1) simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<1>(A); });
+    else simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<2>(A); });
+}
+void sim_soft_max_rows(const float * x, int64_t xrs, float * y, int64_t yrs, int64_t ncols, int64_t nrows, float scale) {
+    simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { soft_max_rows_kernel(x, xrs, y, yrs, ncols, nrows, scale); });
+}
+void sim_argsort_rows(const float * x, int64_t xrs, int32_t * idx, int64_t irs, int64_t ncols, int64_t nrows, int desc) {
+    simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { argsort_rows_kernel(x, xrs, idx, irs, ncols, nrows, desc); });
+}
+void sim_sum_rows(const float * x, int64_t xrs, float * y, int64_t ncols, int64_t nrows) {
+    simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { sum_rows_kernel(x, xrs, y, ncols, nrows); });
+}
+void sim_get_rows_f32_batched(const float * src, int64_t srs, int64_t sbs, int64_t nsr, const int32_t * ids, int64_t ibs, float * dst, int64_t drs, int64_t dbs, int64_t ncols, int64_t n_ids, int64_t n_batch) {
+    simt::launch(dim3(2), dim3(256), 0, [=] { get_rows_f32_3d_kernel(src, srs, sbs, nsr, ids, ibs, dst, drs, dbs, ncols, n_ids, n_batch); });
+}
+void sim_mul_mat_f32(const float * W, int64_t wrs, const float * x, int64_t xcs, float * dst, int64_t dcs, int64_t m, int64_t k, int64_t ncols) {
+    simt::launch(dim3((unsigned)((m * ncols * 32 + 255) / 256)), dim3(256), 0, [=] { mul_mat_f32_kernel(W, wrs, x, xcs, dst, dcs, m, k, ncols); });
 }
 }

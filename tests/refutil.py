@@ -95,6 +95,9 @@ def oracle():
         L.orc_quantize_row_q8_1.argtypes = [vp, vp, i64]
         L.orc_mul_mat_id.argtypes = [i32, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64]
         L.orc_get_rows_q.argtypes = [i32, vp, vp, vp, i64, i64]
+        L.orc_soft_max_rows.argtypes = [vp, vp, i64, i64, f32]
+        L.orc_argsort_rows.argtypes = [vp, vp, i64, i64, i32]
+        L.orc_sum_rows.argtypes = [vp, vp, i64, i64]
         _oracle = L
     return _oracle
 

@@ -70,12 +70,21 @@ def test_q4_0_kv_cache_set_rows_and_flash_attn_vs_oracle(shape):
     assert o["attn_err"] <= 2e-5, o
 
 
+def test_moe_router_glue_vs_oracle():
+    """glue_ext.cu through the C-ABI: f32 router matmul, SOFT_MAX, ARGSORT (ties in the reference's order), batched GET_ROWS, SUM_ROWS, DIV, the
+    broadcast MUL and the ADD over strided expert slices"""
+    o = child("glue")
+    assert o["mul_mat_f32"] <= 1e-5 and o["soft_max"] <= 1e-6, o
+    assert all(o[k] for k in ("argsort_exact", "get_rows_batched_exact", "sum_rows_exact", "div_exact", "mul_bcast_exact", "add_slices_exact")), o
+
+
 @pytest.mark.parametrize("wtype,n_tok", [(3, 1), (11, 4), (23, 1)])
 def test_executor_moe_block_vs_oracle(wtype, n_tok):
+    """a whole Mixtral-style block (tests/moe_graph.py = the node list build_moe_ffn emits) through the graph executor: 15 launches, nothing leaves the device"""
     o = child("executor", wtype, n_tok, wide=True)
     assert all(o["supports"]), o
-    assert max(o["errs"]) <= 5e-5, o                         # chained ops: each re-quantises its input like the oracle does
-    assert o["captures"] >= 1 and o["replays"] >= 1, o
+    assert max(o["errs"]) <= 2e-4, o                         # chained ops, each re-quantising its input like the oracle does; the f32 router sums associate differently
+    assert o["captures"] >= 1 and o["replays"] >= 1 and o["kernels"] == 15, o
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")

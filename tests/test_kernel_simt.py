@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_
 def K():
     so = os.path.join(SIM_DIR, "libkernsim.so")
     deps = [os.path.join(SIM_DIR, f) for f in ("kernsim.cpp", "simt.h")] + [os.path.join(CSRC, f) for f in
-            ("mmvq_ext_kernels.cuh", "fattn_ext_kernels.cuh", "extfmt.cuh", "actquant.cuh", "actquant_ext.cuh", "common.cuh")]
+            ("mmvq_ext_kernels.cuh", "fattn_ext_kernels.cuh", "glue_ext_kernels.cuh", "extfmt.cuh", "actquant.cuh", "actquant_ext.cuh", "common.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + CUDA_INC, "-x", "c++",
                                os.path.join(SIM_DIR, "kernsim.cpp"), "-o", so])
@@ -33,6 +33,12 @@ def K():
     L.sim_get_rows_q.argtypes = [i32, vp, i64, i64, vp, vp, i64, i64, i64]
     L.sim_set_rows_q4_0.argtypes = [vp, i64, vp, vp, i64, i64, i64]
     L.sim_misaligned.restype = C.c_long
+    L.sim_binary_strided.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sim_soft_max_rows.argtypes = [vp, i64, vp, i64, i64, i64, f32]
+    L.sim_argsort_rows.argtypes = [vp, i64, vp, i64, i64, i64, i32]
+    L.sim_sum_rows.argtypes = [vp, i64, vp, i64, i64]
+    L.sim_get_rows_f32_batched.argtypes = [vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64]
+    L.sim_mul_mat_f32.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64]
     L.sim_flash_attn_q4_0.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32]
     return L
 
@@ -139,3 +145,48 @@ def test_q4_0_kv_cache_kernels(K, d, n_head, n_head_kv, n_tok, n_kv, max_bias, s
     K.sim_flash_attn_q4_0(ptr(q), n_head * d, d, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), n_kv, ptr(dst),
                           d, n_head, n_head_kv, n_tok, n_kv, scale, max_bias, softcap)
     assert rel(dst, want) <= 2e-5
+
+
+def i64a(*v):
+    return np.array(v, np.int64)
+
+
+def test_moe_router_glue_kernels(K):
+    """the router of build_moe_ffn, op by op: f32 router matmul, SOFT_MAX, ARGSORT (ties!), batched GET_ROWS of the selected probabilities, SUM_ROWS,
+    DIV, the broadcast MUL by the expert weights and the ADD over strided expert slices"""
+    rng = np.random.default_rng(9)
+    E, NE, NU, NT = 96, 8, 2, 5
+    Wg = rng.standard_normal((NE, E)).astype(np.float32); x = rng.standard_normal((NT, E)).astype(np.float32)
+    logits = np.zeros((NT, NE), np.float32)
+    K.sim_mul_mat_f32(ptr(Wg), E, ptr(x), E, ptr(logits), NE, NE, E, NT)
+    want = (x.astype(np.float64) @ Wg.astype(np.float64).T)
+    assert np.abs(logits - want).max() <= 1e-5 * np.abs(want).max()
+    logits[2, 3] = logits[2, 6]                                  # a tie
+    probs = np.zeros_like(logits); wantp = np.zeros_like(logits)
+    K.sim_soft_max_rows(ptr(logits), NE, ptr(probs), NE, NE, NT, 1.0); oracle().orc_soft_max_rows(ptr(logits), ptr(wantp), NE, NT, 1.0)
+    assert np.abs(probs - wantp).max() <= 1e-6
+    for desc in (1, 0):
+        idx = np.zeros((NT, NE), np.int32); wanti = np.zeros_like(idx)
+        K.sim_argsort_rows(ptr(wantp), NE, ptr(idx), NE, NE, NT, desc); oracle().orc_argsort_rows(ptr(wantp), ptr(wanti), NE, NT, desc)
+        assert np.array_equal(idx, wanti)
+    K.sim_argsort_rows(ptr(wantp), NE, ptr(idx), NE, NE, NT, 1)
+    # selected experts = the first NU columns of the argsort result, as a VIEW (row stride NE): ids_batch_stride = NE
+    w = np.full((NT, NU), 7.0, np.float32)
+    K.sim_get_rows_f32_batched(ptr(wantp), 1, NE, NE, ptr(idx), NE, ptr(w), 1, NU, 1, NU, NT)
+    assert np.array_equal(w, np.take_along_axis(wantp, idx[:, :NU], axis=1))
+    s = np.zeros(NT, np.float32); wants = np.zeros(NT, np.float32)
+    K.sim_sum_rows(ptr(w), NU, ptr(s), NU, NT); oracle().orc_sum_rows(ptr(w), ptr(wants), NU, NT)
+    assert np.array_equal(s, wants)
+    wn = np.zeros_like(w)                                        # DIV: [NU, NT] / [1, NT]
+    K.sim_binary_strided(2, ptr(w), ptr(i64a(4, 4 * NU, 4 * NU * NT, 4 * NU * NT)), ptr(s), ptr(i64a(1, NT, 1, 1)), ptr(i64a(4, 4, 4 * NT, 4 * NT)), ptr(wn),
+                         ptr(i64a(NU, NT, 1, 1)), ptr(i64a(4, 4 * NU, 4 * NU * NT, 4 * NU * NT)))
+    assert np.array_equal(wn, w / s[:, None])
+    ex = rng.standard_normal((NT, NU, E)).astype(np.float32)      # experts [E, NU, NT] * weights [1, NU, NT]
+    exw = np.zeros_like(ex)
+    nb3 = i64a(4, 4 * E, 4 * E * NU, 4 * E * NU * NT)
+    K.sim_binary_strided(1, ptr(ex), ptr(nb3), ptr(wn), ptr(i64a(1, NU, NT, 1)), ptr(i64a(4, 4, 4 * NU, 4 * NU * NT)), ptr(exw), ptr(i64a(E, NU, NT, 1)), ptr(nb3))
+    assert np.array_equal(exw, ex * wn[:, :, None])
+    out = np.zeros((NT, E), np.float32)                          # ADD of the two expert slices: views [E, NT] with row stride E * NU
+    sl = i64a(4, 4 * E * NU, 4 * E * NU * NT, 4 * E * NU * NT)
+    K.sim_binary_strided(0, ptr(exw), ptr(sl), C.c_void_p(exw.ctypes.data + 4 * E), ptr(i64a(E, NT, 1, 1)), ptr(sl), ptr(out), ptr(i64a(E, NT, 1, 1)), ptr(i64a(4, 4 * E, 4 * E * NT, 4 * E * NT)))
+    assert np.array_equal(out, exw[:, 0, :] + exw[:, 1, :])

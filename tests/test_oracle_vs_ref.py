@@ -167,3 +167,31 @@ def test_q4_0_kv_cache_set_rows_and_flash_attn_through_cpu_backend():
     oracle().orc_flash_attn_ext(ptr(q), nh * dk * 4, dk * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), ptr(y),
                                 Q4_0, dk, dk, nh, nhkv, nt, nkv, float(1 / np.sqrt(dk)), 0.0, 0.0)
     assert np.abs(y - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_moe_router_glue_through_cpu_backend():
+    """SOFT_MAX (no mask), ARGSORT incl. ties, SUM_ROWS, DIV with broadcasting, the batched GET_ROWS and the broadcast MUL of build_moe_ffn"""
+    rng = np.random.default_rng(77)
+    ne, nt, nu = 8, 5, 2
+    x = (rng.standard_normal((nt, ne)) * 3).astype(np.float32)
+    _, _, out = run_ref_op("soft_max", [("x", F32, [ne, nt], x)], dict(scale=1.0))
+    want = np.frombuffer(out, np.float32).reshape(nt, ne); y = np.zeros_like(x)
+    oracle().orc_soft_max_rows(ptr(x), ptr(y), ne, nt, 1.0)
+    assert np.abs(y - want).max() <= 1e-6
+    xs = x.copy(); xs[1, 3] = xs[1, 5]; xs[2, :] = 0.25                      # ties: the exchange sort's order is part of the contract
+    for desc in (1, 0):
+        _, _, out = run_ref_op("argsort", [("x", F32, [ne, nt], xs)], dict(desc=desc))
+        idx = np.zeros((nt, ne), np.int32); oracle().orc_argsort_rows(ptr(xs), ptr(idx), ne, nt, desc)
+        assert np.array_equal(idx, np.frombuffer(out, np.int32).reshape(nt, ne))
+    w = rng.uniform(0.01, 1, (nt, nu)).astype(np.float32)
+    _, _, out = run_ref_op("sum_rows", [("x", F32, [nu, nt], w)])
+    s = np.zeros(nt, np.float32); oracle().orc_sum_rows(ptr(w), ptr(s), nu, nt)
+    assert np.array_equal(s, np.frombuffer(out, np.float32))
+    _, _, out = run_ref_op("div", [("a", F32, [nu, nt], w), ("b", F32, [1, nt], s)])
+    assert np.array_equal(np.frombuffer(out, np.float32).reshape(nt, nu), w / s[:, None])
+    probs = y.reshape(nt, ne, 1); ids = np.stack([rng.permutation(ne)[:nu] for _ in range(nt)]).astype(np.int32)
+    _, _, out = run_ref_op("get_rows", [("src", F32, [1, ne, nt], probs), ("ids", I32, [nu, nt], ids)])
+    assert np.array_equal(np.frombuffer(out, np.float32).reshape(nt, nu), np.take_along_axis(y, ids, axis=1))
+    ex = rng.standard_normal((nt, nu, 64)).astype(np.float32)
+    _, _, out = run_ref_op("mul", [("a", F32, [64, nu, nt], ex), ("b", F32, [1, nu, nt], w.reshape(nt, nu, 1))])
+    assert np.array_equal(np.frombuffer(out, np.float32).reshape(nt, nu, 64), ex * w[:, :, None])

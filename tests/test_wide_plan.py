@@ -15,27 +15,31 @@ sys.path.insert(0, %r)
 from conftest import load_pkg
 load_pkg()
 G = importlib.import_module("llama_box_b200.graph")
+import moe_graph
 E, FF, NE, NU, NT, VOC = 4096, 2048, 8, 2, %d, 32000
-base = [0x10000000]
-def buf(n):
-    p = base[0]; base[0] += (n + 0xfffff) & ~0xfffff; return p
-f32 = lambda ne: G.T(buf(4 * ne[0] * ne[1] * (ne[2] if len(ne) > 2 else 1)), G.F32, ne)
-def W(t, ne):
-    rb = G.row_size(t, ne[0]); rows = ne[1] * (ne[2] if len(ne) > 2 else 1)
-    return G.T(buf(rb * rows), t, ne)
+
+
+class Fake:
+    base = 0x10000000
+
+    def buf(self, n):
+        p = Fake.base; Fake.base += (n + 0xfffff) & ~0xfffff; return p
+
+    def f32(self, ne):
+        return G.T(self.buf(4 * ne[0] * ne[1] * (ne[2] if len(ne) > 2 else 1)), G.F32, ne)
+
+    def i32(self, ne):
+        return G.T(self.buf(4 * ne[0] * ne[1]), G.I32, ne)
+
+    def named(self, name, t, ne):
+        rows = 1
+        for d in ne[1:]:
+            rows *= d
+        return G.T(self.buf(G.row_size(t, ne[0]) * rows), t, ne)
+
+
 out = {"wide": int(G._lib.b200_executor_wide_enabled())}
-nl = G.NodeList()
-tok = G.T(buf(64), G.I32, [NT])
-emb = nl.add(G.OP_GET_ROWS, f32([E, NT]), [W(G.Q4_K, [E, VOC]), tok])                       # token embedding on the device
-nrm = nl.add(G.OP_RMS_NORM, f32([E, NT]), [emb], [G.f32_bits(1e-5)])
-cur = nl.add(G.OP_MUL, G.T(nrm.ptr, G.F32, [E, NT]), [nrm, f32([E, 1])])
-proj = nl.add(G.OP_MUL_MAT, f32([E, NT]), [W(%d, [E, E]), cur])                              # a wide-only format consumes the norm
-ids = G.T(buf(4 * NU * NT), G.I32, [NU, NT])
-x3 = nl.view_op(G.T(proj.ptr, G.F32, [E, 1, NT], [4, 4 * E, 4 * E, 4 * E * NT]), proj)
-up = nl.add(G.OP_MUL_MAT_ID, f32([FF, NU, NT]), [W(G.Q4_K, [E, FF, NE]), x3, ids])
-gate = nl.add(G.OP_MUL_MAT_ID, f32([FF, NU, NT]), [W(G.Q4_K, [E, FF, NE]), x3, ids])
-act = nl.add(G.OP_GLU_SWIGLU, f32([FF, NU, NT]), [gate, up], [2, 0])
-down = nl.add(G.OP_MUL_MAT_ID, f32([E, NU, NT]), [W(G.Q6_K, [FF, E, NE]), act, ids])
+nl, _ = moe_graph.build(G, Fake(), E, FF, NE, NU, NT, VOC, %d)
 nodes = nl.build()
 out["supports"] = [int(G._lib.b200_executor_supports(nodes[i])) for i in range(len(nodes))]
 out["ops"] = [int(nodes[i].op) for i in range(len(nodes))]
@@ -59,20 +63,21 @@ def run_child(wide, n_tok=1, wtype=3):
 def test_wide_nodes_are_supported_and_planned_when_switched_on(wtype):
     o = run_child(True, 1, wtype)
     assert o["wide"] == 1 and all(o["supports"]), o
-    # GET_ROWS | RMS_NORM*w materialised (its consumer is not a tuned matvec, so it is NOT elided) | wide MUL_MAT | 2 x MUL_MAT_ID | SwiGLU | MUL_MAT_ID
-    assert o["plan"] == 7, o
+    # GET_ROWS | RMS_NORM*w materialised (its consumer is not a tuned matvec, so it is NOT elided) | wide MUL_MAT | router: f32 MUL_MAT, SOFT_MAX, ARGSORT,
+    # GET_ROWS (batched), SUM_ROWS, DIV | 2 x MUL_MAT_ID | SwiGLU | MUL_MAT_ID | weighted MUL | ADD of the two expert slices
+    assert o["plan"] == 15, o
 
 
 def test_wide_nodes_batch():
     o = run_child(True, 5, 23)
-    assert all(o["supports"]) and o["plan"] == 7, o
+    assert all(o["supports"]) and o["plan"] == 15, o
 
 
 def test_wide_nodes_are_refused_when_switched_off():
     o = run_child(False)
-    G_OP_NONE, G_OP_GET_ROWS, G_OP_MUL_MAT, G_OP_MUL_MAT_ID = 0, 9, 1, 11
+    G_OP_GET_ROWS, G_OP_MUL_MAT, G_OP_MUL_MAT_ID, G_OP_SOFT_MAX, G_OP_ARGSORT, G_OP_SUM_ROWS, G_OP_DIV = 9, 1, 11, 12, 13, 14, 15
     assert o["wide"] == 0
     for op, s in zip(o["ops"], o["supports"]):
-        if op in (G_OP_GET_ROWS, G_OP_MUL_MAT, G_OP_MUL_MAT_ID):
+        if op in (G_OP_GET_ROWS, G_OP_MUL_MAT, G_OP_MUL_MAT_ID, G_OP_SOFT_MAX, G_OP_ARGSORT, G_OP_SUM_ROWS, G_OP_DIV):
             assert s == 0, o              # ggml's scheduler keeps these nodes on its CPU backend, exactly as before this change
     assert o["plan"] < 0

@@ -96,60 +96,129 @@ def do_repack_model(t, k):
 
 
 def do_executor(wtype, n_tok):
-    """token embedding (GET_ROWS on a Q4_K table) -> RMS_NORM * w -> MUL_MAT on a wide-only format -> MoE FFN (3 x MUL_MAT_ID + SwiGLU) through the graph
-    executor, with CUDA graphs + fusion, against the oracle run op by op"""
+    """one Mixtral-style block through the graph executor (CUDA graphs + fusion) against the oracle run op by op: token embedding (GET_ROWS on a Q4_K
+    table) -> RMS_NORM * w -> MUL_MAT on a wide-only format -> build_moe_ffn: f32 router matmul, SOFT_MAX, ARGSORT / top-k view, batched GET_ROWS,
+    SUM_ROWS, DIV, 3 x MUL_MAT_ID + SwiGLU, weighted MUL, ADD over the expert slices (tests/moe_graph.py)"""
     assert os.environ.get("GGML_B200_WIDE") == "1"
+    import moe_graph
     G = importlib.import_module("llama_box_b200.graph")
-    rng = np.random.default_rng(wtype + n_tok)
     E, FF, NE, NU, VOC = 1024, 2048, 6, 2, 512
-    table = ref_quantize_weights(Q4_K, (rng.standard_normal((VOC, E)) * 0.05).astype(np.float32)) if have_ref() else rand_blocks(rng, Q4_K, VOC, E)
-    Wp = weights(rng, wtype, E, E, "quantised")
-    Wup = weights(rng, Q4_K, NE * FF, E, "quantised"); Wgate = weights(rng, Q4_K, NE * FF, E, "quantised"); Wdown = weights(rng, Q6_K, NE * E, FF, "quantised")
-    nw = (1 + 0.1 * rng.standard_normal(E)).astype(np.float32)
-    tok = rng.integers(0, VOC, n_tok).astype(np.int32)
-    ids = np.stack([rng.permutation(NE)[:NU] for _ in range(n_tok)]).astype(np.int32)
-    # ---- oracle
     O = oracle()
-    emb = np.zeros((n_tok, E), np.float32); O.orc_get_rows_q(Q4_K, ptr(table), ptr(tok), ptr(emb), E, n_tok)
-    nrm = np.zeros_like(emb); O.orc_rms_norm(ptr(emb), ptr(nw), ptr(nrm), E, n_tok, 1e-5)
-    proj = orc_mul_mat(wtype, Wp, nrm, E, n_tok, E)
+    for attempt in range(8):                                # a seed whose top-k is not a near-tie (the f32 router sums associate differently)
+        rng = np.random.default_rng(1000 * attempt + 10 * wtype + n_tok)
+        table = ref_quantize_weights(Q4_K, (rng.standard_normal((VOC, E)) * 0.05).astype(np.float32)) if have_ref() else rand_blocks(rng, Q4_K, VOC, E)
+        Wp = weights(rng, wtype, E, E, "quantised")
+        Wg = rng.standard_normal((NE, E)).astype(np.float32)
+        nw = (1 + 0.1 * rng.standard_normal(E)).astype(np.float32)
+        tok = rng.integers(0, VOC, n_tok).astype(np.int32)
+        emb = np.zeros((n_tok, E), np.float32); O.orc_get_rows_q(Q4_K, ptr(table), ptr(tok), ptr(emb), E, n_tok)
+        nrm = np.zeros_like(emb); O.orc_rms_norm(ptr(emb), ptr(nw), ptr(nrm), E, n_tok, 1e-5)
+        proj = orc_mul_mat(wtype, Wp, nrm, E, n_tok, E)
+        logits = (proj.astype(np.float64) @ Wg.astype(np.float64).T).astype(np.float32)
+        probs = np.zeros_like(logits); O.orc_soft_max_rows(ptr(logits), ptr(probs), NE, n_tok, 1.0)
+        srt = np.sort(probs, axis=1)[:, ::-1]
+        if np.all(srt[:, NU - 1] - srt[:, NU] > 1e-3 * srt[:, NU - 1]):
+            break
+    Wup = weights(rng, Q4_K, NE * FF, E, "quantised"); Wgate = weights(rng, Q4_K, NE * FF, E, "quantised"); Wdown = weights(rng, Q6_K, NE * E, FF, "quantised")
+    order = np.zeros((n_tok, NE), np.int32); O.orc_argsort_rows(ptr(probs), ptr(order), NE, n_tok, 1)
+    ids = np.ascontiguousarray(order[:, :NU])
+    w = np.take_along_axis(probs, ids, axis=1)
+    wsum = np.zeros(n_tok, np.float32); O.orc_sum_rows(ptr(np.ascontiguousarray(w)), ptr(wsum), NU, n_tok)
+    wn = (w / wsum[:, None]).astype(np.float32)
     up = np.zeros((n_tok, NU, FF), np.float32); gate = np.zeros_like(up)
     O.orc_mul_mat_id(Q4_K, ptr(Wup), ptr(proj), ptr(ids), ptr(up), FF, E, NE, NU, n_tok, 1, NU)
     O.orc_mul_mat_id(Q4_K, ptr(Wgate), ptr(proj), ptr(ids), ptr(gate), FF, E, NE, NU, n_tok, 1, NU)
     act = np.zeros_like(up); O.orc_swiglu(ptr(gate), ptr(up), ptr(act), act.size)
-    want = np.zeros((n_tok, NU, E), np.float32)
-    O.orc_mul_mat_id(Q6_K, ptr(Wdown), ptr(act), ptr(ids), ptr(want), E, FF, NE, NU, n_tok, NU, NU)
+    down = np.zeros((n_tok, NU, E), np.float32)
+    O.orc_mul_mat_id(Q6_K, ptr(Wdown), ptr(act), ptr(ids), ptr(down), E, FF, NE, NU, n_tok, NU, NU)
+    exw = down * wn[:, :, None]
+    want = exw[:, 0, :].copy()
+    for i in range(1, NU):
+        want = want + exw[:, i, :]
     # ---- executor
     keep = []
+    inputs = {"table": (Q4_K, table, E), "w_proj": (wtype, Wp, E), "up_exps": (Q4_K, Wup, E), "gate_exps": (Q4_K, Wgate, E), "down_exps": (Q6_K, Wdown, FF)}
+    plain = {"tok": tok, "norm_w": nw, "gate_inp": Wg}
 
-    def up_w(t, W, k):
-        d = dev(np.concatenate([repack_rows_np(t, W, k).reshape(-1), np.zeros(64, np.uint8)])); keep.append(d); return d
+    class Alloc:
+        def f32(self, ne):
+            d = torch.zeros(int(np.prod(ne)), dtype=torch.float32, device="cuda"); keep.append(d); return G.T(d.data_ptr(), G.F32, ne)
 
-    def f32t(ne):
-        d = torch.zeros(int(np.prod(ne)), dtype=torch.float32, device="cuda"); keep.append(d); return G.T(d.data_ptr(), G.F32, ne), d
-    nl = G.NodeList()
-    tokd = dev(tok); idd = dev(ids); nwd = dev(nw); keep += [tokd, idd, nwd]
-    tab = G.T(up_w(Q4_K, table, E).data_ptr(), G.Q4_K, [E, VOC])
-    e_t, _ = f32t([E, n_tok]); nl.add(G.OP_GET_ROWS, e_t, [tab, G.T(tokd.data_ptr(), G.I32, [n_tok])])
-    n_t, _ = f32t([E, n_tok]); nl.add(G.OP_RMS_NORM, n_t, [e_t], [G.f32_bits(1e-5)])
-    c_t = G.T(n_t.ptr, G.F32, [E, n_tok]); nl.add(G.OP_MUL, c_t, [n_t, G.T(nwd.data_ptr(), G.F32, [E])])
-    p_t, _ = f32t([E, n_tok]); nl.add(G.OP_MUL_MAT, p_t, [G.T(up_w(wtype, Wp, E).data_ptr(), wtype, [E, E]), c_t])
-    x3 = nl.view_op(G.T(p_t.ptr, G.F32, [E, 1, n_tok], [4, 4 * E, 4 * E, 4 * E * n_tok]), p_t)
-    idt = G.T(idd.data_ptr(), G.I32, [NU, n_tok])
-    u_t, _ = f32t([FF, NU, n_tok]); nl.add(G.OP_MUL_MAT_ID, u_t, [G.T(up_w(Q4_K, Wup, E).data_ptr(), G.Q4_K, [E, FF, NE]), x3, idt])
-    g_t, _ = f32t([FF, NU, n_tok]); nl.add(G.OP_MUL_MAT_ID, g_t, [G.T(up_w(Q4_K, Wgate, E).data_ptr(), G.Q4_K, [E, FF, NE]), x3, idt])
-    a_t, _ = f32t([FF, NU, n_tok]); nl.add(G.OP_GLU_SWIGLU, a_t, [g_t, u_t], [2, 0])
-    d_t, dd = f32t([E, NU, n_tok]); nl.add(G.OP_MUL_MAT_ID, d_t, [G.T(up_w(Q6_K, Wdown, FF).data_ptr(), G.Q6_K, [FF, E, NE]), a_t, idt])
+        def i32(self, ne):
+            d = torch.zeros(int(np.prod(ne)), dtype=torch.int32, device="cuda"); keep.append(d); return G.T(d.data_ptr(), G.I32, ne)
+
+        def named(self, name, t, ne):
+            if name in plain:
+                d = dev(plain[name])
+            else:
+                tt, W, k = inputs[name]
+                d = dev(np.concatenate([repack_rows_np(tt, W, k).reshape(-1), np.zeros(64, np.uint8)]))
+            keep.append(d)
+            return G.T(d.data_ptr(), t, ne)
+    nl, out_t = moe_graph.build(G, Alloc(), E, FF, NE, NU, n_tok, VOC, wtype)
     nodes = nl.build()
     ex = G.Executor(0)
     sup = [bool(ex.supports(nodes[i])) for i in range(len(nodes))]
+    out_d = [d for d in keep if d.data_ptr() == out_t.ptr][0]
     errs = []
     for rep in range(3):                                   # eager, capture, replay
-        dd.zero_()
+        out_d.zero_()
         ex.compute(nodes)
         torch.cuda.synchronize()
-        errs.append(rel(dd.cpu().numpy().reshape(n_tok, NU, E), want))
-    return {"supports": sup, "errs": errs, "captures": int(ex.captures), "replays": int(ex.replays)}
+        errs.append(rel(out_d.cpu().numpy().reshape(n_tok, E), want))
+    return {"supports": sup, "errs": errs, "captures": int(ex.captures), "replays": int(ex.replays), "kernels": int(ex.last_kernels)}
+
+
+def do_glue():
+    """the router glue of build_moe_ffn op by op through the C-ABI (glue_ext.cu) against the oracle / exact numpy semantics"""
+    rng = np.random.default_rng(9)
+    E, NE, NU, NT = 1024, 8, 2, 5
+    O = oracle()
+    i64a = lambda *v: dev(np.array(v, np.int64))  # noqa: E731  (the stride arrays are read by the host wrapper: keep them on the host)
+    h64 = lambda *v: np.array(v, np.int64)  # noqa: E731
+    out = {}
+    Wg = rng.standard_normal((NE, E)).astype(np.float32); x = rng.standard_normal((NT, E)).astype(np.float32)
+    Wd, xd = dev(Wg), dev(x); lg = torch.zeros((NT, NE), dtype=torch.float32, device="cuda")
+    ops.check(L.b200_mul_mat_f32(ops.p(Wd), E, ops.p(xd), E, ops.p(lg), NE, NE, E, NT, ops.stream())); torch.cuda.synchronize()
+    out["mul_mat_f32"] = rel(lg.cpu().numpy(), x.astype(np.float64) @ Wg.astype(np.float64).T)
+    logits = lg.cpu().numpy().copy(); logits[2, 3] = logits[2, 6]
+    ld = dev(logits); pd = torch.zeros_like(ld)
+    ops.check(L.b200_soft_max_rows(ops.p(ld), NE, ops.p(pd), NE, NE, NT, 1.0, ops.stream())); torch.cuda.synchronize()
+    wantp = np.zeros_like(logits); O.orc_soft_max_rows(ptr(logits), ptr(wantp), NE, NT, 1.0)
+    out["soft_max"] = float(np.abs(pd.cpu().numpy() - wantp).max())
+    wpd = dev(wantp); idd = torch.zeros((NT, NE), dtype=torch.int32, device="cuda")
+    ok = True
+    for desc in (0, 1):
+        ops.check(L.b200_argsort_rows(ops.p(wpd), NE, ops.p(idd), NE, NE, NT, desc, ops.stream())); torch.cuda.synchronize()
+        wi = np.zeros((NT, NE), np.int32); O.orc_argsort_rows(ptr(wantp), ptr(wi), NE, NT, desc)
+        ok = ok and bool(np.array_equal(idd.cpu().numpy(), wi))
+    out["argsort_exact"] = ok
+    idx = idd.cpu().numpy()
+    wd = torch.zeros((NT, NU), dtype=torch.float32, device="cuda")
+    ops.check(L.b200_get_rows_f32_batched(ops.p(wpd), 1, NE, NE, ops.p(idd), NE, ops.p(wd), 1, NU, 1, NU, NT, ops.stream())); torch.cuda.synchronize()
+    w = np.take_along_axis(wantp, idx[:, :NU], axis=1)
+    out["get_rows_batched_exact"] = bool(np.array_equal(wd.cpu().numpy(), w))
+    sd = torch.zeros(NT, dtype=torch.float32, device="cuda")
+    ops.check(L.b200_sum_rows(ops.p(wd), NU, ops.p(sd), NU, NT, ops.stream())); torch.cuda.synchronize()
+    ws = np.zeros(NT, np.float32); O.orc_sum_rows(ptr(np.ascontiguousarray(w)), ptr(ws), NU, NT)
+    out["sum_rows_exact"] = bool(np.array_equal(sd.cpu().numpy(), ws))
+    wnd = torch.zeros_like(wd)
+    ops.check(L.b200_binary_strided(2, ops.p(wd), ptr(h64(4, 4 * NU, 4 * NU * NT, 4 * NU * NT)), ops.p(sd), ptr(h64(1, NT, 1, 1)), ptr(h64(4, 4, 4 * NT, 4 * NT)), ops.p(wnd),
+                                    ptr(h64(NU, NT, 1, 1)), ptr(h64(4, 4 * NU, 4 * NU * NT, 4 * NU * NT)), ops.stream())); torch.cuda.synchronize()
+    wn = w / ws[:, None]
+    out["div_exact"] = bool(np.array_equal(wnd.cpu().numpy(), wn))
+    ex = rng.standard_normal((NT, NU, E)).astype(np.float32); exd = dev(ex); exwd = torch.zeros_like(exd)
+    nb3 = h64(4, 4 * E, 4 * E * NU, 4 * E * NU * NT)
+    ops.check(L.b200_binary_strided(1, ops.p(exd), ptr(nb3), ops.p(wnd), ptr(h64(1, NU, NT, 1)), ptr(h64(4, 4, 4 * NU, 4 * NU * NT)), ops.p(exwd), ptr(h64(E, NU, NT, 1)), ptr(nb3), ops.stream()))
+    torch.cuda.synchronize()
+    exw = ex * wn[:, :, None]
+    out["mul_bcast_exact"] = bool(np.array_equal(exwd.cpu().numpy(), exw))
+    od = torch.zeros((NT, E), dtype=torch.float32, device="cuda")
+    sl = h64(4, 4 * E * NU, 4 * E * NU * NT, 4 * E * NU * NT)
+    ops.check(L.b200_binary_strided(0, ops.p(exwd), ptr(sl), C.c_void_p(exwd.data_ptr() + 4 * E), ptr(h64(E, NT, 1, 1)), ptr(sl), ops.p(od), ptr(h64(E, NT, 1, 1)),
+                                    ptr(h64(4, 4 * E, 4 * E * NT, 4 * E * NT)), ops.stream())); torch.cuda.synchronize()
+    out["add_slices_exact"] = bool(np.array_equal(od.cpu().numpy(), exw[:, 0, :] + exw[:, 1, :]))
+    return out
 
 
 def do_kv_q4_0(d, n_head, n_head_kv, n_tok, n_kv):
@@ -217,7 +286,7 @@ def do_type_suite(t):
 def main():
     what = sys.argv[1]; a = [int(v) if v.lstrip("-").isdigit() else v for v in sys.argv[2:]]
     torch.cuda.set_device(0)
-    fn = {"kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
+    fn = {"glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
     print("RESULT " + json.dumps(fn(*a)))
 
 
