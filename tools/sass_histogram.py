@@ -17,6 +17,7 @@ for ln in txt.splitlines():
     m = re.match(r"\s*Function : (\S+)", ln)
     if m:
         kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = kern.replace("(anonymous namespace)::", "")       # the wide path's kernels live in unnamed namespaces
         kern = re.sub(r"\(.*", "", kern)
         hist.setdefault(kern, collections.Counter())
         continue
