@@ -88,7 +88,8 @@ def test_executor_moe_block_vs_oracle(wtype, n_tok):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")
-@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("MUL_MAT", 60), ("GET_ROWS", 4), ("SET_ROWS", 7), ("FLASH_ATTN_EXT", 24)])
+@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("MUL_MAT", 60), ("GET_ROWS", 4), ("SET_ROWS", 7), ("FLASH_ATTN_EXT", 24),
+                                        ("ADD", 6), ("MUL", 6), ("DIV", 4), ("SOFT_MAX", 4), ("ARGSORT", 2), ("SUM_ROWS", 1)])
 def test_reference_backend_ops_harness_with_the_wide_path(op, min_ok):
     """the reference's own parity harness (tests/test-backend-ops.cpp) against the plug-in with GGML_B200_WIDE=1"""
     plugin = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")
