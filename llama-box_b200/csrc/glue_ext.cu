@@ -15,7 +15,7 @@ static int ge_grid(int64_t work, int threads) {
 extern "C" int b200_binary_strided(int op, const float * a, const int64_t * a_nb, const float * b, const int64_t * b_ne, const int64_t * b_nb,
                                    float * dst, const int64_t * ne, const int64_t * d_nb, void * stream) {
     GE_DEV();
-    if (op < 0 || op > 2 || !a || !b || !dst || !a_nb || !b_ne || !b_nb || !ne || !d_nb) { b200_set_error("binary_strided: bad arguments"); return B200_ERR_INVALID; }
+    if (op < 0 || op > 3 || !a || !b || !dst || !a_nb || !b_ne || !b_nb || !ne || !d_nb) { b200_set_error("binary_strided: bad arguments"); return B200_ERR_INVALID; }
     BinArgs A; A.a = a; A.b = b; A.d = dst;
     for (int i = 0; i < 4; i++) {
         A.ne[i] = ne[i]; A.a_nb[i] = a_nb[i]; A.b_ne[i] = b_ne[i]; A.b_nb[i] = b_nb[i]; A.d_nb[i] = d_nb[i];
@@ -25,7 +25,8 @@ extern "C" int b200_binary_strided(int op, const float * a, const int64_t * a_nb
     const int g = ge_grid(ne[0] * ne[1] * ne[2] * ne[3], 256);
     if (op == 0) bin_strided_kernel<0><<<g, 256, 0, (cudaStream_t)stream>>>(A);
     else if (op == 1) bin_strided_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(A);
-    else bin_strided_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(A);
+    else if (op == 2) bin_strided_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(A);
+    else bin_strided_kernel<3><<<g, 256, 0, (cudaStream_t)stream>>>(A);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
@@ -33,7 +34,44 @@ extern "C" int b200_binary_strided(int op, const float * a, const int64_t * a_nb
 extern "C" int b200_soft_max_rows(const float * x, int64_t x_row_stride, float * y, int64_t y_row_stride, int64_t ncols, int64_t nrows, float scale, void * stream) {
     GE_DEV();
     if (!x || !y || ncols <= 0 || nrows <= 0 || (((uintptr_t)x | (uintptr_t)y) & 3)) { b200_set_error("soft_max_rows: bad arguments"); return B200_ERR_INVALID; }
-    soft_max_rows_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, x_row_stride, y, y_row_stride, ncols, nrows, scale);
+    SoftMaxMask M = {};
+    soft_max_rows_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, x_row_stride, y, y_row_stride, ncols, nrows, scale, M);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_soft_max_mask(const float * x, float * y, const void * mask, int mask_is_f16, int64_t mask_row_stride, int64_t ncols, int64_t n_tok, int64_t n_head,
+                                  float scale, float max_bias, void * stream) {
+    GE_DEV();
+    if (!x || !y || !mask || ncols <= 0 || n_tok <= 0 || n_head <= 0 || (((uintptr_t)x | (uintptr_t)y) & 3) || ((uintptr_t)mask & (mask_is_f16 ? 1 : 3))) { b200_set_error("soft_max_mask: bad arguments"); return B200_ERR_INVALID; }
+    SoftMaxMask M = {};
+    M.mask = mask; M.is_f16 = mask_is_f16 ? 1 : 0; M.row_stride = mask_row_stride; M.rows_per_head = n_tok; M.max_bias = max_bias;
+    M.n_head_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    M.m0 = powf(2.0f, -max_bias / (float)M.n_head_log2); M.m1 = powf(2.0f, -(max_bias / 2.0f) / (float)M.n_head_log2);
+    const int64_t nrows = n_tok * n_head;
+    soft_max_rows_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, ncols, y, ncols, ncols, nrows, scale, M);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_mul_mat_f16(const void * A, int64_t a_nb1, int64_t a_nb2, int64_t a_ne2, const float * B, int64_t b_nb1, int64_t b_nb2, float * dst, int64_t d_nb1, int64_t d_nb2,
+                                int64_t m, int64_t n, int64_t n_batch, int64_t k, void * stream) {
+    GE_DEV();
+    if (!A || !B || !dst || m <= 0 || n <= 0 || n_batch <= 0 || k <= 0 || a_ne2 <= 0 || n_batch % a_ne2 != 0 || ((uintptr_t)A & 1) || ((a_nb1 | a_nb2) & 1) ||
+        (((uintptr_t)B | (uintptr_t)dst) & 3) || ((b_nb1 | b_nb2 | d_nb1 | d_nb2) & 3) || m * n * n_batch > ((int64_t)1 << 31)) { b200_set_error("mul_mat_f16: bad arguments"); return B200_ERR_INVALID; }
+    MMF16Args a; a.A = (const char *)A; a.a_nb1 = a_nb1; a.a_nb2 = a_nb2; a.B = (const char *)B; a.b_nb1 = b_nb1; a.b_nb2 = b_nb2; a.D = (char *)dst; a.d_nb1 = d_nb1; a.d_nb2 = d_nb2;
+    a.m = m; a.n = n; a.nbatch = n_batch; a.k = k; a.r2 = n_batch / a_ne2;
+    const int64_t warps = m * n * n_batch;
+    mul_mat_f16_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}
+
+extern "C" int b200_scatter_rows1(const float * src, const int64_t * ids, void * dst, int dst_type, int64_t n, int64_t n_dst, void * stream) {
+    GE_DEV();
+    if (!src || !ids || !dst || n <= 0 || n_dst <= 0 || (dst_type != B200_TYPE_F16 && dst_type != B200_TYPE_F32) || ((uintptr_t)src & 3) || ((uintptr_t)ids & 7) || ((uintptr_t)dst & (dst_type == B200_TYPE_F16 ? 1 : 3))) {
+        b200_set_error("scatter_rows1: bad arguments"); return B200_ERR_INVALID; }
+    scatter_rows1_kernel<<<ge_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ids, dst, dst_type == B200_TYPE_F16 ? 1 : 0, n, n_dst);
     B200_LAUNCH_CHECK();
     return B200_OK;
 }

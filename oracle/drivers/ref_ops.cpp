@@ -111,7 +111,7 @@ int main(int argc, char ** argv) {
         // as [k, m, n_expert], b [k, n_b1, n_tok] f32, ids i32 [n_used, n_tok] (llama-graph.cpp build_moe_ffn)
         out = ggml_mul_mat_id(ctx, need("w"), need("x"), need("ids"));
     } else if (op == "soft_max") {
-        out = ggml_soft_max_ext(ctx, need("x"), nullptr, (float)P("scale", 1), 0.0f);
+        out = ggml_soft_max_ext(ctx, need("x"), opt("mask"), (float)P("scale", 1), (float)P("max_bias", 0));
     } else if (op == "argsort") {
         out = ggml_argsort(ctx, need("x"), P("desc", 1) != 0 ? GGML_SORT_ORDER_DESC : GGML_SORT_ORDER_ASC);
     } else if (op == "sum_rows") {

@@ -119,6 +119,13 @@ void orc_soft_max_rows(const float *x, float *y, int64_t ncols, int64_t nrows, f
 void orc_argsort_rows(const float *x, int32_t *idx, int64_t ncols, int64_t nrows, int descending);
 void orc_sum_rows(const float *x, float *y, int64_t ncols, int64_t nrows);
 
+/* attention without -fa (llama-graph.cpp build_attn_mha): batched MUL_MAT with an f16 src0 broadcast over dim 2 (the f32 operand rounded to f16, f32
+ * accumulation: ggml-cpu.c:1202-1394), SOFT_MAX with mask + ALiBi slopes (ggml-cpu/ops.cpp:5685-5800).  Strides in bytes / mask row stride in elements. */
+void orc_mul_mat_f16(const void *A, int64_t a_nb1, int64_t a_nb2, int64_t a_ne2, const float *B, int64_t b_nb1, int64_t b_nb2,
+                     float *dst, int64_t d_nb1, int64_t d_nb2, int64_t m, int64_t n, int64_t n_batch, int64_t k);
+void orc_soft_max_mask(const float *x, float *y, const void *mask, int mask_is_f16, int64_t mask_row_stride, int64_t ncols, int64_t n_tok, int64_t n_head,
+                       float scale, float max_bias);
+
 /* glue (ggml-cpu/vec.h:691, ops.cpp swiglu / binary-ops.cpp / get_rows / cpy) */
 void orc_swiglu(const float *gate, const float *up, float *y, int64_t n);
 void orc_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows);

@@ -317,3 +317,39 @@ void orc_argsort_rows(const float *x, int32_t *idx, int64_t ncols, int64_t nrows
 void orc_sum_rows(const float *x, float *y, int64_t ncols, int64_t nrows) {
     for (int64_t r = 0; r < nrows; r++) { double s = 0.0; for (int64_t i = 0; i < ncols; i++) s += (double)x[r*ncols + i]; y[r] = (float)s; }
 }
+
+/* ---- attention without -fa (llama-graph.cpp build_attn_mha, non-flash branch) ---- */
+
+/* batched MUL_MAT with an f16 src0 (ggml-cpu/ggml-cpu.c:1202-1394): src1 rows are converted to f16 (vec_dot_type of F16), products accumulated in f32
+ * (ggml_vec_dot_f16); src0 is broadcast over dim 2 (i02 = i12 / r2).  Strides in bytes. */
+void orc_mul_mat_f16(const void *A, int64_t a_nb1, int64_t a_nb2, int64_t a_ne2, const float *B, int64_t b_nb1, int64_t b_nb2,
+                     float *dst, int64_t d_nb1, int64_t d_nb2, int64_t m, int64_t n, int64_t n_batch, int64_t k) {
+    const int64_t r2 = n_batch / a_ne2;
+    for (int64_t i2 = 0; i2 < n_batch; i2++) for (int64_t i1 = 0; i1 < n; i1++) for (int64_t i0 = 0; i0 < m; i0++) {
+        const uint16_t *ar = (const uint16_t *)((const char *)A + i0*a_nb1 + (i2/r2)*a_nb2);
+        const float *br = (const float *)((const char *)B + i1*b_nb1 + i2*b_nb2);
+        float acc = 0.0f;
+        for (int64_t i = 0; i < k; i++) acc += orc_fp16_to_fp32(ar[i]) * orc_fp16_to_fp32(orc_fp32_to_fp16(br[i]));
+        *(float *)((char *)dst + i0*4 + i1*d_nb1 + i2*d_nb2) = acc;
+    }
+}
+/* SOFT_MAX with a mask and ALiBi slopes (ggml-cpu/ops.cpp:5685-5800): x [ncols, n_tok, n_head] contiguous, mask one row per token (f32 or f16) */
+void orc_soft_max_mask(const float *x, float *y, const void *mask, int mask_is_f16, int64_t mask_row_stride, int64_t ncols, int64_t n_tok, int64_t n_head,
+                       float scale, float max_bias) {
+    const uint32_t nh_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    const float m0 = powf(2.0f, -max_bias / (float)nh_log2), m1 = powf(2.0f, -(max_bias / 2.0f) / (float)nh_log2);
+    for (int64_t h = 0; h < n_head; h++) for (int64_t t = 0; t < n_tok; t++) {
+        const float slope = max_bias > 0.0f ? ((uint32_t)h < nh_log2 ? powf(m0, (float)(h + 1)) : powf(m1, (float)(2*(h - nh_log2) + 1))) : 1.0f;
+        const float *xr = x + (h*n_tok + t)*ncols; float *yr = y + (h*n_tok + t)*ncols;
+        float mx = -INFINITY;
+        for (int64_t i = 0; i < ncols; i++) {
+            const float mv = mask_is_f16 ? orc_fp16_to_fp32(((const uint16_t *)mask)[t*mask_row_stride + i]) : ((const float *)mask)[t*mask_row_stride + i];
+            yr[i] = xr[i] * scale + slope * mv;
+            if (yr[i] > mx) mx = yr[i];
+        }
+        double sum = 0.0;
+        for (int64_t i = 0; i < ncols; i++) { const float v = expf(yr[i] - mx); yr[i] = v; sum += (double)v; }
+        const float inv = (float)(1.0 / sum);
+        for (int64_t i = 0; i < ncols; i++) yr[i] *= inv;
+    }
+}

@@ -76,10 +76,29 @@ void sim_binary_strided(int op, const float * a, const int64_t * a_nb, const flo
     for (int i = 0; i < 4; i++) { A.ne[i] = ne[i]; A.a_nb[i] = a_nb[i]; A.b_ne[i] = b_ne[i]; A.b_nb[i] = b_nb[i]; A.d_nb[i] = d_nb[i]; }
     if (op == 0) simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<0>(A); });
     else if (op == 1) simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<1>(A); });
-    else simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<2>(A); });
+    else if (op == 2) simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<2>(A); });
+    else simt::launch(dim3(2), dim3(256), 0, [A] { bin_strided_kernel<3>(A); });
 }
 void sim_soft_max_rows(const float * x, int64_t xrs, float * y, int64_t yrs, int64_t ncols, int64_t nrows, float scale) {
-    simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { soft_max_rows_kernel(x, xrs, y, yrs, ncols, nrows, scale); });
+    SoftMaxMask M = {};
+    simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { soft_max_rows_kernel(x, xrs, y, yrs, ncols, nrows, scale, M); });
+}
+void sim_soft_max_mask(const float * x, float * y, const void * mask, int mask_is_f16, int64_t mask_row_stride, int64_t ncols, int64_t n_tok, int64_t n_head, float scale, float max_bias) {
+    SoftMaxMask M = {};
+    M.mask = mask; M.is_f16 = mask_is_f16; M.row_stride = mask_row_stride; M.rows_per_head = n_tok; M.max_bias = max_bias;
+    M.n_head_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    M.m0 = powf(2.0f, -max_bias / (float)M.n_head_log2); M.m1 = powf(2.0f, -(max_bias / 2.0f) / (float)M.n_head_log2);
+    const int64_t nrows = n_tok * n_head;
+    simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { soft_max_rows_kernel(x, ncols, y, ncols, ncols, nrows, scale, M); });
+}
+void sim_mul_mat_f16(const void * A, int64_t a_nb1, int64_t a_nb2, int64_t a_ne2, const float * B, int64_t b_nb1, int64_t b_nb2, float * dst, int64_t d_nb1, int64_t d_nb2,
+                     int64_t m, int64_t n, int64_t n_batch, int64_t k) {
+    MMF16Args a; a.A = (const char *)A; a.a_nb1 = a_nb1; a.a_nb2 = a_nb2; a.B = (const char *)B; a.b_nb1 = b_nb1; a.b_nb2 = b_nb2; a.D = (char *)dst; a.d_nb1 = d_nb1; a.d_nb2 = d_nb2;
+    a.m = m; a.n = n; a.nbatch = n_batch; a.k = k; a.r2 = n_batch / a_ne2;
+    simt::launch(dim3((unsigned)((m * n * n_batch * 32 + 255) / 256)), dim3(256), 0, [a] { mul_mat_f16_kernel(a); });
+}
+void sim_scatter_rows1(const float * src, const int64_t * ids, void * dst, int dst_f16, int64_t n, int64_t n_dst) {
+    simt::launch(dim3(2), dim3(256), 0, [=] { scatter_rows1_kernel(src, ids, dst, dst_f16, n, n_dst); });
 }
 void sim_argsort_rows(const float * x, int64_t xrs, int32_t * idx, int64_t irs, int64_t ncols, int64_t nrows, int desc) {
     simt::launch(dim3((unsigned)((nrows + 127) / 128)), dim3(128), 0, [=] { argsort_rows_kernel(x, xrs, idx, irs, ncols, nrows, desc); });

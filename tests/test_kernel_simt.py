@@ -39,6 +39,9 @@ def K():
     L.sim_sum_rows.argtypes = [vp, i64, vp, i64, i64]
     L.sim_get_rows_f32_batched.argtypes = [vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64]
     L.sim_mul_mat_f32.argtypes = [vp, i64, vp, i64, vp, i64, i64, i64, i64]
+    L.sim_soft_max_mask.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, f32, f32]
+    L.sim_mul_mat_f16.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, i64, i64]
+    L.sim_scatter_rows1.argtypes = [vp, vp, vp, i32, i64, i64]
     L.sim_flash_attn_q4_0.argtypes = [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32]
     return L
 
@@ -190,3 +193,44 @@ def test_moe_router_glue_kernels(K):
     sl = i64a(4, 4 * E * NU, 4 * E * NU * NT, 4 * E * NU * NT)
     K.sim_binary_strided(0, ptr(exw), ptr(sl), C.c_void_p(exw.ctypes.data + 4 * E), ptr(i64a(E, NT, 1, 1)), ptr(sl), ptr(out), ptr(i64a(E, NT, 1, 1)), ptr(i64a(4, 4 * E, 4 * E * NT, 4 * E * NT)))
     assert np.array_equal(out, exw[:, 0, :] + exw[:, 1, :])
+
+
+def test_non_flash_attention_kernels(K):
+    """attention without -fa, as build_attn_mha emits it: V stored transposed by an element-wise SET_ROWS, KQ = K^T Q over a permuted f16 view of the K cache
+    with GQA broadcast, SOFT_MAX with mask (+ ALiBi), KQV over the transposed V cache, CONT of the permuted result"""
+    rng = np.random.default_rng(21)
+    hd, n_kv, kv_size, nt, nh, nhk = 64, 40, 48, 3, 4, 2
+    E = nhk * hd
+    # K cache rows [kv_size][nhk*hd] f16; V cache TRANSPOSED: element (cell, d, head) at (head*hd + d) * kv_size + cell
+    Kc = rng.standard_normal((kv_size, E)).astype(np.float16)
+    vcur = rng.standard_normal((n_kv, E)).astype(np.float32)
+    Vt = np.zeros(E * kv_size, np.float16)
+    cells = rng.permutation(kv_size)[:n_kv]
+    ids = (np.arange(E, dtype=np.int64)[None, :] * kv_size + cells[:, None]).reshape(-1)          # v_idxs of llama-kv-cache-unified.cpp for v_trans
+    K.sim_scatter_rows1(ptr(vcur), ptr(ids), ptr(Vt), 1, ids.size, Vt.size)
+    want_vt = np.zeros(E * kv_size, np.float16); want_vt[ids] = vcur.reshape(-1).astype(np.float16)
+    assert np.array_equal(Vt.view(np.uint16), want_vt.view(np.uint16))
+    Q = rng.standard_normal((nt, nh, hd)).astype(np.float32)                                     # [hd, n_head, n_tok]; viewed permuted as [hd, n_tok, n_head]
+    kq = np.zeros((nh, nt, kv_size), np.float32); wkq = np.zeros_like(kq)
+    args = (ptr(Kc), E * 2, hd * 2, nhk, ptr(Q), nh * hd * 4, hd * 4)
+    K.sim_mul_mat_f16(*args, ptr(kq), kv_size * 4, nt * kv_size * 4, kv_size, nt, nh, hd)
+    oracle().orc_mul_mat_f16(*args, ptr(wkq), kv_size * 4, nt * kv_size * 4, kv_size, nt, nh, hd)
+    assert rel(kq, wkq) <= 2e-6
+    for is_f16, max_bias in ((0, 0.0), (1, 8.0)):
+        mask = np.full((64, kv_size), -np.inf, np.float32)
+        for t in range(nt):
+            mask[t, cells[:n_kv - nt + t + 1]] = rng.uniform(-1, 0) if max_bias > 0 else 0
+        m = mask.astype(np.float16) if is_f16 else mask
+        p = np.zeros_like(kq); wp = np.zeros_like(kq)
+        K.sim_soft_max_mask(ptr(wkq), ptr(p), ptr(m), is_f16, kv_size, kv_size, nt, nh, 0.125, max_bias)
+        oracle().orc_soft_max_mask(ptr(wkq), ptr(wp), ptr(m), is_f16, kv_size, kv_size, nt, nh, 0.125, max_bias)
+        assert np.abs(p - wp).max() <= 1e-6
+    kqv = np.zeros((nh, nt, hd), np.float32); wkqv = np.zeros_like(kqv)                           # V view [kv_size, hd, nhk]: nb1 = kv_size*2, nb2 = kv_size*hd*2
+    args = (ptr(want_vt), kv_size * 2, kv_size * hd * 2, nhk, ptr(wp), kv_size * 4, nt * kv_size * 4)
+    K.sim_mul_mat_f16(*args, ptr(kqv), hd * 4, nt * hd * 4, hd, nt, nh, kv_size)
+    oracle().orc_mul_mat_f16(*args, ptr(wkqv), hd * 4, nt * hd * 4, hd, nt, nh, kv_size)
+    assert rel(kqv, wkqv) <= 2e-6
+    out = np.zeros((nt, nh, hd), np.float32)                                                      # CONT of permute(kqv, 0, 2, 1, 3): [hd, n_head, n_tok]
+    src_nb = i64a(4, nt * hd * 4, hd * 4, nh * nt * hd * 4)
+    K.sim_binary_strided(3, ptr(wkqv), ptr(src_nb), ptr(wkqv), ptr(i64a(1, 1, 1, 1)), ptr(i64a(4, 4, 4, 4)), ptr(out), ptr(i64a(hd, nh, nt, 1)), ptr(i64a(4, hd * 4, nh * hd * 4, nt * nh * hd * 4)))
+    assert np.array_equal(out, wkqv.transpose(1, 0, 2))

@@ -195,3 +195,24 @@ def test_moe_router_glue_through_cpu_backend():
     ex = rng.standard_normal((nt, nu, 64)).astype(np.float32)
     _, _, out = run_ref_op("mul", [("a", F32, [64, nu, nt], ex), ("b", F32, [1, nu, nt], w.reshape(nt, nu, 1))])
     assert np.array_equal(np.frombuffer(out, np.float32).reshape(nt, nu, 64), ex * w[:, :, None])
+
+
+def test_non_flash_attention_ops_through_cpu_backend():
+    """attention without -fa: the batched f16 MUL_MATs (KQ with GQA broadcast, KQV) and SOFT_MAX with mask + ALiBi"""
+    rng = np.random.default_rng(55)
+    hd, nkv, nt, nh, nhk = 64, 96, 3, 4, 2
+    Kc = rng.standard_normal((nhk, nkv, hd)).astype(np.float16); Q = rng.standard_normal((nh, nt, hd)).astype(np.float32)
+    _, _, out = run_ref_op("mul_mat", [("w", F16, [hd, nkv, nhk], Kc), ("x", F32, [hd, nt, nh], Q)])
+    want = np.frombuffer(out, np.float32).reshape(nh, nt, nkv)
+    kq = np.zeros_like(want)
+    oracle().orc_mul_mat_f16(ptr(Kc), hd * 2, nkv * hd * 2, nhk, ptr(Q), hd * 4, nt * hd * 4, ptr(kq), nkv * 4, nt * nkv * 4, nkv, nt, nh, hd)
+    assert np.abs(kq - want).max() <= 2e-6 * np.abs(want).max()
+    for mask_t, max_bias in ((F32, 0.0), (F16, 8.0)):
+        mask = np.full((64, nkv), -np.inf, np.float32)
+        for t in range(nt):
+            mask[t, :nkv - nt + t + 1] = rng.uniform(-2, 0, nkv - nt + t + 1) if max_bias > 0 else 0
+        m = mask.astype(np.float16) if mask_t == F16 else mask
+        _, _, out = run_ref_op("soft_max", [("x", F32, [nkv, nt, nh], want), ("mask", mask_t, [nkv, 64], m)], dict(scale=0.125, max_bias=max_bias))
+        wp = np.frombuffer(out, np.float32).reshape(nh, nt, nkv); y = np.zeros_like(wp)
+        oracle().orc_soft_max_mask(ptr(want), ptr(y), ptr(m), int(mask_t == F16), nkv, nkv, nt, nh, 0.125, max_bias)
+        assert np.abs(y - wp).max() <= 2e-6
