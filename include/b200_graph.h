@@ -43,10 +43,11 @@ enum b200_op {
     B200_OP_MUL_MAT_ID,      /* src0 experts [K,M,n_expert], src1 f32 [K,n_b1,n_tok], src2 ids i32 [n_used,n_tok] -> dst f32 [M,n_used,n_tok]
                                 (ggml.c:3064-3106).  Wide path (b200_mul_mat_id): see B200_WIDE below                             */
     /* mixture-of-experts router glue (llama-graph.cpp build_moe_ffn), wide path only: */
-    B200_OP_SOFT_MAX,        /* src0 f32 rows, no mask / sinks; op_params[0] = scale (f32 bits), op_params[1] = max_bias (must be 0)               */
+    B200_OP_SOFT_MAX,        /* src0 f32 rows; optional src1 mask f32 / f16 (one row per token, attention without -fa); op_params {scale, max_bias}   */
     B200_OP_ARGSORT,         /* src0 f32 [n, rows] -> dst i32 [n, rows]; op_params[0] = order (0 ascending, 1 descending); the reference's tie order */
     B200_OP_SUM_ROWS,        /* src0 f32 [n, rows] -> dst f32 [1, rows]                                                                             */
     B200_OP_DIV,             /* broadcasting f32, like MUL                                                                                          */
+    B200_OP_CONT,            /* src0 f32, any strides -> dst f32 contiguous, elements in src0's logical order (ggml_cont / ggml_cont_2d); wide path            */
     B200_OP_COUNT
 };
 

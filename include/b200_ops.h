@@ -216,6 +216,20 @@ B200_API int b200_get_rows_f32_batched(const float *src, int64_t src_row_stride,
 B200_API int b200_mul_mat_f32(const float *W, int64_t w_row_stride, const float *x, int64_t x_col_stride, float *dst, int64_t dst_col_stride,
                               int64_t m, int64_t k, int64_t ncols, void *stream);
 
+/* Attention WITHOUT -fa (llama-graph.cpp build_attn_mha, non-flash branch; llama-box's default): KQ = K^T Q and KQV = V^T softmax(KQ) are batched
+ * MUL_MATs over f16 views of the KV cache (K permuted, V stored TRANSPOSED by an element-wise SET_ROWS, llama-kv-cache-unified.cpp:1157-1167), with a masked
+ * SOFT_MAX in between and a CONT of the permuted result.  Replaces the cuBLAS batched route of ggml-cuda (ggml-cuda.cu:1800-1977), soft_max_f32 with mask
+ * (softmax.cu:47-165), k_set_rows for one-element rows and cpy/cont.  Numerics: the CPU oracle's (f32 operand rounded to f16, f32 accumulation).
+ *   b200_mul_mat_f16   : dst[i0, i1, i2] = sum_k A[k, i0, i2 / r2] * f16(B[k, i1, i2]); A f16 with byte strides a_nb1 / a_nb2 and a_ne2 batches (GQA broadcast),
+ *                        B f32 (b_nb1 / b_nb2 bytes), dst f32 (row i1 at d_nb1, batch at d_nb2 bytes)
+ *   b200_soft_max_mask : x, y f32 [ncols, n_tok, n_head] contiguous; mask f32 / f16, row t at t * mask_row_stride elements; ALiBi slopes from max_bias
+ *   b200_scatter_rows1 : dst[ids[i]] = src[i] (dst F16 or F32)                    b200_binary_strided(op 3) : CONT */
+B200_API int b200_mul_mat_f16(const void *A, int64_t a_nb1, int64_t a_nb2, int64_t a_ne2, const float *B, int64_t b_nb1, int64_t b_nb2, float *dst, int64_t d_nb1, int64_t d_nb2,
+                              int64_t m, int64_t n, int64_t n_batch, int64_t k, void *stream);
+B200_API int b200_soft_max_mask(const float *x, float *y, const void *mask, int mask_is_f16, int64_t mask_row_stride, int64_t ncols, int64_t n_tok, int64_t n_head,
+                                float scale, float max_bias, void *stream);
+B200_API int b200_scatter_rows1(const float *src, const int64_t *ids, void *dst, int dst_type, int64_t n, int64_t n_dst, void *stream);
+
 /* KV cache type q4_0 (`-ctk q4_0 -ctv q4_0`): the cache keeps ggml's native 18-byte blocks.  SET_ROWS writes what ggml's from_float writes
  * (ggml-quants.c quantize_row_q4_0_ref; replaces k_set_rows_quant<block_q4_0>, ggml-cuda/set-rows.cu:13-52); FLASH_ATTN_EXT follows the CPU
  * oracle (q8_0 query x Q4_0 K in integers, f32 online softmax, V expanded to f32; replaces the q4_0-q4_0 flash_attn_vec_ext instances,

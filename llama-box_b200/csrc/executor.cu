@@ -111,8 +111,38 @@ bool mul_mat_f32_ok(const b200_node & n) {
 }
 bool rows2d_f32(const b200_tensor & t) { return t.type == B200_TYPE_F32 && t.nb[0] == 4 && contiguous(t) && !((uintptr_t)t.data & 3); }
 bool soft_max_ok(const b200_node & n) {
-    if (!wide_on() || n.n_src < 1 || (n.n_src > 1 && n.src[1].id) || (n.n_src > 2 && n.src[2].id)) return false;        // mask / sinks: attention without -fa, not this path
-    return rows2d_f32(n.src[0]) && rows2d_f32(n.dst) && same_shape(n.src[0], n.dst) && f32_param(n, 1) == 0.0f && n.src[0].ne[0] <= 65536;
+    if (!wide_on() || n.n_src < 1 || (n.n_src > 2 && n.src[2].id)) return false;                                        // sinks: not on this path
+    if (!rows2d_f32(n.src[0]) || !rows2d_f32(n.dst) || !same_shape(n.src[0], n.dst) || n.src[0].ne[0] > 65536) return false;
+    if (n.n_src > 1 && n.src[1].id) {                        // with a mask: attention without -fa — x [n_kv, n_tok, n_head], one mask row per token
+        const b200_tensor & m = n.src[1], & x = n.src[0];
+        if ((m.type != B200_TYPE_F32 && m.type != B200_TYPE_F16) || m.nb[0] != (m.type == B200_TYPE_F16 ? 2 : 4) || m.ne[0] != x.ne[0] || m.ne[1] < x.ne[1] || m.ne[2] != 1 || m.ne[3] != 1) return false;
+        if (x.ne[3] != 1 || (m.nb[1] % m.nb[0]) || !m.data || ((uintptr_t)m.data & (m.nb[0] - 1))) return false;
+        return true;
+    }
+    return f32_param(n, 1) == 0.0f;
+}
+// batched MUL_MAT with an f16 src0 view (attention without -fa: KQ over the permuted K cache, KQV over the transposed V cache; GQA broadcast over dim 2)
+bool mul_mat_f16_ok(const b200_node & n) {
+    const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
+    if (!wide_on() || w.type != B200_TYPE_F16 || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
+    if (w.ne[3] != 1 || x.ne[3] != 1 || d.ne[3] != 1 || w.ne[0] <= 0 || w.ne[1] <= 0 || w.ne[2] <= 0 || x.ne[1] <= 0 || x.ne[2] <= 0 || x.ne[2] % w.ne[2] != 0) return false;
+    if (w.nb[0] != 2 || ((w.nb[1] | w.nb[2]) & 1) || x.ne[0] != w.ne[0] || x.nb[0] != 4 || ((x.nb[1] | x.nb[2]) & 3)) return false;
+    if (d.ne[0] != w.ne[1] || d.ne[1] != x.ne[1] || d.ne[2] != x.ne[2] || d.nb[0] != 4 || ((d.nb[1] | d.nb[2]) & 3)) return false;
+    if (d.ne[0] * d.ne[1] * d.ne[2] > ((int64_t)1 << 31)) return false;
+    return w.data && x.data && d.data && !((uintptr_t)w.data & 1) && !(((uintptr_t)x.data | (uintptr_t)d.data) & 3);
+}
+// SET_ROWS whose rows are single elements (the transposed V cache): src [1, n] f32, ids i64 [n], dst [1, N] f16 / f32
+bool set_rows1_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 2) return false;
+    const b200_tensor & s = n.src[0], & ids = n.src[1], & d = n.dst;
+    if (s.type != B200_TYPE_F32 || ids.type != B200_TYPE_I64 || (d.type != B200_TYPE_F16 && d.type != B200_TYPE_F32)) return false;
+    if (s.ne[0] != 1 || d.ne[0] != 1 || s.ne[2] != 1 || s.ne[3] != 1 || d.ne[2] != 1 || d.ne[3] != 1 || ids.ne[0] != s.ne[1] || ids.ne[1] != 1 || ids.ne[2] != 1) return false;
+    if (s.nb[1] != 4 || ids.nb[0] != 8 || d.nb[1] != (d.type == B200_TYPE_F16 ? 2 : 4)) return false;
+    return s.data && ids.data && d.data && !((uintptr_t)s.data & 3) && !((uintptr_t)ids.data & 7) && !((uintptr_t)d.data & (d.nb[1] - 1));
+}
+bool cont_ok(const b200_node & n) {
+    if (!wide_on() || n.n_src < 1) return false;
+    return f32_strided(n.src[0]) && n.dst.type == B200_TYPE_F32 && contiguous(n.dst) && n.dst.data && !((uintptr_t)n.dst.data & 3) && nelem(n.src[0]) == nelem(n.dst);
 }
 bool argsort_ok(const b200_node & n) {
     if (!wide_on() || n.n_src < 1) return false;
@@ -143,6 +173,7 @@ bool mul_mat_ok(const b200_node & n) {
     const b200_tensor & w = n.src[0], & x = n.src[1], & d = n.dst;
     if (is_wide_only_type(w.type)) return mul_mat_wide_ok(n);
     if (w.type == B200_TYPE_F32) return mul_mat_f32_ok(n);
+    if (w.type == B200_TYPE_F16) return mul_mat_f16_ok(n);
     if (!is_weight_type(w.type) || x.type != B200_TYPE_F32 || d.type != B200_TYPE_F32) return false;
     const int64_t k = w.ne[0], m = w.ne[1];
     // 32-element block types: any multiple of 32 (rows padded to 256 in the private weight layout, see common.cuh padded_k)
@@ -213,7 +244,8 @@ bool node_ok(const b200_node & n) {
         case B200_OP_ARGSORT:  return argsort_ok(n);
         case B200_OP_SUM_ROWS: return sum_rows_ok(n);
         case B200_OP_ROPE:     return n.n_src >= 2 && rope_ok(n);
-        case B200_OP_SET_ROWS: return n.n_src >= 2 && set_rows_ok(n);
+        case B200_OP_SET_ROWS: return n.n_src >= 2 && (set_rows_ok(n) || set_rows1_ok(n));
+        case B200_OP_CONT:     return cont_ok(n);
         case B200_OP_FLASH_ATTN_EXT: return n.n_src >= 3 && fattn_ok(n);
         case B200_OP_GLU_SWIGLU: return n.n_src >= 2 && rows_f32_ok(n.src[0]) && rows_f32_ok(n.src[1]) && rows_f32_ok(n.dst) && same_shape(n.src[0], n.src[1]) && same_shape(n.src[0], n.dst);
         case B200_OP_MUL_MAT_ID: return mul_mat_id_ok(n);
@@ -618,6 +650,13 @@ struct Runner {
         const b200_node & n = nodes[i];
         const b200_tensor & w = n.src[0], & x = n.src[1];
         const int64_t kv = w.ne[0], k = padded_k(w.type, kv), m = w.ne[1], ncols = x.ne[1];   // kv: elements that exist in x; k: padded weight rows
+        if (w.type == B200_TYPE_F16) {
+            // attention without -fa: KQ / KQV over f16 views of the KV cache (GQA broadcast over dim 2)
+            { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+            invalidate_act(n.dst);
+            return KL(b200_mul_mat_f16(w.data, w.nb[1], w.nb[2], w.ne[2], (const float *)x.data, x.nb[1], x.nb[2], (float *)n.dst.data, n.dst.nb[1], n.dst.nb[2],
+                                       w.ne[1], x.ne[1], x.ne[2], w.ne[0], st));
+        }
         if (w.type == B200_TYPE_F32) {
             // the f32 router matrix of a mixture-of-experts layer (ffn_gate_inp): router-sized, one warp per output
             { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
@@ -832,8 +871,17 @@ struct Runner {
                 return KL(b200_rope((const float *)x.data, (float *)n.dst.data, (const int32_t *)n.src[1].data, ff, x.ne[0], x.ne[1], x.ne[2],
                                     x.nb[1] / 4, x.nb[2] / 4, n.dst.nb[1] / 4, n.dst.nb[2] / 4, &p, st));
             }
+            case B200_OP_CONT: {
+                invalidate_act(n.dst);
+                const b200_tensor & s0 = n.src[0];
+                const int64_t one[4] = { 1, 1, 1, 1 }, four[4] = { 4, 4, 4, 4 };
+                const int64_t dnb[4] = { 4, 4 * s0.ne[0], 4 * s0.ne[0] * s0.ne[1], 4 * s0.ne[0] * s0.ne[1] * s0.ne[2] };    // dst is contiguous: src0's logical order
+                return KL(b200_binary_strided(3, (const float *)s0.data, s0.nb, (const float *)s0.data, one, four, (float *)n.dst.data, s0.ne, dnb, st));
+            }
             case B200_OP_SET_ROWS: {
                 const b200_tensor & s = n.src[0], & ids = n.src[1];
+                if (s.ne[0] == 1 && !set_rows_ok(n))         // one-element rows: the transposed V cache of attention without -fa
+                    return KL(b200_scatter_rows1((const float *)s.data, (const int64_t *)ids.data, n.dst.data, n.dst.type, s.ne[1], n.dst.ne[1], st));
                 for (int64_t i3 = 0; i3 < s.ne[3]; i3++) for (int64_t i2 = 0; i2 < s.ne[2]; i2++) {
                     const int64_t i11 = i2 % ids.ne[1], i12 = i3 % ids.ne[2];
                     if (n.dst.type == B200_TYPE_Q4_0) {
@@ -870,6 +918,9 @@ struct Runner {
                 return KL(b200_swiglu((const float *)n.src[0].data, (const float *)n.src[1].data, (float *)n.dst.data, nelem(n.dst), st));
             case B200_OP_SOFT_MAX:
                 invalidate_act(n.dst);
+                if (n.n_src > 1 && n.src[1].id)
+                    return KL(b200_soft_max_mask((const float *)n.src[0].data, (float *)n.dst.data, n.src[1].data, n.src[1].type == B200_TYPE_F16, n.src[1].nb[1] / n.src[1].nb[0],
+                                                 n.src[0].ne[0], n.src[0].ne[1], n.src[0].ne[2], f32_param(n, 0), f32_param(n, 1), st));
                 return KL(b200_soft_max_rows((const float *)n.src[0].data, n.src[0].ne[0], (float *)n.dst.data, n.dst.ne[0], n.src[0].ne[0], nrows_of(n.src[0]), f32_param(n, 0), st));
             case B200_OP_ARGSORT:
                 return KL(b200_argsort_rows((const float *)n.src[0].data, n.src[0].ne[0], (int32_t *)n.dst.data, n.dst.ne[0], n.src[0].ne[0], nrows_of(n.src[0]), n.op_params[0] == 1, st));

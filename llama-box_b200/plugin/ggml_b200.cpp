@@ -268,7 +268,8 @@ static bool node_to_b200(const ggml_tensor * t, b200_node & n) {
         case GGML_OP_SOFT_MAX: n.op = B200_OP_SOFT_MAX; break;
         case GGML_OP_ARGSORT:  n.op = B200_OP_ARGSORT; break;
         case GGML_OP_SUM_ROWS: n.op = B200_OP_SUM_ROWS; break;
-        case GGML_OP_DIV:      n.op = B200_OP_DIV; break;     // wide path (GGML_B200_WIDE=1); refused by b200_executor_supports otherwise
+        case GGML_OP_DIV:      n.op = B200_OP_DIV; break;
+        case GGML_OP_CONT:     n.op = B200_OP_CONT; break;        // attention without -fa (wide path)     // wide path (GGML_B200_WIDE=1); refused by b200_executor_supports otherwise
         default: return false;
     }
     to_b200(t, n.dst);
@@ -484,7 +485,7 @@ static ggml_backend_buffer_type_t dev_host_buft(ggml_backend_dev_t d) { return &
 
 static bool dev_supports_op(ggml_backend_dev_t, const struct ggml_tensor * op) {
     b200_node n;
-    if (op->op == GGML_OP_SOFT_MAX && op->src[1]) {         // with a mask: the attention of a graph built without -fa (a mask-free SOFT_MAX is the MoE router's, below)
+    if (op->op == GGML_OP_SOFT_MAX && op->src[1] && !b200_executor_wide_enabled()) {         // with a mask: the attention of a graph built without -fa (a mask-free SOFT_MAX is the MoE router's, below)
         // attention without -fa (SOFT_MAX + batched KQ / KQV matmuls, llama-graph.cpp:1267-1330) is not on this backend's hot
         // path: ggml's scheduler will run those nodes on the CPU backend.  Say so once, loudly — llama-box only turns flash
         // attention on with -fa (llama-box/engine_param.hpp:772-779).

@@ -102,15 +102,15 @@ def cpu_builds(tmp_path, tmp_path_factory, gguf, **kw):
     return [drv(gguf, str(tmp_path / ("cpu_" + w)), False, ref_dir=variant_ref_dir(tmp_path_factory, w), **kw) for w in ("haswell", "sandybridge")]
 
 
-def drv(gguf, out_prefix, plugin, kv="f16", prompt_len=24, gen=N_STEPS, verify=1, ngl=99, ts=None, embeddings=False, ctx=1024, ref_dir=None, extra_env=None):
+def drv(gguf, out_prefix, plugin, kv="f16", prompt_len=24, gen=N_STEPS, verify=1, ngl=99, ts=None, embeddings=False, ctx=1024, ref_dir=None, extra_env=None, fa=True):
     logits = out_prefix + ".logits"
     env = ENV
     if ref_dir:
         env = dict(ENV, LD_LIBRARY_PATH=ref_dir)
     if extra_env:
         env = dict(env, **extra_env)
-    cmd = [os.path.join(ref_dir or REF_DIR, "llama_drv"), "--model", gguf, "--ctx", str(ctx), "--prompt-len", str(prompt_len), "--gen", str(gen), "--logits-out", logits, "--fa",
-           "--ctk", kv, "--ctv", kv, "--verify-batch", str(verify)]
+    cmd = [os.path.join(ref_dir or REF_DIR, "llama_drv"), "--model", gguf, "--ctx", str(ctx), "--prompt-len", str(prompt_len), "--gen", str(gen), "--logits-out", logits,
+           "--ctk", kv, "--ctv", kv, "--verify-batch", str(verify)] + (["--fa"] if fa else [])
     if plugin:
         cmd += ["--plugin", PLUGIN, "--ngl", str(ngl), "--no-repack"]
         if ts:

@@ -70,6 +70,17 @@ def test_q4_0_kv_cache_set_rows_and_flash_attn_vs_oracle(shape):
     assert o["attn_err"] <= 2e-5, o
 
 
+@pytest.mark.parametrize("n_tok,n_past", [(1, 100), (5, 37)])
+def test_attention_without_fa_block_vs_oracle(n_tok, n_past):
+    """one attention block as libllama emits it WITHOUT -fa (tests/nofa_graph.py) through the graph executor: K rows and transposed-V elements stored
+    exactly, output within the chained-op tolerance (the probabilities are rounded to f16 before KQV on both sides, like ggml-cpu does)"""
+    o = child("nofa", n_tok, n_past, wide=True)
+    assert all(o["supports"]), o
+    assert o["v_store_exact"], o
+    assert max(o["errs"]) <= 2e-3, o
+    assert o["captures"] >= 1 and o["replays"] >= 1, o
+
+
 def test_moe_router_glue_vs_oracle():
     """glue_ext.cu through the C-ABI: f32 router matmul, SOFT_MAX, ARGSORT (ties in the reference's order), batched GET_ROWS, SUM_ROWS, DIV, the
     broadcast MUL and the ADD over strided expert slices"""
@@ -119,6 +130,7 @@ def product():
     ("test-small", "Q4_1", "f16", "MUL_MAT"), ("test-small", "Q5_1", "f16", "MUL_MAT"), ("test-small", "Q2_K", "f16", "MUL_MAT"),
     ("test-small", "Q3_K_M", "f16", "MUL_MAT"), ("test-small", "IQ4_NL", "f16", "MUL_MAT"), ("test-small", "IQ4_XS", "f16", "MUL_MAT"),
     ("test-small", "Q4_K_M", "q4_0", "FLASH_ATTN"),         # -ctk q4_0 -ctv q4_0
+    ("test-small", "Q4_K_M", "f16", "SOFT_MAX"),            # WITHOUT -fa (llama-box's default): KQ / masked SOFT_MAX / KQV / CONT on the device
 ])
 def test_libllama_over_the_wide_path(tmp_path, tmp_path_factory, product, config, ftype, kv, must_be_on_device):
     """llama_decode (prefill of 24 tokens, then greedy decode) on files whose matrices are in the wide path's formats / a mixture-of-experts
@@ -126,9 +138,10 @@ def test_libllama_over_the_wide_path(tmp_path, tmp_path_factory, product, config
     would pass through ggml's CPU fallback), and the run must be as close to ggml-cpu as ggml-cpu's own other builds are."""
     P = product
     gguf = P.model_file(tmp_path_factory, config, ftype, 2)
-    cpu = P.drv(gguf, str(tmp_path / "cpu"), False, kv=kv, gen=9)
-    others = P.cpu_builds(tmp_path, tmp_path_factory, gguf, kv=kv, gen=9)
-    gpu = P.drv(gguf, str(tmp_path / "gpu"), True, kv=kv, gen=9, extra_env=dict(GGML_B200_WIDE="1", GGML_SCHED_DEBUG="2", LLAMA_DRV_LOG_DEBUG="1"))
+    fa = must_be_on_device != "SOFT_MAX"
+    cpu = P.drv(gguf, str(tmp_path / "cpu"), False, kv=kv, gen=9, fa=fa)
+    others = P.cpu_builds(tmp_path, tmp_path_factory, gguf, kv=kv, gen=9, fa=fa)
+    gpu = P.drv(gguf, str(tmp_path / "gpu"), True, kv=kv, gen=9, fa=fa, extra_env=dict(GGML_B200_WIDE="1", GGML_SCHED_DEBUG="2", LLAMA_DRV_LOG_DEBUG="1"))
     placed = re.findall(r"node #\s*\d+ \(\s*" + must_be_on_device + r"\w*\):.*?\[\s*(\w+)", gpu["stderr"])
     assert placed and all(b.startswith("B200") for b in placed), (len(placed), sorted(set(placed)))
     P.assert_within_reference_self_consistency(gpu, cpu, others, f"wide path: {config} {ftype} kv={kv}")

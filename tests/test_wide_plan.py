@@ -81,3 +81,63 @@ def test_wide_nodes_are_refused_when_switched_off():
         if op in (G_OP_GET_ROWS, G_OP_MUL_MAT, G_OP_MUL_MAT_ID, G_OP_SOFT_MAX, G_OP_ARGSORT, G_OP_SUM_ROWS, G_OP_DIV):
             assert s == 0, o              # ggml's scheduler keeps these nodes on its CPU backend, exactly as before this change
     assert o["plan"] < 0
+
+
+NOFA_CHILD = r"""
+import importlib, json, sys
+sys.path.insert(0, %r)
+from conftest import load_pkg
+load_pkg()
+G = importlib.import_module("llama_box_b200.graph")
+import nofa_graph
+
+
+class Fake:
+    base = 0x10000000
+
+    def buf(self, n):
+        p = Fake.base; Fake.base += (n + 0xfffff) & ~0xfffff; return p
+
+    def f32(self, ne):
+        n = 4
+        for d in ne:
+            n *= d
+        return G.T(self.buf(n), G.F32, ne)
+
+    def named(self, name, t, ne):
+        rows = 1
+        for d in ne[1:]:
+            rows *= d
+        return G.T(self.buf(G.row_size(t, ne[0]) * rows), t, ne)
+
+
+rp = [0, 128, 0, 0, 8192, G.f32_bits(5e5), G.f32_bits(1.0), G.f32_bits(0.0), G.f32_bits(1.0), G.f32_bits(32.0), G.f32_bits(1.0)]
+nl, _ = nofa_graph.build(G, Fake(), 4096, 32, 8, 128, %d, 4096, 544, rp)
+nodes = nl.build()
+names = ["NONE", "MUL_MAT", "RMS_NORM", "MUL", "ADD", "ROPE", "SET_ROWS", "FA", "GLU", "GET_ROWS", "CPY", "MUL_MAT_ID", "SOFT_MAX", "ARGSORT", "SUM_ROWS", "DIV", "CONT"]
+print(json.dumps({"wide": int(G._lib.b200_executor_wide_enabled()), "supports": [[names[nodes[i].op], int(G._lib.b200_executor_supports(nodes[i]))] for i in range(len(nodes))],
+                  "plan": G.plan(nodes, G.EXEC_FUSION)}))
+"""
+
+
+@pytest.mark.parametrize("n_tok", [1, 5])
+def test_attention_without_fa_is_supported_when_switched_on(n_tok):
+    import json
+    env = dict(os.environ, GGML_B200_WIDE="1")
+    r = subprocess.run([sys.executable, "-c", NOFA_CHILD % (os.path.join(ROOT, "tests"), n_tok)], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    o = json.loads(r.stdout.strip().splitlines()[-1])
+    assert o["wide"] == 1 and all(s for _, s in o["supports"]), o
+    # QKV in one launch | ROPE(q) | ROPE(k) | SET_ROWS(k) | element scatter of V | KQ | SOFT_MAX | KQV | CONT | wo
+    assert 9 <= o["plan"] <= 12, o
+
+
+def test_attention_without_fa_is_refused_when_switched_off():
+    import json
+    env = dict(os.environ)
+    env.pop("GGML_B200_WIDE", None)
+    r = subprocess.run([sys.executable, "-c", NOFA_CHILD % (os.path.join(ROOT, "tests"), 1)], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    o = json.loads(r.stdout.strip().splitlines()[-1])
+    refused = {name for name, s in o["supports"] if not s}
+    assert {"SOFT_MAX", "CONT"} <= refused and o["plan"] < 0, o

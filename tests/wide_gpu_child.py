@@ -169,6 +169,79 @@ def do_executor(wtype, n_tok):
     return {"supports": sup, "errs": errs, "captures": int(ex.captures), "replays": int(ex.replays), "kernels": int(ex.last_kernels)}
 
 
+def do_nofa(n_tok, n_past):
+    """one attention block WITHOUT -fa through the graph executor (tests/nofa_graph.py = what build_attn_mha emits) against the oracle op by op"""
+    assert os.environ.get("GGML_B200_WIDE") == "1"
+    import nofa_graph
+    from refutil import F16 as T_F16
+    G = importlib.import_module("llama_box_b200.graph")
+    O = oracle()
+    rng = np.random.default_rng(n_tok + n_past)
+    E, H, HK, D, KV_SIZE = 1024, 8, 2, 128, 256
+    NKV = (n_past + n_tok + 31) // 32 * 32
+    x = rng.standard_normal((n_tok, E)).astype(np.float32)
+    Wq = weights(rng, Q4_K, H * D, E, "quantised"); Wk = weights(rng, Q4_K, HK * D, E, "quantised"); Wv = weights(rng, Q4_K, HK * D, E, "quantised"); Wo = weights(rng, Q4_K, E, H * D, "quantised")
+    kc = np.zeros((KV_SIZE, HK * D), np.float16); vt = np.zeros((HK * D, KV_SIZE), np.float16)
+    kc[:n_past] = rng.standard_normal((n_past, HK * D)).astype(np.float16); vt[:, :n_past] = rng.standard_normal((HK * D, n_past)).astype(np.float16)
+    pos = np.arange(n_past, n_past + n_tok, dtype=np.int32); cells = np.arange(n_past, n_past + n_tok, dtype=np.int64)
+    vidx = (np.arange(HK * D, dtype=np.int64)[None, :] * KV_SIZE + cells[:, None]).reshape(-1)
+    mask = np.full((64, NKV), -np.inf, np.float32)
+    for t in range(n_tok):
+        mask[t, :n_past + t + 1] = 0
+    rp = dict(n_dims=D, mode=0, n_ctx_orig=8192, freq_base=5e5, freq_scale=1.0, ext_factor=0.0, attn_factor=1.0, beta_fast=32.0, beta_slow=1.0)
+    # ---- oracle
+    q = orc_mul_mat(Q4_K, Wq, x, H * D, n_tok, E); k = orc_mul_mat(Q4_K, Wk, x, HK * D, n_tok, E); v = orc_mul_mat(Q4_K, Wv, x, HK * D, n_tok, E)
+    qr = np.zeros_like(q); kr = np.zeros_like(k)
+    for src, dst, nh in ((q, qr, H), (k, kr, HK)):
+        O.orc_rope(ptr(src), ptr(dst), ptr(pos), None, D, nh, n_tok, D, 0, 8192, 5e5, 1.0, 0.0, 1.0, 32.0, 1.0)
+    kc_w = kc.copy(); vt_w = vt.copy()
+    kc_w[cells] = kr.astype(np.float16); vt_w.reshape(-1)[vidx] = v.reshape(-1).astype(np.float16)
+    kq = np.zeros((H, n_tok, NKV), np.float32)
+    O.orc_mul_mat_f16(ptr(kc_w), HK * D * 2, D * 2, HK, ptr(qr), H * D * 4, D * 4, ptr(kq), NKV * 4, n_tok * NKV * 4, NKV, n_tok, H, D)
+    sm = np.zeros_like(kq); O.orc_soft_max_mask(ptr(kq), ptr(sm), ptr(mask), 0, NKV, NKV, n_tok, H, float(D ** -0.5), 0.0)
+    kqv = np.zeros((H, n_tok, D), np.float32)
+    O.orc_mul_mat_f16(ptr(vt_w), KV_SIZE * 2, KV_SIZE * D * 2, HK, ptr(sm), NKV * 4, n_tok * NKV * 4, ptr(kqv), D * 4, n_tok * D * 4, D, n_tok, H, NKV)
+    cont = np.ascontiguousarray(kqv.transpose(1, 0, 2)).reshape(n_tok, H * D)
+    want = orc_mul_mat(Q4_K, Wo, cont, E, n_tok, H * D)
+    # ---- executor
+    keep = []
+    plain = {"x": x, "pos": pos, "k_idx": cells, "v_idx": vidx, "mask": mask}
+    wts = {"wq": (Wq, E), "wk": (Wk, E), "wv": (Wv, E), "wo": (Wo, H * D)}
+    caches = {"k_cache": kc, "v_cache": vt}
+    handles = {}
+
+    class Alloc:
+        def f32(self, ne):
+            d = torch.zeros(int(np.prod(ne)), dtype=torch.float32, device="cuda"); keep.append(d); return G.T(d.data_ptr(), G.F32, ne)
+
+        def named(self, name, t, ne):
+            if name in plain:
+                a = plain[name]
+                d = torch.from_numpy(np.ascontiguousarray(a)).cuda() if a.dtype == np.int64 else dev(a)
+            elif name in caches:
+                d = torch.from_numpy(caches[name].view(np.int16).copy()).cuda()
+            else:
+                W, k_ = wts[name]
+                d = dev(np.concatenate([repack_rows_np(Q4_K, W, k_).reshape(-1), np.zeros(64, np.uint8)]))
+            keep.append(d); handles[name] = d
+            return G.T(d.data_ptr(), t, ne)
+    rope_params = [0, D, 0, 0, 8192, G.f32_bits(5e5), G.f32_bits(1.0), G.f32_bits(0.0), G.f32_bits(1.0), G.f32_bits(32.0), G.f32_bits(1.0)]
+    nl, out_t = nofa_graph.build(G, Alloc(), E, H, HK, D, n_tok, KV_SIZE, NKV, rope_params)
+    nodes = nl.build()
+    ex = G.Executor(0)
+    sup = [bool(ex.supports(nodes[i])) for i in range(len(nodes))]
+    out_d = [d for d in keep if d.data_ptr() == out_t.ptr][0]
+    errs = []
+    for rep in range(3):
+        out_d.zero_()
+        ex.compute(nodes)
+        torch.cuda.synchronize()
+        errs.append(rel(out_d.cpu().numpy().reshape(n_tok, E), want))
+    k_ok = bool(np.array_equal(handles["k_cache"].cpu().numpy().view(np.float16).reshape(KV_SIZE, HK * D)[cells].view(np.uint16), kr.astype(np.float16).view(np.uint16)))
+    v_ok = bool(np.array_equal(handles["v_cache"].cpu().numpy().view(np.uint16).reshape(-1)[vidx], v.reshape(-1).astype(np.float16).view(np.uint16)))
+    return {"supports": sup, "errs": errs, "k_store_exact": k_ok, "v_store_exact": v_ok, "captures": int(ex.captures), "replays": int(ex.replays), "kernels": int(ex.last_kernels)}
+
+
 def do_glue():
     """the router glue of build_moe_ffn op by op through the C-ABI (glue_ext.cu) against the oracle / exact numpy semantics"""
     rng = np.random.default_rng(9)
@@ -286,7 +359,7 @@ def do_type_suite(t):
 def main():
     what = sys.argv[1]; a = [int(v) if v.lstrip("-").isdigit() else v for v in sys.argv[2:]]
     torch.cuda.set_device(0)
-    fn = {"glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
+    fn = {"nofa": do_nofa, "glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
     print("RESULT " + json.dumps(fn(*a)))
 
 
