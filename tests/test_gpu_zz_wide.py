@@ -37,29 +37,33 @@ def child(*args, wide=False, timeout=600):
     return json.loads(line[7:])
 
 
-@pytest.mark.parametrize("t", [2, 6, 8, 14])
-def test_numpy_model_of_the_library_layout_matches_the_repack_kernel(t):
-    assert child("repack_model", t, 2048)["equal"]
+def test_numpy_model_of_the_library_layout_matches_the_repack_kernel():
+    o = child("repack_models", "2,6,8,14")
+    assert all(v["equal"] for v in o.values()), o
 
 
-@pytest.mark.parametrize("t", EXT + CORE)
-def test_wide_kernels_vs_oracle(t):
-    """one format: b200_mul_mat_vec_wide (4 shapes x {random bit patterns, reference-quantised weights}, with and without bias + residual; rows that
-    are not a multiple of 256 for the 32-element formats), b200_mul_mat_id (shared / per-expert activations, 1 and 5 tokens), b200_get_rows_q"""
-    o = child("type_suite", t, timeout=1200)
+@pytest.mark.parametrize("group", ["3,7,20,39", "10,11,23", "2,6,8", "12,13,14"])
+def test_wide_kernels_vs_oracle(group):
+    """per format: b200_mul_mat_vec_wide (4 shapes x {random bit patterns, reference-quantised weights}, with and without bias + residual; rows that are
+    not a multiple of 256 for the 32-element formats), b200_mul_mat_id (shared / per-expert activations, 1 and 5 tokens), b200_get_rows_q.  A few formats
+    per child process (the interpreter + torch start-up would otherwise dominate the run time)."""
     bad = {}
-    for name, r in o.items():
-        if "error" in r:
-            bad[name] = r
-        elif name.startswith("mul_mat_id"):
-            if r["err"] > 2e-5:
-                bad[name] = r
-        elif name.startswith("mul_mat"):
-            if r["plain"] > 2e-5 or r["bias_residual"] > 2e-5:
-                bad[name] = r
-        elif not r["bit_exact"]:
-            bad[name] = r
-    assert len(o) >= 13 and not bad, bad
+    o = child("type_suites", group, timeout=1800)
+    for t, cases in o.items():
+        assert len(cases) >= 13, (t, len(cases))
+        for name, r in cases.items():
+            key = f"type {t}: {name}"
+            if "error" in r:
+                bad[key] = r
+            elif name.startswith("mul_mat_id"):
+                if r["err"] > 2e-5:
+                    bad[key] = r
+            elif name.startswith("mul_mat"):
+                if r["plain"] > 2e-5 or r["bias_residual"] > 2e-5:
+                    bad[key] = r
+            elif not r["bit_exact"]:
+                bad[key] = r
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("shape", [(128, 32, 8, 1, 768), (128, 8, 2, 5, 4096), (64, 32, 4, 1, 1024), (64, 8, 8, 33, 256)])
@@ -99,10 +103,10 @@ def test_executor_moe_block_vs_oracle(wtype, n_tok):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref (reference build) not present")
-@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("MUL_MAT", 60), ("GET_ROWS", 4), ("SET_ROWS", 7), ("FLASH_ATTN_EXT", 24),
-                                        ("ADD", 6), ("MUL", 6), ("DIV", 4), ("SOFT_MAX", 4), ("ARGSORT", 2), ("SUM_ROWS", 1)])
+@pytest.mark.parametrize("op,min_ok", [("MUL_MAT_ID", 10), ("GET_ROWS,SET_ROWS,ADD,MUL,DIV,SOFT_MAX,ARGSORT,SUM_ROWS,CONT", 40)])
 def test_reference_backend_ops_harness_with_the_wide_path(op, min_ok):
-    """the reference's own parity harness (tests/test-backend-ops.cpp) against the plug-in with GGML_B200_WIDE=1"""
+    """the reference's own parity harness (tests/test-backend-ops.cpp) against the plug-in with GGML_B200_WIDE=1.  MUL_MAT / FLASH_ATTN_EXT are not re-run here
+    (minutes of CPU reference time that tests/test_gpu_plugin.py already spends on them): the wide formats and the q4_0 cache reach the plug-in through the libllama cases below."""
     plugin = os.path.join(ROOT, "llama-box_b200", "libggml-b200.so")
     env = dict(os.environ, LD_LIBRARY_PATH=REF_DIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), GGML_BACKEND_PATH=plugin, GGML_B200_WIDE="1")
     r = subprocess.run([os.path.join(REF_DIR, "test-backend-ops"), "test", "-b", "B2000", "-o", op], capture_output=True, text=True, env=env, timeout=1800)

@@ -356,10 +356,18 @@ def do_type_suite(t):
     return out
 
 
+def do_repack_models(group):
+    return {str(t): do_repack_model(int(t), 2048) for t in str(group).split(",")}
+
+
+def do_type_suites(group):
+    return {str(t): do_type_suite(int(t)) for t in str(group).split(",")}
+
+
 def main():
     what = sys.argv[1]; a = [int(v) if v.lstrip("-").isdigit() else v for v in sys.argv[2:]]
     torch.cuda.set_device(0)
-    fn = {"nofa": do_nofa, "glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
+    fn = {"repack_models": do_repack_models, "type_suites": do_type_suites, "nofa": do_nofa, "glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
     print("RESULT " + json.dumps(fn(*a)))
 
 
