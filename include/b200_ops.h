@@ -180,7 +180,7 @@ B200_API int     b200_wide_type_supported(int type);                 /* 1 for th
 B200_API int     b200_wide_shape_supported(int type, int64_t k);     /* 1 if rows of k elements of `type` can be read   */
 B200_API int64_t b200_wide_row_bytes(int type, int64_t k);
 /* dst[c][r] = sum_k W[r][k] x[c][k] (+ bias[r]) (+ residual[c][r]); x f32 [ncols][k] with column stride x_col_stride floats (16-byte
- * aligned columns); any ncols (one pass over the weights per column: decode / verify batches) */
+ * aligned columns); any ncols (one pass over the weights per group of up to 8 columns) */
 B200_API int b200_mul_mat_vec_wide(int type, const void *W, const float *x, int64_t x_col_stride, float *dst, int64_t dst_col_stride,
                                    const float *bias, const float *residual, int64_t m, int64_t k, int64_t ncols, void *stream);
 /* MUL_MAT_ID — mixture-of-experts routing (replaces ggml_cuda_mul_mat_id, ggml-cuda.cu:2064-2205; contract ggml.c:3064-3106):

@@ -29,10 +29,17 @@ bool ext_shape_ok(int type, int64_t k) {
     return k % 256 == 0;                                                        // library layout of the other tuned formats
 }
 
-template <int T> int ext_launch_t(const ExtArgs & a0, int64_t n_prob, cudaStream_t st) {
+// n_items: columns of a plain MUL_MAT (grouped up to 8 per CTA while their quantised forms fit shared memory), or (token, slot) pairs of a MUL_MAT_ID
+template <int T> int ext_launch_t(const ExtArgs & a_in, int64_t n_items, cudaStream_t st) {
     const int fam = xf_act_family(T);
-    const int64_t smem = ext_smem_bytes(fam, ext_kp(a0.k));
-    if (smem > 200 * 1024) { b200_set_error("wide matvec: k = %lld does not fit shared memory", (long long)a0.k); return B200_ERR_UNSUPPORTED; }
+    const int64_t col = ext_smem_bytes(fam, ext_kp(a_in.k));
+    ExtArgs a0 = a_in;
+    int64_t C = 1;
+    if (!a0.ids) { C = (96 * 1024) / col;      /* two resident CTAs per SM */ if (C > EXT_MAX_COLS) C = EXT_MAX_COLS; if (C > n_items) C = n_items; if (C < 1) C = 1; }
+    a0.cols_per_cta = (int32_t)C; a0.ncols = n_items;
+    const int64_t n_prob = a0.ids ? n_items : (n_items + C - 1) / C;
+    const int64_t smem = col * C;
+    if (col > 200 * 1024) { b200_set_error("wide matvec: k = %lld does not fit shared memory", (long long)a0.k); return B200_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024) {
         static bool attr[64];
         int dev = 0; cudaGetDevice(&dev);

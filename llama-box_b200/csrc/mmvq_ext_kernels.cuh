@@ -22,7 +22,10 @@ struct ExtArgs {
     float * dst; int64_t dst_col_stride, dst_slot_stride;
     const float * bias; const float * residual; int64_t res_col_stride;
     int64_t m, k, prob0;                                                     // prob0: first problem of this launch (grid.y chunking)
+    int32_t cols_per_cta, _pad; int64_t ncols;                               // plain MUL_MAT: a problem = a GROUP of up to 8 columns sharing one pass over the weights
 };
+
+constexpr int EXT_MAX_COLS = 8;
 
 constexpr int EXT_WARPS = 8;
 
@@ -39,15 +42,13 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) ext_mmv_kernel(const ExtArgs a
     constexpr int FAM = (T == XF_Q2_K || T == XF_Q3_K || T == XF_Q4_K || T == XF_Q5_K || T == XF_Q6_K || T == XF_IQ4_XS) ? 0 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t k = a.k, kp = ext_kp(k);
-    int8_t  * qs = (int8_t *)ext_smem;
-    float   * ad = (float *)(ext_smem + ext_off_d(kp));
-    float   * as = (float *)(ext_smem + ext_off_s(FAM, kp));
-    int16_t * bs = (int16_t *)(ext_smem + ext_off_bs(FAM, kp));
+    const int64_t col_bytes = ext_smem_bytes(FAM, kp);            // a multiple of 16
 
     pdl_wait();                                                    // activations and expert ids come from earlier kernels
 
     const int64_t p = a.prob0 + blockIdx.y;
     const uint8_t * W = a.W; const float * x; float * dst; const float * resid = nullptr;
+    int nc = 1;                                                    // columns this CTA carries
     if (a.ids) {
         const int64_t tok = p / a.n_used, slot = p % a.n_used;
         const int e = a.ids[tok * a.ids_tok_stride + slot];
@@ -56,17 +57,25 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) ext_mmv_kernel(const ExtArgs a
         x   = a.x + tok * a.x_col_stride + (slot % a.n_b1) * a.x_slot_stride;
         dst = a.dst + tok * a.dst_col_stride + slot * a.dst_slot_stride;
     } else {
-        x   = a.x + p * a.x_col_stride;
-        dst = a.dst + p * a.dst_col_stride;
-        if (a.residual) resid = a.residual + p * a.res_col_stride;
+        const int64_t c0 = p * a.cols_per_cta;
+        nc  = (int)(a.ncols - c0 < a.cols_per_cta ? a.ncols - c0 : a.cols_per_cta);
+        x   = a.x + c0 * a.x_col_stride;
+        dst = a.dst + c0 * a.dst_col_stride;
+        if (a.residual) resid = a.residual + c0 * a.res_col_stride;
     }
 
-    // ---- prologue: this column, quantised like the oracle, into shared memory (elements past k: zero)
-    for (int64_t c = warp; c < kp / 256; c += EXT_WARPS) {
+    // ---- prologue: the columns of this CTA, quantised like the oracle, into shared memory (elements past k: zero)
+    for (int64_t w = warp; w < (kp / 256) * nc; w += EXT_WARPS) {
+        const int64_t c = w % (kp / 256); const int j = (int)(w / (kp / 256));
+        uint8_t * col = ext_smem + j * col_bytes;
+        int8_t  * qs = (int8_t *)col;
+        float   * ad = (float *)(col + ext_off_d(kp));
+        float   * as = (float *)(col + ext_off_s(FAM, kp));
+        int16_t * bs = (int16_t *)(col + ext_off_bs(FAM, kp));
         float v[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
         const int64_t e0 = c * 256 + lane * 8;
         if (e0 < k) {                                              // k % 32 == 0: a lane's 8 elements are all inside or all outside
-            const float4 * px = (const float4 *)(x + e0);
+            const float4 * px = (const float4 *)(x + j * a.x_col_stride + e0);
             const float4 f0 = px[0], f1 = px[1];
             v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
         }
@@ -75,18 +84,33 @@ __global__ void __launch_bounds__(EXT_WARPS * 32) ext_mmv_kernel(const ExtArgs a
     }
     __syncthreads();
 
-    XfAct A; A.qs = qs; A.d = ad; A.s = as; A.bs = bs;
     const int64_t nsub = k / 32;
     for (int64_t row = (int64_t)blockIdx.x * EXT_WARPS + warp; row < a.m; row += (int64_t)gridDim.x * EXT_WARPS) {
         const uint8_t * wr = W + row * a.row_bytes;
-        float acc = 0.0f;
-        for (int64_t u = lane; u < nsub; u += 32) acc += xf_sub_dot<T>(wr, a.nb_layout, u, A);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            float r = acc;
-            if (a.bias)  r += a.bias[row];
-            if (resid)   r += resid[row];
-            dst[row] = r;
+        float acc[EXT_MAX_COLS];
+#pragma unroll
+        for (int j = 0; j < EXT_MAX_COLS; j++) acc[j] = 0.0f;
+        for (int64_t u = lane; u < nsub; u += 32) {
+#pragma unroll
+            for (int j = 0; j < EXT_MAX_COLS; j++) {
+                if (j < nc) {                                      // uniform over the CTA; the weight bytes of sub-block u come from L1 after the first column
+                    const uint8_t * col = ext_smem + j * col_bytes;
+                    XfAct A; A.qs = (const int8_t *)col; A.d = (const float *)(col + ext_off_d(kp)); A.s = (const float *)(col + ext_off_s(FAM, kp)); A.bs = (const int16_t *)(col + ext_off_bs(FAM, kp));
+                    acc[j] += xf_sub_dot<T>(wr, a.nb_layout, u, A);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < EXT_MAX_COLS; j++) {
+            if (j < nc) {
+                const float r0 = warp_sum(acc[j]);
+                if (lane == 0) {
+                    float r = r0;
+                    if (a.bias)  r += a.bias[row];
+                    if (resid)   r += resid[j * a.res_col_stride + row];
+                    dst[j * a.dst_col_stride + row] = r;
+                }
+            }
         }
     }
 }

@@ -13,9 +13,16 @@ void b200_set_error(const char *, ...) {}
 extern "C" { long xf_misaligned = 0; long sim_misaligned(void) { return xf_misaligned; } }
 
 namespace {
-template <int T> void run_mmv(const ExtArgs & a, int64_t n_prob, int gx) {
+// the grouping rule of mmvq_ext.cu (ext_launch_t): columns of a plain MUL_MAT share a CTA, up to 8, while their quantised forms fit shared memory
+template <int T> void run_mmv(const ExtArgs & a_in, int64_t n_items, int gx) {
     const int fam = xf_act_family(T);
-    simt::launch(dim3((unsigned)gx, (unsigned)n_prob), dim3(EXT_WARPS * 32), (size_t)ext_smem_bytes(fam, ext_kp(a.k)), [a] { ext_mmv_kernel<T>(a); });
+    const int64_t col = ext_smem_bytes(fam, ext_kp(a_in.k));
+    ExtArgs a = a_in;
+    int64_t C = 1;
+    if (!a.ids) { C = (96 * 1024) / col; if (C > EXT_MAX_COLS) C = EXT_MAX_COLS; if (C > n_items) C = n_items; if (C < 1) C = 1; }
+    a.cols_per_cta = (int32_t)C; a.ncols = n_items;
+    const int64_t n_prob = a.ids ? n_items : (n_items + C - 1) / C;
+    simt::launch(dim3((unsigned)gx, (unsigned)n_prob), dim3(EXT_WARPS * 32), (size_t)(col * C), [a] { ext_mmv_kernel<T>(a); });
 }
 template <int T> void run_get_rows(const uint8_t * src, int64_t rs, int64_t nb, int64_t nrows, const int32_t * ids, float * dst, int64_t drs, int64_t ncols, int64_t n_ids) {
     simt::launch(dim3((unsigned)((ncols / 32 + 127) / 128), (unsigned)n_ids), dim3(128), 0, [=] { ext_get_rows_kernel<T>(src, rs, nb, nrows, ids, dst, drs, ncols, 0); });

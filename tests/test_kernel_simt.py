@@ -74,6 +74,19 @@ def test_wide_matvec_kernel(K, t):
     assert rel(dst, want + bias[None, :] + res) <= 2e-5
 
 
+@pytest.mark.parametrize("t", [12, 3, 11])
+def test_wide_matvec_kernel_column_groups(K, t):
+    """11 columns = one CTA group of 8 and one of 3: the columns of a group share a pass over the weights"""
+    rng = np.random.default_rng(t)
+    m, k, n = 10, 512, 11
+    W = rand_blocks(rng, t, m, k); X = rng.standard_normal((n, k)).astype(np.float32)
+    res = rng.standard_normal((n, m)).astype(np.float32)
+    want = orc_mul_mat(t, W, X, m, n, k) + res
+    dst = np.full((n, m), 7.0, np.float32)
+    K.sim_mul_mat_vec_wide(t, ptr(repack_rows_np(t, W, k)), ptr(X), k, ptr(dst), m, None, ptr(res), m, k, n, 1)
+    assert rel(dst, want) <= 2e-5
+
+
 @pytest.mark.parametrize("t", [3, 7, 20, 39])
 def test_wide_matvec_kernel_rows_not_a_multiple_of_256(K, t):
     rng = np.random.default_rng(t)
