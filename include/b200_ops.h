@@ -240,6 +240,12 @@ B200_API int b200_flash_attn_q4_0(const float *q, int64_t q_tok_stride, int64_t 
                                   const void *v, int64_t v_row_stride, int64_t v_head_stride, const void *mask, int64_t mask_row_stride, float *dst,
                                   int64_t d, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap, void *stream);
 
+/* FLASH_ATTN_EXT for any head size that is a multiple of 32 up to 256 (Gemma 256, Phi 96, ... — b200_flash_attn_ext carries 64 and 128) over an F16, Q8_0 or
+ * Q4_0 cache in ggml's layout; wide path, arguments as b200_flash_attn_ext, no workspace (replaces the other head sizes of fattn.cu:271-338) */
+B200_API int b200_flash_attn_any(int kv_type, const float *q, int64_t q_tok_stride, int64_t q_head_stride, const void *k, int64_t k_row_stride, int64_t k_head_stride,
+                                 const void *v, int64_t v_row_stride, int64_t v_head_stride, const void *mask, int64_t mask_row_stride, float *dst,
+                                 int64_t d, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap, void *stream);
+
 /* ---- MUL_MAT, batched / prefill (replaces ggml_cuda_mul_mat_q, mmq.cu:71-143) -----------
  * dst[c][r] for any ncols; X is f32 [ncols][k].  Internally: activation quantisation as above,
  * then tiles on the tensor cores (tcgen05, TMEM accumulators) when ncols >= B200_MMQ_MIN_COLS,

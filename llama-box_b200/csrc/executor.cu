@@ -220,10 +220,12 @@ bool fattn_ok(const b200_node & n) {
     if (k.type != B200_TYPE_F16 && k.type != B200_TYPE_Q8_0 && !(k.type == B200_TYPE_Q4_0 && wide_on())) return false;
     if (k.type == B200_TYPE_Q4_0 && ((((uintptr_t)k.data | (uintptr_t)v.data) & 1) || ((k.nb[1] | k.nb[2] | v.nb[1] | v.nb[2]) & 1))) return false;
     const int64_t dk = q.ne[0], dv = v.ne[0];
-    if (dk != dv || (dk != 64 && dk != 128) || k.ne[0] != dk) return false;
+    const bool any_d = wide_on() && dk % 32 == 0 && dk > 0 && dk <= 256;                 // head sizes beyond 64 / 128: the wide attention kernel (fattn_ext.cu)
+    if (dk != dv || ((dk != 64 && dk != 128) && !any_d) || k.ne[0] != dk) return false;
     if (q.ne[3] != 1 || k.ne[3] != 1 || v.ne[3] != 1 || k.ne[1] != v.ne[1] || k.ne[2] != v.ne[2] || k.ne[2] <= 0 || q.ne[2] % k.ne[2] != 0) return false;
     if (q.nb[0] != 4 || (q.nb[1] & 15) || (q.nb[2] & 15) || !aligned16(q.data)) return false;
-    if (k.type == B200_TYPE_F16 && ((((uintptr_t)k.data | (uintptr_t)v.data) & 15) || ((k.nb[1] | k.nb[2] | v.nb[1] | v.nb[2]) & 15))) return false;
+    if (k.type == B200_TYPE_F16 && (dk == 64 || dk == 128) && ((((uintptr_t)k.data | (uintptr_t)v.data) & 15) || ((k.nb[1] | k.nb[2] | v.nb[1] | v.nb[2]) & 15))) return false;
+    if (dk != 64 && dk != 128 && ((((uintptr_t)k.data | (uintptr_t)v.data) & 1) || ((k.nb[1] | k.nb[2] | v.nb[1] | v.nb[2]) & 1))) return false;
     if (!contiguous(d) || d.ne[0] != dv || d.ne[1] != q.ne[2] || d.ne[2] != q.ne[1] || q.ne[1] > 65535) return false;
     if (n.n_src > 3 && n.src[3].data) {
         const b200_tensor & m = n.src[3];
@@ -906,6 +908,9 @@ struct Runner {
                 if (mk_try_attn(n)) return B200_OK;
                 if (attn_matches(n)) return launch_fused_attn(n);
                 { const int fs = mk_flush(); if (fs != B200_OK) return fs; }
+                if (q.ne[0] != 64 && q.ne[0] != 128)
+                    return KL(b200_flash_attn_any(k.type, (const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
+                                                  (float *)n.dst.data, q.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1], f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), st));
                 if (k.type == B200_TYPE_Q4_0)
                     return KL(b200_flash_attn_q4_0((const float *)q.data, q.nb[1] / 4, q.nb[2] / 4, k.data, k.nb[1], k.nb[2], v.data, v.nb[1], v.nb[2], mask, mrs,
                                                    (float *)n.dst.data, q.ne[0], q.ne[2], k.ne[2], q.ne[1], k.ne[1], f32_param(n, 0), f32_param(n, 1), f32_param(n, 2), st));

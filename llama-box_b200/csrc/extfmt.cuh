@@ -487,6 +487,15 @@ XF_HD float xf_q4_0n_value(const uint8_t * blk, int e) {
     return xf_mul((float)(nib - 8), xf_h2f((uint16_t)xf_ld16(blk)));
 }
 
+// Q8_0 in ggml's native block layout {d f16, qs[32]} (the KV cache type q8_0), for the any-head-size attention kernel (fattn_ext_kernels.cuh)
+XF_HD float xf_q8_0n_dot(const uint8_t * blk, const int8_t * q8, float ad) {          // ggml-cpu/quants.c:305-333
+    const uint32_t * a = (const uint32_t *)q8;
+    int sumi = 0;
+    for (int i = 0; i < 8; i++) sumi = xf_dp4a(xf_ld16x2(blk + 2 + 4 * i), a[i], sumi);
+    return (float)sumi * (xf_h2f((uint16_t)xf_ld16(blk)) * ad);
+}
+XF_HD float xf_q8_0n_value(const uint8_t * blk, int e) { return xf_mul((float)(int8_t)blk[2 + e], xf_h2f((uint16_t)xf_ld16(blk))); }
+
 // run F<T>(args...) for a runtime type id; false when the type is not one of ours
 #define XF_DISPATCH(t, CALL) \
     switch (t) { \

@@ -44,3 +44,29 @@ extern "C" int b200_flash_attn_q4_0(const float * q, int64_t q_tok_stride, int64
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
+
+// any head size (multiple of 32, at most 256) over an F16 / Q8_0 / Q4_0 cache — the shapes the tuned kernels do not carry (they have 64 and 128)
+extern "C" int b200_flash_attn_any(int kv_type, const float * q, int64_t q_tok_stride, int64_t q_head_stride, const void * k, int64_t k_row_stride, int64_t k_head_stride,
+                                   const void * v, int64_t v_row_stride, int64_t v_head_stride, const void * mask, int64_t mask_row_stride, float * dst,
+                                   int64_t d, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap, void * stream) {
+    if (b200_device_count() <= 0) { b200_set_error("no CUDA device"); return B200_ERR_CUDA; }
+    if (d <= 0 || d % 32 != 0 || d > 256 || (kv_type != B200_TYPE_F16 && kv_type != B200_TYPE_Q8_0 && kv_type != B200_TYPE_Q4_0)) {
+        b200_set_error("flash_attn_any: head size %lld / kv type %d unsupported", (long long)d, kv_type); return B200_ERR_UNSUPPORTED; }
+    if (!q || !k || !v || !dst || n_head <= 0 || n_head_kv <= 0 || n_head % n_head_kv != 0 || n_tok <= 0 || n_tok > 65535 || n_kv <= 0 ||
+        ((uintptr_t)q & 15) || (q_tok_stride & 3) || (q_head_stride & 3) || (((uintptr_t)k | (uintptr_t)v) & 1) || ((k_row_stride | k_head_stride | v_row_stride | v_head_stride) & 1)) {
+        b200_set_error("flash_attn_any: bad arguments"); return B200_ERR_INVALID;
+    }
+    FaWideArgs a = {};
+    a.q = q; a.q_ts = q_tok_stride; a.q_hs = q_head_stride; a.k = (const uint8_t *)k; a.k_rs = k_row_stride; a.k_hs = k_head_stride;
+    a.v = (const uint8_t *)v; a.v_rs = v_row_stride; a.v_hs = v_head_stride; a.mask = (const uint16_t *)mask; a.mask_rs = mask_row_stride;
+    a.dst = dst; a.n_head = n_head; a.n_head_kv = n_head_kv; a.n_kv = n_kv;
+    a.scale = logit_softcap != 0.0f ? scale / logit_softcap : scale; a.max_bias = max_bias; a.softcap = logit_softcap;
+    a.nh_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    a.m0 = powf(2.0f, -max_bias / (float)a.nh_log2); a.m1 = powf(2.0f, -(max_bias / 2.0f) / (float)a.nh_log2);
+    const dim3 grid((unsigned)n_head, (unsigned)n_tok);
+    if (kv_type == B200_TYPE_F16)       fattn_any_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(a, (int)d);
+    else if (kv_type == B200_TYPE_Q8_0) fattn_any_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>(a, (int)d);
+    else                                fattn_any_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(a, (int)d);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -99,6 +99,7 @@ SIGNATURES = {
     "b200_soft_max_mask": (i32, [vp, vp, vp, i32, i64, i64, i64, i64, f32, f32, vp]),
     "b200_scatter_rows1": (i32, [vp, vp, vp, i32, i64, i64, vp]),
     "b200_set_rows_q4_0": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),
+    "b200_flash_attn_any": (i32, [i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32, vp]),
     "b200_flash_attn_q4_0": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32, vp]),
 }
 for _n, (_r, _a) in SIGNATURES.items():

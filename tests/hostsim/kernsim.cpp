@@ -119,4 +119,20 @@ void sim_get_rows_f32_batched(const float * src, int64_t srs, int64_t sbs, int64
 void sim_mul_mat_f32(const float * W, int64_t wrs, const float * x, int64_t xcs, float * dst, int64_t dcs, int64_t m, int64_t k, int64_t ncols) {
     simt::launch(dim3((unsigned)((m * ncols * 32 + 255) / 256)), dim3(256), 0, [=] { mul_mat_f32_kernel(W, wrs, x, xcs, dst, dcs, m, k, ncols); });
 }
+void sim_flash_attn_any(int kv_type, const float * q, int64_t q_tok_stride, int64_t q_head_stride, const void * k, int64_t k_row_stride, int64_t k_head_stride,
+                        const void * v, int64_t v_row_stride, int64_t v_head_stride, const void * mask, int64_t mask_row_stride, float * dst,
+                        int64_t d, int64_t n_head, int64_t n_head_kv, int64_t n_tok, int64_t n_kv, float scale, float max_bias, float logit_softcap) {
+    FaWideArgs a = {};
+    a.q = q; a.q_ts = q_tok_stride; a.q_hs = q_head_stride; a.k = (const uint8_t *)k; a.k_rs = k_row_stride; a.k_hs = k_head_stride;
+    a.v = (const uint8_t *)v; a.v_rs = v_row_stride; a.v_hs = v_head_stride; a.mask = (const uint16_t *)mask; a.mask_rs = mask_row_stride;
+    a.dst = dst; a.n_head = n_head; a.n_head_kv = n_head_kv; a.n_kv = n_kv;
+    a.scale = logit_softcap != 0.0f ? scale / logit_softcap : scale; a.max_bias = max_bias; a.softcap = logit_softcap;
+    a.nh_log2 = 1u << (uint32_t)floor(log2((double)n_head));
+    a.m0 = powf(2.0f, -max_bias / (float)a.nh_log2); a.m1 = powf(2.0f, -(max_bias / 2.0f) / (float)a.nh_log2);
+    const dim3 grid((unsigned)n_head, (unsigned)n_tok);
+    const int D = (int)d;
+    if (kv_type == 1)      simt::launch(grid, dim3(128), 0, [a, D] { fattn_any_kernel<1>(a, D); });
+    else if (kv_type == 8) simt::launch(grid, dim3(128), 0, [a, D] { fattn_any_kernel<8>(a, D); });
+    else                   simt::launch(grid, dim3(128), 0, [a, D] { fattn_any_kernel<2>(a, D); });
+}
 }

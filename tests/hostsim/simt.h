@@ -1,6 +1,6 @@
 // simt.h — TEST INFRASTRUCTURE.  A minimal SIMT emulation so that CUDA kernel SOURCE (the wide path's kernels: llama-box_b200/csrc/
 // mmvq_ext_kernels.cuh, fattn_ext_kernels.cuh, with the warp quantisers of actquant.cuh) runs on the CPU:
-//   * one OS thread per CUDA thread of a block; blocks of a grid run one after the other,
+//   * one OS thread per CUDA thread of a block (reused across the grid); blocks of a grid run one after the other,
 //   * __syncthreads = a block-wide barrier, __shfl_*_sync = a per-warp exchange buffer between two warp-wide barriers,
 //   * __shared__ = static storage (valid because blocks run sequentially), dynamic shared memory = one buffer per launch,
 //   * threadIdx / blockIdx = thread-local, gridDim / blockDim = per launch; round-to-nearest intrinsics = plain IEEE operations
@@ -41,13 +41,20 @@ template <typename F> void launch(dim3 grid, dim3 block, size_t dyn_bytes, F bod
     g.dyn = (uint8_t *)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
     g.warps.clear();
     for (unsigned w = 0; w < block.x / 32; w++) g.warps.emplace_back(new Warp());
-    for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
-        std::barrier<> cta((std::ptrdiff_t)block.x);
-        g.cta = &cta;
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < block.x; t++) th.emplace_back([=] { tl.tid = { t, 0, 0 }; tl.bid = { bx, by, 0 }; body(); });
-        for (auto & x : th) x.join();
-    }
+    // one OS thread per CUDA thread of a block, reused for every block of the grid: the blocks run one after the other with a block-wide barrier in
+    // between (so static __shared__ storage is never shared by two blocks).  A thread that leaves the kernel early simply waits at that barrier — valid
+    // for kernels whose early exits are either uniform over the block or not followed by __syncthreads (true of every kernel run here, and a CUDA rule).
+    std::barrier<> cta((std::ptrdiff_t)block.x);
+    g.cta = &cta;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < block.x; t++) th.emplace_back([=, &cta] {
+        for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+            tl.tid = { t, 0, 0 }; tl.bid = { bx, by, 0 };
+            body();
+            cta.arrive_and_wait();
+        }
+    });
+    for (auto & x : th) x.join();
 }
 } // namespace simt
 

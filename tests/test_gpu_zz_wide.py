@@ -74,6 +74,13 @@ def test_q4_0_kv_cache_set_rows_and_flash_attn_vs_oracle(shape):
     assert o["attn_err"] <= 2e-5, o
 
 
+def test_flash_attn_any_head_size_vs_oracle():
+    """b200_flash_attn_any: head sizes 32 / 96 / 192 / 256 over F16, Q8_0 and Q4_0 caches (the tuned kernels carry 64 and 128)"""
+    o = child("attn_any_suite")
+    bad = {k: v for k, v in o.items() if "error" in v or v["err"] > 2e-5}
+    assert len(o) == 6 and not bad, bad
+
+
 @pytest.mark.parametrize("n_tok,n_past", [(1, 100), (5, 37)])
 def test_attention_without_fa_block_vs_oracle(n_tok, n_past):
     """one attention block as libllama emits it WITHOUT -fa (tests/nofa_graph.py) through the graph executor: K rows and transposed-V elements stored

@@ -33,6 +33,7 @@ def K():
     L.sim_get_rows_q.argtypes = [i32, vp, i64, i64, vp, vp, i64, i64, i64]
     L.sim_set_rows_q4_0.argtypes = [vp, i64, vp, vp, i64, i64, i64]
     L.sim_misaligned.restype = C.c_long
+    L.sim_flash_attn_any.argtypes = [i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32]
     L.sim_binary_strided.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sim_soft_max_rows.argtypes = [vp, i64, vp, i64, i64, i64, f32]
     L.sim_argsort_rows.argtypes = [vp, i64, vp, i64, i64, i64, i32]
@@ -247,3 +248,42 @@ def test_non_flash_attention_kernels(K):
     src_nb = i64a(4, nt * hd * 4, hd * 4, nh * nt * hd * 4)
     K.sim_binary_strided(3, ptr(wkqv), ptr(src_nb), ptr(wkqv), ptr(i64a(1, 1, 1, 1)), ptr(i64a(4, 4, 4, 4)), ptr(out), ptr(i64a(hd, nh, nt, 1)), ptr(i64a(4, hd * 4, nh * hd * 4, nt * nh * hd * 4)))
     assert np.array_equal(out, wkqv.transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("kvt,d", [(1, 256), (1, 96), (8, 256), (8, 80 + 16), (2, 192), (8, 32), (1, 64)])
+def test_flash_attn_any_head_size_kernel(K, kvt, d):
+    """head sizes the tuned kernels do not carry (Gemma 256, Phi 96 ...) over F16 / Q8_0 / Q4_0 caches, GQA, mask, soft-cap"""
+    from refutil import F16, Q8_0
+    rng = np.random.default_rng(kvt * 1000 + d)
+    n_head, n_head_kv, n_tok, n_kv = 4, 2, 2, 45
+    rb_row, rb_head = row_bytes(kvt, n_head_kv * d), row_bytes(kvt, d)
+    kf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32); vf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32)
+    ids = np.arange(n_kv, dtype=np.int64)
+    kc = np.zeros((n_kv, rb_row), np.uint8); vc = kc.copy()
+    oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), kvt, n_head_kv * d, n_kv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), kvt, n_head_kv * d, n_kv, rb_row)
+    q = rng.standard_normal((n_tok, n_head, d)).astype(np.float32)
+    mask = np.full((64, n_kv), -np.inf, np.float32); mask[0, :40] = 0; mask[1, :41] = 0
+    m16 = mask.astype(np.float16)
+    scale, softcap = float(1 / np.sqrt(d)), (20.0 if d == 256 else 0.0)
+    want = np.zeros((n_tok, n_head, d), np.float32)
+    oracle().orc_flash_attn_ext(ptr(q), n_head * d * 4, d * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), ptr(want),
+                                kvt, d, d, n_head, n_head_kv, n_tok, n_kv, scale, 0.0, softcap)
+    dst = np.zeros_like(want)
+    K.sim_flash_attn_any(kvt, ptr(q), n_head * d, d, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), n_kv, ptr(dst),
+                         d, n_head, n_head_kv, n_tok, n_kv, scale, 0.0, softcap)
+    if kvt == 1:
+        # F16 V: the oracle accumulates in fp16 (ops.cpp:8278-8340: ~2e-3 of noise), the kernel in f32 — compare with the f64 value of the same f16 inputs
+        Kd = kc.view(np.float16).reshape(n_kv, n_head_kv, d).astype(np.float64); Vd = vc.view(np.float16).reshape(n_kv, n_head_kv, d).astype(np.float64)
+        exact = np.zeros((n_tok, n_head, d))
+        for t in range(n_tok):
+            for h in range(n_head):
+                sc = Kd[:, h // (n_head // n_head_kv), :] @ q[t, h].astype(np.float16).astype(np.float64) * scale
+                if softcap:
+                    sc = softcap * np.tanh(sc / softcap)
+                sc = sc + mask[t].astype(np.float64)
+                w = np.exp(sc - sc.max()); w /= w.sum()
+                exact[t, h] = w @ Vd[:, h // (n_head // n_head_kv), :]
+        assert rel(dst, exact) <= 2e-5 and rel(want, exact) <= 4e-3
+    else:
+        assert rel(dst, want) <= 2e-5

@@ -333,6 +333,53 @@ def do_kv_q4_0(d, n_head, n_head_kv, n_tok, n_kv):
     return out
 
 
+def do_attn_any(kvt, d, n_head, n_head_kv, n_tok, n_kv):
+    """FLASH_ATTN_EXT at head sizes the tuned kernels do not carry, F16 / Q8_0 / Q4_0 cache, vs the oracle (F16: vs the f64 value of the same f16 inputs)"""
+    rng = np.random.default_rng(kvt * 1000 + d + n_kv)
+    rb_row, rb_head = row_bytes(kvt, n_head_kv * d), row_bytes(kvt, d)
+    kf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32); vf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32)
+    ids = np.arange(n_kv, dtype=np.int64)
+    kc = np.zeros((n_kv, rb_row), np.uint8); vc = kc.copy()
+    oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), kvt, n_head_kv * d, n_kv, rb_row)
+    oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), kvt, n_head_kv * d, n_kv, rb_row)
+    q = rng.standard_normal((n_tok, n_head, d)).astype(np.float32)
+    npad = (n_tok + 63) // 64 * 64
+    mask = np.full((npad, n_kv), -np.inf, np.float32)
+    for t in range(n_tok):
+        mask[t, :max(1, n_kv - n_tok + t + 1)] = 0
+    m16 = mask.astype(np.float16)
+    scale = float(1 / np.sqrt(d))
+    if kvt == 1:
+        Kd = kc.view(np.float16).reshape(n_kv, n_head_kv, d).astype(np.float64); Vd = vc.view(np.float16).reshape(n_kv, n_head_kv, d).astype(np.float64)
+        want = np.zeros((n_tok, n_head, d))
+        for t in range(n_tok):
+            for h in range(n_head):
+                sc = Kd[:, h // (n_head // n_head_kv), :] @ q[t, h].astype(np.float16).astype(np.float64) * scale + mask[t].astype(np.float64)
+                w = np.exp(sc - sc.max()); w /= w.sum()
+                want[t, h] = w @ Vd[:, h // (n_head // n_head_kv), :]
+    else:
+        want = np.zeros((n_tok, n_head, d), np.float32)
+        oracle().orc_flash_attn_ext(ptr(q), n_head * d * 4, d * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)), ptr(want),
+                                    kvt, d, d, n_head, n_head_kv, n_tok, n_kv, scale, 0.0, 0.0)
+    qd = dev(q); md = torch.from_numpy(m16.view(np.int16)).cuda()
+    kd = dev(np.concatenate([kc.reshape(-1), np.zeros(64, np.uint8)])); vd = dev(np.concatenate([vc.reshape(-1), np.zeros(64, np.uint8)]))
+    dst = torch.zeros((n_tok, n_head, d), dtype=torch.float32, device="cuda")
+    ops.check(L.b200_flash_attn_any(kvt, ops.p(qd), n_head * d, d, ops.p(kd), rb_row, rb_head, ops.p(vd), rb_row, rb_head, ops.p(md), n_kv, ops.p(dst),
+                                    d, n_head, n_head_kv, n_tok, n_kv, scale, 0.0, 0.0, ops.stream()))
+    torch.cuda.synchronize()
+    return {"err": rel(dst.cpu().numpy(), want)}
+
+
+def do_attn_any_suite():
+    out = {}
+    for case in [(1, 256, 8, 4, 1, 700), (1, 96, 8, 8, 5, 300), (8, 256, 8, 4, 1, 700), (8, 96, 4, 4, 33, 128), (2, 192, 4, 2, 2, 260), (8, 32, 4, 1, 1, 64)]:
+        try:
+            out[" ".join(map(str, case))] = do_attn_any(*case)
+        except Exception as e:                              # noqa: BLE001
+            out[" ".join(map(str, case))] = {"error": repr(e)[:300]}
+    return out
+
+
 def do_type_suite(t):
     """every C-ABI case of one format in ONE process (a fresh interpreter + torch import per case would dominate the run time)"""
     out = {}
@@ -367,7 +414,7 @@ def do_type_suites(group):
 def main():
     what = sys.argv[1]; a = [int(v) if v.lstrip("-").isdigit() else v for v in sys.argv[2:]]
     torch.cuda.set_device(0)
-    fn = {"repack_models": do_repack_models, "type_suites": do_type_suites, "nofa": do_nofa, "glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
+    fn = {"attn_any_suite": do_attn_any_suite, "repack_models": do_repack_models, "type_suites": do_type_suites, "nofa": do_nofa, "glue": do_glue, "kv_q4_0": do_kv_q4_0, "type_suite": do_type_suite, "mul_mat": do_mul_mat, "mul_mat_id": do_mul_mat_id, "get_rows": do_get_rows, "repack_model": do_repack_model, "executor": do_executor}[what]
     print("RESULT " + json.dumps(fn(*a)))
 
 
