@@ -48,6 +48,8 @@ enum b200_op {
     B200_OP_SUM_ROWS,        /* src0 f32 [n, rows] -> dst f32 [1, rows]                                                                             */
     B200_OP_DIV,             /* broadcasting f32, like MUL                                                                                          */
     B200_OP_CONT,            /* src0 f32, any strides -> dst f32 contiguous, elements in src0's logical order (ggml_cont / ggml_cont_2d); wide path            */
+    B200_OP_SCALE,           /* src0 f32 contiguous; op_params {s, b} (f32 bits): x * s + b; wide path                                                         */
+    B200_OP_UNARY,           /* src0 f32 contiguous; op_params[0] = ggml_unary_op: SILU (10) or SIGMOID (7); wide path                                          */
     B200_OP_COUNT
 };
 

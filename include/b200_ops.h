@@ -213,6 +213,8 @@ B200_API int b200_argsort_rows(const float *x, int64_t x_row_stride, int32_t *id
 B200_API int b200_sum_rows(const float *x, int64_t x_row_stride, float *y, int64_t ncols, int64_t nrows, void *stream);
 B200_API int b200_get_rows_f32_batched(const float *src, int64_t src_row_stride, int64_t src_batch_stride, int64_t n_src_rows, const int32_t *ids, int64_t ids_batch_stride,
                                        float *dst, int64_t dst_row_stride, int64_t dst_batch_stride, int64_t ncols, int64_t n_ids, int64_t n_batch, void *stream);
+/* SCALE / SILU / SIGMOID (op 0 / 1 / 2) on contiguous f32: the unary ops of MoE gating variants (shared-expert gates, weight scaling); unary.cu / scale.cu */
+B200_API int b200_unary(int op, const float *x, float *y, int64_t n, float s, float b, void *stream);
 B200_API int b200_mul_mat_f32(const float *W, int64_t w_row_stride, const float *x, int64_t x_col_stride, float *dst, int64_t dst_col_stride,
                               int64_t m, int64_t k, int64_t ncols, void *stream);
 

@@ -248,6 +248,8 @@ bool node_ok(const b200_node & n) {
         case B200_OP_ROPE:     return n.n_src >= 2 && rope_ok(n);
         case B200_OP_SET_ROWS: return n.n_src >= 2 && (set_rows_ok(n) || set_rows1_ok(n));
         case B200_OP_CONT:     return cont_ok(n);
+        case B200_OP_SCALE:    return wide_on() && n.n_src >= 1 && rows2d_f32(n.src[0]) && rows2d_f32(n.dst) && same_shape(n.src[0], n.dst);
+        case B200_OP_UNARY:    return wide_on() && n.n_src >= 1 && rows2d_f32(n.src[0]) && rows2d_f32(n.dst) && same_shape(n.src[0], n.dst) && (n.op_params[0] == 10 || n.op_params[0] == 7);
         case B200_OP_FLASH_ATTN_EXT: return n.n_src >= 3 && fattn_ok(n);
         case B200_OP_GLU_SWIGLU: return n.n_src >= 2 && rows_f32_ok(n.src[0]) && rows_f32_ok(n.src[1]) && rows_f32_ok(n.dst) && same_shape(n.src[0], n.src[1]) && same_shape(n.src[0], n.dst);
         case B200_OP_MUL_MAT_ID: return mul_mat_id_ok(n);
@@ -873,6 +875,12 @@ struct Runner {
                 return KL(b200_rope((const float *)x.data, (float *)n.dst.data, (const int32_t *)n.src[1].data, ff, x.ne[0], x.ne[1], x.ne[2],
                                     x.nb[1] / 4, x.nb[2] / 4, n.dst.nb[1] / 4, n.dst.nb[2] / 4, &p, st));
             }
+            case B200_OP_SCALE:
+                invalidate_act(n.dst);
+                return KL(b200_unary(0, (const float *)n.src[0].data, (float *)n.dst.data, nelem(n.dst), f32_param(n, 0), f32_param(n, 1), st));
+            case B200_OP_UNARY:
+                invalidate_act(n.dst);
+                return KL(b200_unary(n.op_params[0] == 10 ? 1 : 2, (const float *)n.src[0].data, (float *)n.dst.data, nelem(n.dst), 0.0f, 0.0f, st));
             case B200_OP_CONT: {
                 invalidate_act(n.dst);
                 const b200_tensor & s0 = n.src[0];

@@ -109,3 +109,14 @@ extern "C" int b200_mul_mat_f32(const float * W, int64_t w_row_stride, const flo
     B200_LAUNCH_CHECK();
     return B200_OK;
 }
+
+extern "C" int b200_unary(int op, const float * x, float * y, int64_t n, float s, float b, void * stream) {
+    GE_DEV();
+    if (op < 0 || op > 2 || !x || !y || n <= 0 || (((uintptr_t)x | (uintptr_t)y) & 3)) { b200_set_error("unary: bad arguments (op 0 scale, 1 silu, 2 sigmoid)"); return B200_ERR_INVALID; }
+    const int g = ge_grid(n, 256);
+    if (op == 0) unary_kernel<0><<<g, 256, 0, (cudaStream_t)stream>>>(x, y, n, s, b);
+    else if (op == 1) unary_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(x, y, n, s, b);
+    else unary_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(x, y, n, s, b);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+}

@@ -107,6 +107,21 @@ __global__ void __launch_bounds__(256) mul_mat_f32_kernel(const float * __restri
     if (lane == 0) dst[c * d_cs + r] = acc;
 }
 
+// Unary ops of gating variants (ggml-cpu/unary-ops.cpp, vec.h): OP 0 SCALE (x * s, or fma(x, s, b) when b != 0: ops.cpp:4815-4850), 1 SILU (x / (1 + exp(-x)), the x86
+// vector polynomial of common.cuh silu_x86), 2 SIGMOID (1 / (1 + expf(-x))).  Contiguous f32.
+template <int OP>
+__global__ void __launch_bounds__(256) unary_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float s, float b) {
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        float r;
+        if (OP == 0) r = b == 0.0f ? __fmul_rn(v, s) : fmaf(v, s, b);
+        else if (OP == 1) r = silu_x86(v);
+        else r = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+        y[i] = r;
+    }
+}
+
 // ---- attention without -fa (llama-graph.cpp build_attn_mha, non-flash branch): KQ = K^T Q and KQV = V^T softmax(KQ) are batched MUL_MATs with f16
 // src0 views of the KV cache (permuted / transposed, GQA-broadcast over dim 2); the CPU oracle rounds the f32 operand to f16 (vec_dot_type of F16,
 // ggml-cpu.c:209-303) and accumulates in f32 (ggml_vec_dot_f16).  One warp per output element; strides in BYTES.

@@ -10,7 +10,7 @@ from . import ops
 
 F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K, I32, I64 = 0, 1, 2, 6, 8, 12, 13, 14, 26, 27
 Q4_1, Q5_1, Q2_K, Q3_K, IQ4_NL, IQ4_XS, MXFP4 = 3, 7, 10, 11, 20, 23, 39      # the wide path's formats (b200_ops.h)
-OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY, OP_MUL_MAT_ID, OP_SOFT_MAX, OP_ARGSORT, OP_SUM_ROWS, OP_DIV, OP_CONT = range(17)
+OP_NONE, OP_MUL_MAT, OP_RMS_NORM, OP_MUL, OP_ADD, OP_ROPE, OP_SET_ROWS, OP_FLASH_ATTN_EXT, OP_GLU_SWIGLU, OP_GET_ROWS, OP_CPY, OP_MUL_MAT_ID, OP_SOFT_MAX, OP_ARGSORT, OP_SUM_ROWS, OP_DIV, OP_CONT, OP_SCALE, OP_UNARY = range(19)
 EXEC_CUDA_GRAPHS, EXEC_FUSION, EXEC_MEGAKERNEL, EXEC_MEGA_MMV = 1, 2, 4, 8
 MAX_SRC = 6
 ELEM_SIZE = {F32: 4, F16: 2, I32: 4, I64: 8}

@@ -95,6 +95,7 @@ SIGNATURES = {
     "b200_sum_rows": (i32, [vp, i64, vp, i64, i64, vp]),
     "b200_get_rows_f32_batched": (i32, [vp, i64, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, vp]),
     "b200_mul_mat_f32": (i32, [vp, i64, vp, i64, vp, i64, i64, i64, i64, vp]),
+    "b200_unary": (i32, [i32, vp, vp, i64, f32, f32, vp]),
     "b200_mul_mat_f16": (i32, [vp, i64, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, i64, i64, vp]),
     "b200_soft_max_mask": (i32, [vp, vp, vp, i32, i64, i64, i64, i64, f32, f32, vp]),
     "b200_scatter_rows1": (i32, [vp, vp, vp, i32, i64, i64, vp]),

@@ -269,7 +269,9 @@ static bool node_to_b200(const ggml_tensor * t, b200_node & n) {
         case GGML_OP_ARGSORT:  n.op = B200_OP_ARGSORT; break;
         case GGML_OP_SUM_ROWS: n.op = B200_OP_SUM_ROWS; break;
         case GGML_OP_DIV:      n.op = B200_OP_DIV; break;
-        case GGML_OP_CONT:     n.op = B200_OP_CONT; break;        // attention without -fa (wide path)     // wide path (GGML_B200_WIDE=1); refused by b200_executor_supports otherwise
+        case GGML_OP_CONT:     n.op = B200_OP_CONT; break;        // attention without -fa (wide path)
+        case GGML_OP_SCALE:    n.op = B200_OP_SCALE; break;       // MoE gating variants (wide path)
+        case GGML_OP_UNARY:    n.op = B200_OP_UNARY; break;       // SILU / SIGMOID only (op_params[0] = ggml_unary_op; checked by the executor)     // wide path (GGML_B200_WIDE=1); refused by b200_executor_supports otherwise
         default: return false;
     }
     to_b200(t, n.dst);

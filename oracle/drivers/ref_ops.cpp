@@ -110,6 +110,12 @@ int main(int argc, char ** argv) {
     } else if (op == "mul_mat_id") {
         // as [k, m, n_expert], b [k, n_b1, n_tok] f32, ids i32 [n_used, n_tok] (llama-graph.cpp build_moe_ffn)
         out = ggml_mul_mat_id(ctx, need("w"), need("x"), need("ids"));
+    } else if (op == "scale") {
+        out = ggml_scale_bias(ctx, need("x"), (float)P("s", 1), (float)P("b", 0));
+    } else if (op == "silu") {
+        out = ggml_silu(ctx, need("x"));
+    } else if (op == "sigmoid") {
+        out = ggml_sigmoid(ctx, need("x"));
     } else if (op == "soft_max") {
         out = ggml_soft_max_ext(ctx, need("x"), opt("mask"), (float)P("scale", 1), (float)P("max_bias", 0));
     } else if (op == "argsort") {

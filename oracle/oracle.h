@@ -126,6 +126,9 @@ void orc_mul_mat_f16(const void *A, int64_t a_nb1, int64_t a_nb2, int64_t a_ne2,
 void orc_soft_max_mask(const float *x, float *y, const void *mask, int mask_is_f16, int64_t mask_row_stride, int64_t ncols, int64_t n_tok, int64_t n_head,
                        float scale, float max_bias);
 
+/* SCALE / SILU / SIGMOID (op 0 / 1 / 2) as gating variants use them (ggml-cpu/ops.cpp:4815-4850, vec.h:574,691) */
+void orc_unary(int op, const float *x, float *y, int64_t n, float s, float b);
+
 /* glue (ggml-cpu/vec.h:691, ops.cpp swiglu / binary-ops.cpp / get_rows / cpy) */
 void orc_swiglu(const float *gate, const float *up, float *y, int64_t n);
 void orc_add(const float *a, const float *b, float *y, int64_t ncols, int64_t nrows, int64_t b_rows);

@@ -353,3 +353,14 @@ void orc_soft_max_mask(const float *x, float *y, const void *mask, int mask_is_f
         for (int64_t i = 0; i < ncols; i++) yr[i] *= inv;
     }
 }
+
+/* SCALE (ggml-cpu/ops.cpp:4815-4850: x*s, or the FMA x*s + b of ggml_vec_mad1_f32 when b != 0), SILU and SIGMOID in their scalar forms
+ * (ggml-cpu/vec.h:574,691: expf; the vector body of SILU uses the polynomial exp of orc_swiglu: both within 2 ulp) */
+void orc_unary(int op, const float *x, float *y, int64_t n, float s, float b) {
+    for (int64_t i = 0; i < n; i++) {
+        if (op == 0) y[i] = b == 0.0f ? x[i] * s : fmaf(x[i], s, b);
+        else if (op == 1) y[i] = x[i] / (1.0f + expf(-x[i]));
+        else y[i] = 1.0f / (1.0f + expf(-x[i]));
+    }
+}
+

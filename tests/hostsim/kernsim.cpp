@@ -135,4 +135,9 @@ void sim_flash_attn_any(int kv_type, const float * q, int64_t q_tok_stride, int6
     else if (kv_type == 8) simt::launch(grid, dim3(128), 0, [a, D] { fattn_any_kernel<8>(a, D); });
     else                   simt::launch(grid, dim3(128), 0, [a, D] { fattn_any_kernel<2>(a, D); });
 }
+void sim_unary(int op, const float * x, float * y, int64_t n, float sc, float b) {
+    if (op == 0) simt::launch(dim3(2), dim3(256), 0, [=] { unary_kernel<0>(x, y, n, sc, b); });
+    else if (op == 1) simt::launch(dim3(2), dim3(256), 0, [=] { unary_kernel<1>(x, y, n, sc, b); });
+    else simt::launch(dim3(2), dim3(256), 0, [=] { unary_kernel<2>(x, y, n, sc, b); });
+}
 }

@@ -85,3 +85,15 @@ inline void pdl_wait() {}
 inline void pdl_trigger() {}
 inline float warp_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 inline float warp_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+// common.cuh's silu_x86 (behind #ifdef __CUDACC__ there): the x86 vector polynomial of ggml_v_expf with an FMA at every step — restated for the emulation
+inline float silu_x86(float x) {
+    const float nx = 0.0f - x, r = 0x1.8p23f;
+    const float z = fmaf(nx, 0x1.715476p+0f, r), n = z - r;
+    const float b = fmaf(-n, 0x1.7f7d1cp-20f, fmaf(-n, 0x1.62e4p-1f, nx));
+    const float u = b * b;
+    const float j = fmaf(fmaf(fmaf(0x1.0e4020p-7f, b, 0x1.573e2ep-5f), u, fmaf(0x1.555e66p-3f, b, 0x1.fffdb6p-2f)), u, fmaf(0x1.ffffecp-1f, b, 1.0f));
+    float e = ldexpf(j, (int)n);
+    if (fabsf(n) > 192.0f) e = n <= 0.0f ? 0.0f : INFINITY;
+    return x / (1.0f + e);
+}
+

@@ -98,6 +98,7 @@ def oracle():
         L.orc_soft_max_rows.argtypes = [vp, vp, i64, i64, f32]
         L.orc_argsort_rows.argtypes = [vp, vp, i64, i64, i32]
         L.orc_sum_rows.argtypes = [vp, vp, i64, i64]
+        L.orc_unary.argtypes = [i32, vp, vp, i64, f32, f32]
         L.orc_mul_mat_f16.argtypes = [vp, i64, i64, i64, vp, i64, i64, vp, i64, i64, i64, i64, i64, i64]
         L.orc_soft_max_mask.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, f32, f32]
         _oracle = L

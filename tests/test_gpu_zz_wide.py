@@ -96,7 +96,7 @@ def test_moe_router_glue_vs_oracle():
     """glue_ext.cu through the C-ABI: f32 router matmul, SOFT_MAX, ARGSORT (ties in the reference's order), batched GET_ROWS, SUM_ROWS, DIV, the
     broadcast MUL and the ADD over strided expert slices"""
     o = child("glue")
-    assert o["mul_mat_f32"] <= 1e-5 and o["soft_max"] <= 1e-6, o
+    assert o["mul_mat_f32"] <= 1e-5 and o["soft_max"] <= 1e-6 and o["unary"] <= 1e-6, o
     assert all(o[k] for k in ("argsort_exact", "get_rows_batched_exact", "sum_rows_exact", "div_exact", "mul_bcast_exact", "add_slices_exact")), o
 
 

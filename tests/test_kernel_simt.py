@@ -33,6 +33,7 @@ def K():
     L.sim_get_rows_q.argtypes = [i32, vp, i64, i64, vp, vp, i64, i64, i64]
     L.sim_set_rows_q4_0.argtypes = [vp, i64, vp, vp, i64, i64, i64]
     L.sim_misaligned.restype = C.c_long
+    L.sim_unary.argtypes = [i32, vp, vp, i64, f32, f32]
     L.sim_flash_attn_any.argtypes = [i32, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, vp, i64, i64, i64, i64, i64, f32, f32, f32]
     L.sim_binary_strided.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.sim_soft_max_rows.argtypes = [vp, i64, vp, i64, i64, i64, f32]
@@ -287,3 +288,12 @@ def test_flash_attn_any_head_size_kernel(K, kvt, d):
         assert rel(dst, exact) <= 2e-5 and rel(want, exact) <= 4e-3
     else:
         assert rel(dst, want) <= 2e-5
+
+
+def test_unary_kernels(K):
+    rng = np.random.default_rng(4)
+    x = (rng.standard_normal(1000) * 5).astype(np.float32)
+    for op, sc, b, tol in ((0, 0.37, 0.0, 0.0), (0, 2.5, -0.75, 0.0), (1, 0, 0, 1e-6), (2, 0, 0, 1e-7)):
+        y = np.zeros_like(x); want = np.zeros_like(x)
+        K.sim_unary(op, ptr(x), ptr(y), x.size, sc, b); oracle().orc_unary(op, ptr(x), ptr(want), x.size, sc, b)
+        assert np.abs(y - want).max() <= tol * max(1.0, np.abs(want).max()), op

@@ -216,3 +216,13 @@ def test_non_flash_attention_ops_through_cpu_backend():
         wp = np.frombuffer(out, np.float32).reshape(nh, nt, nkv); y = np.zeros_like(wp)
         oracle().orc_soft_max_mask(ptr(want), ptr(y), ptr(m), int(mask_t == F16), nkv, nkv, nt, nh, 0.125, max_bias)
         assert np.abs(y - wp).max() <= 2e-6
+
+
+def test_unary_ops_through_cpu_backend():
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((3, 40)) * 4).astype(np.float32)
+    for name, op, prm, tol in (("scale", 0, dict(s=0.37, b=0.0), 0.0), ("scale", 0, dict(s=2.5, b=-0.75), 1e-7), ("silu", 1, {}, 1e-6), ("sigmoid", 2, {}, 1e-7)):
+        _, _, out = run_ref_op(name, [("x", F32, [40, 3], x)], prm)
+        want = np.frombuffer(out, np.float32).reshape(3, 40); y = np.zeros_like(x)
+        oracle().orc_unary(op, ptr(x), ptr(y), x.size, float(prm.get("s", 1.0)), float(prm.get("b", 0.0)))
+        assert np.abs(y - want).max() <= tol * max(1.0, np.abs(want).max()), name

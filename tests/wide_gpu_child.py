@@ -291,6 +291,13 @@ def do_glue():
     ops.check(L.b200_binary_strided(0, ops.p(exwd), ptr(sl), C.c_void_p(exwd.data_ptr() + 4 * E), ptr(h64(E, NT, 1, 1)), ptr(sl), ops.p(od), ptr(h64(E, NT, 1, 1)),
                                     ptr(h64(4, 4 * E, 4 * E * NT, 4 * E * NT)), ops.stream())); torch.cuda.synchronize()
     out["add_slices_exact"] = bool(np.array_equal(od.cpu().numpy(), exw[:, 0, :] + exw[:, 1, :]))
+    xu = (rng.standard_normal(4096) * 5).astype(np.float32); xud = dev(xu); yud = torch.zeros_like(xud)
+    worst = 0.0
+    for op, sc, bb in ((0, 0.37, 0.0), (0, 2.5, -0.75), (1, 0.0, 0.0), (2, 0.0, 0.0)):
+        ops.check(L.b200_unary(op, ops.p(xud), ops.p(yud), xu.size, sc, bb, ops.stream())); torch.cuda.synchronize()
+        wu = np.zeros_like(xu); O.orc_unary(op, ptr(xu), ptr(wu), xu.size, sc, bb)
+        worst = max(worst, float(np.abs(yud.cpu().numpy() - wu).max() / max(1.0, np.abs(wu).max())))
+    out["unary"] = worst
     return out
 
 
