@@ -297,3 +297,65 @@ def test_unary_kernels(K):
         y = np.zeros_like(x); want = np.zeros_like(x)
         K.sim_unary(op, ptr(x), ptr(y), x.size, sc, b); oracle().orc_unary(op, ptr(x), ptr(want), x.size, sc, b)
         assert np.abs(y - want).max() <= tol * max(1.0, np.abs(want).max()), op
+
+
+def test_wide_matvec_kernel_random_shapes(K):
+    """seeded sweep over shapes the fixed cases do not hit: one row, fewer rows than warps, odd row counts over several row groups, 1..9 columns
+    (column-group tails), k from one block up to several 256-chunks with a partial last chunk"""
+    rng = np.random.default_rng(2026)
+    for it in range(24):
+        t = int(rng.choice(WEIGHT_TYPES + EXT_TYPES))
+        be = BLOCK_ELEMS[t]
+        if t in EXT_TYPES and be == 32:
+            k = 32 * int(rng.integers(1, 40))
+        elif t == Q6_K:
+            k = 512 * int(rng.integers(1, 3))
+        else:
+            k = 256 * int(rng.integers(1, 4))
+        m = int(rng.choice([1, 3, 7, 8, 9, 17, 33])); n = int(rng.integers(1, 10)); gx = int(rng.integers(1, 4))
+        W = rand_blocks(rng, t, m, k); X = rng.standard_normal((n, k)).astype(np.float32)
+        bias = rng.standard_normal(m).astype(np.float32) if it % 2 else None
+        want = orc_mul_mat(t, W, X, m, n, k) + (bias[None, :] if bias is not None else 0)
+        dst = np.full((n, m), 7.0, np.float32)
+        K.sim_mul_mat_vec_wide(t, ptr(repack_rows_np(t, W, k)), ptr(X), k, ptr(dst), m, ptr(bias), None, m, k, n, gx)
+        assert rel(dst, want) <= 2e-5, (t, m, k, n, gx)
+
+
+def test_mul_mat_id_and_q4_0_attention_random_shapes(K):
+    """seeded sweep: MUL_MAT_ID with 1..5 tokens, 1..4 used experts, activation sharing patterns n_b1 | n_used; q4_0 attention with GQA ratios 1 / 2 / 4,
+    1..3 tokens, KV lengths that are not multiples of the warp count"""
+    rng = np.random.default_rng(77)
+    for it in range(10):
+        t = int(rng.choice([2, 12, 13, 3, 7, 10, 23, 39]))
+        k = 256 * int(rng.integers(1, 3)); m = int(rng.choice([4, 12, 20]))
+        n_expert = int(rng.integers(2, 7)); n_used = int(rng.integers(1, min(4, n_expert) + 1)); n_tok = int(rng.integers(1, 6))
+        n_b1 = int(rng.choice([d for d in range(1, n_used + 1) if n_used % d == 0]))
+        W = rand_blocks(rng, t, n_expert * m, k)
+        b = rng.standard_normal((n_tok, n_b1, k)).astype(np.float32)
+        ids = np.stack([rng.permutation(n_expert)[:n_used] for _ in range(n_tok)]).astype(np.int32)
+        want = np.zeros((n_tok, n_used, m), np.float32)
+        oracle().orc_mul_mat_id(t, ptr(W), ptr(b), ptr(ids), ptr(want), m, k, n_expert, n_used, n_tok, n_b1, n_used)
+        dst = np.zeros_like(want)
+        K.sim_mul_mat_id(t, ptr(repack_rows_np(t, W, k)), m * row_bytes(t, k), ptr(b), n_b1 * k, k, n_b1, ptr(ids), n_used, ptr(dst), n_used * m, m, m, k, n_expert, n_used, n_tok, 1)
+        assert rel(dst, want) <= 2e-5, (t, m, k, n_expert, n_used, n_tok, n_b1)
+    for it in range(6):
+        d = int(rng.choice([64, 128])); n_head_kv = int(rng.choice([1, 2])); n_head = n_head_kv * int(rng.choice([1, 2, 4])); n_tok = int(rng.integers(1, 4)); n_kv = int(rng.integers(3, 70))
+        rb_row, rb_head = row_bytes(Q4_0, n_head_kv * d), row_bytes(Q4_0, d)
+        kf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32); vf = rng.standard_normal((n_kv, n_head_kv * d)).astype(np.float32)
+        ids = np.arange(n_kv, dtype=np.int64)
+        kc = np.zeros((n_kv, rb_row), np.uint8); vc = kc.copy()
+        oracle().orc_set_rows(ptr(kf), ptr(ids), ptr(kc), Q4_0, n_head_kv * d, n_kv, rb_row)
+        oracle().orc_set_rows(ptr(vf), ptr(ids), ptr(vc), Q4_0, n_head_kv * d, n_kv, rb_row)
+        q = rng.standard_normal((n_tok, n_head, d)).astype(np.float32)
+        use_mask = it % 2 == 0
+        mask = np.full((64, n_kv), -np.inf, np.float32)
+        for tt in range(n_tok):
+            mask[tt, :max(1, n_kv - n_tok + tt + 1)] = 0
+        m16 = mask.astype(np.float16)
+        want = np.zeros((n_tok, n_head, d), np.float32)
+        oracle().orc_flash_attn_ext(ptr(q), n_head * d * 4, d * 4, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)) if use_mask else None, ptr(want),
+                                    Q4_0, d, d, n_head, n_head_kv, n_tok, n_kv, 0.1, 0.0, 0.0)
+        dst = np.zeros_like(want)
+        K.sim_flash_attn_q4_0(ptr(q), n_head * d, d, ptr(kc), rb_row, rb_head, ptr(vc), rb_row, rb_head, ptr(m16.view(np.uint16)) if use_mask else None, n_kv, ptr(dst),
+                              d, n_head, n_head_kv, n_tok, n_kv, 0.1, 0.0, 0.0)
+        assert rel(dst, want) <= 2e-5, (d, n_head, n_head_kv, n_tok, n_kv, use_mask)
