@@ -2,6 +2,7 @@
 // mmvq_ext.cu call per 32-element sub-block — with the host compiler, so their bit manipulation is checked against the
 // reference on the CPU (tests/test_extfmt_hostsim.py).  Not linked into any product library.
 #include "../../llama-box_b200/csrc/extfmt.cuh"
+#include "../../llama-box_b200/csrc/repack_layout.cuh"
 
 extern "C" {
 // dot product of one weight row (library layout for Q4_0/Q5_0/Q8_0/Q6_K, ggml layout otherwise) with a quantised column, summed over
@@ -26,6 +27,10 @@ float sim_q4_0n_row_dot(const uint8_t * row, int64_t k, const int8_t * qs, const
     return acc;
 }
 void sim_q4_0n_row_dequant(const uint8_t * row, int64_t k, float * y) { for (int64_t e = 0; e < k; e++) y[e] = xf_q4_0n_value(row + 18 * (e / 32), (int)(e % 32)); }
+// the library's row layout exactly as the repack kernel computes it (repack.cu: every 2-byte unit of a ggml row moved to repacked_off)
+void sim_repack_row(int type, const uint8_t * native, uint8_t * out, int64_t nb, int64_t row_bytes) {
+    for (int64_t u = 0; u < row_bytes; u += 2) { const int64_t r = repacked_off(type, nb, u); out[r] = native[u]; out[r + 1] = native[u + 1]; }
+}
 float sim_h2f(uint16_t h) { return xf_h2f(h); }
 int sim_block_bytes(int t) { return xf_block_bytes(t); }
 int sim_act_family(int t) { return xf_act_family(t); }

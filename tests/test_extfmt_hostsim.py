@@ -17,14 +17,15 @@ SIM_DIR = os.path.join(ROOT, "tests", "hostsim")
 @pytest.fixture(scope="module")
 def sim():
     so = os.path.join(SIM_DIR, "libextsim.so")
-    src = os.path.join(SIM_DIR, "extsim.cpp"); hdr = os.path.join(ROOT, "llama-box_b200", "csrc", "extfmt.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    src = os.path.join(SIM_DIR, "extsim.cpp"); hdr = os.path.join(ROOT, "llama-box_b200", "csrc", "extfmt.cuh"); hdr2 = os.path.join(ROOT, "llama-box_b200", "csrc", "repack_layout.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", src, "-o", so])
     L = C.CDLL(so)
     vp, i64 = C.c_void_p, C.c_int64
     L.sim_row_dot.argtypes = [C.c_int, vp, i64, i64, vp, vp, vp, vp, vp]
     L.sim_row_dequant.argtypes = [C.c_int, vp, i64, i64, vp]
     L.sim_h2f.restype = C.c_float; L.sim_h2f.argtypes = [C.c_uint16]
+    L.sim_repack_row.argtypes = [C.c_int, vp, vp, i64, i64]
     L.sim_q4_0_quantize_row.argtypes = [vp, vp, i64]
     L.sim_q4_0n_row_dot.restype = C.c_float; L.sim_q4_0n_row_dot.argtypes = [vp, i64, vp, vp, vp]
     L.sim_q4_0n_row_dequant.argtypes = [vp, i64, vp]
@@ -112,3 +113,18 @@ def test_q4_0_kv_cache_block_functions(sim):
         assert abs(sim.sim_q4_0n_row_dot(ptr(K[i]), kk, ptr(qs), ptr(d), ptr(bs)) - wantd[i]) <= 2e-6 * np.abs(wantd).max()
         y = np.zeros(kk, np.float32); sim.sim_q4_0n_row_dequant(ptr(K[i]), kk, ptr(y))
         assert np.array_equal(y, deq[i])
+
+
+@pytest.mark.parametrize("t", [2, 6, 8, 14])
+def test_numpy_model_of_the_library_layout_is_the_repack_kernels_permutation(sim, t):
+    """refutil.repack_rows_np — the layout model every CPU test of the wide kernels is built on — against repacked_off (llama-box_b200/csrc/repack_layout.cuh),
+    the function the hardware-verified repack kernel applies to every 2-byte unit of a row"""
+    rng = np.random.default_rng(t)
+    k = 2048
+    W = rand_blocks(rng, t, 5, k)
+    want = repack_rows_np(t, W, k)
+    rb = row_bytes(t, k)
+    for i in range(5):
+        out = np.zeros(rb, np.uint8)
+        sim.sim_repack_row(t, ptr(W[i]), ptr(out), k // BLOCK_ELEMS[t], rb)
+        assert np.array_equal(out, want[i])
